@@ -1,0 +1,187 @@
+"""Configuration of the streaming speech encoder + adapter path.
+
+The yaml schema is the reference's own (``models/utils.py:30-49`` reads ``input_dim``,
+``encoder_conf = {overview_conf, para_conf}`` and ``model_conf``; the dashed option names are the
+argparse flags of ``models/encoder/encoder.py:12-34``, ``models/encoder/transformer.py:134-154``
+and ``models/encoder/subsampling.py:77-84``).  ``PathConfig`` flattens it into the handful of
+integers the C-ABI (``include/fo_b200.h: fo_config``) and the oracle need.
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import Any, Dict, Optional
+
+import yaml
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CONFIG_DIR = os.path.join(os.path.dirname(_HERE), "configs")
+
+# argparse defaults of the reference (transformer.py:136-153, subsampling.py:80-83)
+_TRANSFORMER_DEFAULTS = {
+    "transformer-input-dim": 256, "transformer-output-dim": 4, "transformer-attention-dim": 256,
+    "transformer-attention-heads": 4, "transformer-linear-units": 1024, "transformer-num-blocks": 6,
+    "transformer-input-layer": "linear", "transformer-pos-enc-class": "abs-enc",
+    "transformer-normalize-before": True, "transformer-concat-after": False,
+    "transformer-positionwise-layer-type": "linear", "transformer-positionwise-conv-kernel_size": 1,
+    "transformer-chunk_size": -1, "transformer-left_chunks": -1, "transformer-dynamic-chunks": True,
+}
+_SUBSAMPLING_DEFAULTS = {
+    "subsampling-rate": 4, "subsampling-input-dim": 256, "subsampling-output-dim": 256,
+}
+
+
+@dataclasses.dataclass
+class PathConfig:
+    feat_dim: int = 80            # fbank bins == encoder-input-dim
+    d_model: int = 1024           # subsampling-output-dim == transformer-attention-dim
+    n_heads: int = 16
+    ffn_dim: int = 4096
+    n_layers: int = 24
+    chunk_size: int = 4           # transformer-chunk_size (encoder frames)
+    left_chunks: int = 16         # transformer-left_chunks
+    input_layer: str = "linear"   # transformer-input-layer: linear | none
+    normalize_before: bool = True
+    dynamic_chunks: bool = False
+    pos_max_len: int = 5000       # RelPositionalEncoding max_len default (attention.py:78)
+    # adapter (models/adapter.py:73-110, single-conv branch)
+    llm_dim: int = 3584
+    adapter_kernel: int = 5
+    adapter_act: str = "gelu"
+    adapter_norm: str = "layer"
+    # streaming frontend (bin/inference.py:43-56)
+    sample_rate: int = 16000
+    frame_length_ms: int = 25
+    frame_shift_ms: int = 10
+    frames_per_chunk: int = 16
+    context_frames: int = 3
+    pcm_scale: float = 32768.0
+
+    # ---- derived quantities (attention.py:83,88,291; subsampling.py:34) -----------------------
+    @property
+    def d_k(self) -> int:
+        return self.d_model // self.n_heads
+
+    @property
+    def kv_window(self) -> int:          # MultiHeadedAttention.buffersize
+        return self.chunk_size * self.left_chunks if (self.chunk_size > 0 and self.left_chunks > 0) else 1
+
+    @property
+    def full_chunk_size(self) -> int:    # RelPositionalEncoding.full_chunk_size
+        return (self.left_chunks + 1) * self.chunk_size
+
+    @property
+    def pe_wrap(self) -> int:            # RelPositionalEncoding.max_len after __init__
+        return self.chunk_size * (self.pos_max_len // self.chunk_size) - self.full_chunk_size
+
+    @property
+    def sub_freq(self) -> int:           # ((idim - 1) // 2 - 1) // 2
+        return ((self.feat_dim - 1) // 2 - 1) // 2
+
+    @property
+    def frame_len(self) -> int:
+        return self.sample_rate * self.frame_length_ms // 1000
+
+    @property
+    def frame_shift(self) -> int:
+        return self.sample_rate * self.frame_shift_ms // 1000
+
+    @property
+    def samples_per_chunk(self) -> int:
+        return self.frame_shift * self.frames_per_chunk
+
+    @property
+    def sample_carry(self) -> int:
+        return self.frame_len - self.frame_shift
+
+    @property
+    def chunk_feat_frames(self) -> int:
+        return self.frames_per_chunk + self.context_frames
+
+    @staticmethod
+    def sub_len(t: int) -> int:
+        """Frames after Conv2dSubsampling4: ((T-1)//2 - 1)//2 (subsampling.py:28-34)."""
+        return ((t - 1) // 2 - 1) // 2
+
+    def validate(self) -> None:
+        """The reference exits on an inconsistent config (encoder.py:74-75,86-87,94); here a
+        ValueError.  Variants whose streaming path is broken upstream are refused loudly
+        (SURVEY 2.3): abs-enc has no ``infer``; conv1d FFNs cannot stream."""
+        if self.d_model % self.n_heads:
+            raise ValueError("attention dim must be divisible by heads (attention.py:279)")
+        if self.d_k != 64:
+            raise ValueError("the sm_100a attention kernel is built for d_k == 64 (got %d)" % self.d_k)
+        if self.d_model % 64 or self.ffn_dim % 64 or self.llm_dim % 64:
+            raise ValueError("d_model, ffn_dim and llm_dim must be multiples of 64")
+        if self.input_layer not in ("linear", "none"):
+            raise ValueError("unsupported transformer-input-layer: %s" % self.input_layer)
+        if self.adapter_norm != "layer" or self.adapter_act not in ("gelu", "relu"):
+            raise ValueError("adapter: only norm=layer with gelu/relu is built (adapter.py:100-107)")
+        if self.adapter_kernel < 2:
+            raise ValueError("adapter kernel_size must be >= 2")
+        if not self.normalize_before:
+            raise ValueError("post-norm layers (normalize_before=False) are not built")
+
+
+def load_yaml(name_or_path: str) -> Dict[str, Any]:
+    path = name_or_path
+    if not os.path.exists(path):
+        path = os.path.join(CONFIG_DIR, name_or_path if name_or_path.endswith(".yaml") else name_or_path + ".yaml")
+    with open(path, "r") as fin:
+        return yaml.safe_load(fin)
+
+
+def path_config_from_dict(configs: Dict[str, Any]) -> PathConfig:
+    enc = configs.get("encoder_conf", {})
+    over = enc.get("overview_conf", {})
+    para = enc.get("para_conf", {})
+    layer_cfg = over.get("encoder-layer-config", "subsampling-transformer")
+    if layer_cfg != "subsampling-transformer":
+        raise ValueError("only encoder-layer-config 'subsampling-transformer' is supported "
+                         "(audioLLM.py:378 reads enc[1].num_blocks); got %r" % layer_cfg)
+    tr = dict(_TRANSFORMER_DEFAULTS)
+    tr.update(para.get("transformer", {}))
+    sub = dict(_SUBSAMPLING_DEFAULTS)
+    sub.update(para.get("subsampling", {}))
+    if tr["transformer-pos-enc-class"] != "rel-enc":
+        raise ValueError("only transformer-pos-enc-class 'rel-enc' can stream (attention.py:105)")
+    if tr["transformer-positionwise-layer-type"] != "linear":
+        raise ValueError("only positionwise-layer-type 'linear' streams in the reference "
+                         "(attention.py:254-266 is mis-wired); refusing %r" % tr["transformer-positionwise-layer-type"])
+    if tr["transformer-concat-after"]:
+        raise ValueError("transformer-concat-after is not built")
+    if sub["subsampling-rate"] != 4:
+        raise ValueError("only subsampling-rate 4 exists (subsampling.py:93-96)")
+    feat = int(over.get("encoder-input-dim", configs.get("input_dim", 80)))
+    d = int(tr["transformer-attention-dim"])
+    dims = {int(sub["subsampling-output-dim"]), int(tr["transformer-input-dim"]), d,
+            int(tr["transformer-output-dim"]), int(over.get("encoder-output-dim", d))}
+    if len(dims) != 1 or int(sub["subsampling-input-dim"]) != feat:
+        raise ValueError("WRONG CONFIG: component input/output dims do not chain (encoder.py:82-96)")
+    mc = configs.get("model_conf", {})
+    if mc.get("adpter_type", "subsampling") != "subsampling":
+        raise ValueError("only adpter_type 'subsampling' carries a cache (adapter.py:112)")
+    if int(mc.get("enc_out_dim", d)) != d:
+        raise ValueError("model_conf.enc_out_dim must equal the encoder output dim")
+    if d * 4 < int(mc.get("llm_embed_dim", 3584)):
+        raise ValueError("two-conv CNNSubsampling branch (adapter.py:84-96) is not built")
+    fe = configs.get("frontend", {})
+    cfg = PathConfig(
+        feat_dim=feat, d_model=d, n_heads=int(tr["transformer-attention-heads"]),
+        ffn_dim=int(tr["transformer-linear-units"]), n_layers=int(tr["transformer-num-blocks"]),
+        chunk_size=int(tr["transformer-chunk_size"]), left_chunks=int(tr["transformer-left_chunks"]),
+        input_layer=str(tr["transformer-input-layer"]),
+        normalize_before=bool(tr["transformer-normalize-before"]),
+        dynamic_chunks=bool(tr["transformer-dynamic-chunks"]),
+        llm_dim=int(mc.get("llm_embed_dim", 3584)), adapter_kernel=int(mc.get("kernel_size", 5)),
+        adapter_act=str(mc.get("activation_func", "gelu")), adapter_norm=str(mc.get("norm", "layer")),
+        sample_rate=int(fe.get("sample_rate", 16000)), frame_length_ms=int(fe.get("frame_length_ms", 25)),
+        frame_shift_ms=int(fe.get("frame_shift_ms", 10)), frames_per_chunk=int(fe.get("frames_per_chunk", 16)),
+        context_frames=int(fe.get("context_frames", 3)), pcm_scale=float(fe.get("pcm_scale", 32768.0)),
+    )
+    cfg.validate()
+    return cfg
+
+
+def load_path_config(name_or_path: str = "shipped") -> PathConfig:
+    return path_config_from_dict(load_yaml(name_or_path))

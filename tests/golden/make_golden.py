@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE MODULES (authoring container only).
+
+Run:  PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [--ref /root/reference]
+
+The reference (TheDoctor-JI/Freeze-Omni) ships no tests or golden vectors, so the
+pins for the oracle and the CUDA path are the outputs of its own modules
+(models.encoder.encoder.speechEncoder, models.encoder.cmvn.GlobalCMVN, models.adapter.CNNSubsampling,
+models.AudioFeatureGating, models.masks) imported unmodified from /root/reference, with the
+harness shims of SURVEY 8c:
+  1. models.encoder.encoder.make_pad_mask is injected (encoder.py:142 calls an un-imported name);
+  2. Tensor.to('cuda') is mapped to a no-op on this GPU-less host (transformer.py:279);
+  3. sys.argv is cleared before construction (encoder.py:54-56 parses the process argv).
+Weights are the seeded state dict of freeze_omni_b200/weights.py loaded with strict=True.
+/root/reference does not exist on the GPU box, so nothing else imports this file.
+"""
+import argparse
+import os
+import sys
+import wave
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from freeze_omni_b200.config import load_yaml, path_config_from_dict  # noqa: E402
+from freeze_omni_b200.weights import make_adapter_state, make_encoder_state  # noqa: E402
+
+
+def import_reference(ref_root):
+    sys.path.insert(0, ref_root)
+    sys.dont_write_bytecode = True
+    saved_argv = sys.argv
+    sys.argv = ["x"]
+    import models.encoder.encoder as ref_encoder
+    import models.encoder.cmvn as ref_cmvn
+    import models.adapter as ref_adapter
+    import models.masks as ref_masks
+    import models.AudioFeatureGating as ref_gating
+    ref_encoder.make_pad_mask = lambda lengths, max_len: (
+        torch.arange(max_len).unsqueeze(0) >= lengths.reshape(-1, 1))
+    orig_to = torch.Tensor.to
+
+    def to_shim(self, *a, **k):
+        if a and isinstance(a[0], str) and a[0].startswith("cuda") and not torch.cuda.is_available():
+            return self
+        return orig_to(self, *a, **k)
+    torch.Tensor.to = to_shim
+    sys.argv = saved_argv
+    return ref_encoder, ref_cmvn, ref_adapter, ref_masks, ref_gating
+
+
+def build_reference(mods, yaml_cfg, cfg, seed):
+    ref_encoder, ref_cmvn, ref_adapter, _, _ = mods
+    enc_sd = make_encoder_state(cfg, seed)
+    adp_sd = make_adapter_state(cfg, seed)
+    argv = sys.argv
+    sys.argv = ["x"]
+    cm = ref_cmvn.GlobalCMVN(enc_sd["global_cmvn.mean"].clone(), enc_sd["global_cmvn.istd"].clone())
+    enc = ref_encoder.speechEncoder(cfg.feat_dim, global_cmvn=cm, **yaml_cfg["encoder_conf"])
+    sys.argv = argv
+    enc.load_state_dict(enc_sd, strict=True)
+    mc = yaml_cfg["model_conf"]
+    adp = ref_adapter.CNNSubsampling(mc["enc_out_dim"], mc["llm_embed_dim"], mc["kernel_size"],
+                                     mc["activation_func"], mc["norm"])
+    adp.load_state_dict(adp_sd, strict=True)
+    return enc.eval(), adp.eval()
+
+
+def synth_audio(seed, n):
+    """0.1*N(0,1) band-limited, 200 ms silent gaps, int16-quantised."""
+    g = torch.Generator().manual_seed(seed)
+    x = 0.1 * torch.randn(n + 8, generator=g)
+    x = torch.nn.functional.avg_pool1d(x.view(1, 1, -1), 5, 1).view(-1)[:n] * 2.0
+    t = torch.arange(n)
+    x = x * ((t // 3200) % 5 != 4).float()
+    return torch.clamp((x * 32768.0).round(), -32768, 32767).to(torch.int16)
+
+
+def stream_reference(enc, adp, feats_seq, layers_to_keep=(0,)):
+    """AudioLLM.recognize's encoder/adapter calls (audioLLM.py:377-387), chunk by chunk."""
+    buffer, cache, pe = [None] * enc.enc[1].num_blocks, None, 0
+    enc_outs, adp_outs, pes = [], [], []
+    with torch.no_grad():
+        for feats in feats_seq:
+            eo, buffer, _, _, pe = enc.infer(feats, buffer, 0, None, pe)
+            enc_outs.append(eo.clone())      # the adapter zero-fills through a view of eo
+            mask = torch.full(eo.shape[:2], True).unsqueeze(1)
+            y, _, cache = adp(eo, mask, cache=cache, return_cache=True)
+            adp_outs.append(y.clone())
+            pes.append(pe)
+    out = {"enc_out": torch.stack(enc_outs).numpy(), "adapter_out": torch.stack(adp_outs).numpy(),
+           "pe_index": np.asarray(pes, dtype=np.int64), "adapter_cache": cache[0].contiguous().numpy()}
+    for li in layers_to_keep:
+        out["k_cache_l%d" % li] = buffer[li][0].contiguous().numpy()
+        out["v_cache_l%d" % li] = buffer[li][1].contiguous().numpy()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    mods = import_reference(args.ref)
+    ref_encoder, ref_cmvn, ref_adapter, ref_masks, ref_gating = mods
+    import torchaudio.compliance.kaldi as kaldi
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+
+    def want(name):
+        return not args.only or name in args.only.split(",")
+
+    def save(name, **arrs):
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **arrs)
+        print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+    with wave.open(os.path.join(args.ref, "assets", "question.wav"), "rb") as w:
+        assert w.getframerate() == 16000 and w.getnchannels() == 1 and w.getsampwidth() == 2
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).copy()
+    n_chunks = -(-len(pcm) // 2560)
+    pcm_pad = np.zeros(n_chunks * 2560, dtype=np.int16)
+    pcm_pad[:len(pcm)] = pcm
+
+    # ---------------- fbank ----------------------------------------------------------------
+    def gating_stream(int16_pcm, fbank_config, chunk):
+        g = ref_gating.AudioFeatureGating(16000, fbank_config=fbank_config)
+        outs = []
+        for i in range(len(int16_pcm) // chunk):
+            a = int16_pcm[i * chunk:(i + 1) * chunk].astype(np.float32) / 32768.0
+            outs.append(g._extract_fbank(a).clone())
+        return torch.cat(outs, 0).numpy()
+
+    if want("fbank"):
+        # (a) the survey's known-answer case: offline kaldi.fbank over [240 zeros | signal], scale 1
+        wav = torch.cat([torch.zeros(240), torch.from_numpy(pcm_pad.astype(np.float32))]).unsqueeze(0)
+        off = kaldi.fbank(wav, dither=0, frame_length=25, frame_shift=10, num_mel_bins=80)
+        assert off.shape == (208, 80) and abs(float(off.sum()) - 156308.2261) < 0.5, float(off.sum())
+        # (b) reference's own stateful frontend, default constants (scale 32767, 16+3 frames)
+        g_def = gating_stream(pcm_pad, None, 2560)
+        # (c) the fork's constants (configs/dialog_state_pred_config.yaml:23-30): 16 ms / 8 ms
+        fork = {"feat_dim": 80, "expected_audio_chunk_duration_in_sec": 0.224,
+                "audio_to_proc_per_step_in_sec": 0.016, "step_size_in_sec": 0.008,
+                "context_duration_in_sec": 0.032}
+        n_fork = len(pcm_pad) // 3584
+        g_fork = gating_stream(pcm_pad[:n_fork * 3584], fork, 3584)
+        syn = synth_audio(1000, 16000 * 2).numpy()
+        wav2 = torch.cat([torch.zeros(240), torch.from_numpy(syn.astype(np.float32))]).unsqueeze(0)
+        off2 = kaldi.fbank(wav2, dither=0, frame_length=25, frame_shift=10, num_mel_bins=80)
+        save("fbank", question_pcm=pcm, question_offline=off.numpy(), question_gating_default=g_def,
+             question_gating_fork=g_fork, synth_pcm=syn, synth_offline=off2.numpy(),
+             window=kaldi._feature_window_function("povey", 400, 0.42, torch.device("cpu"), torch.float32).numpy(),
+             mel=kaldi.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)[0].numpy())
+
+    # ---------------- masks ----------------------------------------------------------------
+    if want("masks"):
+        arrs = {}
+        for T in (1, 3, 4, 5, 17, 68, 69, 100):
+            for c in (1, 4, 7):
+                for L in (-1, 0, 1, 16):
+                    m = ref_masks.subsequent_chunk_mask(T, c, L).numpy()
+                    arrs["T%d_c%d_L%d" % (T, c, L)] = np.packbits(m.reshape(-1))
+        save("masks", **arrs)
+
+    def feats_from_pcm(int16_pcm):
+        """bin/inference.py:57-80 (audioEncoderProcessor; not importable: the file needs soundfile
+        and web.*) restated with the reference's own kaldi call, scale 32768."""
+        samples, ring, out = torch.zeros(1, 2800), torch.zeros(1, 19, 80), []
+        for i in range(len(int16_pcm) // 2560):
+            a = torch.from_numpy(int16_pcm[i * 2560:(i + 1) * 2560].astype(np.float32) / 32768.0) * 32768
+            samples = torch.cat([samples[:, -240:], a.view(1, -1)], 1)
+            xs = kaldi.fbank(waveform=samples, dither=0, frame_length=25, frame_shift=10, num_mel_bins=80)
+            ring = torch.cat([ring[:, -3:], xs.unsqueeze(0)], 1)
+            out.append(ring.clone())
+        return out
+
+    # ---------------- tiny config ----------------------------------------------------------
+    if want("tiny"):
+        ycfg = load_yaml("tiny")
+        cfg = path_config_from_dict(ycfg)
+        enc, adp = build_reference(mods, ycfg, cfg, seed=3)
+        B = 3
+        pcm_b = [synth_audio(2000 + b, 2560 * 24).numpy() for b in range(B)]
+        per = [feats_from_pcm(p) for p in pcm_b]
+        feats_seq = [torch.cat([per[b][i] for b in range(B)], 0) for i in range(24)]
+        st = stream_reference(enc, adp, feats_seq, layers_to_keep=(0, 1))
+        # t = 7 frames per call (the fork's 32-frame inputs): position stride 4 != 7
+        g = torch.Generator().manual_seed(5)
+        feats32 = [9.0 + 3.0 * torch.randn(1, 32, 80, generator=g) for _ in range(12)]
+        st7 = stream_reference(enc, adp, feats32, layers_to_keep=(0,))
+        # offline ragged
+        T = 150
+        xs = 9.0 + 3.0 * torch.randn(B, T, 80, generator=g)
+        ilens = torch.tensor([150, 97, 40])
+        off = {}
+        with torch.no_grad():
+            for (c, L) in ((4, 16), (4, 2), (-1, -1), (4, -1), (3, 1)):
+                eo, m = enc(xs, ilens, c, L)
+                eo = eo.clone()
+                y, ym = adp(eo.clone(), m)
+                off["enc_c%d_L%d" % (c, L)] = eo.numpy()
+                off["adp_c%d_L%d" % (c, L)] = y.numpy()
+                off["mask_c%d_L%d" % (c, L)] = m.numpy()
+                off["amask_c%d_L%d" % (c, L)] = ym.numpy()
+        save("tiny", seed=np.int64(3), stream_pcm=np.stack(pcm_b), stream_feats=torch.stack(feats_seq).numpy(),
+             **{"stream_" + k: v for k, v in st.items()},
+             t7_feats=torch.stack(feats32).numpy(), **{"t7_" + k: v for k, v in st7.items()},
+             off_feats=xs.numpy(), off_ilens=ilens.numpy(), **{"off_" + k: v for k, v in off.items()})
+
+    # ---------------- shipped config -------------------------------------------------------
+    if want("shipped"):
+        ycfg = load_yaml("shipped")
+        cfg = path_config_from_dict(ycfg)
+        enc, adp = build_reference(mods, ycfg, cfg, seed=0)
+        # config 1: question.wav, 13 chunks, 1 session
+        fq = feats_from_pcm(pcm_pad)
+        st = stream_reference(enc, adp, fq, layers_to_keep=(0, 23))
+        save("shipped_question", seed=np.int64(0), pcm=pcm_pad, feats=torch.stack(fq).numpy(),
+             **{k: v for k, v in st.items()})
+        # 2 lock-step sessions x 20 chunks: crosses the 17-chunk cache saturation
+        pcm_b = [synth_audio(1000 + b, 2560 * 20).numpy() for b in range(2)]
+        per = [feats_from_pcm(p) for p in pcm_b]
+        feats_seq = [torch.cat([per[b][i] for b in range(2)], 0) for i in range(20)]
+        st2 = stream_reference(enc, adp, feats_seq, layers_to_keep=(0, 23))
+        save("shipped_b2", seed=np.int64(0), pcm=np.stack(pcm_b), feats=torch.stack(feats_seq).numpy(),
+             **{k: v for k, v in st2.items()})
+        # offline ragged pair
+        g = torch.Generator().manual_seed(11)
+        xs = 9.0 + 3.0 * torch.randn(2, 131, 80, generator=g)
+        ilens = torch.tensor([131, 90])
+        with torch.no_grad():
+            eo, m = enc(xs, ilens, 4, 16)
+            eo = eo.clone()
+            y, ym = adp(eo.clone(), m)
+        save("shipped_offline", seed=np.int64(0), feats=xs.numpy(), ilens=ilens.numpy(), enc_out=eo.numpy(),
+             mask=m.numpy(), adapter_out=y.numpy(), adapter_mask=ym.numpy())
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+"""Pin the CPU oracle to the vectors produced by the reference modules (tests/golden/make_golden.py).
+These run without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from freeze_omni_b200.config import load_path_config
+from freeze_omni_b200.weights import make_adapter_state, make_encoder_state
+from oracle import freeze_omni_oracle as O
+
+FP32_TOL = 1e-4      # north_star: encoder and adapter outputs within 1e-4 max-abs in fp32
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+
+
+def test_fbank_known_answers_from_survey(golden):
+    g = golden("fbank")
+    wav = torch.cat([torch.zeros(240), torch.from_numpy(g["question_pcm"].astype(np.float32))])
+    pad = (-(len(g["question_pcm"])) % 2560)
+    wav = torch.cat([wav, torch.zeros(pad)])
+    out = O.fbank(wav)
+    assert out.shape == (208, 80)
+    assert abs(float(out.sum()) - 156308.2261) < 0.5
+    assert abs(float(out.min()) - (-15.9424)) < 1e-3 and int((out < -15.94).sum()) == 2400
+    np.testing.assert_allclose(out[100, :6].numpy(), [11.3679, 13.1892, 12.8945, 19.0391, 20.4948, 21.0801], atol=2e-4)
+    np.testing.assert_allclose(out[150, 40:44].numpy(), [8.4979, 8.0307, 8.7213, 8.4356], atol=2e-4)
+
+
+def test_fbank_matches_reference_vectors(golden):
+    g = golden("fbank")
+    assert torch.equal(O.povey_window(400), torch.from_numpy(g["window"]))
+    assert torch.equal(O.mel_banks(80, 512, 16000.0)[:, :256], torch.from_numpy(g["mel"]))
+    wav = torch.cat([torch.zeros(240), torch.from_numpy(g["synth_pcm"].astype(np.float32))])
+    assert rel_err(O.fbank(wav).numpy(), g["synth_offline"]) < 1e-5
+
+
+def test_streaming_frontend_default_and_fork(golden):
+    g = golden("fbank")
+    pcm = g["question_pcm"]
+    n = -(-len(pcm) // 2560) * 2560
+    x = np.zeros(n, np.float32)
+    x[:len(pcm)] = pcm
+    fe = O.StreamingFrontend()
+    outs = [fe.process(torch.from_numpy(x[i:i + 2560] / 32768.0), 32767.0) for i in range(0, n, 2560)]
+    assert rel_err(torch.cat(outs, 0).numpy(), g["question_gating_default"]) < 1e-5
+    fe = O.StreamingFrontend(16000, 16, 8, 28, 4, 80)
+    nf = (n // 3584) * 3584
+    outs = [fe.process(torch.from_numpy(x[i:i + 3584] / 32768.0), 32767.0) for i in range(0, nf, 3584)]
+    assert outs[0].shape == (1, 32, 80)
+    assert rel_err(torch.cat(outs, 0).numpy(), g["question_gating_fork"]) < 1e-5
+
+
+def test_streaming_fbank_equals_offline(golden):
+    """per-frame DC removal and pre-emphasis make the streamed frames equal the
+    offline frames of [240 zeros | signal]."""
+    g = golden("fbank")
+    pcm = g["synth_pcm"].astype(np.float32)[:2560 * 10]
+    fe = O.StreamingFrontend()
+    st = torch.cat([fe.process(torch.from_numpy(pcm[i:i + 2560]), 1.0)[0, 3:] for i in range(0, len(pcm), 2560)])
+    off = O.fbank(torch.cat([torch.zeros(240), torch.from_numpy(pcm)]))
+    assert torch.equal(st, off)
+
+
+def test_masks_bit_exact(golden):
+    g = golden("masks")
+    for key, packed in g.items():
+        T, c, L = (int(s[1:]) for s in key.split("_"))
+        want = np.unpackbits(packed)[:T * T].reshape(T, T).astype(bool)
+        got = O.subsequent_chunk_mask(T, c, L).numpy()
+        assert np.array_equal(got, want), key
+        for i in range(T):
+            s, e = O.chunk_window(i, T, c, L)
+            assert np.array_equal(np.flatnonzero(want[i]), np.arange(s, e)), key
+
+
+def test_subsampled_lengths():
+    cfg = load_path_config("tiny")
+    x = torch.zeros(2, 67, 80)
+    _, m = O.EncoderOracle(cfg, make_encoder_state(cfg, 3)).forward(x, torch.tensor([67, 40]), 4, 16)
+    assert m.squeeze(1).sum(1).tolist() == [16, 9]       # SURVEY 8c probed values
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg = load_path_config("tiny")
+    return cfg, make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+
+
+def _run_stream(cfg, esd, asd, feats_seq):
+    enc = O.EncoderOracle(cfg, esd)
+    buf, cache, pe = enc.new_buffer(), None, 0
+    eos, ys, pes = [], [], []
+    for f in feats_seq:
+        eo, buf, pe = enc.infer(torch.from_numpy(f), buf, pe)
+        y, _, cache = O.adapter_forward(cfg, asd, eo, torch.ones(eo.size(0), 1, eo.size(1), dtype=torch.bool), cache)
+        eos.append(eo)
+        ys.append(y)
+        pes.append(pe)
+    return torch.stack(eos).numpy(), torch.stack(ys).numpy(), pes, buf, cache
+
+
+def test_tiny_stream(golden, tiny):
+    cfg, esd, asd = tiny
+    g = golden("tiny")
+    eo, y, pes, buf, cache = _run_stream(cfg, esd, asd, g["stream_feats"])
+    assert np.abs(eo - g["stream_enc_out"]).max() < FP32_TOL
+    assert np.abs(y - g["stream_adapter_out"]).max() < FP32_TOL
+    assert pes == g["stream_pe_index"].tolist()
+    for li in (0, 1):
+        assert np.abs(buf[li][0].numpy() - g["stream_k_cache_l%d" % li]).max() < FP32_TOL
+        assert np.abs(buf[li][1].numpy() - g["stream_v_cache_l%d" % li]).max() < FP32_TOL
+    assert buf[0][0].shape[2] == cfg.kv_window
+    assert np.abs(cache[0].numpy() - g["stream_adapter_cache"]).max() < FP32_TOL
+
+
+def test_tiny_stream_from_pcm(golden, tiny):
+    cfg, esd, asd = tiny
+    g = golden("tiny")
+    sess = O.StreamSession(cfg, esd, asd)
+    pcm = g["stream_pcm"][1].astype(np.float32) / 32768.0
+    for i in range(4):
+        feats, eo, y = sess.step_pcm(torch.from_numpy(pcm[i * 2560:(i + 1) * 2560]))
+        assert rel_err(feats.numpy(), g["stream_feats"][i, 1:2]) < 1e-5
+        assert np.abs(eo.numpy() - g["stream_enc_out"][i, 1:2]).max() < FP32_TOL
+
+
+def test_tiny_stream_seven_frames_per_call(golden, tiny):
+    """The fork feeds 32 fbank frames -> 7 encoder frames while pe_index still advances by 4
+    (SURVEY 2.4-2): reproduce, don't repair."""
+    cfg, esd, asd = tiny
+    g = golden("tiny")
+    eo, y, pes, buf, cache = _run_stream(cfg, esd, asd, g["t7_feats"])
+    assert eo.shape[2] == 7
+    assert np.abs(eo - g["t7_enc_out"]).max() < FP32_TOL
+    assert np.abs(y - g["t7_adapter_out"]).max() < FP32_TOL
+    assert pes == g["t7_pe_index"].tolist()
+
+
+@pytest.mark.parametrize("c,L", [(4, 16), (4, 2), (-1, -1), (4, -1), (3, 1)])
+def test_tiny_offline(golden, tiny, c, L):
+    cfg, esd, asd = tiny
+    g = golden("tiny")
+    xs, m, y, ym = O.offline_path(cfg, esd, asd, torch.from_numpy(g["off_feats"]), torch.from_numpy(g["off_ilens"]), c, L)
+    tag = "c%d_L%d" % (c, L)
+    assert np.array_equal(m.numpy(), g["off_mask_" + tag])
+    assert np.array_equal(ym.numpy(), g["off_amask_" + tag])
+    assert np.abs(xs.numpy() - g["off_enc_" + tag]).max() < FP32_TOL
+    assert np.abs(y.numpy() - g["off_adp_" + tag]).max() < FP32_TOL
+
+
+def test_tiny_stream_equals_offline_until_saturation(golden, tiny):
+    """chunks 0..16 match offline(chunk 4, left 16); later ones drift by the
+    one-chunk positional offset of attention.py:112-114."""
+    cfg, esd, asd = tiny
+    g = golden("tiny")
+    pcm = g["stream_pcm"][0].astype(np.float32)
+    off_feats = O.fbank(torch.cat([torch.zeros(240), torch.from_numpy(pcm)])).unsqueeze(0)
+    off_feats = torch.cat([torch.zeros(1, 3, 80), off_feats], 1)     # the ring starts as zeros
+    xs, _ = O.EncoderOracle(cfg, esd).forward(off_feats, torch.tensor([off_feats.size(1)]), 4, 16)
+    st = torch.from_numpy(g["stream_enc_out"][:, 0])                 # (24, 4, D)
+    n = st.shape[0] * 4
+    diff = (xs[0, :n].reshape(-1, 4, cfg.d_model) - st).abs().amax(dim=(1, 2))
+    assert float(diff[:17].max()) < 1e-4
+    assert float(diff[17:].max()) > 1e-4
+
+
+@pytest.fixture(scope="module")
+def shipped():
+    cfg = load_path_config("shipped")
+    return cfg, make_encoder_state(cfg, 0), make_adapter_state(cfg, 0)
+
+
+def test_shipped_question_stream(golden, shipped):
+    """BASELINE.json config 1: question.wav, 13 chunks, 1 session, fp32."""
+    cfg, esd, asd = shipped
+    g = golden("shipped_question")
+    sess = O.StreamSession(cfg, esd, asd)
+    pcm = g["pcm"].astype(np.float32) / 32768.0
+    for i in range(13):
+        feats, eo, y = sess.step_pcm(torch.from_numpy(pcm[i * 2560:(i + 1) * 2560]))
+        assert rel_err(feats.numpy(), g["feats"][i]) < 1e-5
+        assert np.abs(eo.numpy() - g["enc_out"][i]).max() < FP32_TOL, i
+        assert np.abs(y.numpy() - g["adapter_out"][i]).max() < FP32_TOL, i
+        assert sess.pe_index == int(g["pe_index"][i])
+    for li in (0, 23):
+        assert np.abs(sess.buffer[li][0].numpy() - g["k_cache_l%d" % li]).max() < FP32_TOL
+    assert np.abs(sess.cache[0].numpy() - g["adapter_cache"]).max() < FP32_TOL
+
+
+def test_shipped_offline(golden, shipped):
+    cfg, esd, asd = shipped
+    g = golden("shipped_offline")
+    xs, m, y, ym = O.offline_path(cfg, esd, asd, torch.from_numpy(g["feats"]), torch.from_numpy(g["ilens"]), 4, 16)
+    assert np.array_equal(m.numpy(), g["mask"]) and np.array_equal(ym.numpy(), g["adapter_mask"])
+    assert np.abs(xs.numpy() - g["enc_out"]).max() < FP32_TOL
+    assert np.abs(y.numpy() - g["adapter_out"]).max() < FP32_TOL
