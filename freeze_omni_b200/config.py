@@ -131,7 +131,7 @@ def load_yaml(name_or_path: str) -> Dict[str, Any]:
         return yaml.safe_load(fin)
 
 
-def path_config_from_dict(configs: Dict[str, Any]) -> PathConfig:
+def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -> PathConfig:
     enc = configs.get("encoder_conf", {})
     over = enc.get("overview_conf", {})
     para = enc.get("para_conf", {})
@@ -158,7 +158,9 @@ def path_config_from_dict(configs: Dict[str, Any]) -> PathConfig:
             int(tr["transformer-output-dim"]), int(over.get("encoder-output-dim", d))}
     if len(dims) != 1 or int(sub["subsampling-input-dim"]) != feat:
         raise ValueError("WRONG CONFIG: component input/output dims do not chain (encoder.py:82-96)")
-    mc = configs.get("model_conf", {})
+    mc = dict(configs.get("model_conf", {}))
+    if encoder_only:
+        mc = {"enc_out_dim": d, "llm_embed_dim": d}
     if mc.get("adpter_type", "subsampling") != "subsampling":
         raise ValueError("only adpter_type 'subsampling' carries a cache (adapter.py:112)")
     if int(mc.get("enc_out_dim", d)) != d:

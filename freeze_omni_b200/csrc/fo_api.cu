@@ -1,0 +1,1118 @@
+// C ABI (include/fo_b200.h) over the sm_100a kernels: context, weight packing, session slots resident in
+// HBM, and the three step programs (streaming chunk, full utterance, stateless adapter).
+//
+// HBM layout per context
+//   weights     compute dtype (fp32 | bf16), [N][K] row-major (K-major operands for the GEMMs):
+//               conv2 as [C][(kh*3+kw)*C + ci], sub-Linear with K permuted to f*C + c so the conv2 output
+//               (b, t, f, c) feeds it without a transpose, Wq|Wk|Wv stacked to [3D][D], adapter conv as
+//               [2D][tau*D + ci]; biases / LayerNorm / pos_bias in fp32.
+//   pos tables  per layer P_l = pe[0:pos_max_len] * Wpos_l^T (weights-only), [L][pos][D].
+//   sessions    KV ring [L][slot][K|V][H][cap][64] (cap = window + max frames per call, rounded to 8),
+//               n_frames / pe_index / adapter-cache flag int32 [slot], adapter cache fp32 [slot][2][k-1][D]
+//               (double buffered), fbank sample buffer fp32 [slot][carry+chunk], feature ring [slot][ctx+m][F].
+//   workspace   activations of one step, grown on demand, reused.
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fo_b200.h"
+#include "fo_common.cuh"
+
+namespace fo {
+
+long long g_launches = 0;
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct HostTensor {          // staged fp32 weight on device until finalize
+    float* d = nullptr;
+    std::vector<int64_t> shape;
+    long long numel = 0;
+};
+
+struct LayerW {
+    void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr, *ptab = nullptr;
+    float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+    float *pos_u = nullptr, *pos_v = nullptr, *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+};
+
+}  // namespace
+}  // namespace fo
+
+using namespace fo;
+
+struct fo_ctx {
+    fo_config cfg;
+    int device = 0, dtype = FO_F32;
+    size_t esz = 4;                           // bytes per activation / weight element
+    bool finalized = false;
+    long long device_bytes = 0;
+    std::map<std::string, HostTensor> staged;
+    std::vector<void*> owned;                 // every cudaMalloc of this context
+
+    // derived dims
+    int F = 0, F1 = 0, F2 = 0, D = 0, H = 0, FF = 0, L = 0, E = 0, KA = 0;
+    int window = 0, full_chunk = 0, pe_wrap = 0, pos_rows = 0, ring_cap = 0, max_t = 0;
+    int carry = 0, chunk_samples = 0, fft = 0;
+
+    // packed weights
+    float *cmvn_mean = nullptr, *cmvn_istd = nullptr, *conv1_w = nullptr, *conv1_b = nullptr;
+    void *conv2_w = nullptr, *sub_w = nullptr, *emb_w = nullptr;
+    float *conv2_b = nullptr, *sub_b = nullptr, *emb_b = nullptr, *emb_g = nullptr, *emb_beta = nullptr;
+    std::vector<LayerW> layers;
+    float *after_g = nullptr, *after_b = nullptr;
+    void *ad_conv_w = nullptr, *ad_proj_w = nullptr;
+    float *ad_conv_b = nullptr, *ad_ln_g = nullptr, *ad_ln_b = nullptr, *ad_proj_b = nullptr;
+    float *fb_window = nullptr, *fb_mel = nullptr;
+    int *fb_lo = nullptr, *fb_hi = nullptr;
+
+    // sessions
+    void* ring = nullptr;                     // [L][S][2][H][cap][64]
+    int32_t *n_frames = nullptr, *pe_index = nullptr, *ad_valid = nullptr;
+    float *ad_cache = nullptr, *samples = nullptr, *feat_ring = nullptr;
+    std::vector<uint8_t> slot_used;
+    std::vector<int32_t> free_slots;
+    long long sessions_in_use = 0;
+
+    // step plumbing
+    static const int NSTAGE = 8;
+    int32_t* ids_host[NSTAGE] = {nullptr};
+    cudaEvent_t ids_event[NSTAGE] = {nullptr};
+    int ids_cursor = 0;
+    int32_t* ids_dev = nullptr;
+    DevBuf ws[24];                            // named workspaces, see enum below
+    // options
+    int gemm_backend = 0, use_graph = 0, split_k = 1;
+    // stats
+    fo_stats_t stats;
+    std::mutex mu;
+};
+
+namespace {
+
+enum { WS_FEATS = 0, WS_C1, WS_C2, WS_XSUB, WS_EMB, WS_X, WS_H, WS_QKV, WS_ATT, WS_FFH, WS_ENC, WS_XIN, WS_ACONV, WS_AH,
+       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3 };
+
+int dev_alloc(fo_ctx* c, void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return FO_ERR_NOMEM;
+    }
+    c->owned.push_back(*p);
+    c->device_bytes += (long long)bytes;
+    return 0;
+}
+
+int ws_ensure(fo_ctx* c, int which, size_t bytes, void** out) {
+    DevBuf& b = c->ws[which];
+    if (b.cap < bytes) {
+        if (b.p) {
+            // grown buffers are rare (first call at a new size); wait for users of the old one
+            FO_CUDA(cudaDeviceSynchronize());
+            for (auto& q : c->owned)
+                if (q == b.p) { q = nullptr; break; }
+            cudaFree(b.p);
+            c->device_bytes -= (long long)b.cap;
+        }
+        size_t cap = bytes + bytes / 8 + 256;
+        FO_TRY(dev_alloc(c, &b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return 0;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// input: returns a device pointer holding `bytes` of p (copying through workspace `which` when p is host memory)
+int in_dev(fo_ctx* c, const void* p, size_t bytes, int which, cudaStream_t st, const void** out) {
+    if (is_device_ptr(p)) { *out = p; return 0; }
+    void* d;
+    FO_TRY(ws_ensure(c, which, bytes, &d));
+    FO_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, st));
+    *out = d;
+    return 0;
+}
+// output: device pointer to write (user's if device memory, else workspace); finish with out_done
+int out_dev(fo_ctx* c, void* p, size_t bytes, int which, void** out) {
+    if (p && is_device_ptr(p)) { *out = p; return 0; }
+    return ws_ensure(c, which, bytes, out);
+}
+int out_done(void* user, void* dev, size_t bytes, cudaStream_t st) {
+    if (user && user != dev) FO_CUDA(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int check_ids(fo_ctx* c, const int32_t* ids, int n) {
+    FO_CHECK(ids != nullptr && n > 0, "ids must be a host array of n > 0 session ids");
+    FO_CHECK(n <= c->cfg.max_sessions, "n (%d) exceeds max_sessions (%d)", n, c->cfg.max_sessions);
+    for (int i = 0; i < n; ++i) {
+        FO_CHECK(ids[i] >= 0 && ids[i] < c->cfg.max_sessions && c->slot_used[ids[i]], "session id %d is not allocated", ids[i]);
+    }
+    return 0;
+}
+
+int upload_ids(fo_ctx* c, const int32_t* ids, int n, cudaStream_t st) {
+    const int k = c->ids_cursor;
+    c->ids_cursor = (k + 1) % fo_ctx::NSTAGE;
+    FO_CUDA(cudaEventSynchronize(c->ids_event[k]));
+    memcpy(c->ids_host[k], ids, sizeof(int32_t) * n);
+    FO_CUDA(cudaMemcpyAsync(c->ids_dev, c->ids_host[k], sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    FO_CUDA(cudaEventRecord(c->ids_event[k], st));
+    return 0;
+}
+
+// ---- GEMM dispatch ----------------------------------------------------------------------------
+template <typename TA>
+int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+         cudaStream_t st);
+template <>
+int gemm<float>(fo_ctx* c, const float* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+                cudaStream_t st) {
+    return gemm_simt<float>(A, ga, reinterpret_cast<const float*>(W), M, N, K, ep, st);
+}
+template <>
+int gemm<bf16>(fo_ctx* c, const bf16* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+               cudaStream_t st) {
+    if (c->gemm_backend == 1) {
+        int r = gemm_tc(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, c->split_k, st);
+        if (r <= 0) return r;
+    }
+    return gemm_simt<bf16>(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, st);
+}
+
+const HostTensor* staged(fo_ctx* c, const std::string& name) {
+    auto it = c->staged.find(name);
+    return it == c->staged.end() ? nullptr : &it->second;
+}
+
+int need(fo_ctx* c, const std::string& name, std::initializer_list<int64_t> shape, const HostTensor** out) {
+    const HostTensor* t = staged(c, name);
+    FO_CHECK(t != nullptr, "finalize: tensor '%s' was never loaded", name.c_str());
+    bool ok = t->shape.size() == shape.size();
+    size_t i = 0;
+    for (int64_t s : shape) { if (ok && t->shape[i] != s) ok = false; ++i; }
+    FO_CHECK(ok, "finalize: tensor '%s' has the wrong shape", name.c_str());
+    *out = t;
+    return 0;
+}
+
+int keep_f32(fo_ctx* c, const std::string& name, std::initializer_list<int64_t> shape, float** out) {
+    const HostTensor* t;
+    FO_TRY(need(c, name, shape, &t));
+    void* d;
+    FO_TRY(dev_alloc(c, &d, t->numel * sizeof(float)));
+    FO_CUDA(cudaMemcpy(d, t->d, t->numel * sizeof(float), cudaMemcpyDeviceToDevice));
+    *out = reinterpret_cast<float*>(d);
+    return 0;
+}
+
+template <typename TW>
+int keep_w(fo_ctx* c, const std::string& name, std::initializer_list<int64_t> shape, void** out) {
+    const HostTensor* t;
+    FO_TRY(need(c, name, shape, &t));
+    void* d;
+    FO_TRY(dev_alloc(c, &d, t->numel * sizeof(TW)));
+    FO_TRY(convert_weight<TW>(t->d, t->numel, reinterpret_cast<TW*>(d), 0));
+    *out = d;
+    return 0;
+}
+
+template <typename TW>
+int finalize_t(fo_ctx* c) {
+    const int D = c->D, F = c->F, FF = c->FF, L = c->L, E = c->E, KA = c->KA, F2 = c->F2, H = c->H;
+    const fo_config& g = c->cfg;
+    if (g.has_encoder) {
+        if (staged(c, "global_cmvn.mean")) {
+            FO_TRY(keep_f32(c, "global_cmvn.mean", {F}, &c->cmvn_mean));
+            FO_TRY(keep_f32(c, "global_cmvn.istd", {F}, &c->cmvn_istd));
+        }
+        FO_TRY(keep_f32(c, "enc.0.core.conv.0.weight", {D, 1, 3, 3}, &c->conv1_w));
+        FO_TRY(keep_f32(c, "enc.0.core.conv.0.bias", {D}, &c->conv1_b));
+        const HostTensor* t;
+        FO_TRY(need(c, "enc.0.core.conv.2.weight", {D, D, 3, 3}, &t));
+        FO_TRY(dev_alloc(c, &c->conv2_w, (size_t)D * D * 9 * sizeof(TW)));
+        FO_TRY(repack_conv2<TW>(t->d, D, reinterpret_cast<TW*>(c->conv2_w), 0));
+        FO_TRY(keep_f32(c, "enc.0.core.conv.2.bias", {D}, &c->conv2_b));
+        FO_TRY(need(c, "enc.0.core.out.0.weight", {D, (int64_t)D * F2}, &t));
+        FO_TRY(dev_alloc(c, &c->sub_w, (size_t)D * D * F2 * sizeof(TW)));
+        FO_TRY(repack_sublinear<TW>(t->d, D, F2, reinterpret_cast<TW*>(c->sub_w), 0));
+        FO_TRY(keep_f32(c, "enc.0.core.out.0.bias", {D}, &c->sub_b));
+        if (g.input_layer_linear) {
+            FO_TRY(keep_w<TW>(c, "enc.1.embed.0.weight", {D, D}, &c->emb_w));
+            FO_TRY(keep_f32(c, "enc.1.embed.0.bias", {D}, &c->emb_b));
+            FO_TRY(keep_f32(c, "enc.1.embed.1.weight", {D}, &c->emb_g));
+            FO_TRY(keep_f32(c, "enc.1.embed.1.bias", {D}, &c->emb_beta));
+        }
+        // positional table -> per-layer projected tables
+        const HostTensor* pe;
+        FO_TRY(need(c, "pos.table", {c->pos_rows, D}, &pe));
+        void* pe_w;
+        FO_TRY(dev_alloc(c, &pe_w, (size_t)c->pos_rows * D * sizeof(TW)));
+        FO_TRY(convert_weight<TW>(pe->d, (long long)c->pos_rows * D, reinterpret_cast<TW*>(pe_w), 0));
+        c->layers.resize(L);
+        for (int l = 0; l < L; ++l) {
+            LayerW& w = c->layers[l];
+            const std::string p = "enc.1.encoders." + std::to_string(l) + ".";
+            const HostTensor *q, *k, *v, *bq, *bk, *bv;
+            FO_TRY(need(c, p + "self_attn.linear_q.weight", {D, D}, &q));
+            FO_TRY(need(c, p + "self_attn.linear_k.weight", {D, D}, &k));
+            FO_TRY(need(c, p + "self_attn.linear_v.weight", {D, D}, &v));
+            FO_TRY(need(c, p + "self_attn.linear_q.bias", {D}, &bq));
+            FO_TRY(need(c, p + "self_attn.linear_k.bias", {D}, &bk));
+            FO_TRY(need(c, p + "self_attn.linear_v.bias", {D}, &bv));
+            FO_TRY(dev_alloc(c, &w.wqkv, (size_t)3 * D * D * sizeof(TW)));
+            TW* wq = reinterpret_cast<TW*>(w.wqkv);
+            FO_TRY(convert_weight<TW>(q->d, (long long)D * D, wq, 0));
+            FO_TRY(convert_weight<TW>(k->d, (long long)D * D, wq + (size_t)D * D, 0));
+            FO_TRY(convert_weight<TW>(v->d, (long long)D * D, wq + (size_t)2 * D * D, 0));
+            void* bq3;
+            FO_TRY(dev_alloc(c, &bq3, (size_t)3 * D * sizeof(float)));
+            w.bqkv = reinterpret_cast<float*>(bq3);
+            FO_CUDA(cudaMemcpy(w.bqkv, bq->d, D * sizeof(float), cudaMemcpyDeviceToDevice));
+            FO_CUDA(cudaMemcpy(w.bqkv + D, bk->d, D * sizeof(float), cudaMemcpyDeviceToDevice));
+            FO_CUDA(cudaMemcpy(w.bqkv + 2 * D, bv->d, D * sizeof(float), cudaMemcpyDeviceToDevice));
+            FO_TRY(keep_w<TW>(c, p + "self_attn.linear_out.weight", {D, D}, &w.wo));
+            FO_TRY(keep_f32(c, p + "self_attn.linear_out.bias", {D}, &w.bo));
+            FO_TRY(keep_f32(c, p + "self_attn.pos_bias_u", {H, 64}, &w.pos_u));
+            FO_TRY(keep_f32(c, p + "self_attn.pos_bias_v", {H, 64}, &w.pos_v));
+            FO_TRY(keep_w<TW>(c, p + "feed_forward.w_1.weight", {FF, D}, &w.w1));
+            FO_TRY(keep_f32(c, p + "feed_forward.w_1.bias", {FF}, &w.b1));
+            FO_TRY(keep_w<TW>(c, p + "feed_forward.w_2.weight", {D, FF}, &w.w2));
+            FO_TRY(keep_f32(c, p + "feed_forward.w_2.bias", {D}, &w.b2));
+            FO_TRY(keep_f32(c, p + "norm1.weight", {D}, &w.ln1g));
+            FO_TRY(keep_f32(c, p + "norm1.bias", {D}, &w.ln1b));
+            FO_TRY(keep_f32(c, p + "norm2.weight", {D}, &w.ln2g));
+            FO_TRY(keep_f32(c, p + "norm2.bias", {D}, &w.ln2b));
+            // P_l = pe * Wpos^T  (attention.py:433; computed once, weights-only)
+            const HostTensor* wp;
+            FO_TRY(need(c, p + "self_attn.linear_pos.weight", {D, D}, &wp));
+            void* wpos;
+            FO_CUDA(cudaMalloc(&wpos, (size_t)D * D * sizeof(TW)));
+            int r = convert_weight<TW>(wp->d, (long long)D * D, reinterpret_cast<TW*>(wpos), 0);
+            if (r == 0) r = dev_alloc(c, &w.ptab, (size_t)c->pos_rows * D * sizeof(TW));
+            if (r == 0) {
+                Epilogue ep;
+                ep.c_act = w.ptab;
+                ep.ldc = D;
+                r = gemm<TW>(c, reinterpret_cast<const TW*>(pe_w), plain_rows(D), wpos, c->pos_rows, D, D, ep, 0);
+            }
+            cudaDeviceSynchronize();
+            cudaFree(wpos);
+            FO_TRY(r);
+        }
+        FO_TRY(keep_f32(c, "enc.1.after_norm.weight", {D}, &c->after_g));
+        FO_TRY(keep_f32(c, "enc.1.after_norm.bias", {D}, &c->after_b));
+        // frontend constants
+        if (staged(c, "fbank.window")) {
+            FO_TRY(keep_f32(c, "fbank.window", {g.frame_len}, &c->fb_window));
+            FO_TRY(keep_f32(c, "fbank.mel", {F, c->fft / 2 + 1}, &c->fb_mel));
+            std::vector<float> mel((size_t)F * (c->fft / 2 + 1));
+            FO_CUDA(cudaMemcpy(mel.data(), c->fb_mel, mel.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            std::vector<int> lo(F), hi(F);
+            const int nb = c->fft / 2 + 1;
+            for (int m = 0; m < F; ++m) {
+                int a = nb, b = 0;
+                for (int k = 0; k < nb; ++k)
+                    if (mel[(size_t)m * nb + k] != 0.f) { if (k < a) a = k; b = k + 1; }
+                if (a > b) a = b = 0;
+                lo[m] = a;
+                hi[m] = b;
+            }
+            void *dlo, *dhi;
+            FO_TRY(dev_alloc(c, &dlo, F * sizeof(int)));
+            FO_TRY(dev_alloc(c, &dhi, F * sizeof(int)));
+            FO_CUDA(cudaMemcpy(dlo, lo.data(), F * sizeof(int), cudaMemcpyHostToDevice));
+            FO_CUDA(cudaMemcpy(dhi, hi.data(), F * sizeof(int), cudaMemcpyHostToDevice));
+            c->fb_lo = reinterpret_cast<int*>(dlo);
+            c->fb_hi = reinterpret_cast<int*>(dhi);
+        }
+    }
+    if (g.has_adapter) {
+        const HostTensor* t;
+        FO_TRY(need(c, "adapter.conv1d2.weight", {2 * D, D, KA}, &t));
+        FO_TRY(dev_alloc(c, &c->ad_conv_w, (size_t)2 * D * D * KA * sizeof(TW)));
+        FO_TRY(repack_adapter_conv<TW>(t->d, 2 * D, D, KA, reinterpret_cast<TW*>(c->ad_conv_w), 0));
+        FO_TRY(keep_f32(c, "adapter.conv1d2.bias", {2 * D}, &c->ad_conv_b));
+        FO_TRY(keep_f32(c, "adapter.bn2.weight", {2 * D}, &c->ad_ln_g));
+        FO_TRY(keep_f32(c, "adapter.bn2.bias", {2 * D}, &c->ad_ln_b));
+        FO_TRY(keep_w<TW>(c, "adapter.project.weight", {E, 2 * D}, &c->ad_proj_w));
+        FO_TRY(keep_f32(c, "adapter.project.bias", {E}, &c->ad_proj_b));
+    }
+    FO_CUDA(cudaDeviceSynchronize());
+    for (auto& kv : c->staged) cudaFree(kv.second.d);
+    c->staged.clear();
+    c->finalized = true;
+    return 0;
+}
+
+FbankParams fbank_params(fo_ctx* c) {
+    FbankParams p;
+    p.frame_len = c->cfg.frame_len;
+    p.frame_shift = c->cfg.frame_shift;
+    p.fft_size = c->fft;
+    p.n_mel = c->F;
+    p.window = c->fb_window;
+    p.mel = c->fb_mel;
+    p.mel_lo = c->fb_lo;
+    p.mel_hi = c->fb_hi;
+    return p;
+}
+
+// ---- adapter program on device buffers -----------------------------------------------------------
+// enc (B, T, D) fp32 -> y (B, t_out, E) fp32.  Slot-resident cache when ids != null.
+template <typename TA>
+int adapter_program(fo_ctx* c, const float* enc, const uint8_t* mask, int B, int T, const int32_t* ids_dev,
+                    const float* cache_in, float* cache_out, float* y, cudaStream_t st) {
+    const int D = c->D, E = c->E, KA = c->KA, km1 = KA - 1;
+    const int t_out = (T + km1 - KA) / 2 + 1;
+    const int Mo = B * t_out;
+    void *xin, *aconv, *ah;
+    FO_TRY(ws_ensure(c, WS_XIN, (size_t)B * (km1 + T) * D * sizeof(TA), &xin));
+    FO_TRY(ws_ensure(c, WS_ACONV, (size_t)Mo * 2 * D * sizeof(float), &aconv));
+    FO_TRY(ws_ensure(c, WS_AH, (size_t)Mo * 2 * D * sizeof(TA), &ah));
+    FO_TRY(adapter_stage<TA>(enc, mask, B, T, D, km1, ids_dev, c->ad_cache, c->ad_valid, cache_in, cache_out,
+                             reinterpret_cast<TA*>(xin), st));
+    AGather ga{D, t_out, 1, 2, 0, (long long)(km1 + T), KA, 1, 0};
+    Epilogue e1;
+    e1.bias = c->ad_conv_b;
+    e1.c_f32 = reinterpret_cast<float*>(aconv);
+    e1.ldc = 2 * D;
+    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xin), ga, c->ad_conv_w, Mo, 2 * D, KA * D, e1, st));
+    FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(aconv), Mo, 2 * D, c->ad_ln_g, c->ad_ln_b, 1e-3f,
+                          c->cfg.adapter_gelu ? 2 : 1, 1.0f, reinterpret_cast<TA*>(ah), nullptr, st));
+    Epilogue e2;
+    e2.bias = c->ad_proj_b;
+    e2.c_f32 = y;
+    e2.ldc = E;
+    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(ah), plain_rows(2 * D), c->ad_proj_w, Mo, E, 2 * D, e2, st));
+    return 0;
+}
+
+// ---- encoder trunk shared by streaming and offline ------------------------------------------------
+// feats (B, T, F) fp32 device.  Produces the residual stream x (M, D) after `embed` and pos scaling.
+template <typename TA>
+int subsample_program(fo_ctx* c, const float* feats, int B, int T, float** x_out, cudaStream_t st) {
+    const int D = c->D, F = c->F, F1 = c->F1, F2 = c->F2;
+    const int T1 = (T - 1) / 2, T2 = (T1 - 1) / 2, M = B * T2;
+    void *c1, *c2, *xsub, *emb, *x;
+    FO_TRY(ws_ensure(c, WS_C1, (size_t)B * T1 * F1 * D * sizeof(TA), &c1));
+    FO_TRY(ws_ensure(c, WS_C2, (size_t)M * F2 * D * sizeof(TA), &c2));
+    FO_TRY(ws_ensure(c, WS_X, (size_t)M * D * sizeof(float), &x));
+    FO_TRY(cmvn_conv1<TA>(feats, B, T, F, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, D,
+                          reinterpret_cast<TA*>(c1), st));
+    AGather ga{D, F2, T2, 2, 2LL * F1, (long long)T1 * F1, 3, 1, (long long)F1};
+    Epilogue e;
+    e.bias = c->conv2_b;
+    e.relu = 1;
+    e.c_act = c2;
+    e.ldc = D;
+    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c1), ga, c->conv2_w, M * F2, D, 9 * D, e, st));
+    const float xscale = sqrtf((float)D);
+    if (c->cfg.input_layer_linear) {
+        FO_TRY(ws_ensure(c, WS_XSUB, (size_t)M * D * sizeof(TA), &xsub));
+        FO_TRY(ws_ensure(c, WS_EMB, (size_t)M * D * sizeof(float), &emb));
+        Epilogue e2;
+        e2.bias = c->sub_b;
+        e2.c_act = xsub;
+        e2.ldc = D;
+        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c2), plain_rows(F2 * D), c->sub_w, M, D, F2 * D, e2, st));
+        Epilogue e3;
+        e3.bias = c->emb_b;
+        e3.c_f32 = reinterpret_cast<float*>(emb);
+        e3.ldc = D;
+        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xsub), plain_rows(D), c->emb_w, M, D, D, e3, st));
+        FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(emb), M, D, c->emb_g, c->emb_beta, 1e-5f, 1, xscale, nullptr,
+                              reinterpret_cast<float*>(x), st));
+    } else {
+        Epilogue e2;
+        e2.bias = c->sub_b;
+        e2.c_f32 = reinterpret_cast<float*>(x);
+        e2.ldc = D;
+        e2.scale = xscale;
+        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c2), plain_rows(F2 * D), c->sub_w, M, D, F2 * D, e2, st));
+    }
+    *x_out = reinterpret_cast<float*>(x);
+    return 0;
+}
+
+// one transformer layer minus attention core: pre (LN1 + QKV) and post (out-proj, LN2, FFN)
+template <typename TA>
+int layer_pre(fo_ctx* c, const LayerW& w, float* x, int M, TA* h, TA* qkv, cudaStream_t st) {
+    const int D = c->D;
+    FO_TRY(layer_norm<TA>(x, M, D, w.ln1g, w.ln1b, 1e-5f, 0, 1.0f, h, nullptr, st));
+    Epilogue e;
+    e.bias = w.bqkv;
+    e.c_act = qkv;
+    e.ldc = 3 * D;
+    return gemm<TA>(c, h, plain_rows(D), w.wqkv, M, 3 * D, D, e, st);
+}
+template <typename TA>
+int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* ffh, cudaStream_t st) {
+    const int D = c->D, FF = c->FF;
+    Epilogue e;
+    e.bias = w.bo;
+    e.residual = x;
+    e.c_f32 = x;
+    e.ldc = D;
+    FO_TRY(gemm<TA>(c, att, plain_rows(D), w.wo, M, D, D, e, st));
+    FO_TRY(layer_norm<TA>(x, M, D, w.ln2g, w.ln2b, 1e-5f, 0, 1.0f, h, nullptr, st));
+    Epilogue e1;
+    e1.bias = w.b1;
+    e1.relu = 1;
+    e1.c_act = ffh;
+    e1.ldc = FF;
+    FO_TRY(gemm<TA>(c, h, plain_rows(D), w.w1, M, FF, D, e1, st));
+    Epilogue e2;
+    e2.bias = w.b2;
+    e2.residual = x;
+    e2.c_f32 = x;
+    e2.ldc = D;
+    return gemm<TA>(c, ffh, plain_rows(FF), w.w2, M, D, FF, e2, st);
+}
+
+template <typename TA>
+int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_out_dev, float* y_dev, cudaStream_t st) {
+    const int D = c->D, FF = c->FF, H = c->H;
+    const int T1 = (t_in - 1) / 2, t = (T1 - 1) / 2, M = n * t;
+    float* x;
+    FO_TRY(subsample_program<TA>(c, feats, n, t_in, &x, st));
+    void *h, *qkv, *att, *ffh;
+    FO_TRY(ws_ensure(c, WS_H, (size_t)M * D * sizeof(TA), &h));
+    FO_TRY(ws_ensure(c, WS_QKV, (size_t)M * 3 * D * sizeof(TA), &qkv));
+    FO_TRY(ws_ensure(c, WS_ATT, (size_t)M * D * sizeof(TA), &att));
+    FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
+    AttnStream a;
+    a.ids = c->ids_dev;
+    a.n_frames = c->n_frames;
+    a.pe_index = c->pe_index;
+    a.n = n; a.t = t; a.H = H; a.ring_cap = c->ring_cap; a.window = c->window; a.full_chunk = c->full_chunk;
+    a.pe_wrap = c->pe_wrap; a.pos_rows = c->pos_rows;
+    a.ring_slot_stride = 2LL * H * c->ring_cap * 64;
+    const long long layer_stride = (long long)c->cfg.max_sessions * a.ring_slot_stride;
+    for (int l = 0; l < c->L; ++l) {
+        const LayerW& w = c->layers[l];
+        FO_TRY(layer_pre<TA>(c, w, x, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), st));
+        FO_TRY(attention_stream<TA>(a, reinterpret_cast<const TA*>(qkv), reinterpret_cast<TA*>(c->ring) + l * layer_stride,
+                                    reinterpret_cast<const TA*>(w.ptab), w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
+        FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), st));
+    }
+    FO_TRY(layer_norm<TA>(x, M, D, c->after_g, c->after_b, 1e-5f, 0, 1.0f, nullptr, enc_out_dev, st));
+    if (c->cfg.has_adapter && y_dev)
+        FO_TRY(adapter_program<TA>(c, enc_out_dev, nullptr, n, t, c->ids_dev, nullptr, nullptr, y_dev, st));
+    FO_TRY(advance_sessions(c->ids_dev, n, t, c->cfg.chunk_size, c->pe_wrap, c->n_frames, c->pe_index,
+                            (c->cfg.has_adapter && y_dev) ? c->ad_valid : nullptr, st));
+    return 0;
+}
+
+template <typename TA>
+int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int B, int T, int chunk, int left,
+                    float* enc_out_dev, uint8_t* mask2, int32_t* ilens2, float* y_dev, cudaStream_t st) {
+    const int D = c->D, FF = c->FF, H = c->H;
+    const int T1 = (T - 1) / 2, T2 = (T1 - 1) / 2, M = B * T2;
+    FO_TRY(subsample_mask(ilens_dev, B, T, T2, mask2, ilens2, st));
+    float* x;
+    FO_TRY(subsample_program<TA>(c, feats, B, T, &x, st));
+    void *h, *qkv, *att, *ffh;
+    FO_TRY(ws_ensure(c, WS_H, (size_t)M * D * sizeof(TA), &h));
+    FO_TRY(ws_ensure(c, WS_QKV, (size_t)M * 3 * D * sizeof(TA), &qkv));
+    FO_TRY(ws_ensure(c, WS_ATT, (size_t)M * D * sizeof(TA), &att));
+    FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
+    for (int l = 0; l < c->L; ++l) {
+        const LayerW& w = c->layers[l];
+        FO_TRY(layer_pre<TA>(c, w, x, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), st));
+        FO_TRY(attention_offline<TA>(reinterpret_cast<const TA*>(qkv), B, T2, H, ilens2, chunk, left,
+                                     reinterpret_cast<const TA*>(w.ptab), w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
+        FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), st));
+    }
+    FO_TRY(layer_norm<TA>(x, M, D, c->after_g, c->after_b, 1e-5f, 0, 1.0f, nullptr, enc_out_dev, st));
+    if (c->cfg.has_adapter && y_dev)
+        FO_TRY(adapter_program<TA>(c, enc_out_dev, mask2, B, T2, nullptr, nullptr, nullptr, y_dev, st));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int fo_abi_version(void) { return FO_ABI_VERSION; }
+const char* fo_last_error(void) { return g_err; }
+
+int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
+    FO_CHECK(cfg && out, "fo_create: null argument");
+    *out = nullptr;
+    FO_CHECK(dtype == FO_F32 || dtype == FO_BF16, "fo_create: dtype must be FO_F32 or FO_BF16");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("fo_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+        return FO_ERR_CUDA;
+    }
+    FO_CHECK(device >= 0 && device < ndev, "fo_create: device %d out of range", device);
+    FO_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FO_CUDA(cudaGetDeviceProperties(&prop, device));
+    FO_CHECK(prop.major == 10, "fo_create: kernels are built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+    FO_CHECK(cfg->d_model % 128 == 0 && cfg->d_model / cfg->n_heads == 64 && cfg->d_model % cfg->n_heads == 0,
+             "fo_create: d_model must be a multiple of 128 with d_k == 64");
+    FO_CHECK(cfg->ffn_dim % 64 == 0 && cfg->llm_dim % 64 == 0, "fo_create: ffn_dim and llm_dim must be multiples of 64");
+    FO_CHECK(cfg->feat_dim >= 11 && cfg->n_layers > 0 && cfg->max_sessions > 0, "fo_create: bad sizes");
+    FO_CHECK(cfg->adapter_kernel >= 2, "fo_create: adapter kernel must be >= 2");
+    FO_CHECK(cfg->has_encoder || cfg->has_adapter, "fo_create: nothing to build");
+
+    fo_ctx* c = new fo_ctx();
+    c->cfg = *cfg;
+    c->device = device;
+    c->dtype = dtype;
+    c->esz = dtype == FO_BF16 ? 2 : 4;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->F = cfg->feat_dim; c->F1 = (c->F - 1) / 2; c->F2 = (c->F1 - 1) / 2;
+    c->D = cfg->d_model; c->H = cfg->n_heads; c->FF = cfg->ffn_dim; c->L = cfg->n_layers; c->E = cfg->llm_dim;
+    c->KA = cfg->adapter_kernel;
+    const bool streaming = cfg->chunk_size > 0 && cfg->left_chunks > 0;
+    c->window = streaming ? cfg->chunk_size * cfg->left_chunks : 1;                  // attention.py:290-295
+    c->full_chunk = (cfg->left_chunks + 1) * cfg->chunk_size;                         // attention.py:83
+    c->pos_rows = cfg->pos_max_len;
+    c->pe_wrap = cfg->chunk_size > 0 ? cfg->chunk_size * (cfg->pos_max_len / cfg->chunk_size) - c->full_chunk : cfg->pos_max_len;
+    const int msf = cfg->max_stream_frames > 0 ? cfg->max_stream_frames : cfg->frames_per_chunk + cfg->context_frames;
+    c->max_t = (((msf - 1) / 2) - 1) / 2;
+    if (c->max_t < 1) c->max_t = 1;
+    c->ring_cap = ((c->window + c->max_t + 7) / 8) * 8;
+    c->carry = cfg->frame_len - cfg->frame_shift;
+    c->chunk_samples = cfg->frame_shift * cfg->frames_per_chunk;
+    c->fft = 1;
+    while (c->fft < cfg->frame_len) c->fft <<= 1;
+    c->gemm_backend = dtype == FO_BF16 ? 1 : 0;
+
+    int r = 0;
+    const int S = cfg->max_sessions;
+    if (cfg->has_encoder) {
+        const size_t ring_bytes = (size_t)c->L * S * 2 * c->H * c->ring_cap * 64 * c->esz;
+        if (!r) r = dev_alloc(c, &c->ring, ring_bytes);
+        void* p = nullptr;
+        if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->n_frames = (int32_t*)p; }
+        if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->pe_index = (int32_t*)p; }
+        if (!r) { r = dev_alloc(c, &p, (size_t)S * (c->carry + c->chunk_samples) * sizeof(float)); c->samples = (float*)p; }
+        if (!r) { r = dev_alloc(c, &p, (size_t)S * (cfg->context_frames + cfg->frames_per_chunk) * c->F * sizeof(float)); c->feat_ring = (float*)p; }
+        if (!r && cudaMemset(c->ring, 0, ring_bytes) != cudaSuccess) r = FO_ERR_CUDA;
+    }
+    {
+        void* p = nullptr;
+        if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->ad_valid = (int32_t*)p; }
+        if (!r) { r = dev_alloc(c, &p, (size_t)S * 2 * (c->KA - 1) * c->D * sizeof(float)); c->ad_cache = (float*)p; }
+        if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->ids_dev = (int32_t*)p; }
+    }
+    for (int k = 0; k < fo_ctx::NSTAGE && !r; ++k) {
+        if (cudaMallocHost((void**)&c->ids_host[k], S * sizeof(int32_t)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ids_event[k], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("fo_create: pinned staging allocation failed");
+            r = FO_ERR_NOMEM;
+        }
+    }
+    if (r) { fo_destroy(c); return r; }
+    c->slot_used.assign(S, 0);
+    c->free_slots.reserve(S);
+    for (int s = S - 1; s >= 0; --s) c->free_slots.push_back(s);
+    *out = c;
+    return 0;
+}
+
+int fo_destroy(fo_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : c->staged) cudaFree(kv.second.d);
+    for (void* p : c->owned) if (p) cudaFree(p);
+    for (int k = 0; k < fo_ctx::NSTAGE; ++k) {
+        if (c->ids_host[k]) cudaFreeHost(c->ids_host[k]);
+        if (c->ids_event[k]) cudaEventDestroy(c->ids_event[k]);
+    }
+    delete c;
+    return 0;
+}
+
+int fo_load_tensor(fo_ctx* c, const char* name, const void* data, const int64_t* shape, int ndim) {
+    FO_CHECK(c && name && data && shape && ndim > 0 && ndim <= 4, "fo_load_tensor: bad argument");
+    FO_CHECK(!c->finalized, "fo_load_tensor: weights already finalized");
+    FO_CUDA(cudaSetDevice(c->device));
+    HostTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) { FO_CHECK(shape[i] > 0, "fo_load_tensor: bad shape"); t.shape.push_back(shape[i]); t.numel *= shape[i]; }
+    FO_CUDA(cudaMalloc((void**)&t.d, t.numel * sizeof(float)));
+    cudaError_t e = cudaMemcpy(t.d, data, t.numel * sizeof(float), cudaMemcpyDefault);
+    if (e != cudaSuccess) { cudaFree(t.d); set_error("fo_load_tensor(%s): %s", name, cudaGetErrorString(e)); return FO_ERR_CUDA; }
+    auto it = c->staged.find(name);
+    if (it != c->staged.end()) { cudaFree(it->second.d); c->staged.erase(it); }
+    c->staged[name] = t;
+    return 0;
+}
+
+int fo_finalize_weights(fo_ctx* c) {
+    FO_CHECK(c && !c->finalized, "fo_finalize_weights: bad state");
+    FO_CUDA(cudaSetDevice(c->device));
+    if (c->dtype == FO_BF16) gemm_tc_init();
+    return c->dtype == FO_BF16 ? finalize_t<bf16>(c) : finalize_t<float>(c);
+}
+
+// ---- sessions ------------------------------------------------------------------------------------
+static int reset_slot(fo_ctx* c, int s) {
+    const int32_t z = 0;
+    if (c->n_frames) {
+        FO_CUDA(cudaMemcpy(c->n_frames + s, &z, 4, cudaMemcpyHostToDevice));
+        FO_CUDA(cudaMemcpy(c->pe_index + s, &z, 4, cudaMemcpyHostToDevice));
+        FO_CUDA(cudaMemset(c->samples + (size_t)s * (c->carry + c->chunk_samples), 0, (size_t)(c->carry + c->chunk_samples) * 4));
+        FO_CUDA(cudaMemset(c->feat_ring + (size_t)s * (c->cfg.context_frames + c->cfg.frames_per_chunk) * c->F, 0,
+                           (size_t)(c->cfg.context_frames + c->cfg.frames_per_chunk) * c->F * 4));
+    }
+    FO_CUDA(cudaMemcpy(c->ad_valid + s, &z, 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int fo_session_alloc(fo_ctx* c, int n, int32_t* ids_out) {
+    FO_CHECK(c && ids_out && n > 0, "fo_session_alloc: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    FO_CHECK((int)c->free_slots.size() >= n, "fo_session_alloc: %d sessions requested, %zu slots free", n, c->free_slots.size());
+    FO_CUDA(cudaSetDevice(c->device));
+    FO_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < n; ++i) {
+        int s = c->free_slots.back();
+        c->free_slots.pop_back();
+        c->slot_used[s] = 1;
+        ids_out[i] = s;
+        FO_TRY(reset_slot(c, s));
+    }
+    c->sessions_in_use += n;
+    return 0;
+}
+
+int fo_session_reset(fo_ctx* c, int n, const int32_t* ids) {
+    FO_CHECK(c, "null context");
+    FO_TRY(check_ids(c, ids, n));
+    FO_CUDA(cudaSetDevice(c->device));
+    FO_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < n; ++i) FO_TRY(reset_slot(c, ids[i]));
+    return 0;
+}
+
+int fo_session_free(fo_ctx* c, int n, const int32_t* ids) {
+    FO_CHECK(c, "null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    FO_TRY(check_ids(c, ids, n));
+    for (int i = 0; i < n; ++i) {
+        if (!c->slot_used[ids[i]]) continue;
+        c->slot_used[ids[i]] = 0;
+        c->free_slots.push_back(ids[i]);
+        c->sessions_in_use -= 1;
+    }
+    return 0;
+}
+
+int fo_session_get_state(fo_ctx* c, int32_t id, int64_t* n_frames, int64_t* pe_index) {
+    FO_CHECK(c && c->n_frames, "fo_session_get_state: context has no encoder");
+    FO_TRY(check_ids(c, &id, 1));
+    FO_CUDA(cudaSetDevice(c->device));
+    int32_t a = 0, b = 0;
+    FO_CUDA(cudaMemcpy(&a, c->n_frames + id, 4, cudaMemcpyDeviceToHost));
+    FO_CUDA(cudaMemcpy(&b, c->pe_index + id, 4, cudaMemcpyDeviceToHost));
+    if (n_frames) *n_frames = a;
+    if (pe_index) *pe_index = b;
+    return 0;
+}
+
+int fo_session_set_pe_index(fo_ctx* c, int n, const int32_t* ids, const int64_t* pe_index) {
+    FO_CHECK(c && c->pe_index && pe_index, "fo_session_set_pe_index: bad argument");
+    FO_TRY(check_ids(c, ids, n));
+    FO_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < n; ++i) {
+        int32_t v = (int32_t)pe_index[i];
+        FO_CUDA(cudaMemcpy(c->pe_index + ids[i], &v, 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int fo_session_set_frames(fo_ctx* c, int32_t id, int64_t n_frames) {
+    FO_CHECK(c && c->n_frames && n_frames >= 0, "fo_session_set_frames: bad argument");
+    FO_TRY(check_ids(c, &id, 1));
+    FO_CUDA(cudaSetDevice(c->device));
+    int32_t v = (int32_t)n_frames;
+    FO_CUDA(cudaMemcpy(c->n_frames + id, &v, 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int kv_ptrs(fo_ctx* c, int32_t id, int layer, void** k, void** v, int32_t* nf) {
+    FO_CHECK(c && c->ring, "context has no encoder");
+    FO_TRY(check_ids(c, &id, 1));
+    FO_CHECK(layer >= 0 && layer < c->L, "layer %d out of range", layer);
+    FO_CUDA(cudaSetDevice(c->device));
+    FO_CUDA(cudaDeviceSynchronize());
+    FO_CUDA(cudaMemcpy(nf, c->n_frames + id, 4, cudaMemcpyDeviceToHost));
+    const size_t per_kv = (size_t)c->H * c->ring_cap * 64;
+    char* base = reinterpret_cast<char*>(c->ring) + (((size_t)layer * c->cfg.max_sessions + id) * 2) * per_kv * c->esz;
+    *k = base;
+    *v = base + per_kv * c->esz;
+    return 0;
+}
+
+int fo_session_export_kv(fo_ctx* c, int32_t id, int layer, float* K, float* V, int32_t* cache_len) {
+    void *k, *v;
+    int32_t nf;
+    FO_TRY(kv_ptrs(c, id, layer, &k, &v, &nf));
+    const int cl = nf < c->window ? nf : c->window;
+    if (cache_len) *cache_len = cl;
+    if (cl == 0 || (!K && !V)) return 0;
+    const size_t bytes = (size_t)c->H * cl * 64 * sizeof(float);
+    void *dk, *dv;
+    FO_TRY(out_dev(c, K, bytes, WS_TMP0, &dk));
+    FO_TRY(out_dev(c, V, bytes, WS_TMP1, &dv));
+    if (c->dtype == FO_BF16) {
+        FO_TRY(ring_export<bf16>((bf16*)k, c->H, c->ring_cap, nf - cl, cl, (float*)dk, 0));
+        FO_TRY(ring_export<bf16>((bf16*)v, c->H, c->ring_cap, nf - cl, cl, (float*)dv, 0));
+    } else {
+        FO_TRY(ring_export<float>((float*)k, c->H, c->ring_cap, nf - cl, cl, (float*)dk, 0));
+        FO_TRY(ring_export<float>((float*)v, c->H, c->ring_cap, nf - cl, cl, (float*)dv, 0));
+    }
+    if (K) FO_TRY(out_done(K, dk, bytes, 0));
+    if (V) FO_TRY(out_done(V, dv, bytes, 0));
+    FO_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+int fo_session_import_kv(fo_ctx* c, int32_t id, int layer, const float* K, const float* V, int32_t cache_len) {
+    void *k, *v;
+    int32_t nf;
+    FO_TRY(kv_ptrs(c, id, layer, &k, &v, &nf));
+    FO_CHECK(K && V && cache_len >= 0 && cache_len <= c->window, "fo_session_import_kv: bad argument");
+    FO_CHECK(nf >= cache_len, "fo_session_import_kv: set n_frames (fo_session_set_frames) >= cache_len first");
+    if (cache_len == 0) return 0;
+    const size_t bytes = (size_t)c->H * cache_len * 64 * sizeof(float);
+    const void *dk, *dv;
+    FO_TRY(in_dev(c, K, bytes, WS_TMP0, 0, &dk));
+    FO_TRY(in_dev(c, V, bytes, WS_TMP1, 0, &dv));
+    if (c->dtype == FO_BF16) {
+        FO_TRY(ring_import<bf16>((bf16*)k, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dk, 0));
+        FO_TRY(ring_import<bf16>((bf16*)v, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dv, 0));
+    } else {
+        FO_TRY(ring_import<float>((float*)k, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dk, 0));
+        FO_TRY(ring_import<float>((float*)v, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dv, 0));
+    }
+    FO_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+int fo_session_export_adapter_cache(fo_ctx* c, int32_t id, float* cache, int32_t* valid) {
+    FO_CHECK(c && c->ad_cache, "context has no adapter cache");
+    FO_TRY(check_ids(c, &id, 1));
+    FO_CUDA(cudaSetDevice(c->device));
+    FO_CUDA(cudaDeviceSynchronize());
+    int32_t live = 0;
+    FO_CUDA(cudaMemcpy(&live, c->ad_valid + id, 4, cudaMemcpyDeviceToHost));
+    if (valid) *valid = live != 0;
+    if (!live || !cache) return 0;
+    const int km1 = c->KA - 1, D = c->D;
+    std::vector<float> tm((size_t)km1 * D), out((size_t)km1 * D);
+    FO_CUDA(cudaMemcpy(tm.data(), c->ad_cache + ((size_t)id * 2 + (live == 2 ? 1 : 0)) * km1 * D, tm.size() * 4, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < km1; ++r)
+        for (int ch = 0; ch < D; ++ch) out[(size_t)ch * km1 + r] = tm[(size_t)r * D + ch];    // (D, k-1) as adapter.py:141
+    FO_CUDA(cudaMemcpy(cache, out.data(), out.size() * 4, cudaMemcpyDefault));
+    return 0;
+}
+
+int fo_session_import_adapter_cache(fo_ctx* c, int32_t id, const float* cache, int32_t valid) {
+    FO_CHECK(c && c->ad_cache, "context has no adapter cache");
+    FO_TRY(check_ids(c, &id, 1));
+    FO_CUDA(cudaSetDevice(c->device));
+    FO_CUDA(cudaDeviceSynchronize());
+    int32_t live = valid ? 1 : 0;
+    if (valid) {
+        FO_CHECK(cache, "fo_session_import_adapter_cache: null cache");
+        const int km1 = c->KA - 1, D = c->D;
+        std::vector<float> in((size_t)km1 * D), tm((size_t)km1 * D);
+        FO_CUDA(cudaMemcpy(in.data(), cache, in.size() * 4, cudaMemcpyDefault));
+        for (int r = 0; r < km1; ++r)
+            for (int ch = 0; ch < D; ++ch) tm[(size_t)r * D + ch] = in[(size_t)ch * km1 + r];
+        FO_CUDA(cudaMemcpy(c->ad_cache + (size_t)id * 2 * km1 * D, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice));
+    }
+    FO_CUDA(cudaMemcpy(c->ad_valid + id, &live, 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ---- frontend ------------------------------------------------------------------------------------
+int fo_fbank_stream(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
+                    float* feats_out, void* stream) {
+    FO_CHECK(c && c->finalized && c->fb_window, "fo_fbank_stream: context has no finalized frontend");
+    FO_CHECK(pcm && (pcm_dtype == FO_F32 || pcm_dtype == FO_I16), "fo_fbank_stream: pcm must be FO_F32 or FO_I16");
+    FO_TRY(check_ids(c, ids, n));
+    FO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FO_TRY(upload_ids(c, ids, n, st));
+    const size_t in_bytes = (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4);
+    const void* dp;
+    FO_TRY(in_dev(c, pcm, in_bytes, WS_PCM, st, &dp));
+    const int rows = c->cfg.context_frames + c->cfg.frames_per_chunk;
+    const size_t out_bytes = (size_t)n * rows * c->F * sizeof(float);
+    void* dout = nullptr;
+    if (feats_out) FO_TRY(out_dev(c, feats_out, out_bytes, WS_FEATS, &dout));
+    FO_TRY(fbank_stream(fbank_params(c), c->ids_dev, n, dp, pcm_dtype == FO_I16, scale, c->cfg.frames_per_chunk,
+                        c->cfg.context_frames, c->samples, c->feat_ring, (float*)dout, st));
+    if (feats_out) FO_TRY(out_done(feats_out, dout, out_bytes, st));
+    return 0;
+}
+
+int fo_fbank_offline(fo_ctx* c, const void* pcm, int pcm_dtype, int B, int64_t n_samples, float scale, float* out,
+                     void* stream) {
+    FO_CHECK(c && c->finalized && c->fb_window, "fo_fbank_offline: context has no finalized frontend");
+    FO_CHECK(pcm && out && B > 0 && (pcm_dtype == FO_F32 || pcm_dtype == FO_I16), "fo_fbank_offline: bad argument");
+    FO_CHECK(n_samples >= c->cfg.frame_len, "fo_fbank_offline: signal shorter than one frame");
+    FO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t in_bytes = (size_t)B * n_samples * (pcm_dtype == FO_I16 ? 2 : 4);
+    const void* dp;
+    FO_TRY(in_dev(c, pcm, in_bytes, WS_PCM, st, &dp));
+    const int m = (int)(1 + (n_samples - c->cfg.frame_len) / c->cfg.frame_shift);
+    const size_t out_bytes = (size_t)B * m * c->F * sizeof(float);
+    void* dout;
+    FO_TRY(out_dev(c, out, out_bytes, WS_FEATS, &dout));
+    FO_TRY(fbank_offline(fbank_params(c), dp, pcm_dtype == FO_I16, B, n_samples, scale, (float*)dout, st));
+    FO_TRY(out_done(out, dout, out_bytes, st));
+    return 0;
+}
+
+// ---- streaming chunk --------------------------------------------------------------------------------
+static int stream_common(fo_ctx* c, const int32_t* ids, int n, const float* feats_dev, int t_in, float* enc_out,
+                         float* adapter_out, cudaStream_t st) {
+    const int T1 = (t_in - 1) / 2, t = (T1 - 1) / 2;
+    FO_CHECK(t >= 1 && t <= c->max_t, "streaming call of %d feature frames gives %d encoder frames; context allows 1..%d",
+             t_in, t, c->max_t);
+    const int km1 = c->KA - 1, t_out = (t + km1 - c->KA) / 2 + 1;
+    const size_t enc_bytes = (size_t)n * t * c->D * sizeof(float);
+    const size_t y_bytes = (size_t)n * t_out * c->E * sizeof(float);
+    void *denc, *dy = nullptr;
+    FO_TRY(out_dev(c, enc_out, enc_bytes, WS_ENC, &denc));
+    if (adapter_out) {
+        FO_CHECK(c->cfg.has_adapter, "adapter_out requested but the context has no adapter");
+        FO_TRY(out_dev(c, adapter_out, y_bytes, WS_Y, &dy));
+    }
+    int r = c->dtype == FO_BF16 ? stream_program<bf16>(c, n, feats_dev, t_in, (float*)denc, (float*)dy, st)
+                                : stream_program<float>(c, n, feats_dev, t_in, (float*)denc, (float*)dy, st);
+    FO_TRY(r);
+    if (enc_out) FO_TRY(out_done(enc_out, denc, enc_bytes, st));
+    if (adapter_out) FO_TRY(out_done(adapter_out, dy, y_bytes, st));
+    c->stats.stream_steps += 1;
+    c->stats.session_chunks += n;
+    return 0;
+}
+
+int fo_encode_stream(fo_ctx* c, const int32_t* ids, int n, const float* feats, int t_in, float* enc_out,
+                     float* adapter_out, void* stream) {
+    FO_CHECK(c && c->finalized && c->cfg.has_encoder, "fo_encode_stream: context has no finalized encoder");
+    FO_TRY(check_ids(c, ids, n));
+    FO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FO_TRY(upload_ids(c, ids, n, st));
+    const float* dfeats;
+    if (feats) {
+        FO_CHECK(t_in >= 7, "fo_encode_stream: need at least 7 feature frames");
+        const void* p;
+        FO_TRY(in_dev(c, feats, (size_t)n * t_in * c->F * sizeof(float), WS_FEATS, st, &p));
+        dfeats = (const float*)p;
+    } else {
+        // gather the sessions' feature rings into a dense (n, rows, F) block
+        t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
+        void* p;
+        FO_TRY(ws_ensure(c, WS_FEATS, (size_t)n * t_in * c->F * sizeof(float), &p));
+        for (int i = 0; i < n; ++i)
+            FO_CUDA(cudaMemcpyAsync((float*)p + (size_t)i * t_in * c->F, c->feat_ring + (size_t)ids[i] * t_in * c->F,
+                                    (size_t)t_in * c->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        dfeats = (const float*)p;
+    }
+    return stream_common(c, ids, n, dfeats, t_in, enc_out, adapter_out, st);
+}
+
+int fo_stream_step(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale, float* enc_out,
+                   float* adapter_out, void* stream) {
+    FO_CHECK(c && c->finalized && c->cfg.has_encoder && c->fb_window, "fo_stream_step: context has no finalized encoder + frontend");
+    FO_CHECK(pcm && (pcm_dtype == FO_F32 || pcm_dtype == FO_I16), "fo_stream_step: pcm must be FO_F32 or FO_I16");
+    FO_TRY(check_ids(c, ids, n));
+    FO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FO_TRY(upload_ids(c, ids, n, st));
+    const size_t in_bytes = (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4);
+    const void* dp;
+    FO_TRY(in_dev(c, pcm, in_bytes, WS_PCM, st, &dp));
+    const int rows = c->cfg.context_frames + c->cfg.frames_per_chunk;
+    void* dfeats;
+    FO_TRY(ws_ensure(c, WS_FEATS, (size_t)n * rows * c->F * sizeof(float), &dfeats));
+    FO_TRY(fbank_stream(fbank_params(c), c->ids_dev, n, dp, pcm_dtype == FO_I16, scale, c->cfg.frames_per_chunk,
+                        c->cfg.context_frames, c->samples, c->feat_ring, (float*)dfeats, st));
+    return stream_common(c, ids, n, (const float*)dfeats, rows, enc_out, adapter_out, st);
+}
+
+// ---- full utterance -----------------------------------------------------------------------------------
+int fo_encode_offline(fo_ctx* c, const float* feats, const int32_t* ilens, int B, int T, int chunk, int left,
+                      float* enc_out, uint8_t* mask_out, float* adapter_out, uint8_t* adapter_mask_out, void* stream) {
+    FO_CHECK(c && c->finalized && c->cfg.has_encoder, "fo_encode_offline: context has no finalized encoder");
+    FO_CHECK(feats && ilens && B > 0 && T >= 7, "fo_encode_offline: need feats, ilens and T >= 7");
+    const int T1 = (T - 1) / 2, T2 = (T1 - 1) / 2;
+    FO_CHECK(T2 <= c->pos_rows, "fo_encode_offline: %d encoder frames exceed the positional table (%d)", T2, c->pos_rows);
+    FO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const void *dfeats, *dil;
+    FO_TRY(in_dev(c, feats, (size_t)B * T * c->F * sizeof(float), WS_FEATS, st, &dfeats));
+    FO_TRY(in_dev(c, ilens, (size_t)B * sizeof(int32_t), WS_ILENS, st, &dil));
+    const int km1 = c->KA - 1, t_out = (T2 + km1 - c->KA) / 2 + 1;
+    const size_t enc_bytes = (size_t)B * T2 * c->D * sizeof(float), y_bytes = (size_t)B * t_out * c->E * sizeof(float);
+    void *denc, *dy = nullptr, *dmask, *dil2, *damask = nullptr;
+    FO_TRY(out_dev(c, enc_out, enc_bytes, WS_ENC, &denc));
+    FO_TRY(out_dev(c, mask_out, (size_t)B * T2, WS_MASK2, &dmask));
+    FO_TRY(ws_ensure(c, WS_ILENS2, (size_t)B * sizeof(int32_t), &dil2));
+    if (adapter_out || adapter_mask_out) FO_CHECK(c->cfg.has_adapter, "adapter outputs requested but the context has no adapter");
+    if (adapter_out) FO_TRY(out_dev(c, adapter_out, y_bytes, WS_Y, &dy));
+    int r = c->dtype == FO_BF16
+                ? offline_program<bf16>(c, (const float*)dfeats, (const int32_t*)dil, B, T, chunk, left, (float*)denc,
+                                        (uint8_t*)dmask, (int32_t*)dil2, (float*)dy, st)
+                : offline_program<float>(c, (const float*)dfeats, (const int32_t*)dil, B, T, chunk, left, (float*)denc,
+                                         (uint8_t*)dmask, (int32_t*)dil2, (float*)dy, st);
+    FO_TRY(r);
+    if (adapter_mask_out) {
+        FO_TRY(out_dev(c, adapter_mask_out, (size_t)B * t_out, WS_AMASK, &damask));
+        FO_TRY(stride2_mask((const uint8_t*)dmask, B, T2, t_out, (uint8_t*)damask, st));
+        FO_TRY(out_done(adapter_mask_out, damask, (size_t)B * t_out, st));
+    }
+    if (enc_out) FO_TRY(out_done(enc_out, denc, enc_bytes, st));
+    if (mask_out) FO_TRY(out_done(mask_out, dmask, (size_t)B * T2, st));
+    if (adapter_out) FO_TRY(out_done(adapter_out, dy, y_bytes, st));
+    c->stats.offline_calls += 1;
+    c->stats.offline_frames += (long long)B * T2;
+    return 0;
+}
+
+int fo_adapter_forward(fo_ctx* c, const float* x, const uint8_t* mask, int B, int T, const float* cache_in,
+                       float* cache_out, float* y, void* stream) {
+    FO_CHECK(c && c->finalized && c->cfg.has_adapter, "fo_adapter_forward: context has no finalized adapter");
+    FO_CHECK(x && y && B > 0 && T > 0, "fo_adapter_forward: bad argument");
+    FO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int km1 = c->KA - 1, t_out = (T + km1 - c->KA) / 2 + 1;
+    FO_CHECK(t_out >= 1, "fo_adapter_forward: input too short");
+    const void *dx, *dm = nullptr, *dci = nullptr;
+    FO_TRY(in_dev(c, x, (size_t)B * T * c->D * sizeof(float), WS_ENC, st, &dx));
+    if (mask) FO_TRY(in_dev(c, mask, (size_t)B * T, WS_MASK2, st, &dm));
+    const size_t cbytes = (size_t)B * c->D * km1 * sizeof(float);
+    if (cache_in) FO_TRY(in_dev(c, cache_in, cbytes, WS_TMP0, st, &dci));
+    void *dco = nullptr, *dy;
+    if (cache_out) FO_TRY(out_dev(c, cache_out, cbytes, WS_TMP1, &dco));
+    const size_t y_bytes = (size_t)B * t_out * c->E * sizeof(float);
+    FO_TRY(out_dev(c, y, y_bytes, WS_Y, &dy));
+    int r = c->dtype == FO_BF16
+                ? adapter_program<bf16>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, (const float*)dci, (float*)dco, (float*)dy, st)
+                : adapter_program<float>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, (const float*)dci, (float*)dco, (float*)dy, st);
+    FO_TRY(r);
+    if (cache_out) FO_TRY(out_done(cache_out, dco, cbytes, st));
+    FO_TRY(out_done(y, dy, y_bytes, st));
+    return 0;
+}
+
+// ---- introspection --------------------------------------------------------------------------------------
+int fo_stats(fo_ctx* c, fo_stats_t* out) {
+    FO_CHECK(c && out, "fo_stats: null argument");
+    *out = c->stats;
+    out->kernel_launches = g_launches;
+    out->sessions_in_use = c->sessions_in_use;
+    out->device_bytes = c->device_bytes;
+    return 0;
+}
+
+int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
+    FO_CHECK(c && name, "fo_set_option: null argument");
+    if (!strcmp(name, "gemm_backend")) {
+        FO_CHECK(value == 0 || (value == 1 && c->dtype == FO_BF16), "gemm_backend 1 (tcgen05) needs a bf16 context");
+        c->gemm_backend = (int)value;
+    } else if (!strcmp(name, "use_graph")) c->use_graph = value != 0;
+    else if (!strcmp(name, "split_k")) c->split_k = (int)value;
+    else { set_error("fo_set_option: unknown option '%s'", name); return FO_ERR_ARG; }
+    return 0;
+}
+
+int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
+    FO_CHECK(c && name && value, "fo_get_option: null argument");
+    if (!strcmp(name, "gemm_backend")) *value = c->gemm_backend;
+    else if (!strcmp(name, "use_graph")) *value = c->use_graph;
+    else if (!strcmp(name, "split_k")) *value = c->split_k;
+    else if (!strcmp(name, "ring_cap")) *value = c->ring_cap;
+    else if (!strcmp(name, "max_t")) *value = c->max_t;
+    else { set_error("fo_get_option: unknown option '%s'", name); return FO_ERR_ARG; }
+    return 0;
+}
+
+int fo_debug_gemm(fo_ctx* c, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                  int backend, int relu, int iters, float* ms_out, void* stream) {
+    FO_CHECK(c && A && W && C && M > 0 && N > 0 && K > 0, "fo_debug_gemm: bad argument");
+    FO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Epilogue ep;
+    ep.bias = bias;
+    ep.c_f32 = C;
+    ep.ldc = N;
+    ep.relu = relu;
+    const int saved = c->gemm_backend;
+    cudaEvent_t e0, e1;
+    FO_CUDA(cudaEventCreate(&e0));
+    FO_CUDA(cudaEventCreate(&e1));
+    int r = 0;
+    if (c->dtype == FO_BF16) {
+        void *a16, *w16;
+        FO_TRY(ws_ensure(c, WS_TMP2, (size_t)M * K * 2, &a16));
+        FO_TRY(ws_ensure(c, WS_TMP3, (size_t)N * K * 2, &w16));
+        FO_TRY(f32_to_bf16(A, (bf16*)a16, (long long)M * K, st));
+        FO_TRY(f32_to_bf16(W, (bf16*)w16, (long long)N * K, st));
+        c->gemm_backend = backend;
+        r = gemm<bf16>(c, (const bf16*)a16, plain_rows(K), w16, M, N, K, ep, st);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < iters && r == 0; ++i) r = gemm<bf16>(c, (const bf16*)a16, plain_rows(K), w16, M, N, K, ep, st);
+        cudaEventRecord(e1, st);
+    } else {
+        r = gemm<float>(c, A, plain_rows(K), W, M, N, K, ep, st);
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < iters && r == 0; ++i) r = gemm<float>(c, A, plain_rows(K), W, M, N, K, ep, st);
+        cudaEventRecord(e1, st);
+    }
+    c->gemm_backend = saved;
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    FO_TRY(r);
+    FO_CUDA(e);
+    if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,382 @@
+// Chunk attention with key-position rel-pos bias (reference: MultiHeadedAttention.infer / .forward,
+// models/encoder/attention.py:407-459 / 350-405; no rel_shift):
+//     score[i][j] = ((q_i + u) . K_j + (q_i + v) . P[pos_j]) / sqrt(d_k),   softmax over j,   out = sum_j p_ij V_j
+// d_k is 64.  Streaming: one CTA per (session, head); the cached K/V rows come from the session's ring in
+// HBM with cp.async.bulk (TMA bulk copy, mbarrier completion) while the chunk's own rows arrive from the
+// fused QKV GEMM output and are appended to the ring in the same pass.  Offline: one CTA per
+// (utterance, head, 4 query rows); the band [start,end) of models/masks.py:50-56 and the pad mask are
+// evaluated arithmetically, never materialised; key tiles + online softmax cover unbounded left context.
+#include "fo_common.cuh"
+
+namespace fo {
+
+namespace {
+
+constexpr int DK = 64;
+constexpr int TQ_MAX = 8;          // query rows per CTA (streaming chunk: 4, fork: 7)
+constexpr int ATT_THREADS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <typename TA> struct Chunk;        // one 16-byte slice of a 64-wide row
+template <> struct Chunk<float> {
+    static constexpr int EPC = 4, NCH = 16;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <> struct Chunk<bf16> {
+    static constexpr int EPC = 8, NCH = 8;
+    static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    }
+};
+
+// scores of key row j (smem) against nq query rows; chunk order is rotated by j so that the 8 lanes of
+// one shared-memory phase touch 8 different 16-byte bank groups (rows are 128 B / 256 B apart).
+template <typename TA>
+__device__ __forceinline__ void score_row(const TA* Krow, const TA* Prow, const float* qu, const float* qv, int nq,
+                                          int rot, float (&acc)[TQ_MAX]) {
+    constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
+#pragma unroll
+    for (int i = 0; i < TQ_MAX; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < NCH; ++c) {
+        const int cc = (c + rot) & (NCH - 1);
+        float kv[EPC], pv[EPC];
+        Chunk<TA>::load(Krow + cc * EPC, kv);
+        Chunk<TA>::load(Prow + cc * EPC, pv);
+#pragma unroll
+        for (int i = 0; i < TQ_MAX; ++i) {
+            if (i < nq) {
+                const float* a = qu + i * DK + cc * EPC;
+                const float* b = qv + i * DK + cc * EPC;
+                float s = acc[i];
+#pragma unroll
+                for (int e = 0; e < EPC; ++e) s = fmaf(a[e], kv[e], fmaf(b[e], pv[e], s));
+                acc[i] = s;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename TA>
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, TA* __restrict__ ring, const TA* __restrict__ ptab,
+                        const float* __restrict__ pos_u, const float* __restrict__ pos_v, TA* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cap = a.ring_cap;
+    TA* Ks = reinterpret_cast<TA*>(smem_raw);
+    TA* Vs = Ks + cap * DK;
+    TA* Ps = Vs + cap * DK;
+    float* qu = reinterpret_cast<float*>(Ps + cap * DK);
+    float* qv = qu + TQ_MAX * DK;
+    float* prob = qv + TQ_MAX * DK;                 // TQ_MAX x cap
+    __shared__ __align__(8) uint64_t bar;
+
+    const int b = blockIdx.x, h = blockIdx.y;
+    const int t = a.t, D = a.H * DK;
+    const int slot = a.ids[b];
+    const int nf = a.n_frames[slot];
+    const int cl = min(nf, a.window);
+    const int first = nf - cl;
+    const int nk = cl + t;
+    const int pe = a.pe_index[slot] % a.pe_wrap;
+    const int start = max(0, pe - a.full_chunk);     // attention.py:112-114
+    TA* ringK = ring + (long long)slot * a.ring_slot_stride + (long long)h * cap * DK;
+    TA* ringV = ringK + (long long)a.H * cap * DK;
+    const int tid = threadIdx.x;
+
+    if (cl > 0 && tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int p0 = first % cap;
+        const int len1 = min(cl, cap - p0), len2 = cl - len1;
+        const uint32_t rowb = DK * sizeof(TA);
+        mbar_expect_tx(&bar, 2u * cl * rowb);
+        bulk_g2s(Ks, ringK + (long long)p0 * DK, len1 * rowb, &bar);
+        bulk_g2s(Vs, ringV + (long long)p0 * DK, len1 * rowb, &bar);
+        if (len2 > 0) {
+            bulk_g2s(Ks + len1 * DK, ringK, len2 * rowb, &bar);
+            bulk_g2s(Vs + len1 * DK, ringV, len2 * rowb, &bar);
+        }
+    }
+    // the chunk's own K/V rows: QKV GEMM output -> shared + appended to the ring
+    constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
+    for (int i = tid; i < t * NCH * 2; i += ATT_THREADS) {
+        const int which = i / (t * NCH);             // 0: K, 1: V
+        const int r = (i / NCH) % t, c = i % NCH;
+        const TA* src = qkv + (long long)(b * t + r) * 3 * D + (which + 1) * D + h * DK + c * EPC;
+        uint4 val = *reinterpret_cast<const uint4*>(src);
+        TA* sdst = (which ? Vs : Ks) + (cl + r) * DK + c * EPC;
+        *reinterpret_cast<uint4*>(sdst) = val;
+        TA* gdst = (which ? ringV : ringK) + (long long)((nf + r) % cap) * DK + c * EPC;
+        *reinterpret_cast<uint4*>(gdst) = val;
+    }
+    // rel-pos rows P_l[start + j], head slice
+    for (int i = tid; i < nk * NCH; i += ATT_THREADS) {
+        const int j = i / NCH, c = i % NCH;
+        const int pos = min(start + j, a.pos_rows - 1);
+        *reinterpret_cast<uint4*>(Ps + j * DK + c * EPC) =
+            *reinterpret_cast<const uint4*>(ptab + (long long)pos * D + h * DK + c * EPC);
+    }
+    for (int i = tid; i < t * DK; i += ATT_THREADS) {
+        const int r = i / DK, d = i % DK;
+        const float q = to_f(qkv[(long long)(b * t + r) * 3 * D + h * DK + d]);
+        qu[i] = q + pos_u[h * DK + d];
+        qv[i] = q + pos_v[h * DK + d];
+    }
+    __syncthreads();
+    if (cl > 0) mbar_wait(&bar, 0);
+
+    // scores: one key per thread
+    for (int j = tid; j < nk; j += ATT_THREADS) {
+        float acc[TQ_MAX];
+        score_row<TA>(Ks + j * DK, Ps + j * DK, qu, qv, t, j, acc);
+#pragma unroll
+        for (int i = 0; i < TQ_MAX; ++i)
+            if (i < t) prob[i * cap + j] = acc[i] * 0.125f;
+    }
+    __syncthreads();
+    // softmax + PV: one warp per query row
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < t; i += ATT_THREADS / 32) {
+        float* pr = prob + i * cap;
+        float m = -INFINITY;
+        for (int j = lane; j < nk; j += 32) m = fmaxf(m, pr[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < nk; j += 32) {
+            float e = __expf(pr[j] - m);
+            pr[j] = e;
+            s += e;
+        }
+        s = warp_sum(s);
+        __syncwarp();
+        const float inv = 1.f / s;
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < nk; ++j) {
+            const float p = pr[j];
+            o0 = fmaf(p, to_f(Vs[j * DK + 2 * lane]), o0);
+            o1 = fmaf(p, to_f(Vs[j * DK + 2 * lane + 1]), o1);
+        }
+        TA* o = out + (long long)(b * t + i) * D + h * DK + 2 * lane;
+        o[0] = from_f<TA>(o0 * inv);
+        o[1] = from_f<TA>(o1 * inv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int KT = 96;          // key tile (covers the shipped 68-key band in one pass)
+constexpr int QB = 4;           // query rows per CTA
+
+template <typename TA>
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_offline_kernel(const TA* __restrict__ qkv, int T, int H, const int32_t* __restrict__ ilens, int chunk,
+                         int left, const TA* __restrict__ ptab, const float* __restrict__ pos_u,
+                         const float* __restrict__ pos_v, TA* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TA* Ks = reinterpret_cast<TA*>(smem_raw);
+    TA* Vs = Ks + KT * DK;
+    TA* Ps = Vs + KT * DK;
+    float* qu = reinterpret_cast<float*>(Ps + KT * DK);
+    float* qv = qu + TQ_MAX * DK;
+    float* sc = qv + TQ_MAX * DK;                    // QB x KT
+    __shared__ int win[QB][2];
+
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int D = H * DK;
+    const int q0 = qb * QB;
+    const int nq = min(QB, T - q0);
+    const int klen = ilens ? min(ilens[b], T) : T;        // pad mask on keys (masks.py:110-120)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
+
+    if (tid < nq) {
+        const int i = q0 + tid;
+        int s = 0, e = T;
+        if (chunk > 0) {                                   // masks.py:50-56
+            s = left < 0 ? 0 : max((i / chunk - left) * chunk, 0);
+            e = min((i / chunk + 1) * chunk, T);
+        }
+        win[tid][0] = s;
+        win[tid][1] = min(e, klen);
+    }
+    for (int i = tid; i < nq * DK; i += ATT_THREADS) {
+        const int r = i / DK, d = i % DK;
+        const float q = to_f(qkv[((long long)b * T + q0 + r) * 3 * D + h * DK + d]);
+        qu[i] = q + pos_u[h * DK + d];
+        qv[i] = q + pos_v[h * DK + d];
+    }
+    __syncthreads();
+    int k_lo = win[0][0], k_hi = win[0][1];
+    for (int r = 1; r < nq; ++r) { k_lo = min(k_lo, win[r][0]); k_hi = max(k_hi, win[r][1]); }
+
+    // warp `warp` owns query row `warp` (QB == warps)
+    float m_run = -INFINITY, l_run = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int kt = k_lo; kt < k_hi; kt += KT) {
+        const int nk = min(KT, k_hi - kt);
+        __syncthreads();                                   // previous tile fully consumed
+        for (int i = tid; i < nk * NCH * 3; i += ATT_THREADS) {
+            const int which = i / (nk * NCH);              // 0 K, 1 V, 2 P
+            const int j = (i / NCH) % nk, c = i % NCH;
+            const TA* src = which < 2
+                                ? qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + c * EPC
+                                : ptab + (long long)(kt + j) * D + h * DK + c * EPC;
+            TA* dst = (which == 0 ? Ks : which == 1 ? Vs : Ps) + j * DK + c * EPC;
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        }
+        __syncthreads();
+        for (int j = tid; j < nk; j += ATT_THREADS) {
+            float acc[TQ_MAX];
+            score_row<TA>(Ks + j * DK, Ps + j * DK, qu, qv, nq, j, acc);
+#pragma unroll
+            for (int i = 0; i < QB; ++i)
+                if (i < nq) {
+                    const int key = kt + j;
+                    const bool ok = key >= win[i][0] && key < win[i][1];
+                    sc[i * KT + j] = ok ? acc[i] * 0.125f : -INFINITY;
+                }
+        }
+        __syncthreads();
+        if (warp < nq) {
+            float* pr = sc + warp * KT;
+            float m = -INFINITY;
+            for (int j = lane; j < nk; j += 32) m = fmaxf(m, pr[j]);
+            m = warp_max(m);
+            const float m_new = fmaxf(m_run, m);
+            if (m_new != -INFINITY) {
+                const float corr = __expf(m_run - m_new);  // m_run = -inf -> 0
+                float s = 0.f;
+                for (int j = lane; j < nk; j += 32) {
+                    const float e = __expf(pr[j] - m_new);
+                    pr[j] = e;
+                    s += e;
+                }
+                s = warp_sum(s);
+                __syncwarp();
+                l_run = l_run * corr + s;
+                o0 *= corr;
+                o1 *= corr;
+                for (int j = 0; j < nk; ++j) {
+                    const float p = pr[j];
+                    o0 = fmaf(p, to_f(Vs[j * DK + 2 * lane]), o0);
+                    o1 = fmaf(p, to_f(Vs[j * DK + 2 * lane + 1]), o1);
+                }
+                m_run = m_new;
+            }
+        }
+    }
+    if (warp < nq) {
+        // a row whose whole window is masked yields zeros (attention.py:396-397)
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        TA* o = out + ((long long)b * T + q0 + warp) * D + h * DK + 2 * lane;
+        o[0] = from_f<TA>(o0 * inv);
+        o[1] = from_f<TA>(o1 * inv);
+    }
+}
+
+__global__ void advance_sessions_kernel(const int32_t* __restrict__ ids, int n, int t, int chunk_size, int pe_wrap,
+                                        int32_t* n_frames, int32_t* pe_index, int32_t* adapter_valid) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const int s = ids[b];
+    if (n_frames) {
+        n_frames[s] += t;
+        pe_index[s] = pe_index[s] % pe_wrap + chunk_size;   // attention.py:107,120 (+chunk_size, not +t)
+    }
+    if (adapter_valid) adapter_valid[s] = adapter_valid[s] == 1 ? 2 : 1;
+}
+
+}  // namespace
+
+template <typename TA>
+int attention_stream(const AttnStream& a, const TA* qkv, TA* ring, const TA* ptab, const float* pos_u,
+                     const float* pos_v, TA* out, cudaStream_t st) {
+    if (a.n <= 0) return 0;
+    FO_CHECK(a.t <= TQ_MAX, "attention_stream: %d frames per call exceeds %d", a.t, TQ_MAX);
+    FO_CHECK(a.ring_cap >= a.window + a.t, "attention_stream: ring capacity %d < window %d + %d", a.ring_cap, a.window, a.t);
+    const size_t smem = (size_t)3 * a.ring_cap * DK * sizeof(TA) + (size_t)2 * TQ_MAX * DK * sizeof(float) +
+                        (size_t)TQ_MAX * a.ring_cap * sizeof(float);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[sizeof(TA) == 2]) {
+        FO_CUDA(cudaFuncSetAttribute(attention_stream_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set[sizeof(TA) == 2] = true;
+    }
+    FO_CHECK(smem <= 160 * 1024, "attention_stream: window too large for shared memory");
+    dim3 grid(a.n, a.H);
+    attention_stream_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(a, qkv, ring, ptab, pos_u, pos_v, out);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int attention_stream<float>(const AttnStream&, const float*, float*, const float*, const float*, const float*, float*, cudaStream_t);
+template int attention_stream<bf16>(const AttnStream&, const bf16*, bf16*, const bf16*, const float*, const float*, bf16*, cudaStream_t);
+
+template <typename TA>
+int attention_offline(const TA* qkv, int B, int T, int H, const int32_t* ilens, int chunk, int left, const TA* ptab,
+                      const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
+    if (B <= 0 || T <= 0) return 0;
+    dim3 grid(cdiv(T, QB), H, B);
+    const size_t smem = (size_t)3 * KT * DK * sizeof(TA) + (size_t)2 * TQ_MAX * DK * sizeof(float) +
+                        (size_t)QB * KT * sizeof(float);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[sizeof(TA) == 2]) {
+        FO_CUDA(cudaFuncSetAttribute(attention_offline_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set[sizeof(TA) == 2] = true;
+    }
+    attention_offline_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(qkv, T, H, ilens, chunk, left, ptab, pos_u, pos_v, out);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int attention_offline<float>(const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, float*, cudaStream_t);
+template int attention_offline<bf16>(const bf16*, int, int, int, const int32_t*, int, int, const bf16*, const float*, const float*, bf16*, cudaStream_t);
+
+int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,
+                      int32_t* pe_index, int32_t* adapter_valid, cudaStream_t st) {
+    if (n <= 0) return 0;
+    advance_sessions_kernel<<<cdiv(n, 128), 128, 0, st>>>(ids, n, t, chunk_size, pe_wrap, n_frames, pe_index, adapter_valid);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace fo

@@ -1,0 +1,405 @@
+// HBM-bound kernels of the path: CMVN + first subsampling conv, LayerNorm variants, adapter cache
+// staging, mask subsampling, weight repacks and KV-ring import/export.  All of them move each byte
+// once, with the channel dimension innermost so warps read and write full 128-byte lines.
+#include "fo_common.cuh"
+
+namespace fo {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- CMVN + Conv2d(1 -> C, 3x3, stride 2) + ReLU ------------------------------------------------
+// reference: encoder/cmvn.py:32-34 then subsampling.py:28-29.  One CTA per (b, t1): the three input
+// rows are normalised into shared memory once, each thread owns CPT consecutive output channels
+// (weights in registers) and sweeps the F1 frequency positions; stores are channel-contiguous.
+template <typename TA, int CPT>
+__global__ void __launch_bounds__(256)
+cmvn_conv1_kernel(const float* __restrict__ feats, int T, int F, const float* __restrict__ mean,
+                  const float* __restrict__ istd, const float* __restrict__ w1, const float* __restrict__ b1,
+                  int C, int T1, int F1, TA* __restrict__ c1) {
+    extern __shared__ float rows[];     // 3 * F
+    const int b = blockIdx.y, t1 = blockIdx.x;
+    for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) {
+        int r = i / F, f = i - r * F;
+        float v = feats[((long long)b * T + 2 * t1 + r) * F + f];
+        rows[i] = mean ? (v - mean[f]) * istd[f] : v;
+    }
+    __syncthreads();
+    for (int c0 = threadIdx.x * CPT; c0 < C; c0 += blockDim.x * CPT) {
+        float w[CPT][9], bias[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            bias[j] = b1[c0 + j];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) w[j][q] = w1[(c0 + j) * 9 + q];
+        }
+        TA* out = c1 + (((long long)b * T1 + t1) * F1) * C + c0;
+        for (int f1 = 0; f1 < F1; ++f1) {
+            float x[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) x[r * 3 + q] = rows[r * F + 2 * f1 + q];
+            TA v[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                float a = bias[j];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) a = fmaf(w[j][q], x[q], a);
+                v[j] = from_f<TA>(fmaxf(a, 0.f));
+            }
+            if (CPT == 4 && sizeof(TA) == 2) {
+                *reinterpret_cast<uint2*>(out + (long long)f1 * C) = *reinterpret_cast<uint2*>(v);
+            } else if (CPT == 4 && sizeof(TA) == 4) {
+                *reinterpret_cast<uint4*>(out + (long long)f1 * C) = *reinterpret_cast<uint4*>(v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) out[(long long)f1 * C + j] = v[j];
+            }
+        }
+    }
+}
+
+// ---- LayerNorm ---------------------------------------------------------------------------------
+// one warp per row; two-pass in registers (mean, then centred variance) like ATen's CPU kernel.
+template <typename TA, int MAXV>
+__global__ void __launch_bounds__(256)
+layer_norm_kernel(const float* __restrict__ x, int M, int D, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float eps, int act, float out_scale, TA* __restrict__ y_act,
+                  float* __restrict__ y_f32) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+    const int nv = D >> 7;                    // float4 per lane
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            v[i] = xr[i * 32 + lane];
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    const float mu = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+            q += a * a + b * b + c * c + d * d;
+        }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int col = (i * 32 + lane) * 4;
+            float4 g = *reinterpret_cast<const float4*>(gamma + col);
+            float4 bt = *reinterpret_cast<const float4*>(beta + col);
+            float o[4] = {(v[i].x - mu) * rstd * g.x + bt.x, (v[i].y - mu) * rstd * g.y + bt.y,
+                          (v[i].z - mu) * rstd * g.z + bt.z, (v[i].w - mu) * rstd * g.w + bt.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (act == 1) o[j] = fmaxf(o[j], 0.f);
+                else if (act == 2) o[j] = 0.5f * o[j] * (1.f + erff(o[j] * 0.70710678118654752440f));
+                o[j] *= out_scale;
+            }
+            long long off = (long long)row * D + col;
+            if (y_f32) *reinterpret_cast<float4*>(y_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+            if (y_act) {
+                TA t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t[j] = from_f<TA>(o[j]);
+                if (sizeof(TA) == 2) *reinterpret_cast<uint2*>(y_act + off) = *reinterpret_cast<uint2*>(t);
+                else *reinterpret_cast<uint4*>(y_act + off) = *reinterpret_cast<uint4*>(t);
+            }
+        }
+}
+
+__global__ void scale_rows_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float s) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i] * s;
+}
+
+// ---- adapter staging (adapter.py:120-143) ---------------------------------------------------------
+// grid (B, km1 + T); thread = channel.  Rows [0,km1): old cache or zeros; rows [km1, km1+T): masked
+// encoder output.  The new cache is the last km1 rows of that virtual concatenation.  Slot-resident
+// caches are double-buffered per slot: slot_valid = 0 (None), 1 (half 0 live), 2 (half 1 live); the
+// new rows go to the other half and advance_sessions() flips the flag after every block has read it.
+template <typename TA>
+__global__ void adapter_stage_kernel(const float* __restrict__ enc_out, const uint8_t* __restrict__ mask, int T, int D,
+                                     int km1, const int32_t* __restrict__ ids, float* slot_cache,
+                                     const int32_t* __restrict__ slot_valid, const float* __restrict__ cache_in,
+                                     float* cache_out, TA* __restrict__ xin) {
+    const int b = blockIdx.x, r = blockIdx.y;          // r in [0, km1 + T)
+    const int slot = ids ? ids[b] : -1;
+    const int live = ids ? slot_valid[slot] : 0;
+    const bool have_old = ids ? (live != 0) : (cache_in != nullptr);
+    const float* old_half = ids ? slot_cache + ((long long)slot * 2 + (live == 2 ? 1 : 0)) * km1 * D : nullptr;
+    float* new_half = ids ? slot_cache + ((long long)slot * 2 + (live == 1 ? 1 : 0)) * km1 * D : nullptr;
+    const int total = km1 + T;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float v;
+        if (r < km1) {
+            if (!have_old) v = 0.f;
+            else if (ids) v = old_half[(long long)r * D + c];
+            else v = cache_in[((long long)b * D + c) * km1 + r];
+        } else {
+            int t = r - km1;
+            v = enc_out[((long long)b * T + t) * D + c];
+            if (mask && !mask[(long long)b * T + t]) v = 0.f;
+        }
+        xin[((long long)b * total + r) * D + c] = from_f<TA>(v);
+        int cr = r - T;                                  // row of the new cache this element becomes
+        if (cr >= 0) {
+            if (ids) new_half[(long long)cr * D + c] = v;
+            else if (cache_out) cache_out[((long long)b * D + c) * km1 + cr] = v;
+        }
+    }
+}
+
+__global__ void subsample_mask_kernel(const int32_t* __restrict__ ilens, int T, int T2, uint8_t* __restrict__ mask2,
+                                      int32_t* __restrict__ ilens2) {
+    // subsampling.py:65: m'[j] = m[4j + 6]; ilens' = m'.sum  (subsampling.py:100)
+    const int b = blockIdx.x;
+    const int len = ilens[b];
+    int cnt = 0;
+    for (int j = threadIdx.x; j < T2; j += blockDim.x) {
+        uint8_t v = (4 * j + 6) < len ? 1 : 0;
+        mask2[(long long)b * T2 + j] = v;
+    }
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < T2; ++j) cnt += (4 * j + 6) < len ? 1 : 0;
+        ilens2[b] = cnt;
+    }
+}
+
+__global__ void stride2_mask_kernel(const uint8_t* __restrict__ mask, int T, int To, uint8_t* __restrict__ out) {
+    const int b = blockIdx.x;
+    for (int j = threadIdx.x; j < To; j += blockDim.x) out[(long long)b * To + j] = mask[(long long)b * T + 2 * j];
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = __bfloat162float(s[i]);
+}
+
+template <typename TW>
+__global__ void repack_conv2_kernel(const float* __restrict__ w, int C, TW* __restrict__ out) {
+    // out[co][(kh*3+kw)*C + ci] = w[co][ci][kh][kw]
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)C * C * 9;
+    if (i >= total) return;
+    int ci = i % C;
+    int q = (i / C) % 9;
+    int co = i / (9LL * C);
+    out[i] = from_f<TW>(w[((long long)co * C + ci) * 9 + q]);
+}
+template <typename TW>
+__global__ void repack_sublinear_kernel(const float* __restrict__ w, int C, int F2, long long N, TW* __restrict__ out) {
+    // out[n][f*C + c] = w[n][c*F2 + f]      (subsampling.py:63 flattens (c, f))
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long K = (long long)C * F2;
+    if (i >= N * K) return;
+    long long n = i / K;
+    int k = i % K;
+    int f = k / C, c = k % C;
+    out[i] = from_f<TW>(w[n * K + (long long)c * F2 + f]);
+}
+template <typename TW>
+__global__ void repack_adapter_conv_kernel(const float* __restrict__ w, int C2, int C, int k, TW* __restrict__ out) {
+    // out[co][tau*C + ci] = w[co][ci][tau]
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)C2 * C * k;
+    if (i >= total) return;
+    int ci = i % C;
+    int tau = (i / C) % k;
+    long long co = i / ((long long)C * k);
+    out[i] = from_f<TW>(w[(co * C + ci) * k + tau]);
+}
+template <typename TW>
+__global__ void convert_weight_kernel(const float* __restrict__ w, long long n, TW* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = from_f<TW>(w[i]);
+}
+
+template <typename TA>
+__global__ void ring_export_kernel(const TA* __restrict__ ring, int H, int cap, long long first, int n,
+                                   float* __restrict__ out) {
+    // out[h][j][d] = ring[h][(first + j) % cap][d]
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)H * n * 64) return;
+    int d = i & 63;
+    int j = (i >> 6) % n;
+    int h = i / (64LL * n);
+    out[i] = to_f(ring[((long long)h * cap + (first + j) % cap) * 64 + d]);
+}
+template <typename TA>
+__global__ void ring_import_kernel(TA* __restrict__ ring, int H, int cap, long long first, int n,
+                                   const float* __restrict__ in) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)H * n * 64) return;
+    int d = i & 63;
+    int j = (i >> 6) % n;
+    int h = i / (64LL * n);
+    ring[((long long)h * cap + (first + j) % cap) * 64 + d] = from_f<TA>(in[i]);
+}
+
+inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+template <typename TA>
+int cmvn_conv1(const float* feats, int B, int T, int F, const float* mean, const float* istd, const float* w1,
+               const float* b1, int C, TA* c1, cudaStream_t st) {
+    const int T1 = (T - 1) / 2, F1 = (F - 1) / 2;
+    if (B <= 0 || T1 <= 0) return 0;
+    FO_CHECK(C % 4 == 0, "cmvn_conv1: channel count must be a multiple of 4");
+    dim3 grid(T1, B);
+    const int threads = C / 4 >= 256 ? 256 : ((C / 4 + 31) / 32) * 32;
+    cmvn_conv1_kernel<TA, 4><<<grid, threads, 3 * F * sizeof(float), st>>>(feats, T, F, mean, istd, w1, b1, C, T1, F1, c1);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int cmvn_conv1<float>(const float*, int, int, int, const float*, const float*, const float*, const float*, int, float*, cudaStream_t);
+template int cmvn_conv1<bf16>(const float*, int, int, int, const float*, const float*, const float*, const float*, int, bf16*, cudaStream_t);
+
+template <typename TA>
+int layer_norm(const float* x, int M, int D, const float* gamma, const float* beta, float eps, int act,
+               float out_scale, TA* y_act, float* y_f32, cudaStream_t st) {
+    if (M <= 0) return 0;
+    FO_CHECK(D % 128 == 0 && D <= 4096, "layer_norm: D (%d) must be a multiple of 128 and <= 4096", D);
+    const int rows_per_cta = 8;
+    dim3 grid(cdiv(M, rows_per_cta));
+    if (D <= 1024)
+        layer_norm_kernel<TA, 8><<<grid, 256, 0, st>>>(x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32);
+    else
+        layer_norm_kernel<TA, 32><<<grid, 256, 0, st>>>(x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int layer_norm<float>(const float*, int, int, const float*, const float*, float, int, float, float*, float*, cudaStream_t);
+template int layer_norm<bf16>(const float*, int, int, const float*, const float*, float, int, float, bf16*, float*, cudaStream_t);
+
+int scale_rows(const float* x, float* y, long long n, float s, cudaStream_t st) {
+    if (n <= 0) return 0;
+    scale_rows_kernel<<<blocks_for(n, 256), 256, 0, st>>>(x, y, n, s);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename TA>
+int adapter_stage(const float* enc_out, const uint8_t* mask, int B, int T, int D, int km1, const int32_t* ids,
+                  float* slot_cache, int32_t* slot_valid, const float* cache_in, float* cache_out, TA* xin,
+                  cudaStream_t st) {
+    if (B <= 0) return 0;
+    dim3 grid(B, km1 + T);
+    adapter_stage_kernel<TA><<<grid, 256, 0, st>>>(enc_out, mask, T, D, km1, ids, slot_cache, slot_valid, cache_in,
+                                                   cache_out, xin);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int adapter_stage<float>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, float*, cudaStream_t);
+template int adapter_stage<bf16>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, bf16*, cudaStream_t);
+
+int subsample_mask(const int32_t* ilens, int B, int T, int T2, uint8_t* mask2, int32_t* ilens2, cudaStream_t st) {
+    if (B <= 0) return 0;
+    subsample_mask_kernel<<<B, 128, 0, st>>>(ilens, T, T2, mask2, ilens2);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+int stride2_mask(const uint8_t* mask, int B, int T, int To, uint8_t* out, cudaStream_t st) {
+    if (B <= 0) return 0;
+    stride2_mask_kernel<<<B, 128, 0, st>>>(mask, T, To, out);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    f32_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, dst, n);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+int bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    bf16_to_f32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, dst, n);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename TW>
+int repack_conv2(const float* w, int C, TW* out, cudaStream_t st) {
+    long long n = (long long)C * C * 9;
+    repack_conv2_kernel<TW><<<blocks_for(n, 256), 256, 0, st>>>(w, C, out);
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template <typename TW>
+int repack_sublinear(const float* w, int C, int F2, TW* out, cudaStream_t st) {
+    long long n = (long long)C * C * F2;
+    repack_sublinear_kernel<TW><<<blocks_for(n, 256), 256, 0, st>>>(w, C, F2, C, out);
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template <typename TW>
+int repack_adapter_conv(const float* w, int C2, int C, int k, TW* out, cudaStream_t st) {
+    long long n = (long long)C2 * C * k;
+    repack_adapter_conv_kernel<TW><<<blocks_for(n, 256), 256, 0, st>>>(w, C2, C, k, out);
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template <typename TW>
+int convert_weight(const float* w, long long n, TW* out, cudaStream_t st) {
+    if (n <= 0) return 0;
+    convert_weight_kernel<TW><<<blocks_for(n, 256), 256, 0, st>>>(w, n, out);
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int repack_conv2<float>(const float*, int, float*, cudaStream_t);
+template int repack_conv2<bf16>(const float*, int, bf16*, cudaStream_t);
+template int repack_sublinear<float>(const float*, int, int, float*, cudaStream_t);
+template int repack_sublinear<bf16>(const float*, int, int, bf16*, cudaStream_t);
+template int repack_adapter_conv<float>(const float*, int, int, int, float*, cudaStream_t);
+template int repack_adapter_conv<bf16>(const float*, int, int, int, bf16*, cudaStream_t);
+template int convert_weight<float>(const float*, long long, float*, cudaStream_t);
+template int convert_weight<bf16>(const float*, long long, bf16*, cudaStream_t);
+
+template <typename TA>
+int ring_export(const TA* ring_kv, int H, int ring_cap, long long first_frame, int n, float* out, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long tot = (long long)H * n * 64;
+    ring_export_kernel<TA><<<blocks_for(tot, 256), 256, 0, st>>>(ring_kv, H, ring_cap, first_frame, n, out);
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template <typename TA>
+int ring_import(TA* ring_kv, int H, int ring_cap, long long first_frame, int n, const float* in, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long tot = (long long)H * n * 64;
+    ring_import_kernel<TA><<<blocks_for(tot, 256), 256, 0, st>>>(ring_kv, H, ring_cap, first_frame, n, in);
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int ring_export<float>(const float*, int, int, long long, int, float*, cudaStream_t);
+template int ring_export<bf16>(const bf16*, int, int, long long, int, float*, cudaStream_t);
+template int ring_import<float>(float*, int, int, long long, int, const float*, cudaStream_t);
+template int ring_import<bf16>(bf16*, int, int, long long, int, const float*, cudaStream_t);
+
+}  // namespace fo

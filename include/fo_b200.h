@@ -1,0 +1,157 @@
+/*
+ * fo_b200.h -- C ABI of the B200-native streaming speech encoder + adapter path.
+ *
+ * The reference (TheDoctor-JI/Freeze-Omni) has no FFI: its boundary for this path is the Python
+ * nn.Module surface that models/audioLLM.py and models/utils.py touch.  The Python
+ * drop-ins in freeze_omni_b200/ keep that surface and bind the entry points below with ctypes.
+ * Each entry names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; fo_last_error() returns the thread-local
+ *     message of the last failure.  There is no CPU fallback: without a CUDA device fo_create fails.
+ *   - data pointers may be HOST or DEVICE pointers (detected with cudaPointerGetAttributes); host
+ *     buffers are copied on `stream` inside the call (pinned host memory keeps this asynchronous).
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*); calls on one
+ *     context must be serialised by the caller (the reference serialises per pipeline object,
+ *     bin/dialog_state_pred.py:279-283).
+ *   - floating-point tensors cross the boundary as fp32, row-major, innermost dimension last.
+ */
+#ifndef FO_B200_H
+#define FO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FO_ABI_VERSION 1
+
+enum { FO_F32 = 0, FO_BF16 = 1, FO_I16 = 2 };     /* compute dtype / PCM sample type */
+enum { FO_OK = 0, FO_ERR_ARG = -1, FO_ERR_CUDA = -2, FO_ERR_STATE = -3, FO_ERR_NOMEM = -4 };
+
+typedef struct fo_ctx fo_ctx;
+
+/* Shipped values in comments.  Mirrors the yaml the reference feeds to
+ * speechEncoder.__init__ (models/encoder/encoder.py:46-99) and CNNSubsampling.__init__
+ * (models/adapter.py:73-110). */
+typedef struct fo_config {
+    int32_t feat_dim;          /* 80    encoder-input-dim */
+    int32_t d_model;           /* 1024  subsampling-output-dim == transformer-attention-dim */
+    int32_t n_heads;           /* 16 */
+    int32_t ffn_dim;           /* 4096  transformer-linear-units */
+    int32_t n_layers;          /* 24    transformer-num-blocks */
+    int32_t chunk_size;        /* 4     transformer-chunk_size (encoder frames) */
+    int32_t left_chunks;       /* 16    transformer-left_chunks */
+    int32_t input_layer_linear;/* 1     transformer-input-layer == "linear" (0: "none") */
+    int32_t pos_max_len;       /* 5000  RelPositionalEncoding max_len (attention.py:78) */
+    int32_t llm_dim;           /* 3584  llm_embed_dim */
+    int32_t adapter_kernel;    /* 5 */
+    int32_t adapter_gelu;      /* 1     activation_func == "gelu" (0: relu) */
+    int32_t has_encoder;       /* build the encoder part */
+    int32_t has_adapter;       /* build the adapter part */
+    /* streaming frontend (bin/inference.py:43-56 / models/AudioFeatureGating.py:19-41) */
+    int32_t sample_rate;       /* 16000 */
+    int32_t frame_len;         /* 400 samples */
+    int32_t frame_shift;       /* 160 samples */
+    int32_t frames_per_chunk;  /* 16 */
+    int32_t context_frames;    /* 3 */
+    /* capacity */
+    int32_t max_sessions;      /* session slots resident in HBM */
+    int32_t max_stream_frames; /* largest fbank-frame count of one streaming call (>= context+frames_per_chunk) */
+} fo_config;
+
+typedef struct fo_stats_t {
+    int64_t stream_steps;      /* fo_encode_stream / fo_stream_step calls */
+    int64_t session_chunks;    /* sum over steps of sessions advanced */
+    int64_t offline_calls;
+    int64_t offline_frames;    /* encoder frames produced offline */
+    int64_t kernel_launches;   /* kernels of this library enqueued so far (graph replays count their nodes) */
+    int64_t sessions_in_use;
+    int64_t device_bytes;      /* HBM held by the context */
+    int64_t graph_replays;
+} fo_stats_t;
+
+int         fo_abi_version(void);
+const char* fo_last_error(void);
+
+/* ---- lifetime: replaces speechEncoder(...) / CNNSubsampling(...) construction + .to(device) ---- */
+int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out);
+int fo_destroy(fo_ctx* ctx);
+
+/* ---- weights: replaces load_state_dict (models/utils.py:11-20).  `name` is the reference's
+ * state-dict key ("enc.1.encoders.0.self_attn.linear_q.weight", "conv1d2.weight", ...; adapter keys
+ * are prefixed "adapter."), plus the host-built constants "fbank.window" (frame_len),
+ * "fbank.mel" (feat_dim x fft/2+1) and "pos.table" (pos_max_len x d_model).  data is fp32. */
+int fo_load_tensor(fo_ctx* ctx, const char* name, const void* data, const int64_t* shape, int ndim);
+int fo_finalize_weights(fo_ctx* ctx);   /* checks completeness, repacks into kernel layouts */
+
+/* ---- sessions: replace the per-identity cache objects the service keeps
+ * (bin/dialog_state_pred.py:221-232): encoder KV list, adapter cnn cache, pe_index, fbank carry. */
+int fo_session_alloc(fo_ctx* ctx, int n, int32_t* ids_out);     /* fresh == buffer [None]*L, cache None, pe_index 0 */
+int fo_session_reset(fo_ctx* ctx, int n, const int32_t* ids);
+int fo_session_free(fo_ctx* ctx, int n, const int32_t* ids);
+/* scalar state: frames appended so far (cache_len = min(n_frames, chunk*left)) and pe_index */
+int fo_session_get_state(fo_ctx* ctx, int32_t id, int64_t* n_frames, int64_t* pe_index);
+int fo_session_set_pe_index(fo_ctx* ctx, int n, const int32_t* ids, const int64_t* pe_index);
+/* reference layout of one layer's cache (models/encoder/attention.py:415-428): K,V (H, cache_len, d_k) */
+int fo_session_export_kv(fo_ctx* ctx, int32_t id, int layer, float* K, float* V, int32_t* cache_len);
+int fo_session_import_kv(fo_ctx* ctx, int32_t id, int layer, const float* K, const float* V, int32_t cache_len);
+int fo_session_set_frames(fo_ctx* ctx, int32_t id, int64_t n_frames);
+/* adapter cache in the reference layout (models/adapter.py:141-143): (d_model, kernel-1); valid=0 means None */
+int fo_session_export_adapter_cache(fo_ctx* ctx, int32_t id, float* cache, int32_t* valid);
+int fo_session_import_adapter_cache(fo_ctx* ctx, int32_t id, const float* cache, int32_t valid);
+
+/* ---- frontend: replaces audioEncoderProcessor.process (bin/inference.py:71-80) /
+ * AudioFeatureGating._extract_fbank (models/AudioFeatureGating.py:54-75).
+ * pcm: (n, frame_shift*frames_per_chunk) samples, FO_F32 or FO_I16; value used = sample * scale.
+ * feats_out (n, context+frames_per_chunk, feat_dim) may be NULL (the block stays in the session). */
+int fo_fbank_stream(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
+                    float* feats_out, void* stream);
+/* replaces torchaudio.compliance.kaldi.fbank on whole signals (call sites as above).
+ * pcm (B, n_samples); out (B, 1 + (n_samples-frame_len)/frame_shift, feat_dim). */
+int fo_fbank_offline(fo_ctx* ctx, const void* pcm, int pcm_dtype, int B, int64_t n_samples, float scale,
+                     float* out, void* stream);
+
+/* ---- streaming chunk: replaces speechEncoder.infer (models/encoder/encoder.py:149-155) followed by
+ * CNNSubsampling.forward(cache=..., return_cache=True) (models/adapter.py:112-157), i.e. the two
+ * starred calls of AudioLLM.recognize (models/audioLLM.py:380-387), for n sessions at once.
+ * feats (n, t_in, feat_dim) or NULL = the block left in the sessions by fo_fbank_stream.
+ * enc_out (n, t, d_model), adapter_out (n, t_out, llm_dim): either may be NULL.
+ * t = ((t_in-1)/2-1)/2; t_out = (t + kernel-1 - kernel)/2 + 1. */
+int fo_encode_stream(fo_ctx* ctx, const int32_t* ids, int n, const float* feats, int t_in,
+                     float* enc_out, float* adapter_out, void* stream);
+/* fbank + encode in one call (one captured graph): PCM in, embeddings out */
+int fo_stream_step(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
+                   float* enc_out, float* adapter_out, void* stream);
+
+/* ---- full utterance: replaces speechEncoder.forward (models/encoder/encoder.py:104-147) and
+ * CNNSubsampling.forward(cache=None).  feats (B, T, feat_dim), ilens (B) int32 valid lengths.
+ * chunk<=0 means full attention; left<0 means unlimited left context (models/masks.py:50-56,110-122).
+ * enc_out (B, T', d_model), mask_out (B, T') uint8, adapter_out (B, T'', llm_dim),
+ * adapter_mask_out (B, T'') uint8; any output may be NULL. */
+int fo_encode_offline(fo_ctx* ctx, const float* feats, const int32_t* ilens, int B, int T, int chunk, int left,
+                      float* enc_out, uint8_t* mask_out, float* adapter_out, uint8_t* adapter_mask_out,
+                      void* stream);
+
+/* ---- stateless adapter: replaces CNNSubsampling.forward (models/adapter.py:112-157) when the
+ * caller owns the cache tensor.  x (B, T, d_model); mask (B, T) uint8 or NULL (all valid);
+ * cache_in (B, d_model, kernel-1) or NULL (left zero pad); cache_out same shape or NULL;
+ * y (B, (T-1)/2+1, llm_dim). */
+int fo_adapter_forward(fo_ctx* ctx, const float* x, const uint8_t* mask, int B, int T,
+                       const float* cache_in, float* cache_out, float* y, void* stream);
+
+/* ---- introspection / tuning ---- */
+int fo_stats(fo_ctx* ctx, fo_stats_t* out);
+/* options: "gemm_backend" 0 = SIMT FFMA, 1 = tcgen05 (bf16 only); "use_graph" 0/1; "split_k" 0/1 */
+int fo_set_option(fo_ctx* ctx, const char* name, int64_t value);
+int fo_get_option(fo_ctx* ctx, const char* name, int64_t* value);
+/* one GEMM of the library, exposed for kernel-level parity tests and roofline measurement:
+ * C[M,N] = A[M,K] * W[N,K]^T (+bias) in the context's dtype, fp32 in/out on device pointers. */
+int fo_debug_gemm(fo_ctx* ctx, const float* A, const float* W, const float* bias, float* C,
+                  int M, int N, int K, int backend, int relu, int iters, float* ms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FO_B200_H */

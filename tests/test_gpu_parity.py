@@ -1,0 +1,409 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (freeze_omni_b200.engine / .modules),
+against the golden vectors produced by the reference modules and against the CPU oracle on seeded inputs.
+Tolerances are the north star's: fbank 1e-5 relative (fp32), encoder/adapter 1e-4 max-abs in fp32 and
+2e-2 max-abs in bf16, masks / cache indexing / position bookkeeping bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from freeze_omni_b200.config import load_path_config, load_yaml
+from freeze_omni_b200.weights import make_adapter_state, make_encoder_state
+from oracle import freeze_omni_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+FBANK_REL = 1e-5
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+
+
+def maxabs(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+
+
+def make_engine(name, seed, dtype=torch.float32, max_sessions=8, **kw):
+    from freeze_omni_b200.engine import Engine
+    cfg = load_path_config(name)
+    return cfg, Engine(cfg, make_encoder_state(cfg, seed), make_adapter_state(cfg, seed), dtype=dtype,
+                       max_sessions=max_sessions, **kw)
+
+
+@pytest.fixture(scope="module")
+def tiny32():
+    cfg, eng = make_engine("tiny", 3)
+    yield cfg, eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def shipped32():
+    cfg, eng = make_engine("shipped", 0, max_sessions=4)
+    yield cfg, eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def shipped16():
+    cfg, eng = make_engine("shipped", 0, dtype=torch.bfloat16, max_sessions=4)
+    yield cfg, eng
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# frontend
+# ------------------------------------------------------------------------------------------------
+def exact_fbank(wave_f32, cfg):
+    """Exact-arithmetic (fp64) evaluation of the kaldi recipe on the fp32-windowed frames: the yardstick
+    for entries where torchaudio's own fp32 FFT is further than 1e-5 from the true value."""
+    win, shift = cfg.frame_len, cfg.frame_shift
+    m = 1 + (len(wave_f32) - win) // shift
+    fr = torch.from_numpy(wave_f32).as_strided((m, win), (shift, 1)).clone()
+    fr = fr - fr.mean(dim=1, keepdim=True)
+    fr = fr - 0.97 * torch.cat([fr[:, :1], fr[:, :-1]], 1)
+    fr = (fr * O.povey_window(win)).numpy().astype(np.float64)
+    P = 1 << (win - 1).bit_length()
+    power = np.abs(np.fft.rfft(fr, n=P)) ** 2
+    mel = O.mel_banks(cfg.feat_dim, P, float(cfg.sample_rate)).numpy().astype(np.float64)
+    return np.log(np.maximum((power @ mel.T).astype(np.float32), np.float32(O.FLT_EPSILON)))
+
+
+def test_fbank_offline(golden, tiny32):
+    cfg, eng = tiny32
+    g = golden("fbank")
+    for name in ("synth", "question"):
+        pcm = g[name + "_pcm"]
+        if name == "question":
+            pcm = np.concatenate([pcm, np.zeros((-len(pcm)) % 2560, np.int16)])
+        wave = np.concatenate([np.zeros(240, np.float32), pcm.astype(np.float32)])
+        got = eng.fbank_offline(torch.from_numpy(wave).unsqueeze(0), 1.0)[0].cpu().numpy()
+        ref = g[name + "_offline"]
+        assert got.shape == ref.shape
+        exact = exact_fbank(wave, cfg)
+        assert rel_err(got, exact).max() < FBANK_REL, name          # vs exact arithmetic: everywhere
+        r = rel_err(got, ref)
+        trusted = rel_err(ref, exact) < FBANK_REL                   # where torchaudio itself is within 1e-5
+        assert trusted.mean() > 0.99
+        assert r[trusted].max() < 2 * FBANK_REL, name
+        assert r.max() < 5e-4, name
+        if name == "synth":
+            assert r.max() < FBANK_REL
+    # int16 ingest gives the same bits as float ingest of the same samples
+    pcm = g["synth_pcm"][:16000]
+    a = eng.fbank_offline(torch.from_numpy(pcm.copy()).unsqueeze(0), 1.0)
+    b = eng.fbank_offline(torch.from_numpy(pcm.astype(np.float32)).unsqueeze(0), 1.0)
+    assert torch.equal(a, b)
+    # digital silence hits the log floor exactly
+    z = eng.fbank_offline(torch.zeros(1, 4000), 1.0)
+    assert float(z.max()) == float(z.min()) == pytest.approx(-15.942385, abs=1e-5)
+
+
+def test_fbank_stream_matches_reference_frontend(golden, tiny32):
+    cfg, eng = tiny32
+    g = golden("tiny")
+    ids = eng.alloc(3)
+    try:
+        pcm = g["stream_pcm"].astype(np.float32) / 32768.0          # what bin/inference.py feeds (x 32768 inside)
+        for i in range(6):
+            feats = eng.fbank_stream(ids, torch.from_numpy(pcm[:, i * 2560:(i + 1) * 2560].copy()), 32768.0)
+            assert rel_err(feats.cpu().numpy(), g["stream_feats"][i]).max() < FBANK_REL, i
+        # int16 ingest, different session order, same result for the next chunk
+        i = 6
+        perm = np.array([2, 0, 1])
+        feats = eng.fbank_stream(ids[perm], torch.from_numpy(g["stream_pcm"][perm, i * 2560:(i + 1) * 2560].copy()), 1.0)
+        assert rel_err(feats.cpu().numpy(), g["stream_feats"][i][perm]).max() < FBANK_REL
+    finally:
+        eng.free(ids)
+
+
+# ------------------------------------------------------------------------------------------------
+# tiny config, fp32
+# ------------------------------------------------------------------------------------------------
+def test_tiny_stream_fp32(golden, tiny32):
+    cfg, eng = tiny32
+    g = golden("tiny")
+    ids = eng.alloc(3)
+    try:
+        for i in range(24):
+            enc, y = eng.encode_stream(ids, torch.from_numpy(g["stream_feats"][i]))
+            assert maxabs(enc.cpu(), g["stream_enc_out"][i]) < FP32_TOL, i
+            assert maxabs(y.cpu(), g["stream_adapter_out"][i]) < FP32_TOL, i
+            for b in range(3):
+                nf, pe = eng.state(int(ids[b]))
+                assert nf == 4 * (i + 1) and pe == int(g["stream_pe_index"][i])       # bit-exact bookkeeping
+        for li in (0, 1):
+            k = torch.cat([eng.export_kv(int(s), li)[0] for s in ids])
+            v = torch.cat([eng.export_kv(int(s), li)[1] for s in ids])
+            assert k.shape == g["stream_k_cache_l%d" % li].shape
+            assert maxabs(k, g["stream_k_cache_l%d" % li]) < FP32_TOL
+            assert maxabs(v, g["stream_v_cache_l%d" % li]) < FP32_TOL
+        ac = torch.cat([eng.export_adapter_cache(int(s)) for s in ids])
+        assert maxabs(ac, g["stream_adapter_cache"]) < FP32_TOL
+    finally:
+        eng.free(ids)
+
+
+def test_tiny_stream_from_pcm_one_call(golden, tiny32):
+    cfg, eng = tiny32
+    g = golden("tiny")
+    ids = eng.alloc(3)
+    try:
+        for i in range(5):
+            enc, y = eng.stream_step(ids, torch.from_numpy(g["stream_pcm"][:, i * 2560:(i + 1) * 2560].copy()), 1.0)
+            assert maxabs(enc.cpu(), g["stream_enc_out"][i]) < FP32_TOL, i
+            assert maxabs(y.cpu(), g["stream_adapter_out"][i]) < FP32_TOL, i
+    finally:
+        eng.free(ids)
+
+
+def test_tiny_stream_seven_frames(golden, tiny32):
+    cfg, eng = tiny32
+    g = golden("tiny")
+    ids = eng.alloc(1)
+    try:
+        for i in range(12):
+            enc, y = eng.encode_stream(ids, torch.from_numpy(g["t7_feats"][i]))
+            assert enc.shape[1] == 7
+            assert maxabs(enc.cpu(), g["t7_enc_out"][i]) < FP32_TOL, i
+            assert maxabs(y.cpu(), g["t7_adapter_out"][i]) < FP32_TOL, i
+            assert eng.state(int(ids[0])) == (7 * (i + 1), int(g["t7_pe_index"][i]))
+    finally:
+        eng.free(ids)
+
+
+@pytest.mark.parametrize("c,L", [(4, 16), (4, 2), (-1, -1), (4, -1), (3, 1)])
+def test_tiny_offline_fp32(golden, tiny32, c, L):
+    cfg, eng = tiny32
+    g = golden("tiny")
+    enc, mask, y, ymask = eng.encode_offline(torch.from_numpy(g["off_feats"]), g["off_ilens"], c, L)
+    tag = "c%d_L%d" % (c, L)
+    assert np.array_equal(mask.cpu().numpy(), g["off_mask_" + tag])                 # bit-exact masks
+    assert np.array_equal(ymask.cpu().numpy(), g["off_amask_" + tag])
+    assert maxabs(enc.cpu(), g["off_enc_" + tag]) < FP32_TOL
+    assert maxabs(y.cpu(), g["off_adp_" + tag]) < FP32_TOL
+
+
+def test_tiny_ragged_sessions_vs_oracle(tiny32):
+    """Sessions join and leave at different steps and are batched in changing orders (config 3's shape):
+    each must equal its own single-session oracle run."""
+    cfg, eng = tiny32
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    g = torch.Generator().manual_seed(77)
+    n_sess, n_steps = 5, 22
+    start = [0, 0, 3, 7, 12]
+    length = [22, 9, 19, 15, 10]
+    feats = [9.0 + 3.0 * torch.randn(length[s], 19, 80, generator=g) for s in range(n_sess)]
+    oracle = [O.StreamSession(cfg, esd, asd) for _ in range(n_sess)]
+    ids = {}
+    for step in range(n_steps):
+        active = [s for s in range(n_sess) if start[s] <= step < start[s] + length[s]]
+        if not active:
+            continue
+        for s in active:
+            if s not in ids:
+                ids[s] = int(eng.alloc(1)[0])
+        order = active[::-1] if step % 2 else active
+        batch = torch.stack([feats[s][step - start[s]] for s in order])
+        enc, y = eng.encode_stream(np.array([ids[s] for s in order], np.int32), batch)
+        for j, s in enumerate(order):
+            eo, yo = oracle[s].step_feats(feats[s][step - start[s]].unsqueeze(0))
+            assert maxabs(enc[j].cpu(), eo[0]) < FP32_TOL, (step, s)
+            assert maxabs(y[j].cpu(), yo[0]) < FP32_TOL, (step, s)
+        for s in list(ids):
+            if step + 1 == start[s] + length[s]:
+                eng.free([ids.pop(s)])
+    assert eng.stats()["sessions_in_use"] == 0
+
+
+def test_tiny_session_reset_and_cache_roundtrip(golden, tiny32):
+    cfg, eng = tiny32
+    g = golden("tiny")
+    a, b = eng.alloc(1), eng.alloc(1)
+    try:
+        for i in range(20):
+            eng.encode_stream(a, torch.from_numpy(g["stream_feats"][i][:1]))
+        # export session a in the reference layout, import into b, continue both: identical
+        nf, pe = eng.state(int(a[0]))
+        eng.set_frames(int(b[0]), nf)
+        for li in range(cfg.n_layers):
+            k, v = eng.export_kv(int(a[0]), li)
+            eng.import_kv(int(b[0]), li, k, v)
+        eng.set_pe_index(b, pe)
+        eng.import_adapter_cache(int(b[0]), eng.export_adapter_cache(int(a[0])))
+        x = torch.from_numpy(g["stream_feats"][20][:1])
+        ea, ya = eng.encode_stream(a, x)
+        eb, yb = eng.encode_stream(b, x)
+        assert torch.equal(ea, eb) and torch.equal(ya, yb)
+        assert maxabs(ea.cpu(), g["stream_enc_out"][20][:1]) < FP32_TOL
+        # reset == fresh session
+        eng.reset(a)
+        e0, y0 = eng.encode_stream(a, torch.from_numpy(g["stream_feats"][0][:1]))
+        assert maxabs(e0.cpu(), g["stream_enc_out"][0][:1]) < FP32_TOL
+        assert maxabs(y0.cpu(), g["stream_adapter_out"][0][:1]) < FP32_TOL
+    finally:
+        eng.free(a)
+        eng.free(b)
+
+
+def test_tiny_pe_index_wraps(tiny32):
+    """pe_index % 4932 bookkeeping (attention.py:107): start a session near the wrap point."""
+    cfg, eng = tiny32
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    sess = O.StreamSession(cfg, esd, asd)
+    sess.pe_index = cfg.pe_wrap - 8
+    ids = eng.alloc(1)
+    try:
+        eng.set_pe_index(ids, cfg.pe_wrap - 8)
+        g = torch.Generator().manual_seed(5)
+        for i in range(5):
+            x = 9.0 + 3.0 * torch.randn(1, 19, 80, generator=g)
+            eo, _ = sess.step_feats(x)
+            enc, _ = eng.encode_stream(ids, x)
+            assert maxabs(enc.cpu(), eo) < FP32_TOL, i
+            assert eng.state(int(ids[0]))[1] == sess.pe_index
+    finally:
+        eng.free(ids)
+
+
+def test_dropin_modules_tiny(golden):
+    """The nn.Module surface models/audioLLM.py:377-387 drives: infer() with an opaque buffer + adapter with
+    an explicit cache list, same state-dict keys."""
+    from freeze_omni_b200.modules import CNNSubsampling, GlobalCMVN, speechEncoder
+    y = load_yaml("tiny")
+    cfg = load_path_config("tiny")
+    g = golden("tiny")
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    enc = speechEncoder(80, global_cmvn=GlobalCMVN(esd["global_cmvn.mean"], esd["global_cmvn.istd"]), **y["encoder_conf"])
+    enc.load_state_dict(esd, strict=True)
+    mc = y["model_conf"]
+    adp = CNNSubsampling(mc["enc_out_dim"], mc["llm_embed_dim"], mc["kernel_size"], mc["activation_func"], mc["norm"])
+    adp.load_state_dict(asd, strict=True)
+    enc, adp = enc.cuda().eval(), adp.cuda().eval()
+    buffer, cache, pe = [None] * enc.enc[1].num_blocks, None, 0
+    for i in range(19):
+        speech = torch.from_numpy(g["stream_feats"][i][:1]).cuda()
+        eo, buffer, _, _, pe = enc.infer(speech, buffer, 0, None, pe)
+        mask = torch.full(eo.shape[:2], True).unsqueeze(1).to(eo.device)
+        emb, mask, cache = adp(eo, mask, cache=cache, return_cache=True)
+        assert maxabs(eo.cpu(), g["stream_enc_out"][i][:1]) < FP32_TOL, i
+        assert maxabs(emb.cpu(), g["stream_adapter_out"][i][:1]) < FP32_TOL, i
+        assert pe == int(g["stream_pe_index"][i])
+    assert buffer[0][0].size(2) == cfg.kv_window                   # what transformer.py:277 reads
+    # offline forward through the same module
+    xs, m = enc(torch.from_numpy(g["off_feats"]).cuda(), torch.from_numpy(g["off_ilens"]), 4, 16)
+    assert np.array_equal(m.cpu().numpy(), g["off_mask_c4_L16"])
+    assert maxabs(xs.cpu(), g["off_enc_c4_L16"]) < FP32_TOL
+    yy, ym = adp(xs, m)
+    assert maxabs(yy.cpu(), g["off_adp_c4_L16"]) < FP32_TOL
+    assert np.array_equal(ym.cpu().numpy(), g["off_amask_c4_L16"])
+    del buffer
+    enc.invalidate()
+    adp.invalidate()
+
+
+def test_gemm_simt_vs_torch(tiny32):
+    cfg, eng = tiny32
+    g = torch.Generator().manual_seed(1)
+    for (M, N, K) in ((4, 128, 128), (76, 128, 1152), (300, 384, 256), (130, 256, 640)):
+        A = torch.randn(M, K, generator=g).cuda()
+        W = torch.randn(N, K, generator=g).cuda() / K ** 0.5
+        b = torch.randn(N, generator=g).cuda()
+        out, _ = eng.debug_gemm(A, W, b, backend=0, relu=True)
+        ref = torch.relu(A.double() @ W.double().T + b.double()).float()
+        assert maxabs(out.cpu(), ref.cpu()) < 1e-4, (M, N, K)
+
+
+# ------------------------------------------------------------------------------------------------
+# shipped config
+# ------------------------------------------------------------------------------------------------
+def test_shipped_question_fp32(golden, shipped32):
+    """BASELINE.json config 1 on the GPU path: question.wav, 13 chunks, PCM in."""
+    cfg, eng = shipped32
+    g = golden("shipped_question")
+    ids = eng.alloc(1)
+    try:
+        pcm = (g["pcm"].astype(np.float32) / 32768.0).reshape(13, 1, 2560)
+        for i in range(13):
+            enc, y = eng.stream_step(ids, torch.from_numpy(pcm[i]), 32768.0)
+            assert maxabs(enc.cpu(), g["enc_out"][i]) < FP32_TOL, i
+            assert maxabs(y.cpu(), g["adapter_out"][i]) < FP32_TOL, i
+            assert eng.state(int(ids[0]))[1] == int(g["pe_index"][i])
+        for li in (0, 23):
+            k, v = eng.export_kv(int(ids[0]), li)
+            assert maxabs(k, g["k_cache_l%d" % li]) < FP32_TOL and maxabs(v, g["v_cache_l%d" % li]) < FP32_TOL
+        assert maxabs(eng.export_adapter_cache(int(ids[0])), g["adapter_cache"]) < FP32_TOL
+    finally:
+        eng.free(ids)
+
+
+def test_shipped_two_sessions_past_saturation_fp32(golden, shipped32):
+    cfg, eng = shipped32
+    g = golden("shipped_b2")
+    ids = eng.alloc(2)
+    try:
+        for i in range(20):
+            enc, y = eng.encode_stream(ids, torch.from_numpy(g["feats"][i]))
+            assert maxabs(enc.cpu(), g["enc_out"][i]) < FP32_TOL, i
+            assert maxabs(y.cpu(), g["adapter_out"][i]) < FP32_TOL, i
+        k, _ = eng.export_kv(int(ids[1]), 23)
+        assert maxabs(k, g["k_cache_l23"][1:2]) < FP32_TOL
+    finally:
+        eng.free(ids)
+
+
+def test_shipped_offline_fp32(golden, shipped32):
+    cfg, eng = shipped32
+    g = golden("shipped_offline")
+    enc, mask, y, ymask = eng.encode_offline(torch.from_numpy(g["feats"]), g["ilens"], 4, 16)
+    assert np.array_equal(mask.cpu().numpy(), g["mask"]) and np.array_equal(ymask.cpu().numpy(), g["adapter_mask"])
+    assert maxabs(enc.cpu(), g["enc_out"]) < FP32_TOL
+    assert maxabs(y.cpu(), g["adapter_out"]) < FP32_TOL
+
+
+def test_shipped_stream_bf16(golden, shipped16):
+    """bf16 mode (autocast split of models/pipeline.py:67-68) against the fp32 reference vectors."""
+    cfg, eng = shipped16
+    g = golden("shipped_b2")
+    ids = eng.alloc(2)
+    worst_e = worst_y = 0.0
+    try:
+        for i in range(20):
+            enc, y = eng.encode_stream(ids, torch.from_numpy(g["feats"][i]))
+            worst_e = max(worst_e, maxabs(enc.cpu(), g["enc_out"][i]))
+            worst_y = max(worst_y, maxabs(y.cpu(), g["adapter_out"][i]))
+        print("bf16 max-abs: encoder %.4g adapter %.4g" % (worst_e, worst_y))
+        assert worst_e < BF16_TOL and worst_y < BF16_TOL
+    finally:
+        eng.free(ids)
+
+
+def test_shipped_offline_bf16(golden, shipped16):
+    cfg, eng = shipped16
+    g = golden("shipped_offline")
+    enc, mask, y, ymask = eng.encode_offline(torch.from_numpy(g["feats"]), g["ilens"], 4, 16)
+    assert np.array_equal(mask.cpu().numpy(), g["mask"])
+    valid = torch.from_numpy(g["mask"]).squeeze(1).unsqueeze(-1)
+    d = (enc.cpu() - torch.from_numpy(g["enc_out"])).abs()
+    print("bf16 offline max-abs: encoder %.4g adapter %.4g" % (float(d.max()), maxabs(y.cpu(), g["adapter_out"])))
+    assert float(d.max()) < BF16_TOL
+    assert maxabs(y.cpu(), g["adapter_out"]) < BF16_TOL
+
+
+def test_gemm_backends_agree_bf16(shipped16):
+    """tcgen05 kernel vs the FFMA kernel on the same bf16 operands (both accumulate in fp32)."""
+    cfg, eng = shipped16
+    g = torch.Generator().manual_seed(2)
+    for (M, N, K) in ((256, 1024, 1024), (256, 4096, 1024), (256, 1024, 4096), (128, 3584, 2048), (100, 3072, 1024),
+                      (4, 1024, 1024), (1000, 1024, 1024)):
+        A = torch.randn(M, K, generator=g).cuda()
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        b = torch.randn(N, generator=g).cuda()
+        o0, _ = eng.debug_gemm(A, W, b, backend=0)
+        o1, _ = eng.debug_gemm(A, W, b, backend=1)
+        ref = (A.bfloat16().double() @ W.bfloat16().double().T + b.double()).float()
+        assert maxabs(o0.cpu(), ref.cpu()) < 2e-3, (M, N, K)
+        assert maxabs(o1.cpu(), ref.cpu()) < 2e-3, (M, N, K)
