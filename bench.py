@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: streamed audio-seconds per second through fbank -> CMVN -> encoder -> adapter.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = every session of the batch advances one 160 ms chunk (PCM in, LLM-space embeddings out).
+Workload at N=1 is BASELINE.json configs[1]: 64 concurrent sessions, synthetic 16 kHz audio, streaming
+chunks with KV/CNN caches, bf16, shipped config with random-init weights.  With N>1 (torchrun, one rank
+per GPU) every rank owns its own 64 sessions -- sessions are independent, so there is no collective on
+the data path (weak scaling); NCCL only carries the barrier and the final timing reduction.
+
+Output: ONE JSON line on rank 0 (contract in the task statement): value (inputs resident in HBM), e2e
+(pinned-host PCM in, embeddings back to host, through the C ABI), roofline of the dominant kernel class
+(the GEMMs), cpu_baseline (the oracle port on the host cores, bounded sample), clocks, gpu_launches.
+`--impl reference` times the reference's CPU implementation of the same step (oracle port; the reference
+is pure Python/PyTorch and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from freeze_omni_b200.config import load_path_config  # noqa: E402
+from freeze_omni_b200.weights import make_adapter_state, make_encoder_state  # noqa: E402
+
+METRIC = "streamed audio-sec/sec (encoder+adapter)"
+UNIT = "audio-s/s"
+CHUNK_SEC = 0.16
+# algorithmic FLOPs per session-chunk (2*M*N*K of the data-dependent contractions)
+GFLOP_PER_CHUNK = 4.136
+GFLOP_GEMM_PER_CHUNK = 4.136 - 0.0065 - 0.0401     # minus conv1 and the attention core (not GEMM launches)
+
+
+def synth_pcm(n_sessions, n_chunks, samples_per_chunk, seed0=1000):
+    """0.1*N(0,1), band-limited, 200 ms silent gaps, int16-quantised."""
+    out = np.empty((n_chunks, n_sessions, samples_per_chunk), dtype=np.int16)
+    n = n_chunks * samples_per_chunk
+    for s in range(n_sessions):
+        g = torch.Generator().manual_seed(seed0 + s)
+        x = 0.1 * torch.randn(n + 8, generator=g)
+        x = torch.nn.functional.avg_pool1d(x.view(1, 1, -1), 5, 1).view(-1)[:n] * 2.0
+        t = torch.arange(n)
+        x = x * ((t // 3200) % 5 != 4).float()
+        out[:, s, :] = torch.clamp((x * 32768.0).round(), -32768, 32767).to(torch.int16).view(n_chunks, -1).numpy()
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+def cpu_reference_step_rate(cfg, n_sessions, steps, warmup, threads=None):
+    """The reference's CPU implementation of one step (oracle port, fp32, torch CPU ops on all host
+    threads): n_sessions lock-step sessions, fbank per session then batched encoder.infer + adapter --
+    the most favourable way to run the reference's modules (it batches when sessions are in lock step,
+    SURVEY 8c).  Returns (audio-s/s, seconds per step, threads)."""
+    from oracle import freeze_omni_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    esd, asd = make_encoder_state(cfg, 0), make_adapter_state(cfg, 0)
+    pcm = synth_pcm(n_sessions, steps + warmup, cfg.samples_per_chunk)
+    fronts = [O.StreamingFrontend(cfg.sample_rate, cfg.frame_length_ms, cfg.frame_shift_ms, cfg.frames_per_chunk,
+                                  cfg.context_frames, cfg.feat_dim) for _ in range(n_sessions)]
+    enc = O.EncoderOracle(cfg, esd)
+    buf, cache, pe = enc.new_buffer(), None, 0
+    times = []
+    with torch.no_grad():
+        for i in range(steps + warmup):
+            t0 = time.perf_counter()
+            feats = torch.cat([fronts[s].process(torch.from_numpy(pcm[i, s].astype(np.float32)), 1.0) for s in range(n_sessions)])
+            eo, buf, pe = enc.infer(feats, buf, pe)
+            mask = torch.ones(n_sessions, 1, eo.size(1), dtype=torch.bool)
+            y, _, cache = O.adapter_forward(cfg, asd, eo, mask, cache)
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times[warmup:]))
+    return n_sessions * CHUNK_SEC / t, t, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg = load_path_config(args.config)
+    n = min(args.sessions, args.ref_sessions)
+    steps, warm = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
+    v, t, th = cpu_reference_step_rate(cfg, n, steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%d lock-step sessions x 160 ms chunks, shipped config, CPU" % n, "sessions": n},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": th, "kind": "port",
+                             "sample": "%d sessions x %d chunks (oracle port of the reference modules, fp32, torch CPU)" % (n, steps)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sessions", type=int, default=64, help="concurrent sessions per GPU")
+    ap.add_argument("--ref-sessions", type=int, default=64)
+    ap.add_argument("--config", default="shipped")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--cpu-steps", type=int, default=6, help="bounded CPU sample (steps of the same workload)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph", type=int, default=-1, help="override the library's use_graph option")
+    ap.add_argument("--backend", type=int, default=-1, help="override gemm_backend (0 FFMA, 1 tcgen05)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: freeze_omni_b200 has no CPU fallback")
+    from freeze_omni_b200.engine import Engine
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = load_path_config(args.config)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    S, K, W = args.sessions, args.steps, args.warmup
+    eng = Engine(cfg, make_encoder_state(cfg, 0), make_adapter_state(cfg, 0), dtype=dtype, device=local_rank,
+                 max_sessions=S)
+    if args.graph >= 0:
+        eng.set_option("use_graph", args.graph)
+    if args.backend >= 0:
+        eng.set_option("gemm_backend", args.backend)
+    ids = eng.alloc(S)
+    n_pcm = min(K + W, 64)                                   # synthetic audio is cycled after 64 chunks
+    pcm_host = torch.from_numpy(synth_pcm(S, n_pcm, cfg.samples_per_chunk, seed0=1000 + 4096 * rank)).pin_memory()
+    pcm_dev = pcm_host.cuda(non_blocking=True)
+    t_enc, t_out = eng.out_frames(cfg.chunk_feat_frames)
+    y_dev = torch.empty(S, t_out, cfg.llm_dim, device="cuda")
+    y_host = torch.empty(S, t_out, cfg.llm_dim).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(n_steps, host_io, first):
+        for i in range(n_steps):
+            j = (first + i) % n_pcm
+            if host_io:
+                eng.stream_step(ids, pcm_host[j], 1.0, adapter_out=y_host, want_enc=False)
+                stream.synchronize()                         # a server needs the embeddings every chunk
+            else:
+                eng.stream_step(ids, pcm_dev[j], 1.0, adapter_out=y_dev, want_enc=False)
+
+    def timed(n_steps, host_io, first):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_steps(n_steps, host_io, first)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    run_steps(W, False, 0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.stats()["kernel_launches"]
+    ms = timed(K, False, W)
+    launches = eng.stats()["kernel_launches"] - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    value = world * S * CHUNK_SEC * K / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------
+    eng.reset(ids)
+    run_steps(W, True, 0)
+    ms_e2e = timed(K, True, W)
+    e2e = world * S * CHUNK_SEC * K / (ms_e2e * 1e-3)
+
+    # ---- per-step latency distribution (device timed, one event pair per step) --------------------
+    lat = []
+    for i in range(min(K, 200)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        run_steps(1, False, i)
+        b.record(stream)
+        b.synchronize()
+        lat.append(a.elapsed_time(b))
+    lat = np.asarray(lat)
+
+    # ---- roofline of the dominant kernel class: GEMM launches timed with CUDA events inside the library
+    hbm_peak, tf_sustained, tf_burst, peak_kind = load_peaks()
+    roof = None
+    try:
+        eng.set_option("profile_gemm", 1)
+        run_steps(min(K, 20), False, 0)
+        torch.cuda.synchronize()
+        gemm_ms = eng.get_option("profile_gemm_us") / 1e3
+        gemm_n = eng.get_option("profile_gemm_count")
+        eng.set_option("profile_gemm", 0)
+        steps_prof = min(K, 20)
+        gflop = GFLOP_GEMM_PER_CHUNK * S * steps_prof
+        achieved = gflop / gemm_ms                                  # GFLOP / ms == TFLOP/s
+        roof = {"bound": "tensor", "achieved": achieved, "peak": tf_sustained, "unit": "TFLOP/s",
+                "frac": achieved / tf_sustained, "traffic": None, "peak_source": peak_kind + " (sustained bf16)",
+                "kernel": "gemm (all GEMM launches of the step)", "launches_per_step": gemm_n / steps_prof,
+                "gemm_ms_per_step": gemm_ms / steps_prof, "share_of_step": (gemm_ms / steps_prof) / (ms / K)}
+    except Exception as ex:  # library built without the profiling option
+        roof = {"bound": "tensor", "achieved": None, "peak": tf_sustained, "unit": "TFLOP/s", "frac": None,
+                "traffic": None, "note": "gemm profiling unavailable: %s" % ex}
+    step_ms = ms / K
+    step_bytes = 751.6e6 + S * 6.7e6
+    whole = {"tflops": GFLOP_PER_CHUNK * S / step_ms, "frac_of_sustained_bf16": GFLOP_PER_CHUNK * S / step_ms / tf_sustained,
+             "algorithmic_GB_per_step": step_bytes / 1e9, "hbm_gbs": step_bytes / 1e6 / step_ms,
+             "frac_of_hbm": step_bytes / 1e6 / step_ms / hbm_peak}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, t, th = cpu_reference_step_rate(cfg, S, args.cpu_steps, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
+               "sample": "%d sessions x %d chunks, oracle port of the reference modules (fp32 torch CPU), %.2f s/step" % (S, args.cpu_steps, t)}
+
+    if rank == 0:
+        h2d = S * cfg.samples_per_chunk * 2 + S * 4
+        d2h = S * t_out * cfg.llm_dim * 4
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": "%d concurrent sessions per GPU, streaming 160 ms chunks with KV/CNN caches, shipped "
+                                       "config (24x1024, adapter 3584), random-init weights" % S,
+                           "sessions_per_gpu": S, "parallelism": "sessions sharded, no collective",
+                           "l2": "working set per step (752 MB weights + %.0f MB KV) exceeds the 126 MB L2" % (S * 6.3)},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / K},
+                "gpu_launches": int(launches),
+                "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "sessions": S},
+                "roofline": roof, "step_roofline": whole, "cpu_baseline": cpu, "clocks": sampler.summary(),
+                "options": {"gemm_backend": eng.get_option("gemm_backend"), "use_graph": eng.get_option("use_graph")}}
+        print(json.dumps(line))
+    eng.free(ids)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,8 @@ struct fo_ctx {
     DevBuf ws[24];                            // named workspaces, see enum below
     // options
     int gemm_backend = 0, use_graph = 0, split_k = 1;
+    int profile_gemm = 0;                     // time every GEMM launch with a CUDA event pair (bench roofline)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     // stats
     fo_stats_t stats;
     std::mutex mu;
@@ -190,21 +192,34 @@ int upload_ids(fo_ctx* c, const int32_t* ids, int n, cudaStream_t st) {
 
 // ---- GEMM dispatch ----------------------------------------------------------------------------
 template <typename TA>
-int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-         cudaStream_t st);
+int gemm_raw(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+             cudaStream_t st);
 template <>
-int gemm<float>(fo_ctx* c, const float* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+int gemm_raw<float>(fo_ctx* c, const float* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
                 cudaStream_t st) {
     return gemm_simt<float>(A, ga, reinterpret_cast<const float*>(W), M, N, K, ep, st);
 }
 template <>
-int gemm<bf16>(fo_ctx* c, const bf16* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-               cudaStream_t st) {
+int gemm_raw<bf16>(fo_ctx* c, const bf16* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+                   cudaStream_t st) {
     if (c->gemm_backend == 1) {
         int r = gemm_tc(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, c->split_k, st);
         if (r <= 0) return r;
     }
     return gemm_simt<bf16>(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, st);
+}
+template <typename TA>
+int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+         cudaStream_t st) {
+    if (!c->profile_gemm) return gemm_raw<TA>(c, A, ga, W, M, N, K, ep, st);
+    cudaEvent_t e0, e1;
+    FO_CUDA(cudaEventCreate(&e0));
+    FO_CUDA(cudaEventCreate(&e1));
+    FO_CUDA(cudaEventRecord(e0, st));
+    int r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, st);
+    FO_CUDA(cudaEventRecord(e1, st));
+    c->prof_events.emplace_back(e0, e1);
+    return r;
 }
 
 const HostTensor* staged(fo_ctx* c, const std::string& name) {
@@ -1056,6 +1071,13 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
         c->gemm_backend = (int)value;
     } else if (!strcmp(name, "use_graph")) c->use_graph = value != 0;
     else if (!strcmp(name, "split_k")) c->split_k = (int)value;
+    else if (!strcmp(name, "profile_gemm")) {
+        c->profile_gemm = value != 0;
+        if (value) {
+            for (auto& pr : c->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+            c->prof_events.clear();
+        }
+    }
     else { set_error("fo_set_option: unknown option '%s'", name); return FO_ERR_ARG; }
     return 0;
 }
@@ -1065,6 +1087,17 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     if (!strcmp(name, "gemm_backend")) *value = c->gemm_backend;
     else if (!strcmp(name, "use_graph")) *value = c->use_graph;
     else if (!strcmp(name, "split_k")) *value = c->split_k;
+    else if (!strcmp(name, "profile_gemm_count")) *value = (int64_t)c->prof_events.size();
+    else if (!strcmp(name, "profile_gemm_us")) {
+        double us = 0.0;
+        for (auto& pr : c->prof_events) {
+            FO_CUDA(cudaEventSynchronize(pr.second));
+            float ms = 0.f;
+            FO_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            us += 1e3 * ms;
+        }
+        *value = (int64_t)us;
+    }
     else if (!strcmp(name, "ring_cap")) *value = c->ring_cap;
     else if (!strcmp(name, "max_t")) *value = c->max_t;
     else { set_error("fo_get_option: unknown option '%s'", name); return FO_ERR_ARG; }

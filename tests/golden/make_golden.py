@@ -228,6 +228,21 @@ def main():
         st2 = stream_reference(enc, adp, feats_seq, layers_to_keep=(0, 23))
         save("shipped_b2", seed=np.int64(0), pcm=np.stack(pcm_b), feats=torch.stack(feats_seq).numpy(),
              **{k: v for k, v in st2.items()})
+        # the reference's own bf16 regime (models/pipeline.py:67-68 runs it under autocast bf16; on this
+        # GPU-less host the CPU autocast is the executable stand-in): its distance from its fp32 outputs
+        # is the noise floor quoted next to the bf16 parity numbers.
+        eo_l, y_l = [], []
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            buffer, cache, pe = [None] * 24, None, 0
+            for f in feats_seq:
+                eo, buffer, _, _, pe = enc.infer(f, buffer, 0, None, pe)
+                eo_l.append(eo.float().clone())
+                y, _, cache = adp(eo, torch.ones(2, 1, 4, dtype=torch.bool), cache=cache, return_cache=True)
+                y_l.append(y.float().clone())
+        fe = float(np.abs(torch.stack(eo_l).numpy() - st2["enc_out"]).max())
+        fy = float(np.abs(torch.stack(y_l).numpy() - st2["adapter_out"]).max())
+        print("reference autocast-bf16 vs fp32: encoder %.4f adapter %.4f" % (fe, fy))
+        save("shipped_bf16_floor", ref_autocast_vs_fp32_encoder=np.float64(fe), ref_autocast_vs_fp32_adapter=np.float64(fy))
         # offline ragged pair
         g = torch.Generator().manual_seed(11)
         xs = 9.0 + 3.0 * torch.randn(2, 131, 80, generator=g)

