@@ -49,7 +49,8 @@ struct HostTensor {          // staged fp32 weight on device until finalize
 };
 
 struct LayerW {
-    void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr, *ptab = nullptr;
+    void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    float* ptab = nullptr;                    // P_l = pe * Wpos_l^T, fp32 [pos_rows][D]
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
     float *pos_u = nullptr, *pos_v = nullptr, *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
 };
@@ -98,11 +99,24 @@ struct fo_ctx {
     cudaEvent_t ids_event[NSTAGE] = {nullptr};
     int ids_cursor = 0;
     int32_t* ids_dev = nullptr;
-    DevBuf ws[24];                            // named workspaces, see enum below
+    DevBuf ws[32];                            // named workspaces, see enum below
     // options
     int gemm_backend = 0, use_graph = 0, split_k = 1;
+    TcTune tc_tune{-1, -1, -1};               // debugging: force the tile plan of the tcgen05 GEMM
+    TcWorkspace tc_ws;                        // split-K partials + tile counters of the tcgen05 GEMM
     int profile_gemm = 0;                     // time every GEMM launch with a CUDA event pair (bench roofline)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    // captured step graphs, keyed by the shape of the call; invalidated when a workspace moves
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        long long epoch = -1;        // ws_epoch the graph was captured at
+        long long warm_epoch = -1;   // ws_epoch after the last eager run of this key
+        long long launches = 0;      // kernels inside the graph
+    };
+    std::map<std::string, StepGraph> graphs;
+    long long ws_epoch = 0;
+    cudaStream_t cap_stream = nullptr;        // capture happens here (the caller's stream may be the legacy
+                                              // default stream, which cannot be captured); replay on the caller's
     // stats
     fo_stats_t stats;
     std::mutex mu;
@@ -111,7 +125,7 @@ struct fo_ctx {
 namespace {
 
 enum { WS_FEATS = 0, WS_C1, WS_C2, WS_XSUB, WS_EMB, WS_X, WS_H, WS_QKV, WS_ATT, WS_FFH, WS_ENC, WS_XIN, WS_ACONV, WS_AH,
-       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3 };
+       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_COUNT };
 
 int dev_alloc(fo_ctx* c, void** p, size_t bytes) {
     *p = nullptr;
@@ -140,6 +154,7 @@ int ws_ensure(fo_ctx* c, int which, size_t bytes, void** out) {
         size_t cap = bytes + bytes / 8 + 256;
         FO_TRY(dev_alloc(c, &b.p, cap));
         b.cap = cap;
+        c->ws_epoch += 1;                       // captured graphs hold the old pointers
     }
     *out = b.p;
     return 0;
@@ -191,35 +206,41 @@ int upload_ids(fo_ctx* c, const int32_t* ids, int n, cudaStream_t st) {
 }
 
 // ---- GEMM dispatch ----------------------------------------------------------------------------
+// M = GEMM rows over the (possibly padded) row grid of `ga`; rm maps them to rows of C.
 template <typename TA>
 int gemm_raw(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-             cudaStream_t st);
+             const RowMap& rm, cudaStream_t st);
 template <>
 int gemm_raw<float>(fo_ctx* c, const float* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-                cudaStream_t st) {
-    return gemm_simt<float>(A, ga, reinterpret_cast<const float*>(W), M, N, K, ep, st);
+                    const RowMap& rm, cudaStream_t st) {
+    return gemm_simt<float>(A, ga, reinterpret_cast<const float*>(W), M, N, K, ep, rm, st);
 }
 template <>
 int gemm_raw<bf16>(fo_ctx* c, const bf16* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-                   cudaStream_t st) {
+                   const RowMap& rm, cudaStream_t st) {
     if (c->gemm_backend == 1) {
-        int r = gemm_tc(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, c->split_k, st);
+        int r = gemm_tc(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, rm, c->tc_ws, st);
         if (r <= 0) return r;
     }
-    return gemm_simt<bf16>(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, st);
+    return gemm_simt<bf16>(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, rm, st);
 }
 template <typename TA>
 int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-         cudaStream_t st) {
-    if (!c->profile_gemm) return gemm_raw<TA>(c, A, ga, W, M, N, K, ep, st);
+         const RowMap& rm, cudaStream_t st) {
+    if (!c->profile_gemm) return gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st);
     cudaEvent_t e0, e1;
     FO_CUDA(cudaEventCreate(&e0));
     FO_CUDA(cudaEventCreate(&e1));
     FO_CUDA(cudaEventRecord(e0, st));
-    int r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, st);
+    int r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st);
     FO_CUDA(cudaEventRecord(e1, st));
     c->prof_events.emplace_back(e0, e1);
     return r;
+}
+// plain row-major A (M, K)
+template <typename TA>
+int gemm(fo_ctx* c, const TA* A, const void* W, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
+    return gemm<TA>(c, A, plain_rows(K, M), W, M, N, K, ep, RowMap(), st);
 }
 
 const HostTensor* staged(fo_ctx* c, const std::string& name) {
@@ -285,12 +306,9 @@ int finalize_t(fo_ctx* c) {
             FO_TRY(keep_f32(c, "enc.1.embed.1.weight", {D}, &c->emb_g));
             FO_TRY(keep_f32(c, "enc.1.embed.1.bias", {D}, &c->emb_beta));
         }
-        // positional table -> per-layer projected tables
+        // positional table (fp32 sin/cos built on the host exactly as attention.py:13-30 does)
         const HostTensor* pe;
         FO_TRY(need(c, "pos.table", {c->pos_rows, D}, &pe));
-        void* pe_w;
-        FO_TRY(dev_alloc(c, &pe_w, (size_t)c->pos_rows * D * sizeof(TW)));
-        FO_TRY(convert_weight<TW>(pe->d, (long long)c->pos_rows * D, reinterpret_cast<TW*>(pe_w), 0));
         c->layers.resize(L);
         for (int l = 0; l < L; ++l) {
             LayerW& w = c->layers[l];
@@ -325,18 +343,32 @@ int finalize_t(fo_ctx* c) {
             FO_TRY(keep_f32(c, p + "norm1.bias", {D}, &w.ln1b));
             FO_TRY(keep_f32(c, p + "norm2.weight", {D}, &w.ln2g));
             FO_TRY(keep_f32(c, p + "norm2.bias", {D}, &w.ln2b));
-            // P_l = pe * Wpos^T  (attention.py:433; computed once, weights-only)
+            // P_l = pe * Wpos^T  (attention.py:433): a function of the weights only, so it is tabulated once
+            // instead of per layer per chunk.  fp32 FFMA GEMM over the fp32 sin/cos table and the weights as
+            // the context holds them (rounded to bf16 in a bf16 context); the table stays fp32.
             const HostTensor* wp;
             FO_TRY(need(c, p + "self_attn.linear_pos.weight", {D, D}, &wp));
-            void* wpos;
-            FO_CUDA(cudaMalloc(&wpos, (size_t)D * D * sizeof(TW)));
-            int r = convert_weight<TW>(wp->d, (long long)D * D, reinterpret_cast<TW*>(wpos), 0);
-            if (r == 0) r = dev_alloc(c, &w.ptab, (size_t)c->pos_rows * D * sizeof(TW));
+            float* wpos;
+            FO_CUDA(cudaMalloc((void**)&wpos, (size_t)D * D * sizeof(float)));
+            int r = 0;
+            if (sizeof(TW) == 2) {
+                bf16* w16;
+                if (cudaMalloc((void**)&w16, (size_t)D * D * sizeof(bf16)) != cudaSuccess) r = FO_ERR_NOMEM;
+                if (r == 0) r = f32_to_bf16(wp->d, w16, (long long)D * D, 0);
+                if (r == 0) r = bf16_to_f32(w16, wpos, (long long)D * D, 0);
+                cudaDeviceSynchronize();
+                cudaFree(w16);
+            } else {
+                if (cudaMemcpy(wpos, wp->d, (size_t)D * D * sizeof(float), cudaMemcpyDeviceToDevice) != cudaSuccess) r = FO_ERR_CUDA;
+            }
+            void* pt = nullptr;
+            if (r == 0) r = dev_alloc(c, &pt, (size_t)c->pos_rows * D * sizeof(float));
+            w.ptab = reinterpret_cast<float*>(pt);
             if (r == 0) {
                 Epilogue ep;
-                ep.c_act = w.ptab;
+                ep.c_f32 = w.ptab;
                 ep.ldc = D;
-                r = gemm<TW>(c, reinterpret_cast<const TW*>(pe_w), plain_rows(D), wpos, c->pos_rows, D, D, ep, 0);
+                r = gemm_simt<float>(pe->d, plain_rows(D, c->pos_rows), wpos, c->pos_rows, D, D, ep, RowMap(), 0);
             }
             cudaDeviceSynchronize();
             cudaFree(wpos);
@@ -409,24 +441,26 @@ int adapter_program(fo_ctx* c, const float* enc, const uint8_t* mask, int B, int
     const int t_out = (T + km1 - KA) / 2 + 1;
     const int Mo = B * t_out;
     void *xin, *aconv, *ah;
-    FO_TRY(ws_ensure(c, WS_XIN, (size_t)B * (km1 + T) * D * sizeof(TA), &xin));
+    AGather ga;
+    RowMap rm;
+    adapter_gather(B, T, D, KA, &ga, &rm);
+    FO_TRY(ws_ensure(c, WS_XIN, (size_t)2 * ga.rows * D * sizeof(TA), &xin));
     FO_TRY(ws_ensure(c, WS_ACONV, (size_t)Mo * 2 * D * sizeof(float), &aconv));
     FO_TRY(ws_ensure(c, WS_AH, (size_t)Mo * 2 * D * sizeof(TA), &ah));
     FO_TRY(adapter_stage<TA>(enc, mask, B, T, D, km1, ids_dev, c->ad_cache, c->ad_valid, cache_in, cache_out,
                              reinterpret_cast<TA*>(xin), st));
-    AGather ga{D, t_out, 1, 2, 0, (long long)(km1 + T), KA, 1, 0};
     Epilogue e1;
     e1.bias = c->ad_conv_b;
     e1.c_f32 = reinterpret_cast<float*>(aconv);
     e1.ldc = 2 * D;
-    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xin), ga, c->ad_conv_w, Mo, 2 * D, KA * D, e1, st));
+    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xin), ga, c->ad_conv_w, (int)ga.rows, 2 * D, KA * D, e1, rm, st));
     FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(aconv), Mo, 2 * D, c->ad_ln_g, c->ad_ln_b, 1e-3f,
                           c->cfg.adapter_gelu ? 2 : 1, 1.0f, reinterpret_cast<TA*>(ah), nullptr, st));
     Epilogue e2;
     e2.bias = c->ad_proj_b;
     e2.c_f32 = y;
     e2.ldc = E;
-    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(ah), plain_rows(2 * D), c->ad_proj_w, Mo, E, 2 * D, e2, st));
+    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(ah), c->ad_proj_w, Mo, E, 2 * D, e2, st));
     return 0;
 }
 
@@ -437,18 +471,20 @@ int subsample_program(fo_ctx* c, const float* feats, int B, int T, float** x_out
     const int D = c->D, F = c->F, F1 = c->F1, F2 = c->F2;
     const int T1 = (T - 1) / 2, T2 = (T1 - 1) / 2, M = B * T2;
     void *c1, *c2, *xsub, *emb, *x;
-    FO_TRY(ws_ensure(c, WS_C1, (size_t)B * T1 * F1 * D * sizeof(TA), &c1));
+    AGather ga;
+    RowMap rm;
+    conv2_gather(B, T2, F2, D, &ga, &rm);
+    FO_TRY(ws_ensure(c, WS_C1, (size_t)ga.planes * ga.rows * D * sizeof(TA), &c1));
     FO_TRY(ws_ensure(c, WS_C2, (size_t)M * F2 * D * sizeof(TA), &c2));
     FO_TRY(ws_ensure(c, WS_X, (size_t)M * D * sizeof(float), &x));
     FO_TRY(cmvn_conv1<TA>(feats, B, T, F, c->cmvn_mean, c->cmvn_istd, c->conv1_w, c->conv1_b, D,
                           reinterpret_cast<TA*>(c1), st));
-    AGather ga{D, F2, T2, 2, 2LL * F1, (long long)T1 * F1, 3, 1, (long long)F1};
     Epilogue e;
     e.bias = c->conv2_b;
     e.relu = 1;
     e.c_act = c2;
     e.ldc = D;
-    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c1), ga, c->conv2_w, M * F2, D, 9 * D, e, st));
+    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c1), ga, c->conv2_w, (int)ga.rows, D, 9 * D, e, rm, st));
     const float xscale = sqrtf((float)D);
     if (c->cfg.input_layer_linear) {
         FO_TRY(ws_ensure(c, WS_XSUB, (size_t)M * D * sizeof(TA), &xsub));
@@ -457,12 +493,12 @@ int subsample_program(fo_ctx* c, const float* feats, int B, int T, float** x_out
         e2.bias = c->sub_b;
         e2.c_act = xsub;
         e2.ldc = D;
-        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c2), plain_rows(F2 * D), c->sub_w, M, D, F2 * D, e2, st));
+        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c2), c->sub_w, M, D, F2 * D, e2, st));
         Epilogue e3;
         e3.bias = c->emb_b;
         e3.c_f32 = reinterpret_cast<float*>(emb);
         e3.ldc = D;
-        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xsub), plain_rows(D), c->emb_w, M, D, D, e3, st));
+        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xsub), c->emb_w, M, D, D, e3, st));
         FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(emb), M, D, c->emb_g, c->emb_beta, 1e-5f, 1, xscale, nullptr,
                               reinterpret_cast<float*>(x), st));
     } else {
@@ -471,7 +507,7 @@ int subsample_program(fo_ctx* c, const float* feats, int B, int T, float** x_out
         e2.c_f32 = reinterpret_cast<float*>(x);
         e2.ldc = D;
         e2.scale = xscale;
-        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c2), plain_rows(F2 * D), c->sub_w, M, D, F2 * D, e2, st));
+        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c2), c->sub_w, M, D, F2 * D, e2, st));
     }
     *x_out = reinterpret_cast<float*>(x);
     return 0;
@@ -479,14 +515,18 @@ int subsample_program(fo_ctx* c, const float* feats, int B, int T, float** x_out
 
 // one transformer layer minus attention core: pre (LN1 + QKV) and post (out-proj, LN2, FFN)
 template <typename TA>
-int layer_pre(fo_ctx* c, const LayerW& w, float* x, int M, TA* h, TA* qkv, cudaStream_t st) {
+int layer_pre(fo_ctx* c, const LayerW& w, float* x, int M, TA* h, TA* qkv, float* q32, cudaStream_t st) {
     const int D = c->D;
     FO_TRY(layer_norm<TA>(x, M, D, w.ln1g, w.ln1b, 1e-5f, 0, 1.0f, h, nullptr, st));
     Epilogue e;
     e.bias = w.bqkv;
     e.c_act = qkv;
     e.ldc = 3 * D;
-    return gemm<TA>(c, h, plain_rows(D), w.wqkv, M, 3 * D, D, e, st);
+    if (sizeof(TA) == 2) {            // bf16 context: Q stays fp32 (columns < D), K|V are written as bf16
+        e.c_f32 = q32;
+        e.split_col = D;
+    }
+    return gemm<TA>(c, h, w.wqkv, M, 3 * D, D, e, st);
 }
 template <typename TA>
 int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* ffh, cudaStream_t st) {
@@ -496,20 +536,20 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
     e.residual = x;
     e.c_f32 = x;
     e.ldc = D;
-    FO_TRY(gemm<TA>(c, att, plain_rows(D), w.wo, M, D, D, e, st));
+    FO_TRY(gemm<TA>(c, att, w.wo, M, D, D, e, st));
     FO_TRY(layer_norm<TA>(x, M, D, w.ln2g, w.ln2b, 1e-5f, 0, 1.0f, h, nullptr, st));
     Epilogue e1;
     e1.bias = w.b1;
     e1.relu = 1;
     e1.c_act = ffh;
     e1.ldc = FF;
-    FO_TRY(gemm<TA>(c, h, plain_rows(D), w.w1, M, FF, D, e1, st));
+    FO_TRY(gemm<TA>(c, h, w.w1, M, FF, D, e1, st));
     Epilogue e2;
     e2.bias = w.b2;
     e2.residual = x;
     e2.c_f32 = x;
     e2.ldc = D;
-    return gemm<TA>(c, ffh, plain_rows(FF), w.w2, M, D, FF, e2, st);
+    return gemm<TA>(c, ffh, w.w2, M, D, FF, e2, st);
 }
 
 template <typename TA>
@@ -523,6 +563,8 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     FO_TRY(ws_ensure(c, WS_QKV, (size_t)M * 3 * D * sizeof(TA), &qkv));
     FO_TRY(ws_ensure(c, WS_ATT, (size_t)M * D * sizeof(TA), &att));
     FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
+    float* q32 = reinterpret_cast<float*>(qkv);
+    if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
     AttnStream a;
     a.ids = c->ids_dev;
     a.n_frames = c->n_frames;
@@ -533,9 +575,9 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     const long long layer_stride = (long long)c->cfg.max_sessions * a.ring_slot_stride;
     for (int l = 0; l < c->L; ++l) {
         const LayerW& w = c->layers[l];
-        FO_TRY(layer_pre<TA>(c, w, x, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), st));
-        FO_TRY(attention_stream<TA>(a, reinterpret_cast<const TA*>(qkv), reinterpret_cast<TA*>(c->ring) + l * layer_stride,
-                                    reinterpret_cast<const TA*>(w.ptab), w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
+        FO_TRY(layer_pre<TA>(c, w, x, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), q32, st));
+        FO_TRY(attention_stream<TA>(a, reinterpret_cast<const TA*>(qkv), q32, reinterpret_cast<TA*>(c->ring) + l * layer_stride,
+                                    w.ptab, w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
         FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), st));
     }
     FO_TRY(layer_norm<TA>(x, M, D, c->after_g, c->after_b, 1e-5f, 0, 1.0f, nullptr, enc_out_dev, st));
@@ -559,11 +601,13 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
     FO_TRY(ws_ensure(c, WS_QKV, (size_t)M * 3 * D * sizeof(TA), &qkv));
     FO_TRY(ws_ensure(c, WS_ATT, (size_t)M * D * sizeof(TA), &att));
     FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
+    float* q32 = reinterpret_cast<float*>(qkv);
+    if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
     for (int l = 0; l < c->L; ++l) {
         const LayerW& w = c->layers[l];
-        FO_TRY(layer_pre<TA>(c, w, x, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), st));
-        FO_TRY(attention_offline<TA>(reinterpret_cast<const TA*>(qkv), B, T2, H, ilens2, chunk, left,
-                                     reinterpret_cast<const TA*>(w.ptab), w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
+        FO_TRY(layer_pre<TA>(c, w, x, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), q32, st));
+        FO_TRY(attention_offline<TA>(reinterpret_cast<const TA*>(qkv), q32, B, T2, H, ilens2, chunk, left,
+                                     w.ptab, w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
         FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), st));
     }
     FO_TRY(layer_norm<TA>(x, M, D, c->after_g, c->after_b, 1e-5f, 0, 1.0f, nullptr, enc_out_dev, st));
@@ -599,7 +643,7 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
              "fo_create: d_model must be a multiple of 128 with d_k == 64");
     FO_CHECK(cfg->ffn_dim % 64 == 0 && cfg->llm_dim % 64 == 0, "fo_create: ffn_dim and llm_dim must be multiples of 64");
     FO_CHECK(cfg->feat_dim >= 11 && cfg->n_layers > 0 && cfg->max_sessions > 0, "fo_create: bad sizes");
-    FO_CHECK(cfg->adapter_kernel >= 2, "fo_create: adapter kernel must be >= 2");
+    FO_CHECK(cfg->adapter_kernel >= 2 && cfg->adapter_kernel <= AGather::MAX_SEG, "fo_create: adapter kernel must be in 2..9");
     FO_CHECK(cfg->has_encoder || cfg->has_adapter, "fo_create: nothing to build");
 
     fo_ctx* c = new fo_ctx();
@@ -625,6 +669,7 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
     c->fft = 1;
     while (c->fft < cfg->frame_len) c->fft <<= 1;
     c->gemm_backend = dtype == FO_BF16 ? 1 : 0;
+    c->use_graph = 1;
 
     int r = 0;
     const int S = cfg->max_sessions;
@@ -651,6 +696,10 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
             r = FO_ERR_NOMEM;
         }
     }
+    if (!r && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("fo_create: cudaStreamCreate failed");
+        r = FO_ERR_CUDA;
+    }
     if (r) { fo_destroy(c); return r; }
     c->slot_used.assign(S, 0);
     c->free_slots.reserve(S);
@@ -664,6 +713,8 @@ int fo_destroy(fo_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto& kv : c->staged) cudaFree(kv.second.d);
+    for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     for (void* p : c->owned) if (p) cudaFree(p);
     for (int k = 0; k < fo_ctx::NSTAGE; ++k) {
         if (c->ids_host[k]) cudaFreeHost(c->ids_host[k]);
@@ -692,7 +743,13 @@ int fo_load_tensor(fo_ctx* c, const char* name, const void* data, const int64_t*
 int fo_finalize_weights(fo_ctx* c) {
     FO_CHECK(c && !c->finalized, "fo_finalize_weights: bad state");
     FO_CUDA(cudaSetDevice(c->device));
-    if (c->dtype == FO_BF16) gemm_tc_init();
+    if (c->dtype == FO_BF16) {
+        FO_TRY(gemm_tc_init());
+        FO_TRY(gemm_tc_workspace(&c->tc_ws));
+        c->owned.push_back(c->tc_ws.partial);
+        c->owned.push_back(c->tc_ws.counters);
+        c->device_bytes += (long long)c->tc_ws.partial_bytes;
+    }
     return c->dtype == FO_BF16 ? finalize_t<bf16>(c) : finalize_t<float>(c);
 }
 
@@ -920,25 +977,109 @@ int fo_fbank_offline(fo_ctx* c, const void* pcm, int pcm_dtype, int B, int64_t n
 }
 
 // ---- streaming chunk --------------------------------------------------------------------------------
-static int stream_common(fo_ctx* c, const int32_t* ids, int n, const float* feats_dev, int t_in, float* enc_out,
-                         float* adapter_out, cudaStream_t st) {
+// One step = [fbank of the new PCM ->] subsampling -> 24 layers -> after_norm -> adapter -> session advance,
+// ~180 kernels that only touch context-owned buffers (staged input, workspaces, session state).  That body is
+// captured once per call shape into a CUDA graph and replayed; the user's buffers are reached by one copy on
+// either side of the graph.  The first call of a shape runs eagerly (it sizes the workspaces), the second
+// captures.  A workspace that moves (ws_epoch) invalidates the graphs.
+struct StepArgs {
+    int n, t_in;
+    bool with_fbank, want_y;
+    int pcm_is_i16;
+    float scale;
+};
+
+static int step_body(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
+    void *dfeats, *denc, *dy = nullptr;
+    const int T1 = (a.t_in - 1) / 2, t = (T1 - 1) / 2;
+    const int km1 = c->KA - 1, t_out = (t + km1 - c->KA) / 2 + 1;
+    FO_TRY(ws_ensure(c, WS_FEATS, (size_t)a.n * a.t_in * c->F * sizeof(float), &dfeats));
+    FO_TRY(ws_ensure(c, WS_ENC, (size_t)a.n * t * c->D * sizeof(float), &denc));
+    if (a.want_y) FO_TRY(ws_ensure(c, WS_Y, (size_t)a.n * t_out * c->E * sizeof(float), &dy));
+    if (a.with_fbank) {
+        void* dp;
+        FO_TRY(ws_ensure(c, WS_PCM, (size_t)a.n * c->chunk_samples * 4, &dp));
+        FO_TRY(fbank_stream(fbank_params(c), c->ids_dev, a.n, dp, a.pcm_is_i16, a.scale, c->cfg.frames_per_chunk,
+                            c->cfg.context_frames, c->samples, c->feat_ring, (float*)dfeats, st));
+    }
+    return c->dtype == FO_BF16 ? stream_program<bf16>(c, a.n, (const float*)dfeats, a.t_in, (float*)denc, (float*)dy, st)
+                               : stream_program<float>(c, a.n, (const float*)dfeats, a.t_in, (float*)denc, (float*)dy, st);
+}
+
+static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
+    if (!c->use_graph || c->profile_gemm) return step_body(c, a, st);
+    char key[96];
+    uint32_t sbits;
+    memcpy(&sbits, &a.scale, 4);
+    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%08x/%d", a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
+             c->gemm_backend);
+    fo_ctx::StepGraph& g = c->graphs[key];
+    if (g.exec && g.epoch == c->ws_epoch) {
+        FO_CUDA(cudaGraphLaunch(g.exec, st));
+        g_launches += g.launches;
+        c->stats.graph_replays += 1;
+        return 0;
+    }
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if (g.warm_epoch != c->ws_epoch) {             // first call of this shape (or buffers moved): eager
+        FO_TRY(step_body(c, a, st));
+        g.warm_epoch = c->ws_epoch;
+        return 0;
+    }
+    const long long l0 = g_launches, e0 = c->ws_epoch;
+    FO_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed));
+    int r = step_body(c, a, c->cap_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+    if (r != 0) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (ce != cudaSuccess || !graph) {
+        set_error("graph capture of the streaming step failed: %s", cudaGetErrorString(ce));
+        return FO_ERR_CUDA;
+    }
+    FO_CHECK(c->ws_epoch == e0, "a workspace moved during graph capture");
+    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { g.exec = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return FO_ERR_CUDA; }
+    g.epoch = c->ws_epoch;
+    g.launches = g_launches - l0;                  // counted while capturing, not yet run
+    g_launches = l0;
+    FO_CUDA(cudaGraphLaunch(g.exec, st));
+    g_launches += g.launches;
+    c->stats.graph_replays += 1;
+    return 0;
+}
+
+// copies between the caller's buffers and the context's staging buffers, then the step
+static int stream_common(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
+                         const float* feats, int t_in, float* enc_out, float* adapter_out, cudaStream_t st) {
     const int T1 = (t_in - 1) / 2, t = (T1 - 1) / 2;
     FO_CHECK(t >= 1 && t <= c->max_t, "streaming call of %d feature frames gives %d encoder frames; context allows 1..%d",
              t_in, t, c->max_t);
+    if (adapter_out) FO_CHECK(c->cfg.has_adapter, "adapter_out requested but the context has no adapter");
     const int km1 = c->KA - 1, t_out = (t + km1 - c->KA) / 2 + 1;
     const size_t enc_bytes = (size_t)n * t * c->D * sizeof(float);
     const size_t y_bytes = (size_t)n * t_out * c->E * sizeof(float);
-    void *denc, *dy = nullptr;
-    FO_TRY(out_dev(c, enc_out, enc_bytes, WS_ENC, &denc));
-    if (adapter_out) {
-        FO_CHECK(c->cfg.has_adapter, "adapter_out requested but the context has no adapter");
-        FO_TRY(out_dev(c, adapter_out, y_bytes, WS_Y, &dy));
+    FO_TRY(upload_ids(c, ids, n, st));
+    StepArgs a{n, t_in, pcm != nullptr, adapter_out != nullptr, pcm_dtype == FO_I16, scale};
+    void* stage;
+    if (pcm) {
+        const size_t in_bytes = (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4);
+        FO_TRY(ws_ensure(c, WS_PCM, (size_t)n * c->chunk_samples * 4, &stage));
+        FO_CUDA(cudaMemcpyAsync(stage, pcm, in_bytes, cudaMemcpyDefault, st));
+    } else if (feats) {
+        const size_t in_bytes = (size_t)n * t_in * c->F * sizeof(float);
+        FO_TRY(ws_ensure(c, WS_FEATS, in_bytes, &stage));
+        FO_CUDA(cudaMemcpyAsync(stage, feats, in_bytes, cudaMemcpyDefault, st));
+    } else {
+        // the block fo_fbank_stream left in the sessions' feature rings
+        FO_TRY(ws_ensure(c, WS_FEATS, (size_t)n * t_in * c->F * sizeof(float), &stage));
+        for (int i = 0; i < n; ++i)
+            FO_CUDA(cudaMemcpyAsync((float*)stage + (size_t)i * t_in * c->F, c->feat_ring + (size_t)ids[i] * t_in * c->F,
+                                    (size_t)t_in * c->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    int r = c->dtype == FO_BF16 ? stream_program<bf16>(c, n, feats_dev, t_in, (float*)denc, (float*)dy, st)
-                                : stream_program<float>(c, n, feats_dev, t_in, (float*)denc, (float*)dy, st);
-    FO_TRY(r);
-    if (enc_out) FO_TRY(out_done(enc_out, denc, enc_bytes, st));
-    if (adapter_out) FO_TRY(out_done(adapter_out, dy, y_bytes, st));
+    FO_TRY(run_step(c, a, st));
+    if (enc_out) FO_CUDA(cudaMemcpyAsync(enc_out, c->ws[WS_ENC].p, enc_bytes, cudaMemcpyDefault, st));
+    if (adapter_out) FO_CUDA(cudaMemcpyAsync(adapter_out, c->ws[WS_Y].p, y_bytes, cudaMemcpyDefault, st));
     c->stats.stream_steps += 1;
     c->stats.session_chunks += n;
     return 0;
@@ -949,25 +1090,9 @@ int fo_encode_stream(fo_ctx* c, const int32_t* ids, int n, const float* feats, i
     FO_CHECK(c && c->finalized && c->cfg.has_encoder, "fo_encode_stream: context has no finalized encoder");
     FO_TRY(check_ids(c, ids, n));
     FO_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    FO_TRY(upload_ids(c, ids, n, st));
-    const float* dfeats;
-    if (feats) {
-        FO_CHECK(t_in >= 7, "fo_encode_stream: need at least 7 feature frames");
-        const void* p;
-        FO_TRY(in_dev(c, feats, (size_t)n * t_in * c->F * sizeof(float), WS_FEATS, st, &p));
-        dfeats = (const float*)p;
-    } else {
-        // gather the sessions' feature rings into a dense (n, rows, F) block
-        t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
-        void* p;
-        FO_TRY(ws_ensure(c, WS_FEATS, (size_t)n * t_in * c->F * sizeof(float), &p));
-        for (int i = 0; i < n; ++i)
-            FO_CUDA(cudaMemcpyAsync((float*)p + (size_t)i * t_in * c->F, c->feat_ring + (size_t)ids[i] * t_in * c->F,
-                                    (size_t)t_in * c->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        dfeats = (const float*)p;
-    }
-    return stream_common(c, ids, n, dfeats, t_in, enc_out, adapter_out, st);
+    if (feats) FO_CHECK(t_in >= 7, "fo_encode_stream: need at least 7 feature frames");
+    else t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
+    return stream_common(c, ids, n, nullptr, FO_F32, 1.0f, feats, t_in, enc_out, adapter_out, (cudaStream_t)stream);
 }
 
 int fo_stream_step(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale, float* enc_out,
@@ -976,17 +1101,8 @@ int fo_stream_step(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pc
     FO_CHECK(pcm && (pcm_dtype == FO_F32 || pcm_dtype == FO_I16), "fo_stream_step: pcm must be FO_F32 or FO_I16");
     FO_TRY(check_ids(c, ids, n));
     FO_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    FO_TRY(upload_ids(c, ids, n, st));
-    const size_t in_bytes = (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4);
-    const void* dp;
-    FO_TRY(in_dev(c, pcm, in_bytes, WS_PCM, st, &dp));
-    const int rows = c->cfg.context_frames + c->cfg.frames_per_chunk;
-    void* dfeats;
-    FO_TRY(ws_ensure(c, WS_FEATS, (size_t)n * rows * c->F * sizeof(float), &dfeats));
-    FO_TRY(fbank_stream(fbank_params(c), c->ids_dev, n, dp, pcm_dtype == FO_I16, scale, c->cfg.frames_per_chunk,
-                        c->cfg.context_frames, c->samples, c->feat_ring, (float*)dfeats, st));
-    return stream_common(c, ids, n, (const float*)dfeats, rows, enc_out, adapter_out, st);
+    return stream_common(c, ids, n, pcm, pcm_dtype, scale, nullptr, c->cfg.context_frames + c->cfg.frames_per_chunk, enc_out,
+                         adapter_out, (cudaStream_t)stream);
 }
 
 // ---- full utterance -----------------------------------------------------------------------------------
@@ -1071,6 +1187,9 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
         c->gemm_backend = (int)value;
     } else if (!strcmp(name, "use_graph")) c->use_graph = value != 0;
     else if (!strcmp(name, "split_k")) c->split_k = (int)value;
+    else if (!strcmp(name, "tc_swap")) { c->tc_tune.swap = (int)value; gemm_tc_force(c->tc_tune); }
+    else if (!strcmp(name, "tc_bn")) { c->tc_tune.bn = (int)value; gemm_tc_force(c->tc_tune); }
+    else if (!strcmp(name, "tc_split")) { c->tc_tune.split = (int)value; gemm_tc_force(c->tc_tune); }
     else if (!strcmp(name, "profile_gemm")) {
         c->profile_gemm = value != 0;
         if (value) {
@@ -1098,6 +1217,7 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
         }
         *value = (int64_t)us;
     }
+    else if (!strcmp(name, "tc_launches")) *value = gemm_tc_launches();
     else if (!strcmp(name, "ring_cap")) *value = c->ring_cap;
     else if (!strcmp(name, "max_t")) *value = c->max_t;
     else { set_error("fo_get_option: unknown option '%s'", name); return FO_ERR_ARG; }
@@ -1119,21 +1239,46 @@ int fo_debug_gemm(fo_ctx* c, const float* A, const float* W, const float* bias, 
     FO_CUDA(cudaEventCreate(&e0));
     FO_CUDA(cudaEventCreate(&e1));
     int r = 0;
+    // one eager launch (result + lazy initialisation), then `iters` launches captured into a graph and timed as
+    // one graph launch, so the number is device time without host launch overhead
+    const void *pa = A, *pw = W;
     if (c->dtype == FO_BF16) {
         void *a16, *w16;
         FO_TRY(ws_ensure(c, WS_TMP2, (size_t)M * K * 2, &a16));
         FO_TRY(ws_ensure(c, WS_TMP3, (size_t)N * K * 2, &w16));
         FO_TRY(f32_to_bf16(A, (bf16*)a16, (long long)M * K, st));
         FO_TRY(f32_to_bf16(W, (bf16*)w16, (long long)N * K, st));
-        c->gemm_backend = backend;
-        r = gemm<bf16>(c, (const bf16*)a16, plain_rows(K), w16, M, N, K, ep, st);
-        cudaEventRecord(e0, st);
-        for (int i = 0; i < iters && r == 0; ++i) r = gemm<bf16>(c, (const bf16*)a16, plain_rows(K), w16, M, N, K, ep, st);
-        cudaEventRecord(e1, st);
+        pa = a16;
+        pw = w16;
+    }
+    c->gemm_backend = backend;
+    auto one = [&](cudaStream_t s) {
+        return c->dtype == FO_BF16 ? gemm<bf16>(c, (const bf16*)pa, pw, M, N, K, ep, s) : gemm<float>(c, (const float*)pa, pw, M, N, K, ep, s);
+    };
+    r = one(st);
+    if (r == 0 && iters > 0) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        FO_CUDA(cudaStreamSynchronize(st));
+        FO_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed));
+        for (int i = 0; i < iters && r == 0; ++i) r = one(c->cap_stream);
+        cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+        if (r == 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (r == 0 && ce == cudaSuccess) {
+            cudaGraphLaunch(exec, st);
+            cudaEventRecord(e0, st);
+            cudaGraphLaunch(exec, st);
+            cudaEventRecord(e1, st);
+        } else {
+            cudaEventRecord(e0, st);
+            cudaEventRecord(e1, st);
+            if (r == 0) { set_error("fo_debug_gemm: graph capture failed: %s", cudaGetErrorString(ce)); r = FO_ERR_CUDA; }
+        }
+        cudaEventSynchronize(e1);
+        if (exec) cudaGraphExecDestroy(exec);
     } else {
-        r = gemm<float>(c, A, plain_rows(K), W, M, N, K, ep, st);
         cudaEventRecord(e0, st);
-        for (int i = 0; i < iters && r == 0; ++i) r = gemm<float>(c, A, plain_rows(K), W, M, N, K, ep, st);
         cudaEventRecord(e1, st);
     }
     c->gemm_backend = saved;

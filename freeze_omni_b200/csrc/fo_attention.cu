@@ -60,7 +60,7 @@ template <> struct Chunk<bf16> {
 // scores of key row j (smem) against nq query rows; chunk order is rotated by j so that the 8 lanes of
 // one shared-memory phase touch 8 different 16-byte bank groups (rows are 128 B / 256 B apart).
 template <typename TA>
-__device__ __forceinline__ void score_row(const TA* Krow, const TA* Prow, const float* qu, const float* qv, int nq,
+__device__ __forceinline__ void score_row(const TA* Krow, const float* Prow, const float* qu, const float* qv, int nq,
                                           int rot, float (&acc)[TQ_MAX]) {
     constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
 #pragma unroll
@@ -70,7 +70,11 @@ __device__ __forceinline__ void score_row(const TA* Krow, const TA* Prow, const 
         const int cc = (c + rot) & (NCH - 1);
         float kv[EPC], pv[EPC];
         Chunk<TA>::load(Krow + cc * EPC, kv);
-        Chunk<TA>::load(Prow + cc * EPC, pv);
+#pragma unroll
+        for (int e = 0; e < EPC; e += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(Prow + cc * EPC + e);
+            pv[e] = t4.x; pv[e + 1] = t4.y; pv[e + 2] = t4.z; pv[e + 3] = t4.w;
+        }
 #pragma unroll
         for (int i = 0; i < TQ_MAX; ++i) {
             if (i < nq) {
@@ -99,14 +103,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 template <typename TA>
 __global__ void __launch_bounds__(ATT_THREADS)
-attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, TA* __restrict__ ring, const TA* __restrict__ ptab,
-                        const float* __restrict__ pos_u, const float* __restrict__ pos_v, TA* __restrict__ out) {
+attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* __restrict__ q32, TA* __restrict__ ring,
+                        const float* __restrict__ ptab, const float* __restrict__ pos_u, const float* __restrict__ pos_v,
+                        TA* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cap = a.ring_cap;
     TA* Ks = reinterpret_cast<TA*>(smem_raw);
     TA* Vs = Ks + cap * DK;
-    TA* Ps = Vs + cap * DK;
-    float* qu = reinterpret_cast<float*>(Ps + cap * DK);
+    float* Ps = reinterpret_cast<float*>(Vs + cap * DK);
+    float* qu = Ps + cap * DK;
     float* qv = qu + TQ_MAX * DK;
     float* prob = qv + TQ_MAX * DK;                 // TQ_MAX x cap
     __shared__ __align__(8) uint64_t bar;
@@ -150,16 +155,16 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, TA* __restrict
         TA* gdst = (which ? ringV : ringK) + (long long)((nf + r) % cap) * DK + c * EPC;
         *reinterpret_cast<uint4*>(gdst) = val;
     }
-    // rel-pos rows P_l[start + j], head slice
-    for (int i = tid; i < nk * NCH; i += ATT_THREADS) {
-        const int j = i / NCH, c = i % NCH;
+    // rel-pos rows P_l[start + j], head slice (fp32 table)
+    for (int i = tid; i < nk * (DK / 4); i += ATT_THREADS) {
+        const int j = i / (DK / 4), c = i % (DK / 4);
         const int pos = min(start + j, a.pos_rows - 1);
-        *reinterpret_cast<uint4*>(Ps + j * DK + c * EPC) =
-            *reinterpret_cast<const uint4*>(ptab + (long long)pos * D + h * DK + c * EPC);
+        *reinterpret_cast<float4*>(Ps + j * DK + c * 4) =
+            *reinterpret_cast<const float4*>(ptab + (long long)pos * D + h * DK + c * 4);
     }
     for (int i = tid; i < t * DK; i += ATT_THREADS) {
         const int r = i / DK, d = i % DK;
-        const float q = to_f(qkv[(long long)(b * t + r) * 3 * D + h * DK + d]);
+        const float q = q32[(long long)(b * t + r) * 3 * D + h * DK + d];
         qu[i] = q + pos_u[h * DK + d];
         qv[i] = q + pos_v[h * DK + d];
     }
@@ -209,14 +214,14 @@ constexpr int QB = 4;           // query rows per CTA
 
 template <typename TA>
 __global__ void __launch_bounds__(ATT_THREADS)
-attention_offline_kernel(const TA* __restrict__ qkv, int T, int H, const int32_t* __restrict__ ilens, int chunk,
-                         int left, const TA* __restrict__ ptab, const float* __restrict__ pos_u,
-                         const float* __restrict__ pos_v, TA* __restrict__ out) {
+attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q32, int T, int H,
+                         const int32_t* __restrict__ ilens, int chunk, int left, const float* __restrict__ ptab,
+                         const float* __restrict__ pos_u, const float* __restrict__ pos_v, TA* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TA* Ks = reinterpret_cast<TA*>(smem_raw);
     TA* Vs = Ks + KT * DK;
-    TA* Ps = Vs + KT * DK;
-    float* qu = reinterpret_cast<float*>(Ps + KT * DK);
+    float* Ps = reinterpret_cast<float*>(Vs + KT * DK);
+    float* qu = Ps + KT * DK;
     float* qv = qu + TQ_MAX * DK;
     float* sc = qv + TQ_MAX * DK;                    // QB x KT
     __shared__ int win[QB][2];
@@ -241,7 +246,7 @@ attention_offline_kernel(const TA* __restrict__ qkv, int T, int H, const int32_t
     }
     for (int i = tid; i < nq * DK; i += ATT_THREADS) {
         const int r = i / DK, d = i % DK;
-        const float q = to_f(qkv[((long long)b * T + q0 + r) * 3 * D + h * DK + d]);
+        const float q = q32[((long long)b * T + q0 + r) * 3 * D + h * DK + d];
         qu[i] = q + pos_u[h * DK + d];
         qv[i] = q + pos_v[h * DK + d];
     }
@@ -254,14 +259,17 @@ attention_offline_kernel(const TA* __restrict__ qkv, int T, int H, const int32_t
     for (int kt = k_lo; kt < k_hi; kt += KT) {
         const int nk = min(KT, k_hi - kt);
         __syncthreads();                                   // previous tile fully consumed
-        for (int i = tid; i < nk * NCH * 3; i += ATT_THREADS) {
-            const int which = i / (nk * NCH);              // 0 K, 1 V, 2 P
+        for (int i = tid; i < nk * NCH * 2; i += ATT_THREADS) {
+            const int which = i / (nk * NCH);              // 0 K, 1 V
             const int j = (i / NCH) % nk, c = i % NCH;
-            const TA* src = which < 2
-                                ? qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + c * EPC
-                                : ptab + (long long)(kt + j) * D + h * DK + c * EPC;
-            TA* dst = (which == 0 ? Ks : which == 1 ? Vs : Ps) + j * DK + c * EPC;
+            const TA* src = qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + c * EPC;
+            TA* dst = (which == 0 ? Ks : Vs) + j * DK + c * EPC;
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        }
+        for (int i = tid; i < nk * (DK / 4); i += ATT_THREADS) {
+            const int j = i / (DK / 4), c = i % (DK / 4);
+            *reinterpret_cast<float4*>(Ps + j * DK + c * 4) =
+                *reinterpret_cast<const float4*>(ptab + (long long)(kt + j) * D + h * DK + c * 4);
         }
         __syncthreads();
         for (int j = tid; j < nk; j += ATT_THREADS) {
@@ -328,13 +336,13 @@ __global__ void advance_sessions_kernel(const int32_t* __restrict__ ids, int n, 
 }  // namespace
 
 template <typename TA>
-int attention_stream(const AttnStream& a, const TA* qkv, TA* ring, const TA* ptab, const float* pos_u,
-                     const float* pos_v, TA* out, cudaStream_t st) {
+int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* ring, const float* ptab,
+                     const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
     if (a.n <= 0) return 0;
     FO_CHECK(a.t <= TQ_MAX, "attention_stream: %d frames per call exceeds %d", a.t, TQ_MAX);
     FO_CHECK(a.ring_cap >= a.window + a.t, "attention_stream: ring capacity %d < window %d + %d", a.ring_cap, a.window, a.t);
-    const size_t smem = (size_t)3 * a.ring_cap * DK * sizeof(TA) + (size_t)2 * TQ_MAX * DK * sizeof(float) +
-                        (size_t)TQ_MAX * a.ring_cap * sizeof(float);
+    const size_t smem = (size_t)2 * a.ring_cap * DK * sizeof(TA) + (size_t)a.ring_cap * DK * sizeof(float) +
+                        (size_t)2 * TQ_MAX * DK * sizeof(float) + (size_t)TQ_MAX * a.ring_cap * sizeof(float);
     static bool attr_set[2] = {false, false};
     if (!attr_set[sizeof(TA) == 2]) {
         FO_CUDA(cudaFuncSetAttribute(attention_stream_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -342,33 +350,33 @@ int attention_stream(const AttnStream& a, const TA* qkv, TA* ring, const TA* pta
     }
     FO_CHECK(smem <= 160 * 1024, "attention_stream: window too large for shared memory");
     dim3 grid(a.n, a.H);
-    attention_stream_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(a, qkv, ring, ptab, pos_u, pos_v, out);
+    attention_stream_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(a, qkv, q32, ring, ptab, pos_u, pos_v, out);
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
 }
-template int attention_stream<float>(const AttnStream&, const float*, float*, const float*, const float*, const float*, float*, cudaStream_t);
-template int attention_stream<bf16>(const AttnStream&, const bf16*, bf16*, const bf16*, const float*, const float*, bf16*, cudaStream_t);
+template int attention_stream<float>(const AttnStream&, const float*, const float*, float*, const float*, const float*, const float*, float*, cudaStream_t);
+template int attention_stream<bf16>(const AttnStream&, const bf16*, const float*, bf16*, const float*, const float*, const float*, bf16*, cudaStream_t);
 
 template <typename TA>
-int attention_offline(const TA* qkv, int B, int T, int H, const int32_t* ilens, int chunk, int left, const TA* ptab,
-                      const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
+int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,
+                      const float* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
     if (B <= 0 || T <= 0) return 0;
     dim3 grid(cdiv(T, QB), H, B);
-    const size_t smem = (size_t)3 * KT * DK * sizeof(TA) + (size_t)2 * TQ_MAX * DK * sizeof(float) +
-                        (size_t)QB * KT * sizeof(float);
+    const size_t smem = (size_t)2 * KT * DK * sizeof(TA) + (size_t)KT * DK * sizeof(float) +
+                        (size_t)2 * TQ_MAX * DK * sizeof(float) + (size_t)QB * KT * sizeof(float);
     static bool attr_set[2] = {false, false};
     if (!attr_set[sizeof(TA) == 2]) {
         FO_CUDA(cudaFuncSetAttribute(attention_offline_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set[sizeof(TA) == 2] = true;
     }
-    attention_offline_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(qkv, T, H, ilens, chunk, left, ptab, pos_u, pos_v, out);
+    attention_offline_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(qkv, q32, T, H, ilens, chunk, left, ptab, pos_u, pos_v, out);
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
 }
-template int attention_offline<float>(const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, float*, cudaStream_t);
-template int attention_offline<bf16>(const bf16*, int, int, int, const int32_t*, int, int, const bf16*, const float*, const float*, bf16*, cudaStream_t);
+template int attention_offline<float>(const float*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, float*, cudaStream_t);
+template int attention_offline<bf16>(const bf16*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, bf16*, cudaStream_t);
 
 int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,
                       int32_t* pe_index, int32_t* adapter_valid, cudaStream_t st) {

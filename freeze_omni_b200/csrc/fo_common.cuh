@@ -38,26 +38,41 @@ template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
 
-// ---- implicit-GEMM row gather (conv2 of the subsampling, adapter conv) --------------------------
-// Element (row, k) of the A operand lives at  A + (row_off(row) + seg_off(k / seg_len)) * seg_len + k % seg_len
-// with row_off(row) = (row / (d1*d0)) * s2 + ((row / d0) % d1) * s1 + (row % d0) * s0
-// and  seg_off(s)   = (s / seg_w) * seg_s1 + (s % seg_w) * seg_s0.
-// plain row-major A is the special case seg_len = K, d0 = d1 = 1, s2 = 1.
+// ---- implicit-GEMM operand addressing (conv2 of the subsampling, adapter conv) --------------------
+// The activation operand of a GEMM is stored as [planes][rows][seg_len] (seg_len = channels, innermost).
+// Column k of GEMM row r lives in segment s = k / seg_len at
+//     A[(plane[s] * rows + r + rowoff[s]) * seg_len + k % seg_len]
+// i.e. every k-segment is a plain 2-D box of one plane shifted by a row offset -- exactly what one TMA
+// box load fetches.  The producers write their outputs in this layout (cmvn_conv1: 6 planes indexed by
+// (kernel row, column parity); adapter_stage: 2 planes indexed by time parity), so neither convolution
+// ever materialises im2col.  GEMM rows then run over a PADDED row grid; RowMap drops the padding rows
+// and compacts the rest on the way out.  Plain row-major A is the case n_seg = 1.
 struct AGather {
-    int seg_len;          // contiguous run length along k (channels)
-    int d0, d1;           // row index decomposition
-    long long s0, s1, s2; // strides of the decomposition, in units of seg_len elements
-    int seg_w;            // segments per kernel row (kw count); 0 => plain
-    long long seg_s0, seg_s1;
+    static constexpr int MAX_SEG = 9;
+    int seg_len;          // contiguous run along k (channels); K = n_seg * seg_len
+    int n_seg;
+    long long rows;       // rows per plane
+    int planes;
+    int plane[MAX_SEG];
+    int rowoff[MAX_SEG];
 };
-inline AGather plain_rows(int K) { AGather g{K, 1, 1, 0, 0, 1, 0, 0, 0}; return g; }
-
-__host__ __device__ inline long long gather_row_off(const AGather& g, int row) {
-    return (long long)(row / (g.d1 * g.d0)) * g.s2 + (long long)((row / g.d0) % g.d1) * g.s1 +
-           (long long)(row % g.d0) * g.s0;
+inline AGather plain_rows(int K, long long rows) {
+    AGather g;
+    g.seg_len = K; g.n_seg = 1; g.rows = rows; g.planes = 1;
+    for (int i = 0; i < AGather::MAX_SEG; ++i) { g.plane[i] = 0; g.rowoff[i] = 0; }
+    return g;
 }
-__host__ __device__ inline long long gather_seg_off(const AGather& g, int seg) {
-    return g.seg_w ? (long long)(seg / g.seg_w) * g.seg_s1 + (long long)(seg % g.seg_w) * g.seg_s0 : 0;
+// GEMM row r -> output row:  a = r / p1, b = (r % p1) / p0, c = r % p0;  kept iff b < v1 && c < v0;
+// output row = a * q1 + b * q0 + c.  p1 == 0 is the identity.
+struct RowMap {
+    int p0 = 0, p1 = 0, v0 = 0, v1 = 0, q0 = 0, q1 = 0;
+};
+__host__ __device__ inline bool row_map(const RowMap& rm, int r, long long& dst) {
+    if (rm.p1 == 0) { dst = r; return true; }
+    const int a = r / rm.p1, rem = r - a * rm.p1;
+    const int b = rem / rm.p0, c = rem - b * rm.p0;
+    dst = (long long)a * rm.q1 + (long long)b * rm.q0 + c;
+    return b < rm.v1 && c < rm.v0;
 }
 
 // ---- GEMM epilogue ---------------------------------------------------------------------------
@@ -71,18 +86,29 @@ struct Epilogue {
     int ldc = 0;
     int relu = 0;
     float scale = 1.0f;
+    int split_col = 0;                // > 0: columns < split_col go to c_f32 only, columns >= split_col to c_act only
 };
 
-// C[M,N] = A[M,K] * W[N,K]^T.  A/W are TIn (float or bf16), accumulate fp32.
+// C[rowmap(m), n] = A[m, :] . W[n, :]  for m < M (padded GEMM rows), n < N.  A/W are TIn (float or bf16),
+// accumulate fp32.
 template <typename TIn>
 int gemm_simt(const TIn* A, const AGather& ga, const TIn* W, int M, int N, int K, const Epilogue& ep,
-              cudaStream_t st);
+              const RowMap& rmap, cudaStream_t st);
 
-// tcgen05 + TMA path (bf16 only).  Returns 1 if the shape is not supported (caller falls back
-// to gemm_simt), <0 on error.
+// tcgen05 + TMA path (bf16 only).  Returns 1 if the shape is not supported (caller uses gemm_simt),
+// <0 on error.  The workspace (split-K partials + tile counters) belongs to one context / one stream.
+struct TcWorkspace {
+    float* partial = nullptr;
+    size_t partial_bytes = 0;
+    int* counters = nullptr;
+};
+struct TcTune { int swap, bn, split; };      // -1 / 0 = let the cost model decide
 int gemm_tc_init();
+int gemm_tc_workspace(TcWorkspace* ws);       // allocates; the caller frees the two device pointers
+void gemm_tc_force(const TcTune& t);
+long long gemm_tc_launches();                // tcgen05 kernel launches so far (tests check the path taken)
 int gemm_tc(const bf16* A, const AGather& ga, const bf16* W, int M, int N, int K, const Epilogue& ep,
-            int split_k, cudaStream_t st);
+            const RowMap& rmap, const TcWorkspace& ws, cudaStream_t st);
 
 // ---- frontend --------------------------------------------------------------------------------
 struct FbankParams {
@@ -101,10 +127,15 @@ int fbank_offline(const FbankParams& p, const void* pcm, int pcm_is_i16, int B, 
                   float* out, cudaStream_t st);
 
 // ---- elementwise / normalisation ----------------------------------------------------------------
-// CMVN + Conv2d(1->C,3,2) + ReLU, channels-last output c1[b][t1][f1][c]
+// CMVN + Conv2d(1->C,3,2) + ReLU, written as the A operand of the conv2 implicit GEMM:
+// c1[kh*2 + (f1&1)][(b*T2 + t2)*(F2+1) + f1/2][c] = relu(conv1)[b][c][2*t2 + kh][f1]   (see conv2_gather)
 template <typename TA>
 int cmvn_conv1(const float* feats, int B, int T, int F, const float* mean, const float* istd, const float* w1,
                const float* b1, int C, TA* c1, cudaStream_t st);
+// A-operand description and row map of conv2 (3x3, stride 2) over that layout; GEMM rows = B*T2*(F2+1)
+void conv2_gather(int B, int T2, int F2, int C, AGather* ga, RowMap* rm);
+// same for the adapter conv (kernel k, stride 2) over xin[time&1][b*RP + time/2][D], RP = (k-1+T+1)/2
+void adapter_gather(int B, int T, int D, int k, AGather* ga, RowMap* rm);
 // LayerNorm over the last dim of x (M, D) fp32.  y_act (activation type) and/or y_f32 outputs.
 // act: 0 none, 1 relu, 2 gelu(erf); result multiplied by out_scale after the activation.
 template <typename TA>
@@ -112,8 +143,9 @@ int layer_norm(const float* x, int M, int D, const float* gamma, const float* be
                float out_scale, TA* y_act, float* y_f32, cudaStream_t st);
 // scale-copy (input-layer "none"): y = x * s
 int scale_rows(const float* x, float* y, long long n, float s, cudaStream_t st);
-// adapter staging: xin[b][0..k-2] = cache (or 0), xin[b][k-1+i] = enc_out[b][i] (zeroed where mask==0);
-// new_cache = last k-1 rows of xin (fp32).  cache layout (slot, k-1, D) time-major.
+// adapter staging: virtual rows x[b][0..k-2] = cache (or 0), x[b][k-1+i] = enc_out[b][i] (zeroed where
+// mask==0), stored parity-split as xin[time&1][b*RP + time/2][D] (adapter_gather);
+// new_cache = last k-1 rows (fp32).  cache layout (slot, k-1, D) time-major.
 template <typename TA>
 int adapter_stage(const float* enc_out, const uint8_t* mask, int B, int T, int D, int km1,
                   const int32_t* ids, float* slot_cache, int32_t* slot_valid,       // slot-resident (ids != null)
@@ -130,15 +162,16 @@ struct AttnStream {
     int n, t, H, ring_cap, window, full_chunk, pe_wrap, pos_rows;
     long long ring_slot_stride;   // elements between sessions of one layer: 2*H*ring_cap*64
 };
-// qkv (n*t, 3*D) activation type; ring = this layer's (slot, 2, H, ring_cap, 64); ptab (pos_rows, D);
-// out (n*t, D).  Appends the new K/V rows to the ring.
+// qkv (n*t, 3*D) activation type (K and V columns are read from it); q32 (n*t, 3*D) fp32 whose first D
+// columns hold Q (the QKV GEMM keeps Q in fp32, Epilogue::split_col); ring = this layer's
+// (slot, 2, H, ring_cap, 64); ptab (pos_rows, D) fp32; out (n*t, D).  Appends the new K/V rows to the ring.
 template <typename TA>
-int attention_stream(const AttnStream& a, const TA* qkv, TA* ring, const TA* ptab, const float* pos_u,
-                     const float* pos_v, TA* out, cudaStream_t st);
+int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* ring, const float* ptab,
+                     const float* pos_u, const float* pos_v, TA* out, cudaStream_t st);
 // offline: qkv (B*T, 3*D); valid lengths ilens (B); window from (chunk, left); positions 0..T-1.
 template <typename TA>
-int attention_offline(const TA* qkv, int B, int T, int H, const int32_t* ilens, int chunk, int left,
-                      const TA* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st);
+int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,
+                      const float* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st);
 // end of a streaming step: n_frames += t, pe_index = pe_index % wrap + chunk_size (attention.py:107,120),
 // and flip the live half of the double-buffered adapter cache.  Either group may be null.
 int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,

@@ -17,11 +17,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // reference: encoder/cmvn.py:32-34 then subsampling.py:28-29.  One CTA per (b, t1): the three input
 // rows are normalised into shared memory once, each thread owns CPT consecutive output channels
 // (weights in registers) and sweeps the F1 frequency positions; stores are channel-contiguous.
+// Output layout = A operand of the conv2 implicit GEMM (conv2_gather): row t1 lands in the kernel-row
+// plane(s) it serves (t1 odd: kh=1; t1 even: kh=0 at t2=t1/2 and kh=2 at t2=t1/2-1), column f1 in the
+// parity plane f1&1 at f1/2, rows of F2+1 entries.
 template <typename TA, int CPT>
 __global__ void __launch_bounds__(256)
 cmvn_conv1_kernel(const float* __restrict__ feats, int T, int F, const float* __restrict__ mean,
                   const float* __restrict__ istd, const float* __restrict__ w1, const float* __restrict__ b1,
-                  int C, int T1, int F1, TA* __restrict__ c1) {
+                  int C, int T2, int F1, int F2P, long long NR, TA* __restrict__ c1) {
     extern __shared__ float rows[];     // 3 * F
     const int b = blockIdx.y, t1 = blockIdx.x;
     for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) {
@@ -38,7 +41,16 @@ cmvn_conv1_kernel(const float* __restrict__ feats, int T, int F, const float* __
 #pragma unroll
             for (int q = 0; q < 9; ++q) w[j][q] = w1[(c0 + j) * 9 + q];
         }
-        TA* out = c1 + (((long long)b * T1 + t1) * F1) * C + c0;
+        // destinations of this conv1 row: (kernel row kh, output row t2)
+        int kh_a, t2_a, kh_b = -1, t2_b = 0;
+        if (t1 & 1) { kh_a = 1; t2_a = t1 >> 1; }
+        else {
+            kh_a = 0; t2_a = t1 >> 1;
+            if (t1 >= 2) { kh_b = 2; t2_b = (t1 >> 1) - 1; }
+            if (t2_a >= T2) { kh_a = kh_b; t2_a = t2_b; kh_b = -1; }
+        }
+        TA* out_a = c1 + (((long long)kh_a * 2) * NR + ((long long)b * T2 + t2_a) * F2P) * C + c0;
+        TA* out_b = kh_b >= 0 ? c1 + (((long long)kh_b * 2) * NR + ((long long)b * T2 + t2_b) * F2P) * C + c0 : nullptr;
         for (int f1 = 0; f1 < F1; ++f1) {
             float x[9];
 #pragma unroll
@@ -53,13 +65,13 @@ cmvn_conv1_kernel(const float* __restrict__ feats, int T, int F, const float* __
                 for (int q = 0; q < 9; ++q) a = fmaf(w[j][q], x[q], a);
                 v[j] = from_f<TA>(fmaxf(a, 0.f));
             }
-            if (CPT == 4 && sizeof(TA) == 2) {
-                *reinterpret_cast<uint2*>(out + (long long)f1 * C) = *reinterpret_cast<uint2*>(v);
-            } else if (CPT == 4 && sizeof(TA) == 4) {
-                *reinterpret_cast<uint4*>(out + (long long)f1 * C) = *reinterpret_cast<uint4*>(v);
+            const long long off = ((long long)(f1 & 1) * NR + (f1 >> 1)) * C;
+            if (sizeof(TA) == 2) {
+                *reinterpret_cast<uint2*>(out_a + off) = *reinterpret_cast<uint2*>(v);
+                if (out_b) *reinterpret_cast<uint2*>(out_b + off) = *reinterpret_cast<uint2*>(v);
             } else {
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) out[(long long)f1 * C + j] = v[j];
+                *reinterpret_cast<uint4*>(out_a + off) = *reinterpret_cast<uint4*>(v);
+                if (out_b) *reinterpret_cast<uint4*>(out_b + off) = *reinterpret_cast<uint4*>(v);
             }
         }
     }
@@ -141,7 +153,7 @@ __global__ void adapter_stage_kernel(const float* __restrict__ enc_out, const ui
     const bool have_old = ids ? (live != 0) : (cache_in != nullptr);
     const float* old_half = ids ? slot_cache + ((long long)slot * 2 + (live == 2 ? 1 : 0)) * km1 * D : nullptr;
     float* new_half = ids ? slot_cache + ((long long)slot * 2 + (live == 1 ? 1 : 0)) * km1 * D : nullptr;
-    const int total = km1 + T;
+    const int RP = (km1 + T + 1) >> 1;                 // rows per plane and batch entry (adapter_gather)
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
         float v;
         if (r < km1) {
@@ -153,7 +165,7 @@ __global__ void adapter_stage_kernel(const float* __restrict__ enc_out, const ui
             v = enc_out[((long long)b * T + t) * D + c];
             if (mask && !mask[(long long)b * T + t]) v = 0.f;
         }
-        xin[((long long)b * total + r) * D + c] = from_f<TA>(v);
+        xin[(((long long)(r & 1) * gridDim.x + b) * RP + (r >> 1)) * D + c] = from_f<TA>(v);
         int cr = r - T;                                  // row of the new cache this element becomes
         if (cr >= 0) {
             if (ids) new_half[(long long)cr * D + c] = v;
@@ -260,16 +272,34 @@ inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
 template <typename TA>
 int cmvn_conv1(const float* feats, int B, int T, int F, const float* mean, const float* istd, const float* w1,
                const float* b1, int C, TA* c1, cudaStream_t st) {
-    const int T1 = (T - 1) / 2, F1 = (F - 1) / 2;
-    if (B <= 0 || T1 <= 0) return 0;
+    const int T1 = (T - 1) / 2, F1 = (F - 1) / 2, T2 = (T1 - 1) / 2, F2 = (F1 - 1) / 2;
+    if (B <= 0 || T2 <= 0) return 0;
     FO_CHECK(C % 4 == 0, "cmvn_conv1: channel count must be a multiple of 4");
-    dim3 grid(T1, B);
+    dim3 grid(2 * T2 + 1, B);                          // conv1 rows that feed a conv2 output row
     const int threads = C / 4 >= 256 ? 256 : ((C / 4 + 31) / 32) * 32;
-    cmvn_conv1_kernel<TA, 4><<<grid, threads, 3 * F * sizeof(float), st>>>(feats, T, F, mean, istd, w1, b1, C, T1, F1, c1);
+    cmvn_conv1_kernel<TA, 4><<<grid, threads, 3 * F * sizeof(float), st>>>(feats, T, F, mean, istd, w1, b1, C, T2, F1, F2 + 1,
+                                                                           (long long)B * T2 * (F2 + 1), c1);
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
 }
+void conv2_gather(int B, int T2, int F2, int C, AGather* ga, RowMap* rm) {
+    const int F2P = F2 + 1;
+    ga->seg_len = C; ga->n_seg = 9; ga->rows = (long long)B * T2 * F2P; ga->planes = 6;
+    for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+            ga->plane[kh * 3 + kw] = kh * 2 + (kw & 1);
+            ga->rowoff[kh * 3 + kw] = kw >> 1;
+        }
+    rm->p0 = F2P; rm->p1 = T2 * F2P; rm->v0 = F2; rm->v1 = T2; rm->q0 = F2; rm->q1 = T2 * F2;
+}
+void adapter_gather(int B, int T, int D, int k, AGather* ga, RowMap* rm) {
+    const int RP = (k - 1 + T + 1) / 2, t_out = (T - 1) / 2 + 1;
+    ga->seg_len = D; ga->n_seg = k; ga->rows = (long long)B * RP; ga->planes = 2;
+    for (int i = 0; i < AGather::MAX_SEG; ++i) { ga->plane[i] = i & 1; ga->rowoff[i] = i >> 1; }
+    rm->p0 = RP; rm->p1 = RP; rm->v0 = t_out; rm->v1 = 1; rm->q0 = 0; rm->q1 = t_out;
+}
+
 template int cmvn_conv1<float>(const float*, int, int, int, const float*, const float*, const float*, const float*, int, float*, cudaStream_t);
 template int cmvn_conv1<bf16>(const float*, int, int, int, const float*, const float*, const float*, const float*, int, bf16*, cudaStream_t);
 

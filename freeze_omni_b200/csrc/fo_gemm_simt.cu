@@ -1,8 +1,8 @@
 // FFMA GEMM: C[M,N] = A[M,K] * W[N,K]^T with the shared epilogue.  This is the fp32 parity path
 // (north_star: 1e-4 max-abs in fp32 needs true fp32 products, not TF32) and the fallback for bf16
 // shapes the tcgen05 kernel does not take.  64x64x16 tiles, 256 threads, 4x4 outputs per thread,
-// register-prefetched global loads.  The A operand goes through AGather so the subsampling conv2
-// and the adapter conv run as implicit GEMMs without materialising im2col.
+// register-prefetched global loads.  The A operand goes through AGather / RowMap (fo_common.cuh) so the
+// subsampling conv2 and the adapter conv run as implicit GEMMs without materialising im2col.
 #include "fo_common.cuh"
 
 namespace fo {
@@ -30,7 +30,7 @@ template <> struct Vec4<bf16> {
 template <typename TIn, typename TAct>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ W, int M, int N, int K,
-                 Epilogue ep) {
+                 Epilogue ep, RowMap rmap) {
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Ws[BK][BN + PAD];
     const int tid = threadIdx.x;
@@ -40,7 +40,6 @@ gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ 
     const int lrow = tid >> 2, lk = (tid & 3) * 4;
     const int arow = m0 + lrow, wrow = n0 + lrow;
     const bool a_ok = arow < M, w_ok = wrow < N;
-    const long long a_row_off = a_ok ? gather_row_off(ga, arow) : 0;
     const TIn* wp = W + (long long)(w_ok ? wrow : 0) * K + lk;
 
     float acc[4][4];
@@ -51,9 +50,10 @@ gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ 
 
     float ra[4], rw[4];
     auto fetch = [&](int k0) {
-        if (a_ok) {
-            int seg = k0 / ga.seg_len, kin = k0 - seg * ga.seg_len;
-            const TIn* ap = A + (a_row_off + gather_seg_off(ga, seg)) * ga.seg_len + kin + lk;
+        const int seg = k0 / ga.seg_len, kin = k0 - seg * ga.seg_len;
+        const long long r = (long long)arow + ga.rowoff[seg];
+        if (a_ok && r < ga.rows) {
+            const TIn* ap = A + ((long long)ga.plane[seg] * ga.rows + r) * ga.seg_len + kin + lk;
             Vec4<TIn>::load(ap, ra);
         } else {
             ra[0] = ra[1] = ra[2] = ra[3] = 0.f;
@@ -93,20 +93,23 @@ gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int m = m0 + ty * 4 + i;
-        if (m >= M) continue;
+        long long drow;
+        if (m >= M || !row_map(rmap, m, drow)) continue;
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             v[j] = (acc[i][j] + bv[j]) * ep.scale;
             if (ep.relu) v[j] = fmaxf(v[j], 0.f);
         }
-        long long o = (long long)m * ep.ldc + nbase;
+        long long o = drow * ep.ldc + nbase;
         if (ep.residual) {
             float4 r = *reinterpret_cast<const float4*>(ep.residual + o);
             v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
         }
-        if (ep.c_f32) *reinterpret_cast<float4*>(ep.c_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
-        if (ep.c_act) {
+        const bool wf = ep.c_f32 && (!ep.split_col || nbase < ep.split_col);
+        const bool wa = ep.c_act && (!ep.split_col || nbase >= ep.split_col);
+        if (wf) *reinterpret_cast<float4*>(ep.c_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+        if (wa) {
             TAct* c = reinterpret_cast<TAct*>(ep.c_act) + o;
 #pragma unroll
             for (int j = 0; j < 4; ++j) c[j] = from_f<TAct>(v[j]);
@@ -118,19 +121,19 @@ gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ 
 
 template <typename TIn>
 int gemm_simt(const TIn* A, const AGather& ga, const TIn* W, int M, int N, int K, const Epilogue& ep,
-              cudaStream_t st) {
+              const RowMap& rmap, cudaStream_t st) {
     if (M <= 0) return 0;
     FO_CHECK(K % BK == 0 && ga.seg_len % BK == 0, "gemm_simt: K (%d) and segment (%d) must be multiples of %d", K,
              ga.seg_len, BK);
     FO_CHECK(N % 4 == 0 && ep.ldc % 4 == 0, "gemm_simt: N and ldc must be multiples of 4");
     dim3 grid(cdiv(N, BN), cdiv(M, BM));
-    gemm_simt_kernel<TIn, TIn><<<grid, 256, 0, st>>>(A, ga, W, M, N, K, ep);
+    gemm_simt_kernel<TIn, TIn><<<grid, 256, 0, st>>>(A, ga, W, M, N, K, ep, rmap);
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
 }
 
-template int gemm_simt<float>(const float*, const AGather&, const float*, int, int, int, const Epilogue&, cudaStream_t);
-template int gemm_simt<bf16>(const bf16*, const AGather&, const bf16*, int, int, int, const Epilogue&, cudaStream_t);
+template int gemm_simt<float>(const float*, const AGather&, const float*, int, int, int, const Epilogue&, const RowMap&, cudaStream_t);
+template int gemm_simt<bf16>(const bf16*, const AGather&, const bf16*, int, int, int, const Epilogue&, const RowMap&, cudaStream_t);
 
 }  // namespace fo

@@ -415,6 +415,58 @@ def test_shipped_offline_bf16(golden, shipped16):
     assert maxabs(enc.cpu(), g["enc_out"]) < float(floor["ref_autocast_vs_fp32_encoder"])
 
 
+@pytest.mark.parametrize("which", ["tiny32", "shipped16"])
+def test_graph_replay_matches_eager(which, request):
+    """The captured CUDA graph of a step must be bit-identical to the eager launch sequence, across the
+    first (eager), second (capture) and later (replay) calls of a shape."""
+    cfg, eng = request.getfixturevalue(which)
+    g = torch.Generator().manual_seed(11)
+    ids = eng.alloc(2)
+    try:
+        r0 = eng.stats()["graph_replays"]
+        for i in range(6):
+            pcm = (0.05 * torch.randn(1, cfg.samples_per_chunk, generator=g) * 32768).round().to(torch.int16)
+            eng.set_option("use_graph", 1)
+            e1, y1 = eng.stream_step(ids[:1], pcm, 1.0)
+            eng.set_option("use_graph", 0)
+            e0, y0 = eng.stream_step(ids[1:], pcm, 1.0)
+            assert torch.equal(e1, e0) and torch.equal(y1, y0), i
+        assert eng.stats()["graph_replays"] - r0 >= 4
+        assert eng.state(int(ids[0])) == eng.state(int(ids[1]))
+    finally:
+        eng.set_option("use_graph", 1)
+        eng.free(ids)
+
+
+def test_tcgen05_gemm_tile_plans(shipped16):
+    """Every orientation / UMMA-N / split-K plan of the tcgen05 kernel against an fp64 product of the
+    same bf16 operands; checks the kernel really launched (no silent FFMA fallback)."""
+    cfg, eng = shipped16
+    g = torch.Generator().manual_seed(5)
+    plans = [(0, 256, 1), (0, 128, 1), (0, 64, 2), (0, 16, 1), (0, 208, 4), (1, 256, 1), (1, 144, 2), (1, 64, 1),
+             (1, 16, 4), (1, 32, 8), (-1, -1, -1)]
+    shapes = [(256, 1024, 1024), (76, 1024, 9216), (4, 3072, 1024), (300, 3584, 2048), (1000, 1024, 4096), (128, 2048, 5120)]
+    try:
+        for (M, N, K) in shapes:
+            A = torch.randn(M, K, generator=g).cuda()
+            W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+            b = torch.randn(N, generator=g).cuda()
+            ref = (A.bfloat16().double() @ W.bfloat16().double().T + b.double()).float().cpu()
+            for (swap, bn, split) in plans:
+                eng.set_option("tc_swap", swap)
+                eng.set_option("tc_bn", bn)
+                eng.set_option("tc_split", split)
+                n0 = eng.get_option("tc_launches")
+                o, _ = eng.debug_gemm(A, W, b, backend=1)
+                assert eng.get_option("tc_launches") == n0 + 1, "tcgen05 kernel did not launch"
+                err = maxabs(o.cpu(), ref)
+                assert err < 2e-3, ((M, N, K), (swap, bn, split), err)
+    finally:
+        eng.set_option("tc_swap", -1)
+        eng.set_option("tc_bn", -1)
+        eng.set_option("tc_split", -1)
+
+
 def test_gemm_backends_agree_bf16(shipped16):
     """tcgen05 kernel vs the FFMA kernel on the same bf16 operands (both accumulate in fp32)."""
     cfg, eng = shipped16

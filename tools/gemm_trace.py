@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""FO_TC_TRACE=1 python tools/gemm_trace.py: prints the in-kernel %globaltimer timeline of CTA (0,0,0) of the
+tcgen05 GEMM for a few shapes/plans (development aid)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["FO_TC_TRACE"] = "1"
+from freeze_omni_b200.config import load_path_config  # noqa: E402
+from freeze_omni_b200.engine import Engine  # noqa: E402
+from freeze_omni_b200.weights import make_adapter_state, make_encoder_state  # noqa: E402
+
+cfg = load_path_config("tiny")
+eng = Engine(cfg, make_encoder_state(cfg, 0), make_adapter_state(cfg, 0), dtype=torch.bfloat16, max_sessions=2)
+g = torch.Generator().manual_seed(0)
+for (M, N, K) in [(256, 3072, 1024), (256, 1024, 4096), (4096, 4096, 1024)]:
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    for plan in [(0, 64, 1), (0, 256, 1), (1, 256, 1), (0, 64, 4)]:
+        eng.set_option("tc_swap", plan[0]); eng.set_option("tc_bn", plan[1]); eng.set_option("tc_split", plan[2])
+        for rep in range(3):
+            eng.debug_gemm(A, W, None, backend=1, iters=0)
+eng.close()
