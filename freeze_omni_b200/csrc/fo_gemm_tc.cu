@@ -195,6 +195,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = tmem_base_s;
     if (threadIdx.x == 0) TC_TRACE(1);
 
+    const int bn = p.bn;
+    float* stage = reinterpret_cast<float*>(smem_dyn + (base - smem_u32(smem_dyn)));   // reused once the MMAs are done
+    const int ld0 = bn + 4;                                    // swap=0 staging [row][col]
+    constexpr int LD1 = BM + 4;                                // swap=1 staging [col][row]
+
     if (warp == 0 || warp == 6) {
         if (lane == 0) {
             const int w = warp == 0 ? 0 : 1;
@@ -246,10 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int q = warp & 3;
         const int row_l = q * 32 + lane;                       // row of the tile on the UMMA-M side
         const int et = threadIdx.x - 64;                       // 0..127 among the epilogue threads
-        const int ew = et >> 5;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int bn = p.bn;
-        const Epilogue& ep = p.ep;
         // output row of every tile row / column, once
         if (!p.swap) {
             const int ga = tile_a * BM + et;
@@ -262,13 +264,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 s_drow[c] = (m < p.rows_b && row_map(p.rmap, m, d)) ? (int)d : -1;
             }
         }
-        float* stage = reinterpret_cast<float*>(smem_dyn + (base - smem_u32(smem_dyn)));
-        const int ld0 = bn + 4;                                // swap=0 staging [row][col]
-        constexpr int LD1 = BM + 4;                            // swap=1 staging [col][row]
         mbar_wait(accb, 0);
         tc_fence_after();
         if (et == 0) TC_TRACE(8);
-        bool finish = true;
         const long long tile_id = (long long)tile_b * gridDim.x + tile_a;
         if (nsplit > 1) {
             // raw partial tile: [split][tile][col][128 rows] so that a warp's store is one 128-byte line
@@ -285,11 +283,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int prev = atomicAdd(p.counters + tile_id, 1);
                 const int last = prev == nsplit - 1;
                 if (last) p.counters[tile_id] = 0;             // ready for the next launch
-                is_last_s = last;
+                is_last_s = last;                              // also gates the write-out below
             }
             epi_bar();
-            finish = is_last_s != 0;
-            if (finish) {
+            if (is_last_s != 0) {
                 __threadfence();
                 const long long split_stride = (long long)gridDim.x * gridDim.y * bn * BM;
                 const float* part0 = p.partial + (tile_id * bn) * BM + row_l;
@@ -324,53 +321,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
-        if (finish) {
-            epi_bar();                                         // staging tile complete
-            if (et == 0) TC_TRACE(9);
-            // ---- coalesced write-out: consecutive lanes = consecutive output columns, 4 per lane ----
-            // swap=0: staging rows are C rows, bn columns starting at n0;  swap=1: staging "columns" are C rows,
-            // 128 output columns starting at tile_a*128.  The lane's columns (hence bias) are fixed across rows;
-            // rows are unrolled so that several independent load/store chains are in flight per warp.
-            const int n_rows = p.swap ? bn : BM;
-            const int n_cols = p.swap ? BM : bn;
-            const int ld = p.swap ? LD1 : ld0;
-            const int n0 = p.swap ? tile_a * BM : tile_b * bn;
-            const float scale = ep.scale;
-            const int relu = ep.relu, ldc = ep.ldc;
-            const float* __restrict__ resid = ep.residual;
-            float* __restrict__ out32 = ep.c_f32;
-            bf16* __restrict__ out16 = reinterpret_cast<bf16*>(ep.c_act);
-            for (int c = lane * 4; c < n_cols; c += 128) {
-                const int n = n0 + c;
-                if (n >= p.n_out) break;
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n);
-                const bool wf = out32 && (!ep.split_col || n < ep.split_col);
-                const bool wa = out16 && (!ep.split_col || n >= ep.split_col);
-                const float* sp = stage + c;
+        if (nsplit == 1 && et == 0) is_last_s = 1;
+    }
+    // ---- coalesced write-out by all 7 warps: consecutive lanes = consecutive output columns, 4 per lane ----
+    // swap=0: staging rows are C rows, bn columns starting at n0;  swap=1: staging "columns" are C rows,
+    // 128 output columns starting at tile_a*128.  The lane's columns (hence bias) are fixed across rows;
+    // rows are unrolled so that several independent load/store chains are in flight per warp.
+    __syncthreads();                                           // staging tile (or nothing, for a non-final split) complete
+    if (threadIdx.x == 64) TC_TRACE(9);
+    if (is_last_s) {
+        const Epilogue& ep = p.ep;
+        const int n_rows = p.swap ? bn : BM;
+        const int n_cols = p.swap ? BM : bn;
+        const int ld = p.swap ? LD1 : ld0;
+        const int n0 = p.swap ? tile_a * BM : tile_b * bn;
+        const float scale = ep.scale;
+        const int relu = ep.relu, ldc = ep.ldc;
+        const float* __restrict__ resid = ep.residual;
+        float* __restrict__ out32 = ep.c_f32;
+        bf16* __restrict__ out16 = reinterpret_cast<bf16*>(ep.c_act);
+        for (int c = lane * 4; c < n_cols; c += 128) {
+            const int n = n0 + c;
+            if (n >= p.n_out) break;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n);
+            const bool wf = out32 && (!ep.split_col || n < ep.split_col);
+            const bool wa = out16 && (!ep.split_col || n >= ep.split_col);
+            const float* sp = stage + c;
 #pragma unroll 4
-                for (int r = ew; r < n_rows; r += 4) {
-                    const int drow = s_drow[r];
-                    const bool ok = drow >= 0;
-                    const long long o = (long long)(ok ? drow : 0) * ldc + n;
-                    float4 v = *reinterpret_cast<const float4*>(sp + r * ld);
-                    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (resid && ok) rv = *reinterpret_cast<const float4*>(resid + o);
-                    v.x = (v.x + bv.x) * scale; v.y = (v.y + bv.y) * scale; v.z = (v.z + bv.z) * scale; v.w = (v.w + bv.w) * scale;
-                    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                    v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                    if (wf && ok) *reinterpret_cast<float4*>(out32 + o) = v;
-                    if (wa && ok) {
-                        __align__(8) __nv_bfloat162 h[2];
-                        h[0] = __floats2bfloat162_rn(v.x, v.y);
-                        h[1] = __floats2bfloat162_rn(v.z, v.w);
-                        *reinterpret_cast<uint2*>(out16 + o) = *reinterpret_cast<const uint2*>(h);
-                    }
+            for (int r = warp; r < n_rows; r += TC_THREADS / 32) {
+                const int drow = s_drow[r];
+                const bool ok = drow >= 0;
+                const long long o = (long long)(ok ? drow : 0) * ldc + n;
+                float4 v = *reinterpret_cast<const float4*>(sp + r * ld);
+                float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (resid && ok) rv = *reinterpret_cast<const float4*>(resid + o);
+                v.x = (v.x + bv.x) * scale; v.y = (v.y + bv.y) * scale; v.z = (v.z + bv.z) * scale; v.w = (v.w + bv.w) * scale;
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                if (wf && ok) *reinterpret_cast<float4*>(out32 + o) = v;
+                if (wa && ok) {
+                    __align__(8) __nv_bfloat162 h[2];
+                    h[0] = __floats2bfloat162_rn(v.x, v.y);
+                    h[1] = __floats2bfloat162_rn(v.z, v.w);
+                    *reinterpret_cast<uint2*>(out16 + o) = *reinterpret_cast<const uint2*>(h);
                 }
             }
         }
-        if (et == 0) TC_TRACE(10);
     }
+    if (threadIdx.x == 64) TC_TRACE(10);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -390,6 +389,8 @@ TcTune g_forced = {-1, -1, -1};
 long long g_tc_launches = 0;
 
 int make_map(CUtensorMap* map, const bf16* base, int seg_len, long long rows, int planes, int box_rows) {
+    // {k within the segment, rows, planes}; one box = box_rows x 64 elements = one 128B-swizzled smem tile
+    // (a 4-D variant fetching two k-atoms per box measured slower per byte on B200, profiles/r01 notes)
     cuuint64_t dims[3] = {(cuuint64_t)seg_len, (cuuint64_t)rows, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)seg_len * 2, (cuuint64_t)seg_len * 2 * (cuuint64_t)rows};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
@@ -404,38 +405,50 @@ int make_map(CUtensorMap* map, const bf16* base, int seg_len, long long rows, in
 
 int round16(int x) { return (x + 15) / 16 * 16; }
 
-// Cost model (microseconds, coarse): per-CTA time = max(operand ingest at ~100 GB/s per SM, MMA issue) + split-K
-// reduction by the last CTA + a fixed prologue/epilogue, times the number of waves.
+// Tile plan.  Measured on B200 (profiles/r01_*_gemm_sweep*.jsonl):
+//  * skinny GEMMs (<= 384 activation rows: every streaming-step GEMM at 64 sessions) are latency bound, so the
+//    weights go on the 128-row UMMA-M side (`swap`), the activation rows are cut into UMMA-N slices as small as
+//    needed to put ~148 CTAs in flight, and K is split only when a CTA would otherwise walk more than 32 k-blocks
+//    (or when the grid would leave most SMs idle);
+//  * fat GEMMs (offline, conv2) are MMA / L2 bound: activations on the M side, N = 256 when that still fills the
+//    machine, else 128; or weights on the M side with the UMMA-N extent chosen so that the CTA count lands just
+//    under a multiple of the SM count (wave quantisation), whichever model cost is lower.
 struct Plan { int swap, bn, split; double cost; };
 
 Plan choose_plan(long long act_rows, int n_out, int K) {
     const int kblocks = K / BK;
-    Plan best{0, 0, 1, 1e30};
+    const int sms = g_sm_count;
+    if (act_rows <= 384) {
+        const int ta = (n_out + BM - 1) / BM;
+        int split = std::min(4, (kblocks + 31) / 32);
+        int bn = 256;
+        const int cands[5] = {16, 32, 64, 128, 256};
+        for (int ci = 0; ci < 5; ++ci) {                       // smallest slice that keeps the grid within one wave
+            const int b = cands[ci];
+            const long long tb = (act_rows + b - 1) / b;
+            if ((long long)ta * tb * split <= sms) { bn = b; break; }
+        }
+        if (bn > round16((int)act_rows)) bn = round16((int)act_rows);
+        const long long tb = (act_rows + bn - 1) / bn;
+        while (split < 8 && (long long)ta * tb * split * 2 <= sms && kblocks / (split * 2) >= 4) split *= 2;
+        return Plan{1, bn, split, 0.0};
+    }
+    Plan best{0, 128, 1, 1e30};
     for (int swap = 0; swap < 2; ++swap) {
         const long long rows_a = swap ? n_out : act_rows, rows_b = swap ? act_rows : n_out;
-        int cands[8] = {16, 32, 64, 96, 128, 160, 192, 256};
-        for (int ci = 0; ci < 9; ++ci) {
-            int bn = ci < 8 ? cands[ci] : round16((int)std::min<long long>(rows_b, 256));
-            if (bn > 256 || bn < 16) continue;
-            if (rows_b <= 256 && bn > round16((int)rows_b)) continue;
+        for (int bn = 64; bn <= 256; bn += 16) {
             const long long ta = (rows_a + BM - 1) / BM, tb = (rows_b + bn - 1) / bn;
             if (ta * tb > MAX_TILES) continue;
-            for (int split = 1; split <= 16; split *= 2) {
-                if (split > 1 && (kblocks / split) < 2) break;
-                const int kbs = (kblocks + split - 1) / split;
-                if ((long long)(split - 1) * kbs >= kblocks) continue;
-                const long long ctas = ta * tb * split;
-                const uint32_t stage = (BM + bn) * BK * 2;
-                const int occ = std::max(1, std::min<int>(2, (int)((220 * 1024) / (std::min<uint32_t>(SMEM_BUDGET, stage * std::min(kbs, MAX_STAGES)) + 2048))));
-                const double waves = (double)((ctas + (long long)g_sm_count * occ - 1) / ((long long)g_sm_count * occ));
-                const double ingest_us = (double)kbs * stage / 100e3 * occ;             // bytes / (100 GB/s) in us
-                const double mma_us = (double)kbs * 4 * (BM * bn / 256.0) / 1.7e3 * occ;
-                const double tile_bytes = (double)BM * bn * 4;
-                const double red_us = split > 1 ? (tile_bytes / 100e3 + split * tile_bytes / 100e3) : 0.0;
-                const double epi_us = tile_bytes / 200e3;
-                const double cost = waves * (std::max(ingest_us, mma_us) + 1.5 + epi_us) + red_us;
-                if (cost < best.cost) best = Plan{swap, bn, split, cost};
-            }
+            const double stage = (BM + bn) * 128.0;
+            const double tile_stage = swap ? bn * (BM + 4) * 4.0 : BM * (bn + 4) * 4.0;
+            const int occ = (3 * stage <= 110 * 1024 && tile_stage <= 110 * 1024) ? 2 : 1;   // CTAs resident per SM
+            const double waves = (double)((ta * tb + (long long)sms * occ - 1) / ((long long)sms * occ));
+            // per k-block: MMA issue 2*bn cycles vs operand ingest at ~43 B/clk/SM when every SM pulls from L2;
+            // resident CTAs share both; prologue + epilogue (~3000 + 40*bn cycles) overlap only when occ == 2
+            const double per_kb = std::max(2.0 * bn, (BM + bn) * 128.0 / 43.0);
+            const double ovh = (3000.0 + 40.0 * bn) * (occ == 2 ? 0.5 : 1.0);
+            const double cost = waves * (occ * kblocks * per_kb + ovh) * (swap ? 1.02 : 1.0);
+            if (cost < best.cost) best = Plan{swap, bn, 1, cost};
         }
     }
     return best;
@@ -481,8 +494,11 @@ int gemm_tc(const bf16* A, const AGather& ga, const bf16* W, int M, int N, int K
     if (g_forced.bn > 0) pl.bn = g_forced.bn;
     if (g_forced.split > 0) pl.split = g_forced.split;
     const int kblocks = K / BK;
+    if (pl.bn > 256) pl.bn = 256;
+    pl.bn = std::max(16, pl.bn / 16 * 16);
     if (pl.split > kblocks) pl.split = kblocks;
-    int kbs = (kblocks + pl.split - 1) / pl.split;
+    if (pl.split < 1) pl.split = 1;
+    int kbs = (kblocks + pl.split - 1) / pl.split;               // k-blocks per split
     pl.split = (kblocks + kbs - 1) / kbs;                        // no empty split
     const long long rows_a = pl.swap ? N : M, rows_b = pl.swap ? M : N;
     const int ta = (int)((rows_a + BM - 1) / BM), tb = (int)((rows_b + pl.bn - 1) / pl.bn);
@@ -499,6 +515,11 @@ int gemm_tc(const bf16* A, const AGather& ga, const bf16* W, int M, int N, int K
     p.swap = pl.swap;
     const uint32_t stage = (BM + pl.bn) * BK * 2;
     p.stages = std::max(1, std::min<int>(std::min(MAX_STAGES, kbs), (int)(SMEM_BUDGET / stage)));
+    if ((long long)ta * tb * pl.split > g_sm_count) {
+        // more CTAs than SMs: keep two resident per SM (<= ~110 KB each) so one CTA's epilogue overlaps the other's mainloop
+        const int cap = (int)((110 * 1024) / stage);
+        if (cap >= 3) p.stages = std::min(p.stages, cap);
+    }
     p.tmem_cols = 32;
     while (p.tmem_cols < pl.bn) p.tmem_cols <<= 1;
     TcOperand act, wgt;

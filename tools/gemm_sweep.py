@@ -20,7 +20,7 @@ def main():
     cfg = load_path_config("tiny")
     eng = Engine(cfg, make_encoder_state(cfg, 0), make_adapter_state(cfg, 0), dtype=torch.bfloat16, max_sessions=2)
     shapes = [(256, 3072, 1024), (256, 1024, 1024), (256, 4096, 1024), (256, 1024, 4096), (256, 1024, 19456),
-              (128, 3584, 2048), (4, 3072, 1024), (4, 1024, 4096), (512, 4096, 1024), (4096, 4096, 1024)]
+              (128, 3584, 2048), (4, 3072, 1024), (4, 1024, 4096), (512, 4096, 1024), (4096, 4096, 1024), (5120, 1024, 9216)]
     if quick:
         shapes = shapes[:2]
     g = torch.Generator().manual_seed(0)
@@ -28,11 +28,11 @@ def main():
         A = torch.randn(M, K, generator=g).cuda()
         W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
         rows = []
-        plans = [(-1, -1, -1)] + list(itertools.product((0, 1), (16, 32, 64, 128, 256), (1, 2, 4, 8)))
+        plans = [(-1, -1, -1)] + list(itertools.product((0, 1), (16, 32, 64, 128, 144, 256), (1, 2, 4, 8)))
         for (swap, bn, split) in plans:
             if swap == 1 and bn > ((M + 15) // 16) * 16 and bn != 16:
                 continue
-            if split > K // 64:
+            if split > K // 64 or (M > 1024 and (split > 1 or bn < 64)):
                 continue
             eng.set_option("tc_swap", swap)
             eng.set_option("tc_bn", bn)
