@@ -139,7 +139,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sessions", type=int, default=64, help="concurrent sessions per GPU")
     ap.add_argument("--ref-sessions", type=int, default=64)
@@ -149,9 +149,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--graph", type=int, default=-1, help="override the library's use_graph option")
     ap.add_argument("--backend", type=int, default=-1, help="override gemm_backend (0 FFMA, 1 tcgen05)")
+    ap.add_argument("--groups", type=int, default=-1, help="override session_groups (parallel layer streams)")
+    ap.add_argument("--debug-skip", type=int, default=0, help="timing attribution only: bitmask of kernel classes to skip")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    # steady state needs the 64-row KV windows full (16 chunks); shorter warm-ups are topped up untimed below
+    fill_steps = max(0, 17 - args.warmup)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -179,6 +184,10 @@ def main():
         eng.set_option("use_graph", args.graph)
     if args.backend >= 0:
         eng.set_option("gemm_backend", args.backend)
+    if args.groups >= 1:
+        eng.set_option("session_groups", args.groups)
+    if args.debug_skip:
+        eng.set_option("debug_skip", args.debug_skip)
     ids = eng.alloc(S)
     n_pcm = min(K + W, 64)                                   # synthetic audio is cycled after 64 chunks
     pcm_host = torch.from_numpy(synth_pcm(S, n_pcm, cfg.samples_per_chunk, seed0=1000 + 4096 * rank)).pin_memory()
@@ -216,6 +225,7 @@ def main():
         return float(ms.item())
 
     # ---- device-resident throughput ------------------------------------------------------------
+    run_steps(fill_steps, False, 0)                          # untimed: fill the KV windows (steady state)
     run_steps(W, False, 0)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -225,9 +235,15 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     value = world * S * CHUNK_SEC * K / (ms * 1e-3)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms / K, "value": value, "sessions": S, "debug_skip": args.debug_skip,
+                              "groups": eng.get_option("session_groups")}))
+        eng.free(ids)
+        eng.close()
+        return
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
-    eng.reset(ids)
     run_steps(W, True, 0)
     ms_e2e = timed(K, True, W)
     e2e = world * S * CHUNK_SEC * K / (ms_e2e * 1e-3)
@@ -291,7 +307,8 @@ def main():
                 "gpu_launches": int(launches),
                 "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "sessions": S},
                 "roofline": roof, "step_roofline": whole, "cpu_baseline": cpu, "clocks": sampler.summary(),
-                "options": {"gemm_backend": eng.get_option("gemm_backend"), "use_graph": eng.get_option("use_graph")}}
+                "options": {"gemm_backend": eng.get_option("gemm_backend"), "use_graph": eng.get_option("use_graph"),
+                            "session_groups": eng.get_option("session_groups")}}
         print(json.dumps(line))
     eng.free(ids)
     eng.close()

@@ -15,6 +15,7 @@
 #include <string.h>
 #include <math.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -103,7 +104,16 @@ struct fo_ctx {
     // options
     int gemm_backend = 0, use_graph = 0, split_k = 1;
     TcTune tc_tune{-1, -1, -1};               // debugging: force the tile plan of the tcgen05 GEMM
-    TcWorkspace tc_ws;                        // split-K partials + tile counters of the tcgen05 GEMM
+    static const int MAX_GROUPS = 4;
+    TcWorkspace tc_wsg[MAX_GROUPS];           // split-K partials + tile counters of the tcgen05 GEMM, one per session group
+    TcWorkspace* tc_cur = &tc_wsg[0];
+    int debug_skip = 0;                       // timing attribution only (results invalid): bit0 attention, bit1 LayerNorm,
+                                              // bit2 QKV/out GEMMs, bit3 FFN GEMMs, bit4 subsampling GEMMs
+    int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
+                                              // (measured slower than the stand-alone kernel at 64-256 sessions: off)
+    int groups = 1;                           // session groups whose layer kernels run on parallel streams
+    cudaStream_t grp_stream[MAX_GROUPS] = {nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {nullptr};
     int profile_gemm = 0;                     // time every GEMM launch with a CUDA event pair (bench roofline)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     // captured step graphs, keyed by the shape of the call; invalidated when a workspace moves
@@ -206,20 +216,26 @@ int upload_ids(fo_ctx* c, const int32_t* ids, int n, cudaStream_t st) {
 }
 
 // ---- GEMM dispatch ----------------------------------------------------------------------------
-// M = GEMM rows over the (possibly padded) row grid of `ga`; rm maps them to rows of C.
+// M = GEMM rows over the (possibly padded) row grid of `ga`; rm maps them to rows of C.  `fused_ln` reports whether
+// the kernel that ran also did the LayerNorm requested in ep.ln_* (only the tcgen05 kernel does).
 template <typename TA>
 int gemm_raw(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-             const RowMap& rm, cudaStream_t st);
+             const RowMap& rm, cudaStream_t st, bool* fused_ln);
 template <>
 int gemm_raw<float>(fo_ctx* c, const float* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-                    const RowMap& rm, cudaStream_t st) {
+                    const RowMap& rm, cudaStream_t st, bool* fused_ln) {
+    *fused_ln = false;
     return gemm_simt<float>(A, ga, reinterpret_cast<const float*>(W), M, N, K, ep, rm, st);
 }
 template <>
 int gemm_raw<bf16>(fo_ctx* c, const bf16* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-                   const RowMap& rm, cudaStream_t st) {
+                   const RowMap& rm, cudaStream_t st, bool* fused_ln) {
+    *fused_ln = false;
     if (c->gemm_backend == 1) {
-        int r = gemm_tc(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, rm, c->tc_ws, st);
+        Epilogue e = ep;
+        if (!c->fuse_ln) e.ln_gamma = nullptr;
+        int r = gemm_tc(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, e, rm, *c->tc_cur, st);
+        if (r == 0) *fused_ln = e.ln_gamma != nullptr;
         if (r <= 0) return r;
     }
     return gemm_simt<bf16>(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, rm, st);
@@ -227,14 +243,22 @@ int gemm_raw<bf16>(fo_ctx* c, const bf16* A, const AGather& ga, const void* W, i
 template <typename TA>
 int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
          const RowMap& rm, cudaStream_t st) {
-    if (!c->profile_gemm) return gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st);
-    cudaEvent_t e0, e1;
-    FO_CUDA(cudaEventCreate(&e0));
-    FO_CUDA(cudaEventCreate(&e1));
-    FO_CUDA(cudaEventRecord(e0, st));
-    int r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st);
-    FO_CUDA(cudaEventRecord(e1, st));
-    c->prof_events.emplace_back(e0, e1);
+    bool fused = false;
+    int r;
+    if (!c->profile_gemm) {
+        r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st, &fused);
+    } else {
+        cudaEvent_t e0, e1;
+        FO_CUDA(cudaEventCreate(&e0));
+        FO_CUDA(cudaEventCreate(&e1));
+        FO_CUDA(cudaEventRecord(e0, st));
+        r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st, &fused);
+        FO_CUDA(cudaEventRecord(e1, st));
+        c->prof_events.emplace_back(e0, e1);
+    }
+    if (r == 0 && ep.ln_gamma && !fused)          // LayerNorm of the finished rows as its own kernel (fp32 / FFMA paths)
+        r = layer_norm<TA>(ep.c_f32, M, N, ep.ln_gamma, ep.ln_beta, ep.ln_eps, 0, 1.0f, reinterpret_cast<TA*>(ep.ln_act),
+                           ep.ln_f32, st);
     return r;
 }
 // plain row-major A (M, K)
@@ -513,11 +537,17 @@ int subsample_program(fo_ctx* c, const float* feats, int B, int T, float** x_out
     return 0;
 }
 
-// one transformer layer minus attention core: pre (LN1 + QKV) and post (out-proj, LN2, FFN)
+// One transformer layer minus the attention core.  LayerNorms ride on the GEMM that completes the residual stream:
+// out-proj (+residual) -> norm2 -> h;  FFN2 (+residual) -> next layer's norm1 -> h, or after_norm -> encoder output.
+struct NextNorm {
+    const float* gamma;
+    const float* beta;
+    float* out_f32;          // after_norm of the last layer: fp32 encoder output rows (else null -> h)
+};
 template <typename TA>
-int layer_pre(fo_ctx* c, const LayerW& w, float* x, int M, TA* h, TA* qkv, float* q32, cudaStream_t st) {
+int layer_pre(fo_ctx* c, const LayerW& w, int M, TA* h, TA* qkv, float* q32, cudaStream_t st) {
     const int D = c->D;
-    FO_TRY(layer_norm<TA>(x, M, D, w.ln1g, w.ln1b, 1e-5f, 0, 1.0f, h, nullptr, st));
+    if (c->debug_skip & 4) return 0;
     Epilogue e;
     e.bias = w.bqkv;
     e.c_act = qkv;
@@ -529,15 +559,18 @@ int layer_pre(fo_ctx* c, const LayerW& w, float* x, int M, TA* h, TA* qkv, float
     return gemm<TA>(c, h, w.wqkv, M, 3 * D, D, e, st);
 }
 template <typename TA>
-int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* ffh, cudaStream_t st) {
+int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* ffh, const NextNorm& nn, cudaStream_t st) {
     const int D = c->D, FF = c->FF;
     Epilogue e;
     e.bias = w.bo;
     e.residual = x;
     e.c_f32 = x;
     e.ldc = D;
-    FO_TRY(gemm<TA>(c, att, w.wo, M, D, D, e, st));
-    FO_TRY(layer_norm<TA>(x, M, D, w.ln2g, w.ln2b, 1e-5f, 0, 1.0f, h, nullptr, st));
+    e.ln_gamma = w.ln2g;
+    e.ln_beta = w.ln2b;
+    e.ln_act = h;
+    if (!(c->debug_skip & 4)) FO_TRY(gemm<TA>(c, att, w.wo, M, D, D, e, st));
+    if (c->debug_skip & 8) return 0;
     Epilogue e1;
     e1.bias = w.b1;
     e1.relu = 1;
@@ -549,6 +582,10 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
     e2.residual = x;
     e2.c_f32 = x;
     e2.ldc = D;
+    e2.ln_gamma = nn.gamma;
+    e2.ln_beta = nn.beta;
+    if (nn.out_f32) e2.ln_f32 = nn.out_f32;
+    else e2.ln_act = h;
     return gemm<TA>(c, ffh, w.w2, M, D, FF, e2, st);
 }
 
@@ -565,22 +602,61 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
     float* q32 = reinterpret_cast<float*>(qkv);
     if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
-    AttnStream a;
-    a.ids = c->ids_dev;
-    a.n_frames = c->n_frames;
-    a.pe_index = c->pe_index;
-    a.n = n; a.t = t; a.H = H; a.ring_cap = c->ring_cap; a.window = c->window; a.full_chunk = c->full_chunk;
-    a.pe_wrap = c->pe_wrap; a.pos_rows = c->pos_rows;
-    a.ring_slot_stride = 2LL * H * c->ring_cap * 64;
-    const long long layer_stride = (long long)c->cfg.max_sessions * a.ring_slot_stride;
+    // The 24 layers run per SESSION GROUP on parallel streams (fork/join with events, also under graph capture):
+    // sessions are independent, every layer kernel of a 64-session step is latency bound (<= 148 CTAs, 8-16 us), so
+    // two groups' kernels overlap each other's pipeline fill, epilogue and launch gaps.  Rows of one group are
+    // contiguous, so the groups just take slices of the same workspaces.
+    int G = c->profile_gemm ? 1 : c->groups;
+    if (G > fo_ctx::MAX_GROUPS) G = fo_ctx::MAX_GROUPS;
+    while (G > 1 && n < 8 * G) --G;
+    const long long layer_stride = (long long)c->cfg.max_sessions * 2LL * H * c->ring_cap * 64;
+    if (G > 1) {
+        FO_CUDA(cudaEventRecord(c->ev_fork, st));
+        for (int g = 1; g < G; ++g) FO_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->ev_fork, 0));
+    }
+    const int per = (n + G - 1) / G;
     for (int l = 0; l < c->L; ++l) {
         const LayerW& w = c->layers[l];
-        FO_TRY(layer_pre<TA>(c, w, x, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), q32, st));
-        FO_TRY(attention_stream<TA>(a, reinterpret_cast<const TA*>(qkv), q32, reinterpret_cast<TA*>(c->ring) + l * layer_stride,
-                                    w.ptab, w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
-        FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), st));
+        const bool last = l + 1 == c->L;
+        for (int g = 0; g < G; ++g) {
+            const int s0 = g * per, ng = std::min(per, n - s0);
+            if (ng <= 0) continue;
+            cudaStream_t sg = g == 0 ? st : c->grp_stream[g];
+            c->tc_cur = &c->tc_wsg[g];
+            const long long r0 = (long long)s0 * t;
+            const int Mg = ng * t;
+            AttnStream a;
+            a.ids = c->ids_dev + s0;
+            a.n_frames = c->n_frames;
+            a.pe_index = c->pe_index;
+            a.n = ng; a.t = t; a.H = H; a.ring_cap = c->ring_cap; a.window = c->window; a.full_chunk = c->full_chunk;
+            a.pe_wrap = c->pe_wrap; a.pos_rows = c->pos_rows;
+            a.ring_slot_stride = 2LL * H * c->ring_cap * 64;
+            TA* hg = reinterpret_cast<TA*>(h) + r0 * D;
+            TA* qkvg = reinterpret_cast<TA*>(qkv) + r0 * 3 * D;
+            TA* attg = reinterpret_cast<TA*>(att) + r0 * D;
+            TA* ffhg = reinterpret_cast<TA*>(ffh) + r0 * FF;
+            float* q32g = q32 + r0 * 3 * D;
+            float* xg = x + r0 * D;
+            int r = 0;
+            if (l == 0) r = layer_norm<TA>(xg, Mg, D, w.ln1g, w.ln1b, 1e-5f, 0, 1.0f, hg, nullptr, sg);
+            if (r == 0) r = layer_pre<TA>(c, w, Mg, hg, qkvg, q32g, sg);
+            if (r == 0 && !(c->debug_skip & 1))
+                r = attention_stream<TA>(a, qkvg, q32g, reinterpret_cast<TA*>(c->ring) + l * layer_stride, w.ptab, w.pos_u, w.pos_v,
+                                         attg, sg);
+            NextNorm nn{last ? c->after_g : c->layers[l + 1].ln1g, last ? c->after_b : c->layers[l + 1].ln1b,
+                        last ? enc_out_dev + r0 * D : nullptr};
+            if (r == 0) r = layer_post<TA>(c, w, xg, Mg, attg, hg, ffhg, nn, sg);
+            if (r != 0) { c->tc_cur = &c->tc_wsg[0]; return r; }
+        }
     }
-    FO_TRY(layer_norm<TA>(x, M, D, c->after_g, c->after_b, 1e-5f, 0, 1.0f, nullptr, enc_out_dev, st));
+    c->tc_cur = &c->tc_wsg[0];
+    if (G > 1) {
+        for (int g = 1; g < G; ++g) {
+            FO_CUDA(cudaEventRecord(c->ev_join[g], c->grp_stream[g]));
+            FO_CUDA(cudaStreamWaitEvent(st, c->ev_join[g], 0));
+        }
+    }
     if (c->cfg.has_adapter && y_dev)
         FO_TRY(adapter_program<TA>(c, enc_out_dev, nullptr, n, t, c->ids_dev, nullptr, nullptr, y_dev, st));
     FO_TRY(advance_sessions(c->ids_dev, n, t, c->cfg.chunk_size, c->pe_wrap, c->n_frames, c->pe_index,
@@ -603,14 +679,17 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
     FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
     float* q32 = reinterpret_cast<float*>(qkv);
     if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
+    FO_TRY(layer_norm<TA>(x, M, D, c->layers[0].ln1g, c->layers[0].ln1b, 1e-5f, 0, 1.0f, reinterpret_cast<TA*>(h), nullptr, st));
     for (int l = 0; l < c->L; ++l) {
         const LayerW& w = c->layers[l];
-        FO_TRY(layer_pre<TA>(c, w, x, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), q32, st));
+        const bool last = l + 1 == c->L;
+        FO_TRY(layer_pre<TA>(c, w, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), q32, st));
         FO_TRY(attention_offline<TA>(reinterpret_cast<const TA*>(qkv), q32, B, T2, H, ilens2, chunk, left,
                                      w.ptab, w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
-        FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), st));
+        NextNorm nn{last ? c->after_g : c->layers[l + 1].ln1g, last ? c->after_b : c->layers[l + 1].ln1b,
+                    last ? enc_out_dev : nullptr};
+        FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), nn, st));
     }
-    FO_TRY(layer_norm<TA>(x, M, D, c->after_g, c->after_b, 1e-5f, 0, 1.0f, nullptr, enc_out_dev, st));
     if (c->cfg.has_adapter && y_dev)
         FO_TRY(adapter_program<TA>(c, enc_out_dev, mask2, B, T2, nullptr, nullptr, nullptr, y_dev, st));
     return 0;
@@ -700,6 +779,14 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
         set_error("fo_create: cudaStreamCreate failed");
         r = FO_ERR_CUDA;
     }
+    for (int g = 1; g < fo_ctx::MAX_GROUPS && !r; ++g) {
+        if (cudaStreamCreateWithFlags(&c->grp_stream[g], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join[g], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("fo_create: group stream creation failed");
+            r = FO_ERR_CUDA;
+        }
+    }
+    if (!r && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) r = FO_ERR_CUDA;
     if (r) { fo_destroy(c); return r; }
     c->slot_used.assign(S, 0);
     c->free_slots.reserve(S);
@@ -715,6 +802,11 @@ int fo_destroy(fo_ctx* c) {
     for (auto& kv : c->staged) cudaFree(kv.second.d);
     for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    for (int g = 1; g < fo_ctx::MAX_GROUPS; ++g) {
+        if (c->grp_stream[g]) cudaStreamDestroy(c->grp_stream[g]);
+        if (c->ev_join[g]) cudaEventDestroy(c->ev_join[g]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (void* p : c->owned) if (p) cudaFree(p);
     for (int k = 0; k < fo_ctx::NSTAGE; ++k) {
         if (c->ids_host[k]) cudaFreeHost(c->ids_host[k]);
@@ -745,10 +837,12 @@ int fo_finalize_weights(fo_ctx* c) {
     FO_CUDA(cudaSetDevice(c->device));
     if (c->dtype == FO_BF16) {
         FO_TRY(gemm_tc_init());
-        FO_TRY(gemm_tc_workspace(&c->tc_ws));
-        c->owned.push_back(c->tc_ws.partial);
-        c->owned.push_back(c->tc_ws.counters);
-        c->device_bytes += (long long)c->tc_ws.partial_bytes;
+        for (int g = 0; g < fo_ctx::MAX_GROUPS; ++g) {
+            FO_TRY(gemm_tc_workspace(&c->tc_wsg[g]));
+            c->owned.push_back(c->tc_wsg[g].partial);
+            c->owned.push_back(c->tc_wsg[g].counters);
+            c->device_bytes += (long long)c->tc_wsg[g].partial_bytes;
+        }
     }
     return c->dtype == FO_BF16 ? finalize_t<bf16>(c) : finalize_t<float>(c);
 }
@@ -1011,8 +1105,8 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     char key[96];
     uint32_t sbits;
     memcpy(&sbits, &a.scale, 4);
-    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%08x/%d", a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
-             c->gemm_backend);
+    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%08x/%d/%d/%d", a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
+             c->gemm_backend, c->groups, c->debug_skip * 2 + c->fuse_ln);
     fo_ctx::StepGraph& g = c->graphs[key];
     if (g.exec && g.epoch == c->ws_epoch) {
         FO_CUDA(cudaGraphLaunch(g.exec, st));
@@ -1187,6 +1281,12 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
         c->gemm_backend = (int)value;
     } else if (!strcmp(name, "use_graph")) c->use_graph = value != 0;
     else if (!strcmp(name, "split_k")) c->split_k = (int)value;
+    else if (!strcmp(name, "debug_skip")) c->debug_skip = (int)value;
+    else if (!strcmp(name, "fuse_ln")) c->fuse_ln = value != 0;
+    else if (!strcmp(name, "session_groups")) {
+        FO_CHECK(value >= 1 && value <= fo_ctx::MAX_GROUPS, "session_groups must be 1..%d", fo_ctx::MAX_GROUPS);
+        c->groups = (int)value;
+    }
     else if (!strcmp(name, "tc_swap")) { c->tc_tune.swap = (int)value; gemm_tc_force(c->tc_tune); }
     else if (!strcmp(name, "tc_bn")) { c->tc_tune.bn = (int)value; gemm_tc_force(c->tc_tune); }
     else if (!strcmp(name, "tc_split")) { c->tc_tune.split = (int)value; gemm_tc_force(c->tc_tune); }
@@ -1206,6 +1306,8 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     if (!strcmp(name, "gemm_backend")) *value = c->gemm_backend;
     else if (!strcmp(name, "use_graph")) *value = c->use_graph;
     else if (!strcmp(name, "split_k")) *value = c->split_k;
+    else if (!strcmp(name, "session_groups")) *value = c->groups;
+    else if (!strcmp(name, "fuse_ln")) *value = c->fuse_ln;
     else if (!strcmp(name, "profile_gemm_count")) *value = (int64_t)c->prof_events.size();
     else if (!strcmp(name, "profile_gemm_us")) {
         double us = 0.0;

@@ -60,7 +60,7 @@ template <> struct Chunk<bf16> {
 // scores of key row j (smem) against nq query rows; chunk order is rotated by j so that the 8 lanes of
 // one shared-memory phase touch 8 different 16-byte bank groups (rows are 128 B / 256 B apart).
 template <typename TA>
-__device__ __forceinline__ void score_row(const TA* Krow, const float* Prow, const float* qu, const float* qv, int nq,
+__device__ __forceinline__ void score_row(const TA* Krow, const TA* Prow, const float* qu, const float* qv, int nq,
                                           int rot, float (&acc)[TQ_MAX]) {
     constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
 #pragma unroll
@@ -70,11 +70,7 @@ __device__ __forceinline__ void score_row(const TA* Krow, const float* Prow, con
         const int cc = (c + rot) & (NCH - 1);
         float kv[EPC], pv[EPC];
         Chunk<TA>::load(Krow + cc * EPC, kv);
-#pragma unroll
-        for (int e = 0; e < EPC; e += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(Prow + cc * EPC + e);
-            pv[e] = t4.x; pv[e + 1] = t4.y; pv[e + 2] = t4.z; pv[e + 3] = t4.w;
-        }
+        Chunk<TA>::load(Prow + cc * EPC, pv);
 #pragma unroll
         for (int i = 0; i < TQ_MAX; ++i) {
             if (i < nq) {
@@ -101,23 +97,35 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Streaming chunk attention, one CTA per (session, head), 4 warps.  Steady state: 64 cached + 4 new keys, 4 queries.
+//   load   thread 0 starts the bulk copies of the ring's K/V rows (HBM -> smem, mbarrier); meanwhile every thread
+//          fetches its share of the chunk's own K/V rows (appended to the ring in the same pass), the rel-pos rows
+//          P_l[start + j] and Q, all issued before the first use so that one memory latency covers them
+//   score  warp = query row, lane = keys lane, lane+32, lane+64: ((q+u).K_j + (q+v).P_j)/8 with the 16-byte chunks
+//          of a row visited in a lane-rotated order (conflict-free); scores stay in registers
+//   soft   warp-shuffle max / sum in fp32, probabilities to a 1 KB smem strip
+//   PV     lane = output dims (2*lane, 2*lane+1), loop over the keys
+// smem rows are sized by window + t (68), not by the ring capacity, so 7 CTAs fit per SM and the 1024 CTAs of a
+// 64-session layer are ONE wave.
 template <typename TA>
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 7)
 attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* __restrict__ q32, TA* __restrict__ ring,
                         const float* __restrict__ ptab, const float* __restrict__ pos_u, const float* __restrict__ pos_v,
                         TA* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
     const int cap = a.ring_cap;
+    const int t = a.t, D = a.H * DK;
+    const int rows = a.window + t;                  // most keys a call can see
     TA* Ks = reinterpret_cast<TA*>(smem_raw);
-    TA* Vs = Ks + cap * DK;
-    float* Ps = reinterpret_cast<float*>(Vs + cap * DK);
-    float* qu = Ps + cap * DK;
-    float* qv = qu + TQ_MAX * DK;
-    float* prob = qv + TQ_MAX * DK;                 // TQ_MAX x cap
+    TA* Vs = Ks + rows * DK;
+    TA* Ps = Vs + rows * DK;                        // rel-pos rows, rounded from the fp32 table to the activation type
+    float* qu = reinterpret_cast<float*>(Ps + rows * DK);
+    float* qv = qu + t * DK;
+    float* prob = qv + t * DK;                      // t x rows
     __shared__ __align__(8) uint64_t bar;
 
     const int b = blockIdx.x, h = blockIdx.y;
-    const int t = a.t, D = a.H * DK;
     const int slot = a.ids[b];
     const int nf = a.n_frames[slot];
     const int cl = min(nf, a.window);
@@ -127,7 +135,7 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
     const int start = max(0, pe - a.full_chunk);     // attention.py:112-114
     TA* ringK = ring + (long long)slot * a.ring_slot_stride + (long long)h * cap * DK;
     TA* ringV = ringK + (long long)a.H * cap * DK;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (cl > 0 && tid == 0) {
         mbar_init(&bar, 1);
@@ -143,26 +151,85 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
             bulk_g2s(Vs + len1 * DK, ringV, len2 * rowb, &bar);
         }
     }
-    // the chunk's own K/V rows: QKV GEMM output -> shared + appended to the ring
-    constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
-    for (int i = tid; i < t * NCH * 2; i += ATT_THREADS) {
-        const int which = i / (t * NCH);             // 0: K, 1: V
-        const int r = (i / NCH) % t, c = i % NCH;
-        const TA* src = qkv + (long long)(b * t + r) * 3 * D + (which + 1) * D + h * DK + c * EPC;
-        uint4 val = *reinterpret_cast<const uint4*>(src);
-        TA* sdst = (which ? Vs : Ks) + (cl + r) * DK + c * EPC;
-        *reinterpret_cast<uint4*>(sdst) = val;
-        TA* gdst = (which ? ringV : ringK) + (long long)((nf + r) % cap) * DK + c * EPC;
-        *reinterpret_cast<uint4*>(gdst) = val;
+    // ---- loads into registers (no dependent use before they are all issued) ----
+    // (a) chunk's own K/V rows: t rows x NCH chunks x {K,V}
+    const int n_new = t * NCH * 2;
+    uint4 newv = make_uint4(0, 0, 0, 0);
+    int new_which = 0, new_r = 0, new_c = 0;
+    const bool has_new = tid < n_new;                // t <= 8, NCH <= 16: n_new <= 256 -> second slot below
+    if (has_new) {
+        new_which = tid / (t * NCH);
+        new_r = (tid / NCH) % t;
+        new_c = tid % NCH;
+        newv = *reinterpret_cast<const uint4*>(qkv + (long long)(b * t + new_r) * 3 * D + (new_which + 1) * D + h * DK + new_c * EPC);
     }
-    // rel-pos rows P_l[start + j], head slice (fp32 table)
-    for (int i = tid; i < nk * (DK / 4); i += ATT_THREADS) {
+    // (b) rel-pos rows, 4 floats per item
+    constexpr int PMAX = 9;                          // ceil(68 rows * 16 float4 / 128 threads)
+    float4 pv[PMAX];
+    const int n_p = nk * (DK / 4);
+#pragma unroll
+    for (int k = 0; k < PMAX; ++k) {
+        const int i = tid + k * ATT_THREADS;
+        if (i < n_p) {
+            const int j = i / (DK / 4), c = i % (DK / 4);
+            const int pos = min(start + j, a.pos_rows - 1);
+            pv[k] = *reinterpret_cast<const float4*>(ptab + (long long)pos * D + h * DK + c * 4);
+        }
+    }
+    // (c) Q + biases: t*64 floats, two per thread when t <= 4
+    float qreg[4], ureg[4], vreg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * ATT_THREADS;
+        if (i < t * DK) {
+            const int r = i / DK, d = i % DK;
+            qreg[k] = q32[(long long)(b * t + r) * 3 * D + h * DK + d];
+            ureg[k] = pos_u[h * DK + d];
+            vreg[k] = pos_v[h * DK + d];
+        }
+    }
+    // ---- registers -> smem / ring ----
+    if (has_new) {
+        TA* sdst = (new_which ? Vs : Ks) + (cl + new_r) * DK + new_c * EPC;
+        *reinterpret_cast<uint4*>(sdst) = newv;
+        TA* gdst = (new_which ? ringV : ringK) + (long long)((nf + new_r) % cap) * DK + new_c * EPC;
+        *reinterpret_cast<uint4*>(gdst) = newv;
+    }
+    for (int i = tid + ATT_THREADS; i < n_new; i += ATT_THREADS) {      // only when t*NCH*2 > 128 (fp32 context or t > 8)
+        const int which = i / (t * NCH), r = (i / NCH) % t, c = i % NCH;
+        const uint4 val = *reinterpret_cast<const uint4*>(qkv + (long long)(b * t + r) * 3 * D + (which + 1) * D + h * DK + c * EPC);
+        *reinterpret_cast<uint4*>((which ? Vs : Ks) + (cl + r) * DK + c * EPC) = val;
+        *reinterpret_cast<uint4*>((which ? ringV : ringK) + (long long)((nf + r) % cap) * DK + c * EPC) = val;
+    }
+#pragma unroll
+    for (int k = 0; k < PMAX; ++k) {
+        const int i = tid + k * ATT_THREADS;
+        if (i < n_p) {
+            const int j = i / (DK / 4), c = i % (DK / 4);
+            TA* d = Ps + j * DK + c * 4;
+            if (sizeof(TA) == 2) {
+                __align__(8) __nv_bfloat162 hh[2];
+                hh[0] = __floats2bfloat162_rn(pv[k].x, pv[k].y);
+                hh[1] = __floats2bfloat162_rn(pv[k].z, pv[k].w);
+                *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hh);
+            } else {
+                *reinterpret_cast<float4*>(d) = pv[k];
+            }
+        }
+    }
+    for (int i = tid + PMAX * ATT_THREADS; i < n_p; i += ATT_THREADS) {   // windows larger than the register budget
         const int j = i / (DK / 4), c = i % (DK / 4);
         const int pos = min(start + j, a.pos_rows - 1);
-        *reinterpret_cast<float4*>(Ps + j * DK + c * 4) =
-            *reinterpret_cast<const float4*>(ptab + (long long)pos * D + h * DK + c * 4);
+        const float4 v4 = *reinterpret_cast<const float4*>(ptab + (long long)pos * D + h * DK + c * 4);
+        TA* d = Ps + j * DK + c * 4;
+        d[0] = from_f<TA>(v4.x); d[1] = from_f<TA>(v4.y); d[2] = from_f<TA>(v4.z); d[3] = from_f<TA>(v4.w);
     }
-    for (int i = tid; i < t * DK; i += ATT_THREADS) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * ATT_THREADS;
+        if (i < t * DK) { qu[i] = qreg[k] + ureg[k]; qv[i] = qreg[k] + vreg[k]; }
+    }
+    for (int i = tid + 4 * ATT_THREADS; i < t * DK; i += ATT_THREADS) {
         const int r = i / DK, d = i % DK;
         const float q = q32[(long long)(b * t + r) * 3 * D + h * DK + d];
         qu[i] = q + pos_u[h * DK + d];
@@ -171,40 +238,86 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
     __syncthreads();
     if (cl > 0) mbar_wait(&bar, 0);
 
-    // scores: one key per thread
-    for (int j = tid; j < nk; j += ATT_THREADS) {
-        float acc[TQ_MAX];
-        score_row<TA>(Ks + j * DK, Ps + j * DK, qu, qv, t, j, acc);
-#pragma unroll
-        for (int i = 0; i < TQ_MAX; ++i)
-            if (i < t) prob[i * cap + j] = acc[i] * 0.125f;
-    }
-    __syncthreads();
-    // softmax + PV: one warp per query row
-    const int warp = tid >> 5, lane = tid & 31;
+    // ---- scores + softmax + PV: warp = query row ----
+    constexpr int KPL = 4;                                // keys per lane (<= 128 keys per call)
     for (int i = warp; i < t; i += ATT_THREADS / 32) {
-        float* pr = prob + i * cap;
-        float m = -INFINITY;
-        for (int j = lane; j < nk; j += 32) m = fmaxf(m, pr[j]);
-        m = warp_max(m);
-        float s = 0.f;
-        for (int j = lane; j < nk; j += 32) {
-            float e = __expf(pr[j] - m);
-            pr[j] = e;
-            s += e;
+        const float* qui = qu + i * DK;
+        const float* qvi = qv + i * DK;
+        float sc[KPL];
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) sc[k] = 0.f;
+#pragma unroll 2
+        for (int c = 0; c < NCH; ++c) {
+            const int cc = (c + lane) & (NCH - 1);
+            float au[EPC], av[EPC];
+#pragma unroll
+            for (int e = 0; e < EPC; e += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(qui + cc * EPC + e);
+                const float4 y = *reinterpret_cast<const float4*>(qvi + cc * EPC + e);
+                au[e] = x.x; au[e + 1] = x.y; au[e + 2] = x.z; au[e + 3] = x.w;
+                av[e] = y.x; av[e + 1] = y.y; av[e + 2] = y.z; av[e + 3] = y.w;
+            }
+#pragma unroll
+            for (int k = 0; k < KPL; ++k) {
+                const int j = lane + 32 * k;
+                if (j < nk) {
+                    float kv[EPC], pp[EPC];
+                    Chunk<TA>::load(Ks + j * DK + cc * EPC, kv);
+                    Chunk<TA>::load(Ps + j * DK + cc * EPC, pp);
+                    float s = sc[k];
+#pragma unroll
+                    for (int e = 0; e < EPC; ++e) s = fmaf(au[e], kv[e], fmaf(av[e], pp[e], s));
+                    sc[k] = s;
+                }
+            }
         }
-        s = warp_sum(s);
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            sc[k] = (lane + 32 * k < nk) ? sc[k] * 0.125f : -INFINITY;
+            m = fmaxf(m, sc[k]);
+        }
+        m = warp_max(m);
+        float ssum = 0.f;
+        float* pr = prob + i * rows;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            const int j = lane + 32 * k;
+            if (j < nk) {
+                const float e = __expf(sc[k] - m);
+                pr[j] = e;
+                ssum += e;
+            }
+        }
+        for (int j = lane + 32 * KPL; j < nk; j += 32) pr[j] = 0.f;      // unreachable for nk <= 128 (checked on the host)
+        ssum = warp_sum(ssum);
         __syncwarp();
-        const float inv = 1.f / s;
+        const float inv = 1.f / ssum;
         float o0 = 0.f, o1 = 0.f;
-        for (int j = 0; j < nk; ++j) {
-            const float p = pr[j];
-            o0 = fmaf(p, to_f(Vs[j * DK + 2 * lane]), o0);
-            o1 = fmaf(p, to_f(Vs[j * DK + 2 * lane + 1]), o1);
+        if (sizeof(TA) == 2) {
+            const __nv_bfloat162* vp = reinterpret_cast<const __nv_bfloat162*>(Vs) + lane;
+#pragma unroll 4
+            for (int j = 0; j < nk; ++j) {
+                const float p = pr[j];
+                const float2 vv = __bfloat1622float2(vp[j * (DK / 2)]);
+                o0 = fmaf(p, vv.x, o0);
+                o1 = fmaf(p, vv.y, o1);
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < nk; ++j) {
+                const float p = pr[j];
+                o0 = fmaf(p, to_f(Vs[j * DK + 2 * lane]), o0);
+                o1 = fmaf(p, to_f(Vs[j * DK + 2 * lane + 1]), o1);
+            }
         }
         TA* o = out + (long long)(b * t + i) * D + h * DK + 2 * lane;
-        o[0] = from_f<TA>(o0 * inv);
-        o[1] = from_f<TA>(o1 * inv);
+        if (sizeof(TA) == 2) {
+            *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+        } else {
+            o[0] = from_f<TA>(o0 * inv);
+            o[1] = from_f<TA>(o1 * inv);
+        }
     }
 }
 
@@ -220,8 +333,8 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TA* Ks = reinterpret_cast<TA*>(smem_raw);
     TA* Vs = Ks + KT * DK;
-    float* Ps = reinterpret_cast<float*>(Vs + KT * DK);
-    float* qu = Ps + KT * DK;
+    TA* Ps = Vs + KT * DK;
+    float* qu = reinterpret_cast<float*>(Ps + KT * DK);
     float* qv = qu + TQ_MAX * DK;
     float* sc = qv + TQ_MAX * DK;                    // QB x KT
     __shared__ int win[QB][2];
@@ -268,8 +381,9 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
         }
         for (int i = tid; i < nk * (DK / 4); i += ATT_THREADS) {
             const int j = i / (DK / 4), c = i % (DK / 4);
-            *reinterpret_cast<float4*>(Ps + j * DK + c * 4) =
-                *reinterpret_cast<const float4*>(ptab + (long long)(kt + j) * D + h * DK + c * 4);
+            const float4 v4 = *reinterpret_cast<const float4*>(ptab + (long long)(kt + j) * D + h * DK + c * 4);
+            TA* d = Ps + j * DK + c * 4;
+            d[0] = from_f<TA>(v4.x); d[1] = from_f<TA>(v4.y); d[2] = from_f<TA>(v4.z); d[3] = from_f<TA>(v4.w);
         }
         __syncthreads();
         for (int j = tid; j < nk; j += ATT_THREADS) {
@@ -341,8 +455,10 @@ int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* r
     if (a.n <= 0) return 0;
     FO_CHECK(a.t <= TQ_MAX, "attention_stream: %d frames per call exceeds %d", a.t, TQ_MAX);
     FO_CHECK(a.ring_cap >= a.window + a.t, "attention_stream: ring capacity %d < window %d + %d", a.ring_cap, a.window, a.t);
-    const size_t smem = (size_t)2 * a.ring_cap * DK * sizeof(TA) + (size_t)a.ring_cap * DK * sizeof(float) +
-                        (size_t)2 * TQ_MAX * DK * sizeof(float) + (size_t)TQ_MAX * a.ring_cap * sizeof(float);
+    const int rows = a.window + a.t;
+    FO_CHECK(rows <= 128, "attention_stream: window + frames per call (%d) exceeds 128 keys", rows);
+    const size_t smem = (size_t)3 * rows * DK * sizeof(TA) + (size_t)2 * a.t * DK * sizeof(float) +
+                        (size_t)a.t * rows * sizeof(float);
     static bool attr_set[2] = {false, false};
     if (!attr_set[sizeof(TA) == 2]) {
         FO_CUDA(cudaFuncSetAttribute(attention_stream_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -363,8 +479,8 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
                       const float* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
     if (B <= 0 || T <= 0) return 0;
     dim3 grid(cdiv(T, QB), H, B);
-    const size_t smem = (size_t)2 * KT * DK * sizeof(TA) + (size_t)KT * DK * sizeof(float) +
-                        (size_t)2 * TQ_MAX * DK * sizeof(float) + (size_t)QB * KT * sizeof(float);
+    const size_t smem = (size_t)3 * KT * DK * sizeof(TA) + (size_t)2 * TQ_MAX * DK * sizeof(float) +
+                        (size_t)QB * KT * sizeof(float);
     static bool attr_set[2] = {false, false};
     if (!attr_set[sizeof(TA) == 2]) {
         FO_CUDA(cudaFuncSetAttribute(attention_offline_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

@@ -87,6 +87,16 @@ struct Epilogue {
     int relu = 0;
     float scale = 1.0f;
     int split_col = 0;                // > 0: columns < split_col go to c_f32 only, columns >= split_col to c_act only
+    // Fused LayerNorm of the finished rows of c_f32 (the residual stream; requires N == ldc): the CTA that completes a
+    // block of rows (last of the column tiles to arrive on the block's counter) normalises those rows and writes them
+    // as the activation type (ln_act) and/or fp32 (ln_f32).  tcgen05 kernel only; gemm_ln() in fo_api.cu launches the
+    // stand-alone kernel on the other paths.
+    const float* ln_gamma = nullptr;
+    const float* ln_beta = nullptr;
+    float ln_eps = 1e-5f;
+    void* ln_act = nullptr;
+    float* ln_f32 = nullptr;
+    int* ln_counters = nullptr;
 };
 
 // C[rowmap(m), n] = A[m, :] . W[n, :]  for m < M (padded GEMM rows), n < N.  A/W are TIn (float or bf16),
@@ -100,7 +110,8 @@ int gemm_simt(const TIn* A, const AGather& ga, const TIn* W, int M, int N, int K
 struct TcWorkspace {
     float* partial = nullptr;
     size_t partial_bytes = 0;
-    int* counters = nullptr;
+    int* counters = nullptr;       // split-K arrivals per output tile
+    int* ln_counters = nullptr;    // fused-LayerNorm arrivals per row block
 };
 struct TcTune { int swap, bn, split; };      // -1 / 0 = let the cost model decide
 int gemm_tc_init();

@@ -155,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __shared__ __align__(8) uint64_t acc_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int is_last_s;
+    __shared__ int ln_last_s;
     __shared__ int s_plane[2][AGather::MAX_SEG + 1], s_rowoff[2][AGather::MAX_SEG + 1];
     __shared__ int s_drow[256];              // output row of each tile row (swap=0) / tile column (swap=1); -1 = dropped
 
@@ -370,6 +371,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     }
     if (threadIdx.x == 64) TC_TRACE(10);
+    // ---- fused LayerNorm over the rows this CTA completed last ----
+    if (p.ep.ln_gamma != nullptr && is_last_s) {
+        const Epilogue& ep = p.ep;
+        __threadfence();                                       // this CTA's C stores before its arrival
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int rb = p.swap ? tile_b : tile_a;
+            const int total = p.swap ? gridDim.x : gridDim.y;  // column tiles covering a row block
+            const int prev = atomicAdd(ep.ln_counters + rb, 1);
+            ln_last_s = prev == total - 1;
+            if (ln_last_s) ep.ln_counters[rb] = 0;
+        }
+        __syncthreads();
+        if (ln_last_s) {
+            __threadfence();
+            const int n_rows = p.swap ? bn : BM;
+            const int N = p.n_out;
+            const int nv = N >> 7;                             // float4 per lane (N is a multiple of 128, <= 4096)
+            for (int r = warp; r < n_rows; r += TC_THREADS / 32) {
+                const int drow = s_drow[r];
+                if (drow < 0) continue;
+                const float4* xr = reinterpret_cast<const float4*>(ep.c_f32 + (long long)drow * ep.ldc);
+                float4 v[8];
+                float sum = 0.f;
+                for (int base_i = 0; base_i < nv; base_i += 8) {   // one pass for N <= 1024
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (base_i + i < nv) {
+                            v[i] = __ldcg(xr + (base_i + i) * 32 + lane);
+                            sum += v[i].x + v[i].y + v[i].z + v[i].w;
+                        }
+                }
+                float tot = sum;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                const float mu = tot / N;
+                float q = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < nv) {
+                        const float a0 = v[i].x - mu, a1 = v[i].y - mu, a2 = v[i].z - mu, a3 = v[i].w - mu;
+                        q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                const float rstd = rsqrtf(q / N + ep.ln_eps);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < nv) {
+                        const int col = (i * 32 + lane) * 4;
+                        const float4 g = *reinterpret_cast<const float4*>(ep.ln_gamma + col);
+                        const float4 bt = *reinterpret_cast<const float4*>(ep.ln_beta + col);
+                        const float o0 = (v[i].x - mu) * rstd * g.x + bt.x, o1 = (v[i].y - mu) * rstd * g.y + bt.y;
+                        const float o2 = (v[i].z - mu) * rstd * g.z + bt.z, o3 = (v[i].w - mu) * rstd * g.w + bt.w;
+                        const long long off = (long long)drow * ep.ldc + col;
+                        if (ep.ln_f32) *reinterpret_cast<float4*>(ep.ln_f32 + off) = make_float4(o0, o1, o2, o3);
+                        if (ep.ln_act) {
+                            __align__(8) __nv_bfloat162 hh[2];
+                            hh[0] = __floats2bfloat162_rn(o0, o1);
+                            hh[1] = __floats2bfloat162_rn(o2, o3);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.ln_act) + off) = *reinterpret_cast<const uint2*>(hh);
+                        }
+                    }
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -475,6 +542,8 @@ int gemm_tc_init() {
 int gemm_tc_workspace(TcWorkspace* ws) {
     FO_CUDA(cudaMalloc(&ws->counters, MAX_TILES * sizeof(int)));
     FO_CUDA(cudaMemset(ws->counters, 0, MAX_TILES * sizeof(int)));
+    FO_CUDA(cudaMalloc(&ws->ln_counters, MAX_TILES * sizeof(int)));
+    FO_CUDA(cudaMemset(ws->ln_counters, 0, MAX_TILES * sizeof(int)));
     ws->partial_bytes = 96ull << 20;
     FO_CUDA(cudaMalloc(&ws->partial, ws->partial_bytes));
     return 0;
@@ -515,7 +584,12 @@ int gemm_tc(const bf16* A, const AGather& ga, const bf16* W, int M, int N, int K
     p.swap = pl.swap;
     const uint32_t stage = (BM + pl.bn) * BK * 2;
     p.stages = std::max(1, std::min<int>(std::min(MAX_STAGES, kbs), (int)(SMEM_BUDGET / stage)));
-    if ((long long)ta * tb * pl.split > g_sm_count) {
+    if (M <= 384) {
+        // skinny GEMMs: ~100 KB in flight per CTA covers the L2 latency; staying under half of the shared memory lets a
+        // second CTA (another session group's GEMM, or the next kernel's first wave) be resident on the same SM
+        const int cap = (int)((100 * 1024) / stage);
+        if (cap >= 3) p.stages = std::min(p.stages, cap);
+    } else if ((long long)ta * tb * pl.split > g_sm_count) {
         // more CTAs than SMs: keep two resident per SM (<= ~110 KB each) so one CTA's epilogue overlaps the other's mainloop
         const int cap = (int)((110 * 1024) / stage);
         if (cap >= 3) p.stages = std::min(p.stages, cap);
@@ -532,6 +606,10 @@ int gemm_tc(const bf16* A, const AGather& ga, const bf16* W, int M, int N, int K
     p.op_b = pl.swap ? act : wgt;
     p.rmap = rmap;
     p.ep = ep;
+    if (ep.ln_gamma) {
+        if (N != ep.ldc || N % 128 != 0 || N > 1024 || !ep.c_f32 || ep.split_col) return 1;   // caller runs the stand-alone kernel
+        p.ep.ln_counters = ws.ln_counters;
+    }
     p.n_out = N;
     p.partial = ws.partial;
     p.counters = ws.counters;

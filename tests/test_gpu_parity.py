@@ -438,6 +438,48 @@ def test_graph_replay_matches_eager(which, request):
         eng.free(ids)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_session_groups_match_single_group(dtype):
+    """Layer kernels of different session groups run on parallel streams; the result must not depend on the
+    grouping (bit-identical in fp32, where the GEMM summation order does not depend on the row count)."""
+    cfg, eng = make_engine("tiny", 3, dtype=dtype, max_sessions=48)
+    g = torch.Generator().manual_seed(21)
+    try:
+        ids_a, ids_b = eng.alloc(24), eng.alloc(24)
+        for i in range(4):
+            pcm = (0.05 * torch.randn(24, cfg.samples_per_chunk, generator=g) * 32768).round().to(torch.int16)
+            eng.set_option("session_groups", 1)
+            e1, y1 = eng.stream_step(ids_a, pcm, 1.0)
+            eng.set_option("session_groups", 3)
+            e3, y3 = eng.stream_step(ids_b, pcm, 1.0)
+            if dtype == torch.float32:
+                assert torch.equal(e1, e3) and torch.equal(y1, y3), i
+            else:
+                assert maxabs(e1.cpu(), e3.cpu()) < 1e-3 and maxabs(y1.cpu(), y3.cpu()) < 1e-3, i
+        assert eng.state(int(ids_a[5])) == eng.state(int(ids_b[5]))
+    finally:
+        eng.close()
+
+
+def test_fused_layernorm_matches_standalone(shipped16):
+    """LayerNorm fused into the epilogue of the GEMM that completes the residual rows (last-arriving CTA of a row
+    block) must be bit-identical to the stand-alone kernel."""
+    cfg, eng = shipped16
+    g = torch.Generator().manual_seed(31)
+    ids = eng.alloc(2)
+    try:
+        for i in range(3):
+            pcm = (0.05 * torch.randn(1, cfg.samples_per_chunk, generator=g) * 32768).round().to(torch.int16)
+            eng.set_option("fuse_ln", 1)
+            e1, y1 = eng.stream_step(ids[:1], pcm, 1.0)
+            eng.set_option("fuse_ln", 0)
+            e0, y0 = eng.stream_step(ids[1:], pcm, 1.0)
+            assert torch.equal(e1, e0) and torch.equal(y1, y0), i
+    finally:
+        eng.set_option("fuse_ln", 0)
+        eng.free(ids)
+
+
 def test_tcgen05_gemm_tile_plans(shipped16):
     """Every orientation / UMMA-N / split-K plan of the tcgen05 kernel against an fp64 product of the
     same bf16 operands; checks the kernel really launched (no silent FFMA fallback)."""

@@ -28,7 +28,7 @@ def main():
         A = torch.randn(M, K, generator=g).cuda()
         W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
         rows = []
-        plans = [(-1, -1, -1)] + list(itertools.product((0, 1), (16, 32, 64, 128, 144, 256), (1, 2, 4, 8)))
+        plans = [(-1, -1, -1), (-1, -1, -1)] + list(itertools.product((0, 1), (16, 32, 64, 128, 144, 256), (1, 2, 4, 8)))
         for (swap, bn, split) in plans:
             if swap == 1 and bn > ((M + 15) // 16) * 16 and bn != 16:
                 continue
@@ -43,7 +43,8 @@ def main():
                 print("fail", (M, N, K), (swap, bn, split), str(ex)[:100])
                 continue
             rows.append((ms * 1e3, swap, bn, split))
-        auto = rows[0]
+        auto = min(rows[0], rows[1])
+        print("auto runs", rows[0], rows[1])
         rows.sort()
         print(json.dumps({"shape": [M, N, K], "auto_us": round(auto[0], 2), "best": [[round(r[0], 2), r[1], r[2], r[3]] for r in rows[:6]],
                           "tflops_best": round(2.0 * M * N * K / rows[0][0] / 1e6, 1),
