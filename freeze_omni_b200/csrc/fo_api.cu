@@ -225,20 +225,20 @@ template <>
 int gemm_raw<float>(fo_ctx* c, const float* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
                     const RowMap& rm, cudaStream_t st, bool* fused_ln) {
     *fused_ln = false;
-    return gemm_simt<float>(A, ga, reinterpret_cast<const float*>(W), M, N, K, ep, rm, st);
+    return gemm_simt<float, float>(A, ga, reinterpret_cast<const float*>(W), M, N, K, ep, rm, st);
 }
 template <>
-int gemm_raw<bf16>(fo_ctx* c, const bf16* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-                   const RowMap& rm, cudaStream_t st, bool* fused_ln) {
+int gemm_raw<act16>(fo_ctx* c, const act16* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+                    const RowMap& rm, cudaStream_t st, bool* fused_ln) {
     *fused_ln = false;
     if (c->gemm_backend == 1) {
         Epilogue e = ep;
         if (!c->fuse_ln) e.ln_gamma = nullptr;
-        int r = gemm_tc(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, e, rm, *c->tc_cur, st);
+        int r = gemm_tc(A, 1, ga, W, M, N, K, e, rm, *c->tc_cur, st);
         if (r == 0) *fused_ln = e.ln_gamma != nullptr;
         if (r <= 0) return r;
     }
-    return gemm_simt<bf16>(A, ga, reinterpret_cast<const bf16*>(W), M, N, K, ep, rm, st);
+    return gemm_simt<act16, act16>(A, ga, reinterpret_cast<const act16*>(W), M, N, K, ep, rm, st);
 }
 template <typename TA>
 int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
@@ -392,7 +392,7 @@ int finalize_t(fo_ctx* c) {
                 Epilogue ep;
                 ep.c_f32 = w.ptab;
                 ep.ldc = D;
-                r = gemm_simt<float>(pe->d, plain_rows(D, c->pos_rows), wpos, c->pos_rows, D, D, ep, RowMap(), 0);
+                r = gemm_simt<float, float>(pe->d, plain_rows(D, c->pos_rows), wpos, c->pos_rows, D, D, ep, RowMap(), 0);
             }
             cudaDeviceSynchronize();
             cudaFree(wpos);
@@ -844,7 +844,7 @@ int fo_finalize_weights(fo_ctx* c) {
             c->device_bytes += (long long)c->tc_wsg[g].partial_bytes;
         }
     }
-    return c->dtype == FO_BF16 ? finalize_t<bf16>(c) : finalize_t<float>(c);
+    return c->dtype == FO_BF16 ? finalize_t<act16>(c) : finalize_t<float>(c);
 }
 
 // ---- sessions ------------------------------------------------------------------------------------
@@ -958,8 +958,8 @@ int fo_session_export_kv(fo_ctx* c, int32_t id, int layer, float* K, float* V, i
     FO_TRY(out_dev(c, K, bytes, WS_TMP0, &dk));
     FO_TRY(out_dev(c, V, bytes, WS_TMP1, &dv));
     if (c->dtype == FO_BF16) {
-        FO_TRY(ring_export<bf16>((bf16*)k, c->H, c->ring_cap, nf - cl, cl, (float*)dk, 0));
-        FO_TRY(ring_export<bf16>((bf16*)v, c->H, c->ring_cap, nf - cl, cl, (float*)dv, 0));
+        FO_TRY(ring_export<act16>((act16*)k, c->H, c->ring_cap, nf - cl, cl, (float*)dk, 0));
+        FO_TRY(ring_export<act16>((act16*)v, c->H, c->ring_cap, nf - cl, cl, (float*)dv, 0));
     } else {
         FO_TRY(ring_export<float>((float*)k, c->H, c->ring_cap, nf - cl, cl, (float*)dk, 0));
         FO_TRY(ring_export<float>((float*)v, c->H, c->ring_cap, nf - cl, cl, (float*)dv, 0));
@@ -982,8 +982,8 @@ int fo_session_import_kv(fo_ctx* c, int32_t id, int layer, const float* K, const
     FO_TRY(in_dev(c, K, bytes, WS_TMP0, 0, &dk));
     FO_TRY(in_dev(c, V, bytes, WS_TMP1, 0, &dv));
     if (c->dtype == FO_BF16) {
-        FO_TRY(ring_import<bf16>((bf16*)k, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dk, 0));
-        FO_TRY(ring_import<bf16>((bf16*)v, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dv, 0));
+        FO_TRY(ring_import<act16>((act16*)k, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dk, 0));
+        FO_TRY(ring_import<act16>((act16*)v, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dv, 0));
     } else {
         FO_TRY(ring_import<float>((float*)k, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dk, 0));
         FO_TRY(ring_import<float>((float*)v, c->H, c->ring_cap, nf - cache_len, cache_len, (const float*)dv, 0));
@@ -1096,7 +1096,7 @@ static int step_body(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
         FO_TRY(fbank_stream(fbank_params(c), c->ids_dev, a.n, dp, a.pcm_is_i16, a.scale, c->cfg.frames_per_chunk,
                             c->cfg.context_frames, c->samples, c->feat_ring, (float*)dfeats, st));
     }
-    return c->dtype == FO_BF16 ? stream_program<bf16>(c, a.n, (const float*)dfeats, a.t_in, (float*)denc, (float*)dy, st)
+    return c->dtype == FO_BF16 ? stream_program<act16>(c, a.n, (const float*)dfeats, a.t_in, (float*)denc, (float*)dy, st)
                                : stream_program<float>(c, a.n, (const float*)dfeats, a.t_in, (float*)denc, (float*)dy, st);
 }
 
@@ -1220,7 +1220,7 @@ int fo_encode_offline(fo_ctx* c, const float* feats, const int32_t* ilens, int B
     if (adapter_out || adapter_mask_out) FO_CHECK(c->cfg.has_adapter, "adapter outputs requested but the context has no adapter");
     if (adapter_out) FO_TRY(out_dev(c, adapter_out, y_bytes, WS_Y, &dy));
     int r = c->dtype == FO_BF16
-                ? offline_program<bf16>(c, (const float*)dfeats, (const int32_t*)dil, B, T, chunk, left, (float*)denc,
+                ? offline_program<act16>(c, (const float*)dfeats, (const int32_t*)dil, B, T, chunk, left, (float*)denc,
                                         (uint8_t*)dmask, (int32_t*)dil2, (float*)dy, st)
                 : offline_program<float>(c, (const float*)dfeats, (const int32_t*)dil, B, T, chunk, left, (float*)denc,
                                          (uint8_t*)dmask, (int32_t*)dil2, (float*)dy, st);
@@ -1256,7 +1256,7 @@ int fo_adapter_forward(fo_ctx* c, const float* x, const uint8_t* mask, int B, in
     const size_t y_bytes = (size_t)B * t_out * c->E * sizeof(float);
     FO_TRY(out_dev(c, y, y_bytes, WS_Y, &dy));
     int r = c->dtype == FO_BF16
-                ? adapter_program<bf16>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, (const float*)dci, (float*)dco, (float*)dy, st)
+                ? adapter_program<act16>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, (const float*)dci, (float*)dco, (float*)dy, st)
                 : adapter_program<float>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, (const float*)dci, (float*)dco, (float*)dy, st);
     FO_TRY(r);
     if (cache_out) FO_TRY(out_done(cache_out, dco, cbytes, st));
@@ -1348,14 +1348,14 @@ int fo_debug_gemm(fo_ctx* c, const float* A, const float* W, const float* bias, 
         void *a16, *w16;
         FO_TRY(ws_ensure(c, WS_TMP2, (size_t)M * K * 2, &a16));
         FO_TRY(ws_ensure(c, WS_TMP3, (size_t)N * K * 2, &w16));
-        FO_TRY(f32_to_bf16(A, (bf16*)a16, (long long)M * K, st));
-        FO_TRY(f32_to_bf16(W, (bf16*)w16, (long long)N * K, st));
+        FO_TRY(f32_to_act16(A, (act16*)a16, (long long)M * K, st));
+        FO_TRY(f32_to_weight16(W, (act16*)w16, (long long)N * K, st));
         pa = a16;
         pw = w16;
     }
     c->gemm_backend = backend;
     auto one = [&](cudaStream_t s) {
-        return c->dtype == FO_BF16 ? gemm<bf16>(c, (const bf16*)pa, pw, M, N, K, ep, s) : gemm<float>(c, (const float*)pa, pw, M, N, K, ep, s);
+        return c->dtype == FO_BF16 ? gemm<act16>(c, (const act16*)pa, pw, M, N, K, ep, s) : gemm<float>(c, (const float*)pa, pw, M, N, K, ep, s);
     };
     r = one(st);
     if (r == 0 && iters > 0) {

@@ -47,6 +47,15 @@ template <> struct Chunk<float> {
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
 };
+template <> struct Chunk<__half> {
+    static constexpr int EPC = 8, NCH = 8;
+    static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
+};
 template <> struct Chunk<bf16> {
     static constexpr int EPC = 8, NCH = 8;
     static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
@@ -207,11 +216,11 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
         if (i < n_p) {
             const int j = i / (DK / 4), c = i % (DK / 4);
             TA* d = Ps + j * DK + c * 4;
-            if (sizeof(TA) == 2) {
-                __align__(8) __nv_bfloat162 hh[2];
-                hh[0] = __floats2bfloat162_rn(pv[k].x, pv[k].y);
-                hh[1] = __floats2bfloat162_rn(pv[k].z, pv[k].w);
-                *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(hh);
+            if constexpr (sizeof(TA) == 2) {
+                uint2 hh;
+                hh.x = pack2<TA>(pv[k].x, pv[k].y);
+                hh.y = pack2<TA>(pv[k].z, pv[k].w);
+                *reinterpret_cast<uint2*>(d) = hh;
             } else {
                 *reinterpret_cast<float4*>(d) = pv[k];
             }
@@ -294,12 +303,12 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
         __syncwarp();
         const float inv = 1.f / ssum;
         float o0 = 0.f, o1 = 0.f;
-        if (sizeof(TA) == 2) {
-            const __nv_bfloat162* vp = reinterpret_cast<const __nv_bfloat162*>(Vs) + lane;
+        if constexpr (sizeof(TA) == 2) {
+            const uint32_t* vp = reinterpret_cast<const uint32_t*>(Vs) + lane;
 #pragma unroll 4
             for (int j = 0; j < nk; ++j) {
                 const float p = pr[j];
-                const float2 vv = __bfloat1622float2(vp[j * (DK / 2)]);
+                const float2 vv = unpack2<TA>(vp[j * (DK / 2)]);
                 o0 = fmaf(p, vv.x, o0);
                 o1 = fmaf(p, vv.y, o1);
             }
@@ -312,8 +321,8 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
             }
         }
         TA* o = out + (long long)(b * t + i) * D + h * DK + 2 * lane;
-        if (sizeof(TA) == 2) {
-            *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+        if constexpr (sizeof(TA) == 2) {
+            *reinterpret_cast<uint32_t*>(o) = pack2<TA>(o0 * inv, o1 * inv);
         } else {
             o[0] = from_f<TA>(o0 * inv);
             o[1] = from_f<TA>(o1 * inv);
@@ -473,6 +482,7 @@ int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* r
 }
 template int attention_stream<float>(const AttnStream&, const float*, const float*, float*, const float*, const float*, const float*, float*, cudaStream_t);
 template int attention_stream<bf16>(const AttnStream&, const bf16*, const float*, bf16*, const float*, const float*, const float*, bf16*, cudaStream_t);
+template int attention_stream<__half>(const AttnStream&, const __half*, const float*, __half*, const float*, const float*, const float*, __half*, cudaStream_t);
 
 template <typename TA>
 int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,
@@ -493,6 +503,7 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
 }
 template int attention_offline<float>(const float*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, float*, cudaStream_t);
 template int attention_offline<bf16>(const bf16*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, bf16*, cudaStream_t);
+template int attention_offline<__half>(const __half*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, __half*, cudaStream_t);
 
 int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,
                       int32_t* pe_index, int32_t* adapter_valid, cudaStream_t st) {

@@ -199,6 +199,10 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = __float2bfloat16_rn(s[i]);
 }
+__global__ void f32_to_act16_kernel(const float* __restrict__ s, act16* __restrict__ d, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = from_f<act16>(s[i]);
+}
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ s, float* __restrict__ d, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = __bfloat162float(s[i]);
@@ -213,7 +217,7 @@ __global__ void repack_conv2_kernel(const float* __restrict__ w, int C, TW* __re
     int ci = i % C;
     int q = (i / C) % 9;
     int co = i / (9LL * C);
-    out[i] = from_f<TW>(w[((long long)co * C + ci) * 9 + q]);
+    out[i] = weight_cast<TW>(w[((long long)co * C + ci) * 9 + q]);
 }
 template <typename TW>
 __global__ void repack_sublinear_kernel(const float* __restrict__ w, int C, int F2, long long N, TW* __restrict__ out) {
@@ -224,7 +228,7 @@ __global__ void repack_sublinear_kernel(const float* __restrict__ w, int C, int 
     long long n = i / K;
     int k = i % K;
     int f = k / C, c = k % C;
-    out[i] = from_f<TW>(w[n * K + (long long)c * F2 + f]);
+    out[i] = weight_cast<TW>(w[n * K + (long long)c * F2 + f]);
 }
 template <typename TW>
 __global__ void repack_adapter_conv_kernel(const float* __restrict__ w, int C2, int C, int k, TW* __restrict__ out) {
@@ -235,12 +239,12 @@ __global__ void repack_adapter_conv_kernel(const float* __restrict__ w, int C2, 
     int ci = i % C;
     int tau = (i / C) % k;
     long long co = i / ((long long)C * k);
-    out[i] = from_f<TW>(w[(co * C + ci) * k + tau]);
+    out[i] = weight_cast<TW>(w[(co * C + ci) * k + tau]);
 }
 template <typename TW>
 __global__ void convert_weight_kernel(const float* __restrict__ w, long long n, TW* __restrict__ out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = from_f<TW>(w[i]);
+    if (i < n) out[i] = weight_cast<TW>(w[i]);
 }
 
 template <typename TA>
@@ -302,6 +306,7 @@ void adapter_gather(int B, int T, int D, int k, AGather* ga, RowMap* rm) {
 
 template int cmvn_conv1<float>(const float*, int, int, int, const float*, const float*, const float*, const float*, int, float*, cudaStream_t);
 template int cmvn_conv1<bf16>(const float*, int, int, int, const float*, const float*, const float*, const float*, int, bf16*, cudaStream_t);
+template int cmvn_conv1<__half>(const float*, int, int, int, const float*, const float*, const float*, const float*, int, __half*, cudaStream_t);
 
 template <typename TA>
 int layer_norm(const float* x, int M, int D, const float* gamma, const float* beta, float eps, int act,
@@ -320,6 +325,7 @@ int layer_norm(const float* x, int M, int D, const float* gamma, const float* be
 }
 template int layer_norm<float>(const float*, int, int, const float*, const float*, float, int, float, float*, float*, cudaStream_t);
 template int layer_norm<bf16>(const float*, int, int, const float*, const float*, float, int, float, bf16*, float*, cudaStream_t);
+template int layer_norm<__half>(const float*, int, int, const float*, const float*, float, int, float, __half*, float*, cudaStream_t);
 
 int scale_rows(const float* x, float* y, long long n, float s, cudaStream_t st) {
     if (n <= 0) return 0;
@@ -343,6 +349,7 @@ int adapter_stage(const float* enc_out, const uint8_t* mask, int B, int T, int D
 }
 template int adapter_stage<float>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, float*, cudaStream_t);
 template int adapter_stage<bf16>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, bf16*, cudaStream_t);
+template int adapter_stage<__half>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, __half*, cudaStream_t);
 
 int subsample_mask(const int32_t* ilens, int B, int T, int T2, uint8_t* mask2, int32_t* ilens2, cudaStream_t st) {
     if (B <= 0) return 0;
@@ -366,6 +373,14 @@ int f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t st) {
     FO_CUDA(cudaGetLastError());
     return 0;
 }
+int f32_to_act16(const float* src, act16* dst, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    f32_to_act16_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, dst, n);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+int f32_to_weight16(const float* src, act16* dst, long long n, cudaStream_t st) { return convert_weight<act16>(src, n, dst, st); }
 int bf16_to_f32(const bf16* src, float* dst, long long n, cudaStream_t st) {
     if (n <= 0) return 0;
     bf16_to_f32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(src, dst, n);
@@ -404,6 +419,10 @@ int convert_weight(const float* w, long long n, TW* out, cudaStream_t st) {
 }
 template int repack_conv2<float>(const float*, int, float*, cudaStream_t);
 template int repack_conv2<bf16>(const float*, int, bf16*, cudaStream_t);
+template int repack_conv2<__half>(const float*, int, __half*, cudaStream_t);
+template int repack_sublinear<__half>(const float*, int, int, __half*, cudaStream_t);
+template int repack_adapter_conv<__half>(const float*, int, int, int, __half*, cudaStream_t);
+template int convert_weight<__half>(const float*, long long, __half*, cudaStream_t);
 template int repack_sublinear<float>(const float*, int, int, float*, cudaStream_t);
 template int repack_sublinear<bf16>(const float*, int, int, bf16*, cudaStream_t);
 template int repack_adapter_conv<float>(const float*, int, int, int, float*, cudaStream_t);
@@ -429,7 +448,9 @@ int ring_import(TA* ring_kv, int H, int ring_cap, long long first_frame, int n, 
 }
 template int ring_export<float>(const float*, int, int, long long, int, float*, cudaStream_t);
 template int ring_export<bf16>(const bf16*, int, int, long long, int, float*, cudaStream_t);
+template int ring_export<__half>(const __half*, int, int, long long, int, float*, cudaStream_t);
 template int ring_import<float>(float*, int, int, long long, int, const float*, cudaStream_t);
 template int ring_import<bf16>(bf16*, int, int, long long, int, const float*, cudaStream_t);
+template int ring_import<__half>(__half*, int, int, long long, int, const float*, cudaStream_t);
 
 }  // namespace fo

@@ -18,6 +18,14 @@ template <> struct Vec4<float> {
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
 };
+template <> struct Vec4<__half> {
+    static __device__ __forceinline__ void load(const __half* p, float (&v)[4]) {
+        uint2 t = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&t.x));
+        const float2 b = __half22float2(*reinterpret_cast<__half2*>(&t.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+};
 template <> struct Vec4<bf16> {
     static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
         uint2 t = *reinterpret_cast<const uint2*>(p);
@@ -27,9 +35,9 @@ template <> struct Vec4<bf16> {
     }
 };
 
-template <typename TIn, typename TAct>
+template <typename TIn, typename TWt, typename TAct>
 __global__ void __launch_bounds__(256)
-gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ W, int M, int N, int K,
+gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TWt* __restrict__ W, int M, int N, int K,
                  Epilogue ep, RowMap rmap) {
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Ws[BK][BN + PAD];
@@ -40,7 +48,7 @@ gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ 
     const int lrow = tid >> 2, lk = (tid & 3) * 4;
     const int arow = m0 + lrow, wrow = n0 + lrow;
     const bool a_ok = arow < M, w_ok = wrow < N;
-    const TIn* wp = W + (long long)(w_ok ? wrow : 0) * K + lk;
+    const TWt* wp = W + (long long)(w_ok ? wrow : 0) * K + lk;
 
     float acc[4][4];
 #pragma unroll
@@ -58,7 +66,7 @@ gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ 
         } else {
             ra[0] = ra[1] = ra[2] = ra[3] = 0.f;
         }
-        if (w_ok) Vec4<TIn>::load(wp + k0, rw);
+        if (w_ok) Vec4<TWt>::load(wp + k0, rw);
         else rw[0] = rw[1] = rw[2] = rw[3] = 0.f;
     };
     fetch(0);
@@ -119,21 +127,22 @@ gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TIn* __restrict__ 
 
 }  // namespace
 
-template <typename TIn>
-int gemm_simt(const TIn* A, const AGather& ga, const TIn* W, int M, int N, int K, const Epilogue& ep,
+template <typename TIn, typename TWt>
+int gemm_simt(const TIn* A, const AGather& ga, const TWt* W, int M, int N, int K, const Epilogue& ep,
               const RowMap& rmap, cudaStream_t st) {
     if (M <= 0) return 0;
     FO_CHECK(K % BK == 0 && ga.seg_len % BK == 0, "gemm_simt: K (%d) and segment (%d) must be multiples of %d", K,
              ga.seg_len, BK);
     FO_CHECK(N % 4 == 0 && ep.ldc % 4 == 0, "gemm_simt: N and ldc must be multiples of 4");
     dim3 grid(cdiv(N, BN), cdiv(M, BM));
-    gemm_simt_kernel<TIn, TIn><<<grid, 256, 0, st>>>(A, ga, W, M, N, K, ep, rmap);
+    gemm_simt_kernel<TIn, TWt, TIn><<<grid, 256, 0, st>>>(A, ga, W, M, N, K, ep, rmap);
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
 }
 
-template int gemm_simt<float>(const float*, const AGather&, const float*, int, int, int, const Epilogue&, const RowMap&, cudaStream_t);
-template int gemm_simt<bf16>(const bf16*, const AGather&, const bf16*, int, int, int, const Epilogue&, const RowMap&, cudaStream_t);
+template int gemm_simt<float, float>(const float*, const AGather&, const float*, int, int, int, const Epilogue&, const RowMap&, cudaStream_t);
+template int gemm_simt<bf16, bf16>(const bf16*, const AGather&, const bf16*, int, int, int, const Epilogue&, const RowMap&, cudaStream_t);
+template int gemm_simt<__half, __half>(const __half*, const AGather&, const __half*, int, int, int, const Epilogue&, const RowMap&, cudaStream_t);
 
 }  // namespace fo

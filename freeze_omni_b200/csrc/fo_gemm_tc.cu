@@ -49,6 +49,7 @@ struct TcParams {
     int kblocks, kb_per_split;
     int bn;                      // UMMA N
     int swap;                    // 0: M side = activations (C rows), 1: M side = weights (C columns)
+    int act_fp16;                // activations (and c_act / ln_act outputs) are IEEE fp16 instead of bf16
     int stages;
     int tmem_cols;
     TcOperand op_a, op_b;
@@ -228,7 +229,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            // operand format (both operands must agree): 0 = fp16, 1 = bf16
+            const uint32_t fmt_a = p.act_fp16 ? 0u : 1u, fmt_b = fmt_a;
+            const uint32_t idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int s = 0;
             uint32_t ph = 0, sa = base;
             for (int i = 0; i < nkb; ++i) {
@@ -362,10 +365,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
                 if (wf && ok) *reinterpret_cast<float4*>(out32 + o) = v;
                 if (wa && ok) {
-                    __align__(8) __nv_bfloat162 h[2];
-                    h[0] = __floats2bfloat162_rn(v.x, v.y);
-                    h[1] = __floats2bfloat162_rn(v.z, v.w);
-                    *reinterpret_cast<uint2*>(out16 + o) = *reinterpret_cast<const uint2*>(h);
+                    uint2 h;
+                    if (p.act_fp16) { h.x = pack2<__half>(v.x, v.y); h.y = pack2<__half>(v.z, v.w); }
+                    else { h.x = pack2<bf16>(v.x, v.y); h.y = pack2<bf16>(v.z, v.w); }
+                    *reinterpret_cast<uint2*>(out16 + o) = h;
                 }
             }
         }
@@ -428,10 +431,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const long long off = (long long)drow * ep.ldc + col;
                         if (ep.ln_f32) *reinterpret_cast<float4*>(ep.ln_f32 + off) = make_float4(o0, o1, o2, o3);
                         if (ep.ln_act) {
-                            __align__(8) __nv_bfloat162 hh[2];
-                            hh[0] = __floats2bfloat162_rn(o0, o1);
-                            hh[1] = __floats2bfloat162_rn(o2, o3);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.ln_act) + off) = *reinterpret_cast<const uint2*>(hh);
+                            uint2 hh;
+                            if (p.act_fp16) { hh.x = pack2<__half>(o0, o1); hh.y = pack2<__half>(o2, o3); }
+                            else { hh.x = pack2<bf16>(o0, o1); hh.y = pack2<bf16>(o2, o3); }
+                            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.ln_act) + off) = hh;
                         }
                     }
             }
@@ -552,8 +555,8 @@ int gemm_tc_workspace(TcWorkspace* ws) {
 void gemm_tc_force(const TcTune& t) { g_forced = t; }
 long long gemm_tc_launches() { return g_tc_launches; }
 
-int gemm_tc(const bf16* A, const AGather& ga, const bf16* W, int M, int N, int K, const Epilogue& ep, const RowMap& rmap,
-            const TcWorkspace& ws, cudaStream_t st) {
+int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
+            const RowMap& rmap, const TcWorkspace& ws, cudaStream_t st) {
     if (!g_encode || !ws.partial) return 1;
     if (K % BK != 0 || ga.seg_len % BK != 0 || ep.ldc % 8 != 0 || N % 8 != 0 || ep.split_col % 16 != 0) return 1;
     if (ep.residual && ep.residual != ep.c_f32) { /* residual rows are read at the remapped output row: fine */ }
@@ -582,6 +585,7 @@ int gemm_tc(const bf16* A, const AGather& ga, const bf16* W, int M, int N, int K
     p.kb_per_split = kbs;
     p.bn = pl.bn;
     p.swap = pl.swap;
+    p.act_fp16 = act_fp16;
     const uint32_t stage = (BM + pl.bn) * BK * 2;
     p.stages = std::max(1, std::min<int>(std::min(MAX_STAGES, kbs), (int)(SMEM_BUDGET / stage)));
     if (M <= 384) {
@@ -626,8 +630,8 @@ int gemm_tc(const bf16* A, const AGather& ga, const bf16* W, int M, int N, int K
         FO_CHECK(need <= ws.partial_bytes, "gemm_tc: split-K workspace too small (%zu bytes needed)", need);
     }
     CUtensorMap map_act, map_w;
-    FO_TRY(make_map(&map_act, A, ga.seg_len, ga.rows, ga.planes, pl.swap ? pl.bn : BM));
-    FO_TRY(make_map(&map_w, W, K, N, 1, pl.swap ? BM : pl.bn));
+    FO_TRY(make_map(&map_act, reinterpret_cast<const bf16*>(A), ga.seg_len, ga.rows, ga.planes, pl.swap ? pl.bn : BM));
+    FO_TRY(make_map(&map_w, reinterpret_cast<const bf16*>(W), K, N, 1, pl.swap ? BM : pl.bn));
     dim3 grid(ta, tb, pl.split);
     const size_t tile_stage = pl.swap ? (size_t)pl.bn * (BM + 4) * 4 : (size_t)BM * (pl.bn + 4) * 4;
     const size_t smem = std::max((size_t)p.stages * stage, tile_stage) + 1024;

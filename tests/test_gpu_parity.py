@@ -493,7 +493,7 @@ def test_tcgen05_gemm_tile_plans(shipped16):
             A = torch.randn(M, K, generator=g).cuda()
             W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
             b = torch.randn(N, generator=g).cuda()
-            ref = (A.bfloat16().double() @ W.bfloat16().double().T + b.double()).float().cpu()
+            ref = (A.half().double() @ W.bfloat16().double().T + b.double()).float().cpu()   # fp16 activations x bf16 weights
             for (swap, bn, split) in plans:
                 eng.set_option("tc_swap", swap)
                 eng.set_option("tc_bn", bn)
@@ -520,6 +520,6 @@ def test_gemm_backends_agree_bf16(shipped16):
         b = torch.randn(N, generator=g).cuda()
         o0, _ = eng.debug_gemm(A, W, b, backend=0)
         o1, _ = eng.debug_gemm(A, W, b, backend=1)
-        ref = (A.bfloat16().double() @ W.bfloat16().double().T + b.double()).float()
+        ref = (A.half().double() @ W.bfloat16().double().T + b.double()).float()
         assert maxabs(o0.cpu(), ref.cpu()) < 2e-3, (M, N, K)
         assert maxabs(o1.cpu(), ref.cpu()) < 2e-3, (M, N, K)
