@@ -1,19 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: streamed audio-seconds per second through fbank -> CMVN -> encoder -> adapter.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload stream|latency|offline]
 
-One "step" = every session of the batch advances one 160 ms chunk (PCM in, LLM-space embeddings out).
-Workload at N=1 is BASELINE.json configs[1]: 64 concurrent sessions, synthetic 16 kHz audio, streaming
-chunks with KV/CNN caches, bf16, shipped config with random-init weights.  With N>1 (torchrun, one rank
-per GPU) every rank owns its own 64 sessions -- sessions are independent, so there is no collective on
-the data path (weak scaling); NCCL only carries the barrier and the final timing reduction.
+One "step" = every session of the batch advances one 160 ms chunk (int16 PCM in, LLM-space embeddings out).
+Workload at N=1 is BASELINE.json configs[1]: 64 concurrent sessions, synthetic 16 kHz audio, streaming chunks with
+KV/CNN caches, bf16 context, shipped config with random-init weights.  With N>1 (torchrun, one rank per GPU) every
+rank owns its own 64 sessions -- sessions are independent, so there is no collective on the data path (weak
+scaling); NCCL only carries the barrier and the max-over-ranks timing reduction.
+Other workloads (BASELINE.json configs 4 and 5) are selectable for the record: `--workload latency` (1 session,
+p50/p99 per chunk) and `--workload offline` (full-utterance encode, batch x 30 s).
 
-Output: ONE JSON line on rank 0 (contract in the task statement): value (inputs resident in HBM), e2e
-(pinned-host PCM in, embeddings back to host, through the C ABI), roofline of the dominant kernel class
-(the GEMMs), cpu_baseline (the oracle port on the host cores, bounded sample), clocks, gpu_launches.
-`--impl reference` times the reference's CPU implementation of the same step (oracle port; the reference
-is pure Python/PyTorch and cannot travel to the GPU box).
+Output: ONE JSON line on rank 0: value (inputs resident in HBM), e2e (pinned-host PCM in, embeddings back to host,
+through the C ABI), roofline of the dominant kernel class (the tcgen05 GEMM launches, timed with CUDA events on the
+launching stream inside the library), cpu_baseline (the oracle port of the reference modules on the host cores,
+bounded sample), clocks, gpu_launches.  `--impl reference` times the reference's CPU implementation of the same
+step (oracle port; the reference is pure Python/PyTorch and cannot travel to the GPU box).
 """
 import argparse
 import json
@@ -38,6 +40,8 @@ CHUNK_SEC = 0.16
 # algorithmic FLOPs per session-chunk (2*M*N*K of the data-dependent contractions)
 GFLOP_PER_CHUNK = 4.136
 GFLOP_GEMM_PER_CHUNK = 4.136 - 0.0065 - 0.0401     # minus conv1 and the attention core (not GEMM launches)
+DTYPE_NOTE = ("bf16-rounded weights in fp16 containers x fp16 activations, fp32 accumulate (tcgen05 kind::f16); "
+              "LayerNorm/softmax/residual fp32")
 
 
 def synth_pcm(n_sessions, n_chunks, samples_per_chunk, seed0=1000):
@@ -72,7 +76,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
@@ -92,10 +96,10 @@ def load_peaks():
 
 
 def cpu_reference_step_rate(cfg, n_sessions, steps, warmup, threads=None):
-    """The reference's CPU implementation of one step (oracle port, fp32, torch CPU ops on all host
-    threads): n_sessions lock-step sessions, fbank per session then batched encoder.infer + adapter --
-    the most favourable way to run the reference's modules (it batches when sessions are in lock step,
-    SURVEY 8c).  Returns (audio-s/s, seconds per step, threads)."""
+    """The reference's CPU implementation of one step (oracle port, fp32, torch CPU ops on all host threads):
+    n_sessions lock-step sessions, fbank per session then batched encoder.infer + adapter -- the most favourable way
+    to run the reference's modules (it batches when sessions are in lock step).
+    Returns (audio-s/s, seconds per step, threads)."""
     from oracle import freeze_omni_oracle as O
     if threads:
         torch.set_num_threads(threads)
@@ -118,6 +122,11 @@ def cpu_reference_step_rate(cfg, n_sessions, steps, warmup, threads=None):
     return n_sessions * CHUNK_SEC / t, t, torch.get_num_threads()
 
 
+def workload_text(S):
+    return ("%d concurrent sessions per GPU, streaming 160 ms chunks with KV/CNN caches (windows full), shipped config "
+            "(24x1024, adapter 3584), random-init weights" % S)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -128,11 +137,44 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d lock-step sessions x 160 ms chunks, shipped config, CPU" % n, "sessions": n},
+            "config": {"workload": workload_text(n), "sessions_per_gpu": n,
+                       "note": "reference CPU path: oracle port of the reference modules, torch CPU fp32, bounded sample of %d steps" % steps},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": th, "kind": "port",
                              "sample": "%d sessions x %d chunks (oracle port of the reference modules, fp32, torch CPU)" % (n, steps)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def bench_offline(args, eng, cfg, rank, world):
+    """BASELINE.json config 4: full-utterance encode, batch x 30 s synthetic audio, processed in slices."""
+    B, sl = args.offline_batch, args.offline_slice
+    n_samples = 30 * cfg.sample_rate
+    g = torch.Generator().manual_seed(7 + rank)
+    pcm = (0.05 * torch.randn(sl, n_samples, generator=g) * 32768).round().clamp(-32768, 32767).to(torch.int16).cuda()
+
+    def one_pass():
+        for _ in range(B // sl):
+            feats = eng.fbank_offline(pcm, 1.0)
+            il = np.full((sl,), feats.shape[1], dtype=np.int32)
+            eng.encode_offline(feats, il, cfg.chunk_size, cfg.left_chunks)
+
+    one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(1, args.steps // 50)
+    e0.record()
+    for _ in range(reps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if rank == 0:
+        _, tf_sus, _, _ = load_peaks()
+        gflop = 773.0 * B                                     # SURVEY 8d: ~773 GFLOP per 30 s utterance (banded attention)
+        print(json.dumps({"workload": "offline full-utterance encode, batch %d x 30 s in slices of %d" % (B, sl),
+                          "metric": "offline audio-sec/sec (fbank+encoder+adapter)", "value": world * B * 30.0 / (ms * 1e-3),
+                          "unit": UNIT, "ms_per_pass": ms, "tflops": gflop / ms, "frac_of_sustained_bf16": gflop / ms / tf_sus,
+                          "n_gpus": world, "dtype": "bf16", "dtype_note": DTYPE_NOTE}))
 
 
 def main():
@@ -141,8 +183,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="stream", choices=["stream", "latency", "offline"])
     ap.add_argument("--sessions", type=int, default=64, help="concurrent sessions per GPU")
     ap.add_argument("--ref-sessions", type=int, default=64)
+    ap.add_argument("--offline-batch", type=int, default=256)
+    ap.add_argument("--offline-slice", type=int, default=32)
     ap.add_argument("--config", default="shipped")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--cpu-steps", type=int, default=6, help="bounded CPU sample (steps of the same workload)")
@@ -155,8 +200,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    # steady state needs the 64-row KV windows full (16 chunks); shorter warm-ups are topped up untimed below
-    fill_steps = max(0, 17 - args.warmup)
+    if args.workload == "latency":
+        args.sessions = 1
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -179,7 +224,7 @@ def main():
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     S, K, W = args.sessions, args.steps, args.warmup
     eng = Engine(cfg, make_encoder_state(cfg, 0), make_adapter_state(cfg, 0), dtype=dtype, device=local_rank,
-                 max_sessions=S)
+                 max_sessions=S, max_stream_frames=cfg.chunk_feat_frames)
     if args.graph >= 0:
         eng.set_option("use_graph", args.graph)
     if args.backend >= 0:
@@ -188,8 +233,15 @@ def main():
         eng.set_option("session_groups", args.groups)
     if args.debug_skip:
         eng.set_option("debug_skip", args.debug_skip)
+    if args.workload == "offline":
+        bench_offline(args, eng, cfg, rank, world)
+        eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     ids = eng.alloc(S)
-    n_pcm = min(K + W, 64)                                   # synthetic audio is cycled after 64 chunks
+    n_pcm = 64                                               # synthetic audio is cycled after 64 chunks
     pcm_host = torch.from_numpy(synth_pcm(S, n_pcm, cfg.samples_per_chunk, seed0=1000 + 4096 * rank)).pin_memory()
     pcm_dev = pcm_host.cuda(non_blocking=True)
     t_enc, t_out = eng.out_frames(cfg.chunk_feat_frames)
@@ -225,27 +277,30 @@ def main():
         return float(ms.item())
 
     # ---- device-resident throughput ------------------------------------------------------------
-    run_steps(fill_steps, False, 0)                          # untimed: fill the KV windows (steady state)
+    run_steps(max(0, 17 - W), False, 0)                      # untimed: fill the 64-row KV windows (steady state)
     run_steps(W, False, 0)
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = eng.stats()["kernel_launches"]
     ms = timed(K, False, W)
     launches = eng.stats()["kernel_launches"] - l0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     value = world * S * CHUNK_SEC * K / (ms * 1e-3)
     if args.quick:
+        sampler.stop_flag = True
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms / K, "value": value, "sessions": S, "debug_skip": args.debug_skip,
                               "groups": eng.get_option("session_groups")}))
         eng.free(ids)
         eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
         return
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     run_steps(W, True, 0)
     ms_e2e = timed(K, True, W)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
     e2e = world * S * CHUNK_SEC * K / (ms_e2e * 1e-3)
 
     # ---- per-step latency distribution (device timed, one event pair per step) --------------------
@@ -259,27 +314,38 @@ def main():
         lat.append(a.elapsed_time(b))
     lat = np.asarray(lat)
 
-    # ---- roofline of the dominant kernel class: GEMM launches timed with CUDA events inside the library
+    # ---- roofline of the dominant kernel class: every tcgen05 GEMM launch of a step, timed with a CUDA event pair on
+    # the launching stream inside the library (eager launches for this pass; tensor maps are cached so the host stays
+    # ahead of the device)
     hbm_peak, tf_sustained, tf_burst, peak_kind = load_peaks()
-    roof = None
+    step_ms = ms / K
+    roof, shapes = None, []
     try:
+        steps_prof = min(K, 10)
+        run_steps(2, False, 0)
         eng.set_option("profile_gemm", 1)
-        run_steps(min(K, 20), False, 0)
+        run_steps(steps_prof, False, 0)
         torch.cuda.synchronize()
-        gemm_ms = eng.get_option("profile_gemm_us") / 1e3
-        gemm_n = eng.get_option("profile_gemm_count")
+        rows = eng.profile_dump()
         eng.set_option("profile_gemm", 0)
-        steps_prof = min(K, 20)
+        gemm_ms = sum(r[4] for r in rows) / 1e3
+        gemm_n = sum(r[3] for r in rows)
         gflop = GFLOP_GEMM_PER_CHUNK * S * steps_prof
         achieved = gflop / gemm_ms                                  # GFLOP / ms == TFLOP/s
         roof = {"bound": "tensor", "achieved": achieved, "peak": tf_sustained, "unit": "TFLOP/s",
-                "frac": achieved / tf_sustained, "traffic": None, "peak_source": peak_kind + " (sustained bf16)",
-                "kernel": "gemm (all GEMM launches of the step)", "launches_per_step": gemm_n / steps_prof,
-                "gemm_ms_per_step": gemm_ms / steps_prof, "share_of_step": (gemm_ms / steps_prof) / (ms / K)}
+                "frac": achieved / tf_sustained, "traffic": None, "peak_source": peak_kind + " (sustained bf16 cuBLAS)",
+                "kernel": "gemm_tc_kernel (all %d GEMM launches of a step; algorithmic %.2f GFLOP per session-chunk)"
+                          % (gemm_n // steps_prof, GFLOP_GEMM_PER_CHUNK),
+                "launches_per_step": gemm_n / steps_prof, "gemm_ms_per_step": gemm_ms / steps_prof,
+                "share_of_step": (gemm_ms / steps_prof) / step_ms,
+                "note": "M = 4 rows per session puts the layer GEMMs on the weight-streaming / latency side of the ridge; "
+                        "gemm_shapes gives the per-shape rates (conv2, M = sessions*80 padded rows, is the tensor-bound one)"}
+        for (m, n, k, cnt, us) in sorted(rows, key=lambda r: -r[4]):
+            shapes.append({"M": m, "N": n, "K": k, "launches_per_step": cnt / steps_prof, "us_per_launch": us / cnt,
+                           "tflops": 2.0 * m * n * k * cnt / us / 1e6, "weight_GBs": 2.0 * n * k * cnt / us / 1e3})
     except Exception as ex:  # library built without the profiling option
         roof = {"bound": "tensor", "achieved": None, "peak": tf_sustained, "unit": "TFLOP/s", "frac": None,
                 "traffic": None, "note": "gemm profiling unavailable: %s" % ex}
-    step_ms = ms / K
     step_bytes = 751.6e6 + S * 6.7e6
     whole = {"tflops": GFLOP_PER_CHUNK * S / step_ms, "frac_of_sustained_bf16": GFLOP_PER_CHUNK * S / step_ms / tf_sustained,
              "algorithmic_GB_per_step": step_bytes / 1e9, "hbm_gbs": step_bytes / 1e6 / step_ms,
@@ -297,16 +363,18 @@ def main():
         d2h = S * t_out * cfg.llm_dim * 4
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": "%d concurrent sessions per GPU, streaming 160 ms chunks with KV/CNN caches, shipped "
-                                       "config (24x1024, adapter 3584), random-init weights" % S,
-                           "sessions_per_gpu": S, "parallelism": "sessions sharded, no collective",
-                           "l2": "working set per step (752 MB weights + %.0f MB KV) exceeds the 126 MB L2" % (S * 6.3)},
+                "dtype": "bf16" if args.dtype == "bf16" else "f32",
+                "dtype_note": DTYPE_NOTE if args.dtype == "bf16" else "fp32 FFMA",
+                "data": "synthetic",
+                "config": {"workload": workload_text(S), "sessions_per_gpu": S,
+                           "parallelism": "sessions sharded over ranks, no collective",
+                           "l2": "inputs larger than L2: each step streams 752 MB of weights + %.0f MB of KV rings (L2 is 126 MB)" % (S * 6.3)},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(launches),
                 "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "sessions": S},
-                "roofline": roof, "step_roofline": whole, "cpu_baseline": cpu, "clocks": sampler.summary(),
+                "roofline": roof, "gemm_shapes": shapes[:12], "step_roofline": whole, "cpu_baseline": cpu,
+                "clocks": sampler.summary(),
                 "options": {"gemm_backend": eng.get_option("gemm_backend"), "use_graph": eng.get_option("use_graph"),
                             "session_groups": eng.get_option("session_groups")}}
         print(json.dumps(line))

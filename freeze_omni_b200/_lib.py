@@ -56,6 +56,7 @@ SYMBOLS = {
     "fo_stats": (C.c_int, [_P, C.POINTER(FoStats)]),
     "fo_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "fo_get_option": (C.c_int, [_P, C.c_char_p, _I64P]),
+    "fo_profile_dump": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "fo_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(C.c_float), _P]),
 }

@@ -115,7 +115,8 @@ struct fo_ctx {
     cudaStream_t grp_stream[MAX_GROUPS] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {nullptr};
     int profile_gemm = 0;                     // time every GEMM launch with a CUDA event pair (bench roofline)
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    struct ProfRec { cudaEvent_t e0, e1; int M, N, K; };
+    std::vector<ProfRec> prof_events;
     // captured step graphs, keyed by the shape of the call; invalidated when a workspace moves
     struct StepGraph {
         cudaGraphExec_t exec = nullptr;
@@ -254,7 +255,7 @@ int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N,
         FO_CUDA(cudaEventRecord(e0, st));
         r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st, &fused);
         FO_CUDA(cudaEventRecord(e1, st));
-        c->prof_events.emplace_back(e0, e1);
+        c->prof_events.push_back(fo_ctx::ProfRec{e0, e1, M, N, K});
     }
     if (r == 0 && ep.ln_gamma && !fused)          // LayerNorm of the finished rows as its own kernel (fp32 / FFMA paths)
         r = layer_norm<TA>(ep.c_f32, M, N, ep.ln_gamma, ep.ln_beta, ep.ln_eps, 0, 1.0f, reinterpret_cast<TA*>(ep.ln_act),
@@ -1293,7 +1294,7 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "profile_gemm")) {
         c->profile_gemm = value != 0;
         if (value) {
-            for (auto& pr : c->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+            for (auto& pr : c->prof_events) { cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1); }
             c->prof_events.clear();
         }
     }
@@ -1312,9 +1313,9 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     else if (!strcmp(name, "profile_gemm_us")) {
         double us = 0.0;
         for (auto& pr : c->prof_events) {
-            FO_CUDA(cudaEventSynchronize(pr.second));
+            FO_CUDA(cudaEventSynchronize(pr.e1));
             float ms = 0.f;
-            FO_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            FO_CUDA(cudaEventElapsedTime(&ms, pr.e0, pr.e1));
             us += 1e3 * ms;
         }
         *value = (int64_t)us;
@@ -1323,6 +1324,29 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     else if (!strcmp(name, "ring_cap")) *value = c->ring_cap;
     else if (!strcmp(name, "max_t")) *value = c->max_t;
     else { set_error("fo_get_option: unknown option '%s'", name); return FO_ERR_ARG; }
+    return 0;
+}
+
+int fo_profile_dump(fo_ctx* c, char* buf, int cap) {
+    FO_CHECK(c && buf && cap > 0, "fo_profile_dump: bad argument");
+    std::map<std::string, std::pair<long long, double>> agg;       // "M N K" -> (launches, microseconds)
+    for (auto& pr : c->prof_events) {
+        FO_CUDA(cudaEventSynchronize(pr.e1));
+        float ms = 0.f;
+        FO_CUDA(cudaEventElapsedTime(&ms, pr.e0, pr.e1));
+        char key[64];
+        snprintf(key, sizeof(key), "%d %d %d", pr.M, pr.N, pr.K);
+        auto& a = agg[key];
+        a.first += 1;
+        a.second += 1e3 * ms;
+    }
+    int off = 0;
+    for (auto& kv : agg) {
+        int w = snprintf(buf + off, cap - off, "%s %lld %.3f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        if (w < 0 || w >= cap - off) break;
+        off += w;
+    }
+    buf[off < cap ? off : cap - 1] = 0;
     return 0;
 }
 

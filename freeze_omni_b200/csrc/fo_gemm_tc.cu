@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 
 #include "fo_common.cuh"
@@ -458,7 +459,32 @@ int g_sm_count = 148;
 TcTune g_forced = {-1, -1, -1};
 long long g_tc_launches = 0;
 
+// encoded tensor maps are pure functions of (pointer, extents, box): cached so that eager launches stay cheap on the host
+struct MapKey {
+    const void* base; long long rows; int seg_len, planes, box_rows;
+    bool operator<(const MapKey& o) const {
+        if (base != o.base) return base < o.base;
+        if (rows != o.rows) return rows < o.rows;
+        if (seg_len != o.seg_len) return seg_len < o.seg_len;
+        if (planes != o.planes) return planes < o.planes;
+        return box_rows < o.box_rows;
+    }
+};
+std::map<MapKey, CUtensorMap> g_map_cache;
+std::mutex g_map_mu;
+
+int make_map_uncached(CUtensorMap* map, const bf16* base, int seg_len, long long rows, int planes, int box_rows);
 int make_map(CUtensorMap* map, const bf16* base, int seg_len, long long rows, int planes, int box_rows) {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    const MapKey k{base, rows, seg_len, planes, box_rows};
+    auto it = g_map_cache.find(k);
+    if (it != g_map_cache.end()) { *map = it->second; return 0; }
+    FO_TRY(make_map_uncached(map, base, seg_len, rows, planes, box_rows));
+    if (g_map_cache.size() > 8192) g_map_cache.clear();
+    g_map_cache[k] = *map;
+    return 0;
+}
+int make_map_uncached(CUtensorMap* map, const bf16* base, int seg_len, long long rows, int planes, int box_rows) {
     // {k within the segment, rows, planes}; one box = box_rows x 64 elements = one 128B-swizzled smem tile
     // (a 4-D variant fetching two k-atoms per box measured slower per byte on B200, profiles/r01 notes)
     cuuint64_t dims[3] = {(cuuint64_t)seg_len, (cuuint64_t)rows, (cuuint64_t)planes};

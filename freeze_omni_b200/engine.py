@@ -123,6 +123,16 @@ class Engine:
         _lib.check(self.lib.fo_get_option(self._h, name.encode(), C.byref(v)))
         return int(v.value)
 
+    def profile_dump(self):
+        """[(M, N, K, launches, microseconds)] of the GEMM launches timed under option profile_gemm."""
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(self.lib.fo_profile_dump(self._h, buf, len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            m, n, k, cnt, us = line.split()
+            rows.append((int(m), int(n), int(k), int(cnt), float(us)))
+        return rows
+
     def stats(self) -> Dict[str, int]:
         s = _lib.FoStats()
         _lib.check(self.lib.fo_stats(self._h, C.byref(s)))

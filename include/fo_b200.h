@@ -143,9 +143,14 @@ int fo_adapter_forward(fo_ctx* ctx, const float* x, const uint8_t* mask, int B, 
 
 /* ---- introspection / tuning ---- */
 int fo_stats(fo_ctx* ctx, fo_stats_t* out);
-/* options: "gemm_backend" 0 = SIMT FFMA, 1 = tcgen05 (bf16 only); "use_graph" 0/1; "split_k" 0/1 */
+/* options: "gemm_backend" 0 = SIMT FFMA, 1 = tcgen05 (bf16 context only); "use_graph" 0/1 (CUDA-graph replay of the streaming
+ * step); "session_groups" 1..4 (layer kernels of session groups on parallel streams); "fuse_ln" 0/1; "profile_gemm" 0/1;
+ * "tc_swap"/"tc_bn"/"tc_split" force the tile plan of the tcgen05 GEMM (-1 = cost model); "debug_skip" (timing attribution). */
 int fo_set_option(fo_ctx* ctx, const char* name, int64_t value);
 int fo_get_option(fo_ctx* ctx, const char* name, int64_t* value);
+/* per-shape totals of the GEMM launches timed while option "profile_gemm" was 1: text lines "M N K launches microseconds"
+ * (M = GEMM rows incl. the padding rows of the implicit-GEMM convolutions). */
+int fo_profile_dump(fo_ctx* ctx, char* buf, int cap);
 /* one GEMM of the library, exposed for kernel-level parity tests and roofline measurement:
  * C[M,N] = A[M,K] * W[N,K]^T (+bias) in the context's dtype, fp32 in/out on device pointers. */
 int fo_debug_gemm(fo_ctx* ctx, const float* A, const float* W, const float* bias, float* C,
