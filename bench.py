@@ -168,13 +168,25 @@ def bench_offline(args, eng, cfg, rank, world):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    shapes = []
+    try:
+        eng.set_option("profile_gemm", 1)
+        one_pass()
+        torch.cuda.synchronize()
+        rows = eng.profile_dump()
+        eng.set_option("profile_gemm", 0)
+        for (m, n, k, cnt, us) in sorted(rows, key=lambda r: -r[4]):
+            shapes.append({"M": m, "N": n, "K": k, "launches": cnt, "ms_total": us / 1e3, "tflops": 2.0 * m * n * k * cnt / us / 1e6})
+    except Exception:
+        pass
     if rank == 0:
         _, tf_sus, _, _ = load_peaks()
         gflop = 773.0 * B                                     # ~773 GFLOP per 30 s utterance (banded attention)
         print(json.dumps({"workload": "offline full-utterance encode, batch %d x 30 s in slices of %d" % (B, sl),
                           "metric": "offline audio-sec/sec (fbank+encoder+adapter)", "value": world * B * 30.0 / (ms * 1e-3),
                           "unit": UNIT, "ms_per_pass": ms, "tflops": gflop / ms, "frac_of_sustained_bf16": gflop / ms / tf_sus,
-                          "n_gpus": world, "dtype": "bf16", "dtype_note": DTYPE_NOTE}))
+                          "n_gpus": world, "dtype": "bf16", "dtype_note": DTYPE_NOTE,
+                          "gemm_ms_per_pass": sum(x["ms_total"] for x in shapes), "gemm_shapes": shapes}))
 
 
 def main():

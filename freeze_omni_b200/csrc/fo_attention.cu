@@ -331,21 +331,28 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int KT = 96;          // key tile (covers the shipped 68-key band in one pass)
-constexpr int QB = 4;           // query rows per CTA
+constexpr int KT = 96;          // key tile: the shipped band of a 32-query block (64 left + 32 own keys) in one pass
+constexpr int QB = 32;          // query rows per CTA
+constexpr int QPW = QB / (ATT_THREADS / 32);   // queries per warp
 
+// Full-utterance attention.  CTA = (32-query block, head, utterance), 4 warps x 8 queries.  The union of the block's
+// key windows is walked in tiles of 96 keys (K, V and the rel-pos rows staged once per tile and shared by the 32
+// queries); per query: lane = keys lane, lane+32, lane+64 of the tile, window [start,end) of masks.py:50-56 and the pad
+// mask (masks.py:110-120) applied arithmetically, online softmax across tiles (unbounded left context works), PV with
+// lane = output dims.  A row whose whole window is masked yields zeros (attention.py:396-397).
 template <typename TA>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q32, int T, int H,
                          const int32_t* __restrict__ ilens, int chunk, int left, const float* __restrict__ ptab,
                          const float* __restrict__ pos_u, const float* __restrict__ pos_v, TA* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
     TA* Ks = reinterpret_cast<TA*>(smem_raw);
     TA* Vs = Ks + KT * DK;
     TA* Ps = Vs + KT * DK;
-    float* qu = reinterpret_cast<float*>(Ps + KT * DK);
-    float* qv = qu + TQ_MAX * DK;
-    float* sc = qv + TQ_MAX * DK;                    // QB x KT
+    float* qu = reinterpret_cast<float*>(Ps + KT * DK);    // QB x 64
+    float* qv = qu + QB * DK;
+    float* prob = qv + QB * DK;                            // warps x KT
     __shared__ int win[QB][2];
 
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -354,7 +361,6 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
     const int nq = min(QB, T - q0);
     const int klen = ilens ? min(ilens[b], T) : T;        // pad mask on keys (masks.py:110-120)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
 
     if (tid < nq) {
         const int i = q0 + tid;
@@ -366,18 +372,23 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
         win[tid][0] = s;
         win[tid][1] = min(e, klen);
     }
-    for (int i = tid; i < nq * DK; i += ATT_THREADS) {
-        const int r = i / DK, d = i % DK;
-        const float q = q32[((long long)b * T + q0 + r) * 3 * D + h * DK + d];
-        qu[i] = q + pos_u[h * DK + d];
-        qv[i] = q + pos_v[h * DK + d];
+    for (int i = tid; i < nq * (DK / 4); i += ATT_THREADS) {
+        const int r = i / (DK / 4), c = (i % (DK / 4)) * 4;
+        const float4 q = *reinterpret_cast<const float4*>(q32 + ((long long)b * T + q0 + r) * 3 * D + h * DK + c);
+        const float4 u = *reinterpret_cast<const float4*>(pos_u + h * DK + c);
+        const float4 v = *reinterpret_cast<const float4*>(pos_v + h * DK + c);
+        *reinterpret_cast<float4*>(qu + r * DK + c) = make_float4(q.x + u.x, q.y + u.y, q.z + u.z, q.w + u.w);
+        *reinterpret_cast<float4*>(qv + r * DK + c) = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
     }
     __syncthreads();
     int k_lo = win[0][0], k_hi = win[0][1];
     for (int r = 1; r < nq; ++r) { k_lo = min(k_lo, win[r][0]); k_hi = max(k_hi, win[r][1]); }
 
-    // warp `warp` owns query row `warp` (QB == warps)
-    float m_run = -INFINITY, l_run = 0.f, o0 = 0.f, o1 = 0.f;
+    float m_run[QPW], l_run[QPW], o0[QPW], o1[QPW];
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) { m_run[qi] = -INFINITY; l_run[qi] = 0.f; o0[qi] = 0.f; o1[qi] = 0.f; }
+    float* pr = prob + warp * KT;
+
     for (int kt = k_lo; kt < k_hi; kt += KT) {
         const int nk = min(KT, k_hi - kt);
         __syncthreads();                                   // previous tile fully consumed
@@ -392,55 +403,110 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
             const int j = i / (DK / 4), c = i % (DK / 4);
             const float4 v4 = *reinterpret_cast<const float4*>(ptab + (long long)(kt + j) * D + h * DK + c * 4);
             TA* d = Ps + j * DK + c * 4;
-            d[0] = from_f<TA>(v4.x); d[1] = from_f<TA>(v4.y); d[2] = from_f<TA>(v4.z); d[3] = from_f<TA>(v4.w);
-        }
-        __syncthreads();
-        for (int j = tid; j < nk; j += ATT_THREADS) {
-            float acc[TQ_MAX];
-            score_row<TA>(Ks + j * DK, Ps + j * DK, qu, qv, nq, j, acc);
-#pragma unroll
-            for (int i = 0; i < QB; ++i)
-                if (i < nq) {
-                    const int key = kt + j;
-                    const bool ok = key >= win[i][0] && key < win[i][1];
-                    sc[i * KT + j] = ok ? acc[i] * 0.125f : -INFINITY;
-                }
-        }
-        __syncthreads();
-        if (warp < nq) {
-            float* pr = sc + warp * KT;
-            float m = -INFINITY;
-            for (int j = lane; j < nk; j += 32) m = fmaxf(m, pr[j]);
-            m = warp_max(m);
-            const float m_new = fmaxf(m_run, m);
-            if (m_new != -INFINITY) {
-                const float corr = __expf(m_run - m_new);  // m_run = -inf -> 0
-                float s = 0.f;
-                for (int j = lane; j < nk; j += 32) {
-                    const float e = __expf(pr[j] - m_new);
-                    pr[j] = e;
-                    s += e;
-                }
-                s = warp_sum(s);
-                __syncwarp();
-                l_run = l_run * corr + s;
-                o0 *= corr;
-                o1 *= corr;
-                for (int j = 0; j < nk; ++j) {
-                    const float p = pr[j];
-                    o0 = fmaf(p, to_f(Vs[j * DK + 2 * lane]), o0);
-                    o1 = fmaf(p, to_f(Vs[j * DK + 2 * lane + 1]), o1);
-                }
-                m_run = m_new;
+            if constexpr (sizeof(TA) == 2) {
+                uint2 hh;
+                hh.x = pack2<TA>(v4.x, v4.y);
+                hh.y = pack2<TA>(v4.z, v4.w);
+                *reinterpret_cast<uint2*>(d) = hh;
+            } else {
+                *reinterpret_cast<float4*>(d) = v4;
             }
         }
+        __syncthreads();
+#pragma unroll
+        for (int qi = 0; qi < QPW; ++qi) {
+            const int r = warp * QPW + qi;
+            if (r >= nq) break;                            // warp-uniform
+            const int lo = win[r][0], hi = win[r][1];
+            if (hi <= kt || lo >= kt + nk || hi <= lo) continue;     // tile outside this query's window (warp-uniform)
+            const float* qui = qu + r * DK;
+            const float* qvi = qv + r * DK;
+            float sc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 2
+            for (int c = 0; c < NCH; ++c) {
+                const int cc = (c + lane) & (NCH - 1);
+                float au[EPC], av[EPC];
+#pragma unroll
+                for (int e = 0; e < EPC; e += 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(qui + cc * EPC + e);
+                    const float4 y = *reinterpret_cast<const float4*>(qvi + cc * EPC + e);
+                    au[e] = x.x; au[e + 1] = x.y; au[e + 2] = x.z; au[e + 3] = x.w;
+                    av[e] = y.x; av[e + 1] = y.y; av[e + 2] = y.z; av[e + 3] = y.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int j = lane + 32 * k;
+                    if (j < nk) {
+                        float kv[EPC], pp[EPC];
+                        Chunk<TA>::load(Ks + j * DK + cc * EPC, kv);
+                        Chunk<TA>::load(Ps + j * DK + cc * EPC, pp);
+                        float s = sc[k];
+#pragma unroll
+                        for (int e = 0; e < EPC; ++e) s = fmaf(au[e], kv[e], fmaf(av[e], pp[e], s));
+                        sc[k] = s;
+                    }
+                }
+            }
+            float m = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int key = kt + lane + 32 * k;
+                sc[k] = (lane + 32 * k < nk && key >= lo && key < hi) ? sc[k] * 0.125f : -INFINITY;
+                m = fmaxf(m, sc[k]);
+            }
+            m = warp_max(m);
+            const float m_new = fmaxf(m_run[qi], m);       // finite: the tile intersects the window
+            const float corr = __expf(m_run[qi] - m_new);  // m_run = -inf -> 0
+            float ssum = 0.f;
+            __syncwarp();                                  // previous query's PV done with the strip
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int j = lane + 32 * k;
+                if (j < nk) {
+                    const float e = __expf(sc[k] - m_new); // masked keys: exp(-inf) = 0
+                    pr[j] = e;
+                    ssum += e;
+                }
+            }
+            ssum = warp_sum(ssum);
+            __syncwarp();
+            l_run[qi] = l_run[qi] * corr + ssum;
+            float a0 = o0[qi] * corr, a1 = o1[qi] * corr;
+            const int j0 = max(lo - kt, 0), j1 = min(hi - kt, nk);
+            if constexpr (sizeof(TA) == 2) {
+                const uint32_t* vp = reinterpret_cast<const uint32_t*>(Vs) + lane;
+#pragma unroll 4
+                for (int j = j0; j < j1; ++j) {
+                    const float2 vv = unpack2<TA>(vp[j * (DK / 2)]);
+                    const float p = pr[j];
+                    a0 = fmaf(p, vv.x, a0);
+                    a1 = fmaf(p, vv.y, a1);
+                }
+            } else {
+#pragma unroll 4
+                for (int j = j0; j < j1; ++j) {
+                    const float p = pr[j];
+                    a0 = fmaf(p, to_f(Vs[j * DK + 2 * lane]), a0);
+                    a1 = fmaf(p, to_f(Vs[j * DK + 2 * lane + 1]), a1);
+                }
+            }
+            o0[qi] = a0;
+            o1[qi] = a1;
+            m_run[qi] = m_new;
+        }
     }
-    if (warp < nq) {
-        // a row whose whole window is masked yields zeros (attention.py:396-397)
-        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-        TA* o = out + ((long long)b * T + q0 + warp) * D + h * DK + 2 * lane;
-        o[0] = from_f<TA>(o0 * inv);
-        o[1] = from_f<TA>(o1 * inv);
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) {
+        const int r = warp * QPW + qi;
+        if (r >= nq) break;
+        const float inv = l_run[qi] > 0.f ? 1.f / l_run[qi] : 0.f;
+        TA* o = out + ((long long)b * T + q0 + r) * D + h * DK + 2 * lane;
+        if constexpr (sizeof(TA) == 2) {
+            *reinterpret_cast<uint32_t*>(o) = pack2<TA>(o0[qi] * inv, o1[qi] * inv);
+        } else {
+            o[0] = from_f<TA>(o0[qi] * inv);
+            o[1] = from_f<TA>(o1[qi] * inv);
+        }
     }
 }
 
@@ -489,8 +555,8 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
                       const float* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
     if (B <= 0 || T <= 0) return 0;
     dim3 grid(cdiv(T, QB), H, B);
-    const size_t smem = (size_t)3 * KT * DK * sizeof(TA) + (size_t)2 * TQ_MAX * DK * sizeof(float) +
-                        (size_t)QB * KT * sizeof(float);
+    const size_t smem = (size_t)3 * KT * DK * sizeof(TA) + (size_t)2 * QB * DK * sizeof(float) +
+                        (size_t)(ATT_THREADS / 32) * KT * sizeof(float);
     static bool attr_set[2] = {false, false};
     if (!attr_set[sizeof(TA) == 2]) {
         FO_CUDA(cudaFuncSetAttribute(attention_offline_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
