@@ -337,9 +337,12 @@ constexpr int QPW = QB / (ATT_THREADS / 32);   // queries per warp
 
 // Full-utterance attention.  CTA = (32-query block, head, utterance), 4 warps x 8 queries.  The union of the block's
 // key windows is walked in tiles of 96 keys (K, V and the rel-pos rows staged once per tile and shared by the 32
-// queries); per query: lane = keys lane, lane+32, lane+64 of the tile, window [start,end) of masks.py:50-56 and the pad
-// mask (masks.py:110-120) applied arithmetically, online softmax across tiles (unbounded left context works), PV with
-// lane = output dims.  A row whose whole window is masked yields zeros (attention.py:396-397).
+// queries; rows padded by 16 B so that lanes reading different rows hit different banks).  Scores are register
+// blocked: lane = keys lane, lane+32, lane+64 of the tile against FOUR queries at a time, so every K / P chunk read
+// from shared memory feeds four dot products and the query chunks are warp-wide broadcasts.  Window [start,end) of
+// masks.py:50-56 and the pad mask (masks.py:110-120) are applied arithmetically; online softmax across tiles
+// (unbounded left context works); PV with lane = output dims.  A row whose whole window is masked yields zeros
+// (attention.py:396-397).
 template <typename TA>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q32, int T, int H,
@@ -347,10 +350,12 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
                          const float* __restrict__ pos_u, const float* __restrict__ pos_v, TA* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
+    constexpr int DKP = DK + EPC;                          // padded row (16 B): conflict-free 16-byte row reads
+    constexpr int QG = 4;                                  // queries per register block
     TA* Ks = reinterpret_cast<TA*>(smem_raw);
-    TA* Vs = Ks + KT * DK;
-    TA* Ps = Vs + KT * DK;
-    float* qu = reinterpret_cast<float*>(Ps + KT * DK);    // QB x 64
+    TA* Vs = Ks + KT * DKP;
+    TA* Ps = Vs + KT * DKP;
+    float* qu = reinterpret_cast<float*>(Ps + KT * DKP);   // QB x 64
     float* qv = qu + QB * DK;
     float* prob = qv + QB * DK;                            // warps x KT
     __shared__ int win[QB][2];
@@ -362,27 +367,33 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
     const int klen = ilens ? min(ilens[b], T) : T;        // pad mask on keys (masks.py:110-120)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid < nq) {
-        const int i = q0 + tid;
-        int s = 0, e = T;
-        if (chunk > 0) {                                   // masks.py:50-56
-            s = left < 0 ? 0 : max((i / chunk - left) * chunk, 0);
-            e = min((i / chunk + 1) * chunk, T);
+    if (tid < QB) {
+        int s = 0, e = 0;                                  // rows past the end: empty window
+        if (tid < nq) {
+            const int i = q0 + tid;
+            s = 0; e = T;
+            if (chunk > 0) {                               // masks.py:50-56
+                s = left < 0 ? 0 : max((i / chunk - left) * chunk, 0);
+                e = min((i / chunk + 1) * chunk, T);
+            }
+            e = min(e, klen);
         }
         win[tid][0] = s;
-        win[tid][1] = min(e, klen);
+        win[tid][1] = e;
     }
-    for (int i = tid; i < nq * (DK / 4); i += ATT_THREADS) {
+    for (int i = tid; i < QB * (DK / 4); i += ATT_THREADS) {
         const int r = i / (DK / 4), c = (i % (DK / 4)) * 4;
-        const float4 q = *reinterpret_cast<const float4*>(q32 + ((long long)b * T + q0 + r) * 3 * D + h * DK + c);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nq) q = *reinterpret_cast<const float4*>(q32 + ((long long)b * T + q0 + r) * 3 * D + h * DK + c);
         const float4 u = *reinterpret_cast<const float4*>(pos_u + h * DK + c);
         const float4 v = *reinterpret_cast<const float4*>(pos_v + h * DK + c);
         *reinterpret_cast<float4*>(qu + r * DK + c) = make_float4(q.x + u.x, q.y + u.y, q.z + u.z, q.w + u.w);
         *reinterpret_cast<float4*>(qv + r * DK + c) = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
     }
     __syncthreads();
-    int k_lo = win[0][0], k_hi = win[0][1];
-    for (int r = 1; r < nq; ++r) { k_lo = min(k_lo, win[r][0]); k_hi = max(k_hi, win[r][1]); }
+    int k_lo = T, k_hi = 0;
+    for (int r = 0; r < nq; ++r)
+        if (win[r][1] > win[r][0]) { k_lo = min(k_lo, win[r][0]); k_hi = max(k_hi, win[r][1]); }
 
     float m_run[QPW], l_run[QPW], o0[QPW], o1[QPW];
 #pragma unroll
@@ -396,13 +407,13 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
             const int which = i / (nk * NCH);              // 0 K, 1 V
             const int j = (i / NCH) % nk, c = i % NCH;
             const TA* src = qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + c * EPC;
-            TA* dst = (which == 0 ? Ks : Vs) + j * DK + c * EPC;
+            TA* dst = (which == 0 ? Ks : Vs) + j * DKP + c * EPC;
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
         }
         for (int i = tid; i < nk * (DK / 4); i += ATT_THREADS) {
             const int j = i / (DK / 4), c = i % (DK / 4);
             const float4 v4 = *reinterpret_cast<const float4*>(ptab + (long long)(kt + j) * D + h * DK + c * 4);
-            TA* d = Ps + j * DK + c * 4;
+            TA* d = Ps + j * DKP + c * 4;
             if constexpr (sizeof(TA) == 2) {
                 uint2 hh;
                 hh.x = pack2<TA>(v4.x, v4.y);
@@ -414,98 +425,111 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
         }
         __syncthreads();
 #pragma unroll
-        for (int qi = 0; qi < QPW; ++qi) {
-            const int r = warp * QPW + qi;
-            if (r >= nq) break;                            // warp-uniform
-            const int lo = win[r][0], hi = win[r][1];
-            if (hi <= kt || lo >= kt + nk || hi <= lo) continue;     // tile outside this query's window (warp-uniform)
-            const float* qui = qu + r * DK;
-            const float* qvi = qv + r * DK;
-            float sc[3] = {0.f, 0.f, 0.f};
-#pragma unroll 2
-            for (int c = 0; c < NCH; ++c) {
-                const int cc = (c + lane) & (NCH - 1);
-                float au[EPC], av[EPC];
+        for (int g = 0; g < QPW / QG; ++g) {
+            const int rb = warp * QPW + g * QG;            // first query of the register block
+            bool any = false;
 #pragma unroll
-                for (int e = 0; e < EPC; e += 4) {
-                    const float4 x = *reinterpret_cast<const float4*>(qui + cc * EPC + e);
-                    const float4 y = *reinterpret_cast<const float4*>(qvi + cc * EPC + e);
-                    au[e] = x.x; au[e + 1] = x.y; au[e + 2] = x.z; au[e + 3] = x.w;
-                    av[e] = y.x; av[e + 1] = y.y; av[e + 2] = y.z; av[e + 3] = y.w;
-                }
+            for (int q = 0; q < QG; ++q) any = any || (win[rb + q][1] > kt && win[rb + q][0] < kt + nk && win[rb + q][1] > win[rb + q][0]);
+            if (!any) continue;                            // warp-uniform
+            float sc[QG][3];
+#pragma unroll
+            for (int q = 0; q < QG; ++q) { sc[q][0] = 0.f; sc[q][1] = 0.f; sc[q][2] = 0.f; }
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                float au[QG][EPC], av[QG][EPC];
+#pragma unroll
+                for (int q = 0; q < QG; ++q)
+#pragma unroll
+                    for (int e = 0; e < EPC; e += 4) {     // same address in every lane: broadcast
+                        const float4 x = *reinterpret_cast<const float4*>(qu + (rb + q) * DK + c * EPC + e);
+                        const float4 y = *reinterpret_cast<const float4*>(qv + (rb + q) * DK + c * EPC + e);
+                        au[q][e] = x.x; au[q][e + 1] = x.y; au[q][e + 2] = x.z; au[q][e + 3] = x.w;
+                        av[q][e] = y.x; av[q][e + 1] = y.y; av[q][e + 2] = y.z; av[q][e + 3] = y.w;
+                    }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int j = lane + 32 * k;
                     if (j < nk) {
                         float kv[EPC], pp[EPC];
-                        Chunk<TA>::load(Ks + j * DK + cc * EPC, kv);
-                        Chunk<TA>::load(Ps + j * DK + cc * EPC, pp);
-                        float s = sc[k];
+                        Chunk<TA>::load(Ks + j * DKP + c * EPC, kv);
+                        Chunk<TA>::load(Ps + j * DKP + c * EPC, pp);
 #pragma unroll
-                        for (int e = 0; e < EPC; ++e) s = fmaf(au[e], kv[e], fmaf(av[e], pp[e], s));
-                        sc[k] = s;
+                        for (int q = 0; q < QG; ++q) {
+                            float s = sc[q][k];
+#pragma unroll
+                            for (int e = 0; e < EPC; ++e) s = fmaf(au[q][e], kv[e], fmaf(av[q][e], pp[e], s));
+                            sc[q][k] = s;
+                        }
                     }
                 }
             }
-            float m = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int key = kt + lane + 32 * k;
-                sc[k] = (lane + 32 * k < nk && key >= lo && key < hi) ? sc[k] * 0.125f : -INFINITY;
-                m = fmaxf(m, sc[k]);
-            }
-            m = warp_max(m);
-            const float m_new = fmaxf(m_run[qi], m);       // finite: the tile intersects the window
-            const float corr = __expf(m_run[qi] - m_new);  // m_run = -inf -> 0
-            float ssum = 0.f;
-            __syncwarp();                                  // previous query's PV done with the strip
+            for (int q = 0; q < QG; ++q) {
+                const int qi = g * QG + q;
+                const int lo = win[rb + q][0], hi = win[rb + q][1];
+                float m = -INFINITY;
+                float sq[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int j = lane + 32 * k;
-                if (j < nk) {
-                    const float e = __expf(sc[k] - m_new); // masked keys: exp(-inf) = 0
-                    pr[j] = e;
-                    ssum += e;
+                for (int k = 0; k < 3; ++k) {
+                    const int key = kt + lane + 32 * k;
+                    sq[k] = (lane + 32 * k < nk && key >= lo && key < hi) ? sc[q][k] * 0.125f : -INFINITY;
+                    m = fmaxf(m, sq[k]);
                 }
-            }
-            ssum = warp_sum(ssum);
-            __syncwarp();
-            l_run[qi] = l_run[qi] * corr + ssum;
-            float a0 = o0[qi] * corr, a1 = o1[qi] * corr;
-            const int j0 = max(lo - kt, 0), j1 = min(hi - kt, nk);
-            if constexpr (sizeof(TA) == 2) {
-                const uint32_t* vp = reinterpret_cast<const uint32_t*>(Vs) + lane;
+                m = warp_max(m);
+                if (m == -INFINITY) continue;              // this query sees nothing in this tile (warp-uniform)
+                const float m_new = fmaxf(m_run[qi], m);
+                const float corr = __expf(m_run[qi] - m_new);  // m_run = -inf -> 0
+                float ssum = 0.f;
+                __syncwarp();                              // previous query's PV is done with the strip
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int j = lane + 32 * k;
+                    if (j < nk) {
+                        const float e = __expf(sq[k] - m_new); // masked keys: exp(-inf) = 0
+                        pr[j] = e;
+                        ssum += e;
+                    }
+                }
+                ssum = warp_sum(ssum);
+                __syncwarp();
+                l_run[qi] = l_run[qi] * corr + ssum;
+                float a0 = o0[qi] * corr, a1 = o1[qi] * corr;
+                const int j0 = max(lo - kt, 0), j1 = min(hi - kt, nk);
+                if constexpr (sizeof(TA) == 2) {
+                    const uint32_t* vp = reinterpret_cast<const uint32_t*>(Vs) + lane;
 #pragma unroll 4
-                for (int j = j0; j < j1; ++j) {
-                    const float2 vv = unpack2<TA>(vp[j * (DK / 2)]);
-                    const float p = pr[j];
-                    a0 = fmaf(p, vv.x, a0);
-                    a1 = fmaf(p, vv.y, a1);
-                }
-            } else {
+                    for (int j = j0; j < j1; ++j) {
+                        const float2 vv = unpack2<TA>(vp[j * (DKP / 2)]);
+                        const float p = pr[j];
+                        a0 = fmaf(p, vv.x, a0);
+                        a1 = fmaf(p, vv.y, a1);
+                    }
+                } else {
 #pragma unroll 4
-                for (int j = j0; j < j1; ++j) {
-                    const float p = pr[j];
-                    a0 = fmaf(p, to_f(Vs[j * DK + 2 * lane]), a0);
-                    a1 = fmaf(p, to_f(Vs[j * DK + 2 * lane + 1]), a1);
+                    for (int j = j0; j < j1; ++j) {
+                        const float p = pr[j];
+                        a0 = fmaf(p, to_f(Vs[j * DKP + 2 * lane]), a0);
+                        a1 = fmaf(p, to_f(Vs[j * DKP + 2 * lane + 1]), a1);
+                    }
                 }
+                o0[qi] = a0;
+                o1[qi] = a1;
+                m_run[qi] = m_new;
             }
-            o0[qi] = a0;
-            o1[qi] = a1;
-            m_run[qi] = m_new;
         }
     }
 #pragma unroll
     for (int qi = 0; qi < QPW; ++qi) {
         const int r = warp * QPW + qi;
-        if (r >= nq) break;
-        const float inv = l_run[qi] > 0.f ? 1.f / l_run[qi] : 0.f;
-        TA* o = out + ((long long)b * T + q0 + r) * D + h * DK + 2 * lane;
-        if constexpr (sizeof(TA) == 2) {
-            *reinterpret_cast<uint32_t*>(o) = pack2<TA>(o0[qi] * inv, o1[qi] * inv);
-        } else {
-            o[0] = from_f<TA>(o0[qi] * inv);
-            o[1] = from_f<TA>(o1[qi] * inv);
+        if (r < nq) {
+            const float inv = l_run[qi] > 0.f ? 1.f / l_run[qi] : 0.f;
+            TA* o = out + ((long long)b * T + q0 + r) * D + h * DK + 2 * lane;
+            if constexpr (sizeof(TA) == 2) {
+                *reinterpret_cast<uint32_t*>(o) = pack2<TA>(o0[qi] * inv, o1[qi] * inv);
+            } else {
+                o[0] = from_f<TA>(o0[qi] * inv);
+                o[1] = from_f<TA>(o1[qi] * inv);
+            }
         }
     }
 }
@@ -555,7 +579,7 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
                       const float* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
     if (B <= 0 || T <= 0) return 0;
     dim3 grid(cdiv(T, QB), H, B);
-    const size_t smem = (size_t)3 * KT * DK * sizeof(TA) + (size_t)2 * QB * DK * sizeof(float) +
+    const size_t smem = (size_t)3 * KT * (DK + 16 / sizeof(TA)) * sizeof(TA) + (size_t)2 * QB * DK * sizeof(float) +
                         (size_t)(ATT_THREADS / 32) * KT * sizeof(float);
     static bool attr_set[2] = {false, false};
     if (!attr_set[sizeof(TA) == 2]) {
