@@ -133,7 +133,8 @@ def run_reference(args, rank, world):
     cfg = load_path_config(args.config)
     n = min(args.sessions, args.ref_sessions)
     steps, warm = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
-    v, t, th = cpu_reference_step_rate(cfg, n, steps, warm)
+    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1, which would starve the reference)
+    v, t, th = cpu_reference_step_rate(cfg, n, steps, warm, threads=os.cpu_count())
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -209,6 +210,7 @@ def main():
     ap.add_argument("--groups", type=int, default=-1, help="override session_groups (parallel layer streams)")
     ap.add_argument("--debug-skip", type=int, default=0, help="timing attribution only: bitmask of kernel classes to skip")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (fo_set_option), repeatable")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -245,6 +247,9 @@ def main():
         eng.set_option("session_groups", args.groups)
     if args.debug_skip:
         eng.set_option("debug_skip", args.debug_skip)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     if args.workload == "offline":
         bench_offline(args, eng, cfg, rank, world)
         eng.close()
@@ -366,7 +371,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, t, th = cpu_reference_step_rate(cfg, S, args.cpu_steps, 1)
+        v, t, th = cpu_reference_step_rate(cfg, S, args.cpu_steps, 1, threads=os.cpu_count())
         cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
                "sample": "%d sessions x %d chunks, oracle port of the reference modules (fp32 torch CPU), %.2f s/step" % (S, args.cpu_steps, t)}
 

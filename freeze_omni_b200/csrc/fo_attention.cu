@@ -123,6 +123,8 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
                         TA* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
+    FO_PDL_TRIGGER();
+    FO_PDL_WAIT();
     const int cap = a.ring_cap;
     const int t = a.t, D = a.H * DK;
     const int rows = a.window + t;                  // most keys a call can see
@@ -197,6 +199,7 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
             vreg[k] = pos_v[h * DK + d];
         }
     }
+    l2_prefetch_slice(a.prefetch, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, tid, ATT_THREADS);
     // ---- registers -> smem / ring ----
     if (has_new) {
         TA* sdst = (new_which ? Vs : Ks) + (cl + new_r) * DK + new_c * EPC;
@@ -536,6 +539,8 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
 
 __global__ void advance_sessions_kernel(const int32_t* __restrict__ ids, int n, int t, int chunk_size, int pe_wrap,
                                         int32_t* n_frames, int32_t* pe_index, int32_t* adapter_valid) {
+    FO_PDL_TRIGGER();
+    FO_PDL_WAIT();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
     const int s = ids[b];
@@ -565,7 +570,7 @@ int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* r
     }
     FO_CHECK(smem <= 160 * 1024, "attention_stream: window too large for shared memory");
     dim3 grid(a.n, a.H);
-    attention_stream_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(a, qkv, q32, ring, ptab, pos_u, pos_v, out);
+    FO_CUDA(launch_pdl(attention_stream_kernel<TA>, grid, dim3(ATT_THREADS), smem, st, a, qkv, q32, ring, ptab, pos_u, pos_v, out));
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
@@ -598,7 +603,7 @@ template int attention_offline<__half>(const __half*, const float*, int, int, in
 int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,
                       int32_t* pe_index, int32_t* adapter_valid, cudaStream_t st) {
     if (n <= 0) return 0;
-    advance_sessions_kernel<<<cdiv(n, 128), 128, 0, st>>>(ids, n, t, chunk_size, pe_wrap, n_frames, pe_index, adapter_valid);
+    FO_CUDA(launch_pdl(advance_sessions_kernel, dim3(cdiv(n, 128)), dim3(128), 0, st, ids, n, t, chunk_size, pe_wrap, n_frames, pe_index, adapter_valid));
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;

@@ -40,6 +40,30 @@ extern long long g_launches;      // kernels enqueued by this library (fo_stats.
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------
+// The kernels of the streaming chain are launched with programmaticStreamSerialization: a kernel may start (launch
+// latency, barrier/TMEM set-up, and in the GEMM the first WEIGHT stages, which do not depend on the previous kernel)
+// while its predecessor is still draining.  FO_PDL_TRIGGER lets the successor launch as soon as every CTA of this
+// grid has started; FO_PDL_WAIT returns once the predecessor grid has completed and its memory is visible.  Every
+// thread executes FO_PDL_WAIT before it touches global memory that another kernel of the chain writes or reads.
+extern int g_use_pdl;
+#define FO_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define FO_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- dtype helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
@@ -104,6 +128,31 @@ __host__ __device__ inline bool row_map(const RowMap& rm, int r, long long& dst)
     return b < rm.v1 && c < rm.v0;
 }
 
+// ---- next-kernel L2 prefetch ------------------------------------------------------------------------
+// A streaming step is a chain of short kernels, each of which starts by pulling data nobody has touched since the
+// previous step (this GEMM's weights, this layer's KV rings) from HBM.  Those addresses do not depend on the
+// activations, so every kernel asks L2 for the NEXT kernel's cold inputs while it runs (cp.async.bulk.prefetch.L2),
+// taking the HBM latency off the critical path of the chain.
+struct L2Prefetch {
+    const void* ptr[2] = {nullptr, nullptr};
+    long long bytes[2] = {0, 0};
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void l2_prefetch_slice(const L2Prefetch& pf, int cta, int nctas, int tid, int nthreads) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (pf.ptr[k] == nullptr) continue;
+        const long long per = ((pf.bytes[k] + nctas - 1) / nctas + 2047) & ~2047LL;
+        const long long start = (long long)cta * per, end = min(pf.bytes[k], start + per);
+        const char* base = reinterpret_cast<const char*>(pf.ptr[k]);
+        for (long long off = start + (long long)tid * 2048; off < end; off += (long long)nthreads * 2048) {
+            const unsigned sz = (unsigned)min(2048LL, end - off) & ~15u;
+            if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
+        }
+    }
+}
+#endif
+
 // ---- GEMM epilogue ---------------------------------------------------------------------------
 // C[m][n] = act((acc + bias[n]) * scale) (+ residual[m][n]);  written as fp32 (c_f32) and/or as the
 // activation type (c_act).  residual may alias c_f32 (in-place residual stream).
@@ -126,6 +175,7 @@ struct Epilogue {
     void* ln_act = nullptr;
     float* ln_f32 = nullptr;
     int* ln_counters = nullptr;
+    L2Prefetch prefetch;              // cold inputs of the kernels that follow (tcgen05 kernel only)
 };
 
 // C[rowmap(m), n] = A[m, :] . W[n, :]  for m < M (padded GEMM rows), n < N.  A/W are TIn (float or bf16),
@@ -146,6 +196,7 @@ struct TcTune { int swap, bn, split; };      // -1 / 0 = let the cost model deci
 int gemm_tc_init();
 int gemm_tc_workspace(TcWorkspace* ws);       // allocates; the caller frees the two device pointers
 void gemm_tc_force(const TcTune& t);
+void gemm_tc_force_producers(int npa, int npb);   // 0 = default
 long long gemm_tc_launches();                // tcgen05 kernel launches so far (tests check the path taken)
 // A and W: 16-bit operands of ONE format (fp16 when is_fp16, else bf16); c_act / ln_act are written in the same type.
 int gemm_tc(const void* A, int is_fp16, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
@@ -202,6 +253,7 @@ struct AttnStream {
     const int32_t* pe_index;  // per slot
     int n, t, H, ring_cap, window, full_chunk, pe_wrap, pos_rows;
     long long ring_slot_stride;   // elements between sessions of one layer: 2*H*ring_cap*64
+    L2Prefetch prefetch;          // cold inputs of the kernels that follow
 };
 // qkv (n*t, 3*D) activation type (K and V columns are read from it); q32 (n*t, 3*D) fp32 whose first D
 // columns hold Q (the QKV GEMM keeps Q in fp32, Epilogue::split_col); ring = this layer's

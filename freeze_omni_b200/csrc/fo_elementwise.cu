@@ -26,6 +26,8 @@ cmvn_conv1_kernel(const float* __restrict__ feats, int T, int F, const float* __
                   const float* __restrict__ istd, const float* __restrict__ w1, const float* __restrict__ b1,
                   int C, int T2, int F1, int F2P, long long NR, TA* __restrict__ c1) {
     extern __shared__ float rows[];     // 3 * F
+    FO_PDL_TRIGGER();
+    FO_PDL_WAIT();
     const int b = blockIdx.y, t1 = blockIdx.x;
     for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) {
         int r = i / F, f = i - r * F;
@@ -84,8 +86,10 @@ __global__ void __launch_bounds__(256)
 layer_norm_kernel(const float* __restrict__ x, int M, int D, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, int act, float out_scale, TA* __restrict__ y_act,
                   float* __restrict__ y_f32) {
+    FO_PDL_TRIGGER();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    FO_PDL_WAIT();
     if (row >= M) return;
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
     const int nv = D >> 7;                    // float4 per lane
@@ -147,6 +151,8 @@ __global__ void adapter_stage_kernel(const float* __restrict__ enc_out, const ui
                                      int km1, const int32_t* __restrict__ ids, float* slot_cache,
                                      const int32_t* __restrict__ slot_valid, const float* __restrict__ cache_in,
                                      float* cache_out, TA* __restrict__ xin) {
+    FO_PDL_TRIGGER();
+    FO_PDL_WAIT();
     const int b = blockIdx.x, r = blockIdx.y;          // r in [0, km1 + T)
     const int slot = ids ? ids[b] : -1;
     const int live = ids ? slot_valid[slot] : 0;
@@ -281,8 +287,8 @@ int cmvn_conv1(const float* feats, int B, int T, int F, const float* mean, const
     FO_CHECK(C % 4 == 0, "cmvn_conv1: channel count must be a multiple of 4");
     dim3 grid(2 * T2 + 1, B);                          // conv1 rows that feed a conv2 output row
     const int threads = C / 4 >= 256 ? 256 : ((C / 4 + 31) / 32) * 32;
-    cmvn_conv1_kernel<TA, 4><<<grid, threads, 3 * F * sizeof(float), st>>>(feats, T, F, mean, istd, w1, b1, C, T2, F1, F2 + 1,
-                                                                           (long long)B * T2 * (F2 + 1), c1);
+    FO_CUDA(launch_pdl(cmvn_conv1_kernel<TA, 4>, grid, dim3(threads), 3 * F * sizeof(float), st, feats, T, F, mean, istd, w1, b1, C,
+                       T2, F1, F2 + 1, (long long)B * T2 * (F2 + 1), c1));
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
@@ -316,9 +322,9 @@ int layer_norm(const float* x, int M, int D, const float* gamma, const float* be
     const int rows_per_cta = 8;
     dim3 grid(cdiv(M, rows_per_cta));
     if (D <= 1024)
-        layer_norm_kernel<TA, 8><<<grid, 256, 0, st>>>(x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32);
+        FO_CUDA(launch_pdl(layer_norm_kernel<TA, 8>, grid, dim3(256), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
     else
-        layer_norm_kernel<TA, 32><<<grid, 256, 0, st>>>(x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32);
+        FO_CUDA(launch_pdl(layer_norm_kernel<TA, 32>, grid, dim3(256), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
@@ -341,8 +347,8 @@ int adapter_stage(const float* enc_out, const uint8_t* mask, int B, int T, int D
                   cudaStream_t st) {
     if (B <= 0) return 0;
     dim3 grid(B, km1 + T);
-    adapter_stage_kernel<TA><<<grid, 256, 0, st>>>(enc_out, mask, T, D, km1, ids, slot_cache, slot_valid, cache_in,
-                                                   cache_out, xin);
+    FO_CUDA(launch_pdl(adapter_stage_kernel<TA>, grid, dim3(256), 0, st, enc_out, mask, T, D, km1, ids, slot_cache,
+                       (const int32_t*)slot_valid, cache_in, cache_out, xin));
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;

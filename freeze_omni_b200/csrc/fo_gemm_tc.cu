@@ -32,7 +32,7 @@ namespace fo {
 
 namespace {
 
-constexpr int TC_THREADS = 224;
+constexpr int TC_THREADS = 352;   // warp 1 MMA, warps 2..5 epilogue, warps 0 and 6..10 TMA producers (up to 6)
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
@@ -50,6 +50,8 @@ struct TcParams {
     int kblocks, kb_per_split;
     int bn;                      // UMMA N
     int swap;                    // 0: M side = activations (C rows), 1: M side = weights (C columns)
+    int npa, npb;                // TMA producer threads per operand: each loads a 128/npa (bn/npb) row slice of every stage,
+                                 // several bulk-tensor copies in flight per SM instead of one large one
     int act_fp16;                // activations (and c_act / ln_act outputs) are IEEE fp16 instead of bf16
     int stages;
     int tmem_cols;
@@ -173,9 +175,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), accb = smem_u32(&acc_bar);
 
+    FO_PDL_TRIGGER();
     if (threadIdx.x == 0) TC_TRACE(0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 2); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, p.npa + p.npb); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(accb, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -203,15 +206,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int ld0 = bn + 4;                                    // swap=0 staging [row][col]
     constexpr int LD1 = BM + 4;                                // swap=1 staging [col][row]
 
-    if (warp == 0 || warp == 6) {
-        if (lane == 0) {
-            const int w = warp == 0 ? 0 : 1;
+    const int pi = warp == 0 ? 0 : warp - 5;                   // producer index of warps 0, 6, 7, ...
+    if (warp == 0 || warp >= 6) {
+        if (lane == 0 && pi < p.npa + p.npb) {
+            const int w = pi < p.npa ? 0 : 1;
+            // the weight operand does not depend on the previous kernel: its stages fill while that kernel drains
+            if ((w == 0) != (p.swap != 0)) FO_PDL_WAIT();
+            const int sub = w ? pi - p.npa : pi;                 // row slice of the operand tile this thread loads
+            const int sub_rows = w ? p.bn / p.npb : BM / p.npa;
             const CUtensorMap* map = w ? &map_b : &map_a;
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
             const int segb = w ? p.op_b.seg_blocks : p.op_a.seg_blocks;
-            const int row0 = w ? tile_b * p.bn : tile_a * BM;
-            const uint32_t bytes = w ? b_bytes : a_bytes;
-            uint32_t dst = base + (w ? a_bytes : 0u);
+            const int row0 = (w ? tile_b * p.bn : tile_a * BM) + sub * sub_rows;
+            const uint32_t bytes = (uint32_t)sub_rows * BK * 2;
+            uint32_t dst = base + (w ? a_bytes : 0u) + (uint32_t)sub * bytes;
             int seg = kb0 / segb, cblk = kb0 - seg * segb;
             int row = row0 + s_rowoff[w][seg], plane = s_plane[w][seg];
             int s = 0;
@@ -224,7 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 dst += stage_bytes;
                 if (++s == stages) { s = 0; ph ^= 1u; dst -= stages * stage_bytes; }
             }
-            if (w == 0) TC_TRACE(4);
+            if (pi == 0) TC_TRACE(4);
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -257,6 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int row_l = q * 32 + lane;                       // row of the tile on the UMMA-M side
         const int et = threadIdx.x - 64;                       // 0..127 among the epilogue threads
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        FO_PDL_WAIT();
         // output row of every tile row / column, once
         if (!p.swap) {
             const int ga = tile_a * BM + et;
@@ -269,6 +278,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 s_drow[c] = (m < p.rows_b && row_map(p.rmap, m, d)) ? (int)d : -1;
             }
         }
+        // while the mainloop runs: ask L2 for the cold inputs of the kernels that follow
+        l2_prefetch_slice(p.ep.prefetch, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x,
+                          gridDim.x * gridDim.y * gridDim.z, et, 128);
         mbar_wait(accb, 0);
         tc_fence_after();
         if (et == 0) TC_TRACE(8);
@@ -332,6 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // swap=0: staging rows are C rows, bn columns starting at n0;  swap=1: staging "columns" are C rows,
     // 128 output columns starting at tile_a*128.  The lane's columns (hence bias) are fixed across rows;
     // rows are unrolled so that several independent load/store chains are in flight per warp.
+    FO_PDL_WAIT();                                             // producer / MMA warps: before their first global access
     __syncthreads();                                           // staging tile (or nothing, for a non-final split) complete
     if (threadIdx.x == 64) TC_TRACE(9);
     if (is_last_s) {
@@ -458,6 +471,7 @@ constexpr int MAX_TILES = 16384;
 int g_sm_count = 148;
 TcTune g_forced = {-1, -1, -1};
 long long g_tc_launches = 0;
+int g_forced_npa = 0, g_forced_npb = 0;
 
 // encoded tensor maps are pure functions of (pointer, extents, box): cached so that eager launches stay cheap on the host
 struct MapKey {
@@ -579,6 +593,7 @@ int gemm_tc_workspace(TcWorkspace* ws) {
 }
 
 void gemm_tc_force(const TcTune& t) { g_forced = t; }
+void gemm_tc_force_producers(int npa, int npb) { g_forced_npa = npa; g_forced_npb = npb; }
 long long gemm_tc_launches() { return g_tc_launches; }
 
 int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
@@ -612,6 +627,9 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     p.bn = pl.bn;
     p.swap = pl.swap;
     p.act_fp16 = act_fp16;
+    p.npa = g_forced_npa > 0 ? g_forced_npa : 4;
+    p.npb = g_forced_npb > 0 ? g_forced_npb : (pl.bn >= 64 ? 2 : 1);
+    if (pl.bn % (8 * p.npb) != 0) p.npb = 1;
     const uint32_t stage = (BM + pl.bn) * BK * 2;
     p.stages = std::max(1, std::min<int>(std::min(MAX_STAGES, kbs), (int)(SMEM_BUDGET / stage)));
     if (M <= 384) {
@@ -656,15 +674,12 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
         FO_CHECK(need <= ws.partial_bytes, "gemm_tc: split-K workspace too small (%zu bytes needed)", need);
     }
     CUtensorMap map_act, map_w;
-    FO_TRY(make_map(&map_act, reinterpret_cast<const bf16*>(A), ga.seg_len, ga.rows, ga.planes, pl.swap ? pl.bn : BM));
-    FO_TRY(make_map(&map_w, reinterpret_cast<const bf16*>(W), K, N, 1, pl.swap ? BM : pl.bn));
+    FO_TRY(make_map(&map_act, reinterpret_cast<const bf16*>(A), ga.seg_len, ga.rows, ga.planes, pl.swap ? pl.bn / p.npb : BM / p.npa));
+    FO_TRY(make_map(&map_w, reinterpret_cast<const bf16*>(W), K, N, 1, pl.swap ? BM / p.npa : pl.bn / p.npb));
     dim3 grid(ta, tb, pl.split);
     const size_t tile_stage = pl.swap ? (size_t)pl.bn * (BM + 4) * 4 : (size_t)BM * (pl.bn + 4) * 4;
     const size_t smem = std::max((size_t)p.stages * stage, tile_stage) + 1024;
-    if (pl.swap)
-        gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_w, map_act, p);
-    else
-        gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_act, map_w, p);
+    FO_CUDA(launch_pdl(gemm_tc_kernel, grid, dim3(TC_THREADS), smem, st, pl.swap ? map_w : map_act, pl.swap ? map_act : map_w, p));
     FO_LAUNCHED();
     ++g_tc_launches;
     if (trace_on) {
