@@ -17,7 +17,7 @@ class FoConfig(C.Structure):
         "feat_dim", "d_model", "n_heads", "ffn_dim", "n_layers", "chunk_size", "left_chunks",
         "input_layer_linear", "pos_max_len", "llm_dim", "adapter_kernel", "adapter_gelu",
         "has_encoder", "has_adapter", "sample_rate", "frame_len", "frame_shift", "frames_per_chunk",
-        "context_frames", "max_sessions", "max_stream_frames")]
+        "context_frames", "max_sessions", "max_stream_frames", "ffn_conv_kernel")]
 
 
 class FoStats(C.Structure):
@@ -47,6 +47,7 @@ SYMBOLS = {
     "fo_session_import_kv": (C.c_int, [_P, C.c_int32, C.c_int, _P, _P, C.c_int32]),
     "fo_session_export_adapter_cache": (C.c_int, [_P, C.c_int32, _P, _I32P]),
     "fo_session_import_adapter_cache": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
+    "fo_session_export_ffn_cache": (C.c_int, [_P, C.c_int32, C.c_int, _P]),
     "fo_fbank_stream": (C.c_int, [_P, _I32P, C.c_int, _P, C.c_int, C.c_float, _P, _P]),
     "fo_fbank_offline": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_float, _P, _P]),
     "fo_encode_stream": (C.c_int, [_P, _I32P, C.c_int, _P, C.c_int, _P, _P, _P]),
@@ -78,7 +79,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.fo_abi_version() != 1:
+    if lib.fo_abi_version() != 2:
         raise RuntimeError("libfo_b200.so ABI version mismatch")
     _lib = lib
     return lib

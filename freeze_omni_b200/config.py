@@ -43,6 +43,10 @@ class PathConfig:
     input_layer: str = "linear"   # transformer-input-layer: linear | none
     normalize_before: bool = True
     dynamic_chunks: bool = False
+    # positionwise layer (transformer.py:205-217): "linear" = PositionwiseFeedForward (attention.py:122-143);
+    # "conv1d-linear" = Conv1dLinear (attention.py:198-266): causal depthwise Conv1d(k) + 1x1 Conv1d + ReLU + Linear
+    ffn_type: str = "linear"
+    ffn_conv_kernel: int = 1
     pos_max_len: int = 5000       # RelPositionalEncoding max_len default (attention.py:78)
     # adapter (models/adapter.py:73-110, single-conv branch)
     llm_dim: int = 3584
@@ -121,6 +125,11 @@ class PathConfig:
             raise ValueError("adapter kernel_size must be >= 2")
         if not self.normalize_before:
             raise ValueError("post-norm layers (normalize_before=False) are not built")
+        if self.ffn_type not in ("linear", "conv1d-linear"):
+            raise ValueError("positionwise-layer-type %r: 'conv1d' (MultiLayeredConv1d, attention.py:145-196) pads "
+                             "symmetrically and has no streaming form; only linear / conv1d-linear are built" % self.ffn_type)
+        if self.ffn_type == "conv1d-linear" and not (2 <= self.ffn_conv_kernel <= 16):
+            raise ValueError("conv1d-linear needs 2 <= positionwise-conv-kernel_size <= 16")
 
 
 def load_yaml(name_or_path: str) -> Dict[str, Any]:
@@ -145,9 +154,9 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
     sub.update(para.get("subsampling", {}))
     if tr["transformer-pos-enc-class"] != "rel-enc":
         raise ValueError("only transformer-pos-enc-class 'rel-enc' can stream (attention.py:105)")
-    if tr["transformer-positionwise-layer-type"] != "linear":
-        raise ValueError("only positionwise-layer-type 'linear' streams in the reference "
-                         "(attention.py:254-266 is mis-wired); refusing %r" % tr["transformer-positionwise-layer-type"])
+    if tr["transformer-positionwise-layer-type"] not in ("linear", "conv1d-linear"):
+        raise ValueError("positionwise-layer-type %r is not built (MultiLayeredConv1d has no causal / streaming form, "
+                         "attention.py:145-196)" % tr["transformer-positionwise-layer-type"])
     if tr["transformer-concat-after"]:
         raise ValueError("transformer-concat-after is not built")
     if sub["subsampling-rate"] != 4:
@@ -175,6 +184,8 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
         input_layer=str(tr["transformer-input-layer"]),
         normalize_before=bool(tr["transformer-normalize-before"]),
         dynamic_chunks=bool(tr["transformer-dynamic-chunks"]),
+        ffn_type=str(tr["transformer-positionwise-layer-type"]),
+        ffn_conv_kernel=int(tr["transformer-positionwise-conv-kernel_size"]) if tr["transformer-positionwise-layer-type"] == "conv1d-linear" else 1,
         llm_dim=int(mc.get("llm_embed_dim", 3584)), adapter_kernel=int(mc.get("kernel_size", 5)),
         adapter_act=str(mc.get("activation_func", "gelu")), adapter_norm=str(mc.get("norm", "layer")),
         sample_rate=int(fe.get("sample_rate", 16000)), frame_length_ms=int(fe.get("frame_length_ms", 25)),

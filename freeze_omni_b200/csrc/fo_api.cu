@@ -55,6 +55,7 @@ struct LayerW {
     void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
     float* ptab = nullptr;                    // P_l = pe * Wpos_l^T, fp32 [pos_rows][D]
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+    float *dw_w = nullptr, *dw_b = nullptr;   // Conv1dLinear depthwise taps [C][k] and bias (fp32); w1 is then the 1x1 conv
     float *pos_u = nullptr, *pos_v = nullptr, *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
 };
 
@@ -74,6 +75,8 @@ struct fo_ctx {
 
     // derived dims
     int F = 0, F1 = 0, F2 = 0, D = 0, H = 0, FF = 0, L = 0, E = 0, KA = 0;
+    int KF = 0;                               // Conv1dLinear kernel size (0: plain feed-forward)
+    float* ffn_cache = nullptr;               // [slot][L][KF-1][D] fp32: left context of the depthwise conv
     int window = 0, full_chunk = 0, pe_wrap = 0, pos_rows = 0, ring_cap = 0, max_t = 0;
     int carry = 0, chunk_samples = 0, fft = 0;
 
@@ -141,7 +144,7 @@ struct fo_ctx {
 namespace {
 
 enum { WS_FEATS = 0, WS_C1, WS_C2, WS_XSUB, WS_EMB, WS_X, WS_H, WS_QKV, WS_ATT, WS_FFH, WS_ENC, WS_XIN, WS_ACONV, WS_AH,
-       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_COUNT };
+       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_COUNT };
 
 int dev_alloc(fo_ctx* c, void** p, size_t bytes) {
     *p = nullptr;
@@ -365,8 +368,15 @@ int finalize_t(fo_ctx* c) {
             FO_TRY(keep_f32(c, p + "self_attn.linear_out.bias", {D}, &w.bo));
             FO_TRY(keep_f32(c, p + "self_attn.pos_bias_u", {H, 64}, &w.pos_u));
             FO_TRY(keep_f32(c, p + "self_attn.pos_bias_v", {H, 64}, &w.pos_v));
-            FO_TRY(keep_w<TW>(c, p + "feed_forward.w_1.weight", {FF, D}, &w.w1));
-            FO_TRY(keep_f32(c, p + "feed_forward.w_1.bias", {FF}, &w.b1));
+            if (c->KF >= 2) {                         // Conv1dLinear (attention.py:217-233)
+                FO_TRY(keep_f32(c, p + "feed_forward.w_1.0.weight", {D, 1, c->KF}, &w.dw_w));
+                FO_TRY(keep_f32(c, p + "feed_forward.w_1.0.bias", {D}, &w.dw_b));
+                FO_TRY(keep_w<TW>(c, p + "feed_forward.w_1.1.weight", {FF, D, 1}, &w.w1));
+                FO_TRY(keep_f32(c, p + "feed_forward.w_1.1.bias", {FF}, &w.b1));
+            } else {
+                FO_TRY(keep_w<TW>(c, p + "feed_forward.w_1.weight", {FF, D}, &w.w1));
+                FO_TRY(keep_f32(c, p + "feed_forward.w_1.bias", {FF}, &w.b1));
+            }
             FO_TRY(keep_w<TW>(c, p + "feed_forward.w_2.weight", {D, FF}, &w.w2));
             FO_TRY(keep_f32(c, p + "feed_forward.w_2.bias", {D}, &w.b2));
             FO_TRY(keep_f32(c, p + "norm1.weight", {D}, &w.ln1g));
@@ -570,9 +580,15 @@ int layer_pre(fo_ctx* c, const LayerW& w, int M, TA* h, TA* qkv, float* q32, con
     }
     return gemm<TA>(c, h, w.wqkv, M, 3 * D, D, e, st);
 }
+struct FfnConv {                  // Conv1dLinear only: where the rows come from
+    int B = 0, T = 0;             // rows = B * T
+    const int32_t* ids = nullptr; // streaming: session slots (left context carried); offline: null (zero padding)
+    int layer = 0;
+    void* hc = nullptr;           // depthwise output buffer (M, D), activation type
+};
 template <typename TA>
 int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* ffh, const NextNorm& nn,
-               const void* next_wqkv, cudaStream_t st) {
+               const void* next_wqkv, const FfnConv& fc, cudaStream_t st) {
     const int D = c->D, FF = c->FF;
     const long long wsz = (long long)c->esz;
     Epilogue e;
@@ -586,13 +602,22 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
     e.ln_act = h;
     if (!(c->debug_skip & 4)) FO_TRY(gemm<TA>(c, att, w.wo, M, D, D, e, st));
     if (c->debug_skip & 8) return 0;
+    const TA* ffn_in = h;
+    if (c->KF >= 2) {
+        // Conv1dLinear: causal depthwise conv over time on norm2's output, then the 1x1 conv is the FFN1 GEMM
+        const long long slot_stride = (long long)c->L * (c->KF - 1) * D;
+        FO_TRY(depthwise_conv<TA>(h, fc.B, fc.T, D, c->KF, w.dw_w, w.dw_b, fc.ids,
+                                  c->ffn_cache + (long long)fc.layer * (c->KF - 1) * D, slot_stride,
+                                  reinterpret_cast<TA*>(fc.hc), st));
+        ffn_in = reinterpret_cast<const TA*>(fc.hc);
+    }
     Epilogue e1;
     if (c->use_prefetch && next_wqkv) e1.prefetch = pf1(next_wqkv, 3LL * D * D * wsz);   // FFN1 runs: next layer's QKV weights
     e1.bias = w.b1;
     e1.relu = 1;
     e1.c_act = ffh;
     e1.ldc = FF;
-    FO_TRY(gemm<TA>(c, h, w.w1, M, FF, D, e1, st));
+    FO_TRY(gemm<TA>(c, ffn_in, w.w1, M, FF, D, e1, st));
     Epilogue e2;
     e2.bias = w.b2;
     e2.residual = x;
@@ -618,6 +643,8 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
     float* q32 = reinterpret_cast<float*>(qkv);
     if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
+    void* hc = nullptr;
+    if (c->KF >= 2) FO_TRY(ws_ensure(c, WS_HC, (size_t)M * D * sizeof(TA), &hc));
     // The 24 layers run per SESSION GROUP on parallel streams (fork/join with events, also under graph capture):
     // sessions are independent, every layer kernel of a 64-session step is latency bound (<= 148 CTAs, 8-16 us), so
     // two groups' kernels overlap each other's pipeline fill, epilogue and launch gaps.  Rows of one group are
@@ -671,7 +698,10 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
                                          attg, sg);
             NextNorm nn{last ? c->after_g : c->layers[l + 1].ln1g, last ? c->after_b : c->layers[l + 1].ln1b,
                         last ? enc_out_dev + r0 * D : nullptr};
-            if (r == 0) r = layer_post<TA>(c, w, xg, Mg, attg, hg, ffhg, nn, last ? nullptr : c->layers[l + 1].wqkv, sg);
+            FfnConv fc;
+            fc.B = ng; fc.T = t; fc.ids = c->ids_dev + s0; fc.layer = l;
+            fc.hc = hc ? reinterpret_cast<TA*>(hc) + r0 * D : nullptr;
+            if (r == 0) r = layer_post<TA>(c, w, xg, Mg, attg, hg, ffhg, nn, last ? nullptr : c->layers[l + 1].wqkv, fc, sg);
             if (r != 0) { c->tc_cur = &c->tc_wsg[0]; return r; }
         }
     }
@@ -704,6 +734,8 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
     FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
     float* q32 = reinterpret_cast<float*>(qkv);
     if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
+    void* hc = nullptr;
+    if (c->KF >= 2) FO_TRY(ws_ensure(c, WS_HC, (size_t)M * D * sizeof(TA), &hc));
     FO_TRY(layer_norm<TA>(x, M, D, c->layers[0].ln1g, c->layers[0].ln1b, 1e-5f, 0, 1.0f, reinterpret_cast<TA*>(h), nullptr, st));
     for (int l = 0; l < c->L; ++l) {
         const LayerW& w = c->layers[l];
@@ -713,7 +745,9 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
                                      w.ptab, w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
         NextNorm nn{last ? c->after_g : c->layers[l + 1].ln1g, last ? c->after_b : c->layers[l + 1].ln1b,
                     last ? enc_out_dev : nullptr};
-        FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), nn, nullptr, st));
+        FfnConv fc;
+        fc.B = B; fc.T = T2; fc.ids = nullptr; fc.layer = l; fc.hc = hc;
+        FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), nn, nullptr, fc, st));
     }
     if (c->cfg.has_adapter && y_dev)
         FO_TRY(adapter_program<TA>(c, enc_out_dev, mask2, B, T2, nullptr, nullptr, nullptr, y_dev, st));
@@ -759,6 +793,7 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
     c->F = cfg->feat_dim; c->F1 = (c->F - 1) / 2; c->F2 = (c->F1 - 1) / 2;
     c->D = cfg->d_model; c->H = cfg->n_heads; c->FF = cfg->ffn_dim; c->L = cfg->n_layers; c->E = cfg->llm_dim;
     c->KA = cfg->adapter_kernel;
+    c->KF = cfg->ffn_conv_kernel >= 2 ? cfg->ffn_conv_kernel : 0;
     const bool streaming = cfg->chunk_size > 0 && cfg->left_chunks > 0;
     c->window = streaming ? cfg->chunk_size * cfg->left_chunks : 1;                  // attention.py:290-295
     c->full_chunk = (cfg->left_chunks + 1) * cfg->chunk_size;                         // attention.py:83
@@ -786,6 +821,12 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
         if (!r) { r = dev_alloc(c, &p, (size_t)S * (c->carry + c->chunk_samples) * sizeof(float)); c->samples = (float*)p; }
         if (!r) { r = dev_alloc(c, &p, (size_t)S * (cfg->context_frames + cfg->frames_per_chunk) * c->F * sizeof(float)); c->feat_ring = (float*)p; }
         if (!r && cudaMemset(c->ring, 0, ring_bytes) != cudaSuccess) r = FO_ERR_CUDA;
+        if (!r && c->KF >= 2) {
+            if (c->KF > 16) { set_error("fo_create: ffn_conv_kernel must be <= 16"); r = FO_ERR_ARG; }
+            const size_t fb = (size_t)S * c->L * (c->KF - 1) * c->D * sizeof(float);
+            if (!r) { r = dev_alloc(c, &p, fb); c->ffn_cache = (float*)p; }
+            if (!r && cudaMemset(c->ffn_cache, 0, fb) != cudaSuccess) r = FO_ERR_CUDA;
+        }
     }
     {
         void* p = nullptr;
@@ -883,6 +924,10 @@ static int reset_slot(fo_ctx* c, int s) {
                            (size_t)(c->cfg.context_frames + c->cfg.frames_per_chunk) * c->F * 4));
     }
     FO_CUDA(cudaMemcpy(c->ad_valid + s, &z, 4, cudaMemcpyHostToDevice));
+    if (c->ffn_cache) {
+        const size_t per = (size_t)c->L * (c->KF - 1) * c->D;
+        FO_CUDA(cudaMemset(c->ffn_cache + (size_t)s * per, 0, per * sizeof(float)));     // left_padding zeros (attention.py:215,251)
+    }
     return 0;
 }
 
@@ -1051,6 +1096,21 @@ int fo_session_import_adapter_cache(fo_ctx* c, int32_t id, const float* cache, i
         FO_CUDA(cudaMemcpy(c->ad_cache + (size_t)id * 2 * km1 * D, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice));
     }
     FO_CUDA(cudaMemcpy(c->ad_valid + id, &live, 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int fo_session_export_ffn_cache(fo_ctx* c, int32_t id, int layer, float* cache) {
+    FO_CHECK(c && c->ffn_cache && cache, "fo_session_export_ffn_cache: context has no Conv1dLinear cache");
+    FO_TRY(check_ids(c, &id, 1));
+    FO_CHECK(layer >= 0 && layer < c->L, "layer %d out of range", layer);
+    FO_CUDA(cudaSetDevice(c->device));
+    FO_CUDA(cudaDeviceSynchronize());
+    const int km1 = c->KF - 1, D = c->D;
+    std::vector<float> tm((size_t)km1 * D), out((size_t)km1 * D);
+    FO_CUDA(cudaMemcpy(tm.data(), c->ffn_cache + ((size_t)id * c->L + layer) * km1 * D, tm.size() * 4, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < km1; ++r)
+        for (int ch = 0; ch < D; ++ch) out[(size_t)ch * km1 + r] = tm[(size_t)r * D + ch];    // (D, k-1) as attention.py:258
+    FO_CUDA(cudaMemcpy(cache, out.data(), out.size() * 4, cudaMemcpyDefault));
     return 0;
 }
 

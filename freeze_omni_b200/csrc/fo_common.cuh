@@ -243,6 +243,13 @@ int adapter_stage(const float* enc_out, const uint8_t* mask, int B, int T, int D
                   const int32_t* ids, float* slot_cache, int32_t* slot_valid,       // slot-resident (ids != null)
                   const float* cache_in, float* cache_out,                          // explicit (B, D, km1) layout
                   TA* xin, cudaStream_t st);
+// Conv1dLinear's causal depthwise Conv1d over time (attention.py:217-224,251): y[r][c] = b[c] + sum_tau w[c][tau] *
+// xin[r + tau][c], xin = [left context (k-1 rows) | x].  Streaming (ids != null): x is (n, t, C), the left context of
+// session ids[b] lives in slot_cache (fp32, (k-1, C) per slot, stride slot_stride) and is replaced by the last k-1 rows
+// of xin.  Offline (ids == null): x is (B, T, C) with zero left padding per utterance.
+template <typename TA>
+int depthwise_conv(const TA* x, int B, int T, int C, int k, const float* w, const float* bias, const int32_t* ids,
+                   float* slot_cache, long long slot_stride, TA* y, cudaStream_t st);
 int subsample_mask(const int32_t* ilens, int B, int T, int T2, uint8_t* mask2, int32_t* ilens2, cudaStream_t st);
 int stride2_mask(const uint8_t* mask, int B, int T, int To, uint8_t* out, cudaStream_t st);
 

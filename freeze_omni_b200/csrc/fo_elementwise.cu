@@ -180,6 +180,59 @@ __global__ void adapter_stage_kernel(const float* __restrict__ enc_out, const ui
     }
 }
 
+// grid (ceil(T / DW_TB), B), block = channels (strided).  Each thread owns one channel of DW_TB consecutive output rows:
+// it walks the k-1+DW_TB input rows once (sliding window in registers), so every input element is read once per CTA.
+constexpr int DW_TB = 16;
+constexpr int DW_KMAX = 16;
+template <typename TA>
+__global__ void __launch_bounds__(256)
+depthwise_conv_kernel(const TA* __restrict__ x, int T, int C, int k, const float* __restrict__ w,
+                      const float* __restrict__ bias, const int32_t* __restrict__ ids, float* slot_cache,
+                      long long slot_stride, TA* __restrict__ y) {
+    FO_PDL_TRIGGER();
+    FO_PDL_WAIT();
+    const int b = blockIdx.y, r0 = blockIdx.x * DW_TB;
+    const int nr = min(DW_TB, T - r0);
+    const int km1 = k - 1;
+    float* cache = ids ? slot_cache + (long long)ids[b] * slot_stride : nullptr;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float wv[DW_KMAX], win[DW_KMAX];
+#pragma unroll
+        for (int q = 0; q < DW_KMAX; ++q) wv[q] = q < k ? w[c * k + q] : 0.f;
+        const float bv = bias[c];
+        // left context of the first output row: rows r0-km1 .. r0-1 of the virtual [context | x]
+#pragma unroll
+        for (int q = 0; q < DW_KMAX - 1; ++q) {
+            if (q < km1) {
+                const int r = r0 - km1 + q;
+                float v = 0.f;
+                if (r >= 0) v = to_f(x[((long long)b * T + r) * C + c]);
+                else if (cache) v = cache[(long long)(km1 + r) * C + c];        // row r of the old context, r in [-km1, -1]
+                win[q] = v;
+            }
+        }
+        for (int i = 0; i < nr; ++i) {
+            const float cur = to_f(x[((long long)b * T + r0 + i) * C + c]);
+            float acc = bv;
+#pragma unroll
+            for (int q = 0; q < DW_KMAX - 1; ++q)
+                if (q < km1) acc = fmaf(wv[q], win[q], acc);
+            acc = fmaf(wv[km1], cur, acc);
+            y[((long long)b * T + r0 + i) * C + c] = from_f<TA>(acc);
+#pragma unroll
+            for (int q = 0; q < DW_KMAX - 2; ++q)
+                if (q < km1 - 1) win[q] = win[q + 1];
+            win[km1 - 1] = cur;
+        }
+        // streaming: the CTA that owns the last rows writes the new context (single CTA per session when T <= DW_TB;
+        // for longer calls the old context is only read by the first CTA and written by the last one, after a
+        // kernel-wide ordering that a second launch provides: the host rejects streaming calls with T > DW_TB)
+        if (cache && r0 + nr == T) {
+            for (int q = 0; q < km1; ++q) cache[(long long)q * C + c] = win[q];
+        }
+    }
+}
+
 __global__ void subsample_mask_kernel(const int32_t* __restrict__ ilens, int T, int T2, uint8_t* __restrict__ mask2,
                                       int32_t* __restrict__ ilens2) {
     // subsampling.py:65: m'[j] = m[4j + 6]; ilens' = m'.sum  (subsampling.py:100)
@@ -356,6 +409,20 @@ int adapter_stage(const float* enc_out, const uint8_t* mask, int B, int T, int D
 template int adapter_stage<float>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, float*, cudaStream_t);
 template int adapter_stage<bf16>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, bf16*, cudaStream_t);
 template int adapter_stage<__half>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, __half*, cudaStream_t);
+
+template <typename TA>
+int depthwise_conv(const TA* x, int B, int T, int C, int k, const float* w, const float* bias, const int32_t* ids,
+                   float* slot_cache, long long slot_stride, TA* y, cudaStream_t st) {
+    if (B <= 0 || T <= 0) return 0;
+    FO_CHECK(k >= 2 && k <= DW_KMAX, "depthwise_conv: kernel size %d outside 2..%d", k, DW_KMAX);
+    FO_CHECK(!ids || T <= DW_TB, "depthwise_conv: a streaming call may carry at most %d frames", DW_TB);
+    dim3 grid(cdiv(T, DW_TB), B);
+    FO_CUDA(launch_pdl(depthwise_conv_kernel<TA>, grid, dim3(256), 0, st, x, T, C, k, w, bias, ids, slot_cache, slot_stride, y));
+    FO_LAUNCHED();
+    return 0;
+}
+template int depthwise_conv<float>(const float*, int, int, int, int, const float*, const float*, const int32_t*, float*, long long, float*, cudaStream_t);
+template int depthwise_conv<__half>(const __half*, int, int, int, int, const float*, const float*, const int32_t*, float*, long long, __half*, cudaStream_t);
 
 int subsample_mask(const int32_t* ilens, int B, int T, int T2, uint8_t* mask2, int32_t* ilens2, cudaStream_t st) {
     if (B <= 0) return 0;

@@ -63,7 +63,8 @@ class Engine:
             adapter_kernel=cfg.adapter_kernel, adapter_gelu=int(cfg.adapter_act == "gelu"),
             has_encoder=int(self.has_encoder), has_adapter=int(self.has_adapter), sample_rate=cfg.sample_rate,
             frame_len=cfg.frame_len, frame_shift=cfg.frame_shift, frames_per_chunk=cfg.frames_per_chunk,
-            context_frames=cfg.context_frames, max_sessions=int(max_sessions), max_stream_frames=int(msf))
+            context_frames=cfg.context_frames, max_sessions=int(max_sessions), max_stream_frames=int(msf),
+            ffn_conv_kernel=int(cfg.ffn_conv_kernel) if cfg.ffn_type == "conv1d-linear" else 0)
         h = C.c_void_p()
         _lib.check(self.lib.fo_create(C.byref(c), self.device, _lib.FO_BF16 if dtype == torch.bfloat16 else _lib.FO_F32,
                                       C.byref(h)))
@@ -182,6 +183,12 @@ class Engine:
 
     def set_frames(self, sid: int, n_frames: int) -> None:
         _lib.check(self.lib.fo_session_set_frames(self._h, int(sid), int(n_frames)))
+
+    def export_ffn_cache(self, sid: int, layer: int) -> torch.Tensor:
+        """Conv1dLinear left context of one layer, reference layout (1, d_model, k-1) (attention.py:258)."""
+        buf = torch.empty(1, self.cfg.d_model, self.cfg.ffn_conv_kernel - 1)
+        _lib.check(self.lib.fo_session_export_ffn_cache(self._h, int(sid), int(layer), buf.data_ptr()))
+        return buf
 
     def export_adapter_cache(self, sid: int) -> Optional[torch.Tensor]:
         buf = torch.empty(1, self.cfg.d_model, self.cfg.adapter_kernel - 1)

@@ -126,7 +126,11 @@ class speechEncoder(nn.Module):
             nn.init.xavier_uniform_(att.pos_bias_u)
             nn.init.xavier_uniform_(att.pos_bias_v)
             ff = _Holder()
-            ff.w_1, ff.w_2 = nn.Linear(d, cfg.ffn_dim), nn.Linear(cfg.ffn_dim, d)
+            if cfg.ffn_type == "conv1d-linear":        # Conv1dLinear (attention.py:217-234)
+                ff.w_1 = nn.Sequential(nn.Conv1d(d, d, cfg.ffn_conv_kernel, groups=d), nn.Conv1d(d, cfg.ffn_dim, 1))
+            else:
+                ff.w_1 = nn.Linear(d, cfg.ffn_dim)
+            ff.w_2 = nn.Linear(cfg.ffn_dim, d)
             lay.self_attn, lay.feed_forward = att, ff
             lay.norm1, lay.norm2 = nn.LayerNorm(d), nn.LayerNorm(d)
             layers.append(lay)

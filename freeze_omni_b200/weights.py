@@ -38,8 +38,14 @@ def encoder_param_shapes(cfg: PathConfig) -> List[Tuple[str, Tuple[int, ...], in
         out += [(p + "self_attn.linear_pos.weight", (d, d), d),
                 (p + "self_attn.pos_bias_u", (cfg.n_heads, cfg.d_k), -3),
                 (p + "self_attn.pos_bias_v", (cfg.n_heads, cfg.d_k), -3),
-                (p + "feed_forward.w_1.weight", (ff, d), d), (p + "feed_forward.w_1.bias", (ff,), d),
-                (p + "feed_forward.w_2.weight", (d, ff), ff), (p + "feed_forward.w_2.bias", (d,), ff),
+                ]
+        if cfg.ffn_type == "conv1d-linear":        # Conv1dLinear (attention.py:217-233): depthwise (d,1,k) + pointwise (ff,d,1)
+            kf = cfg.ffn_conv_kernel
+            out += [(p + "feed_forward.w_1.0.weight", (d, 1, kf), kf), (p + "feed_forward.w_1.0.bias", (d,), kf),
+                    (p + "feed_forward.w_1.1.weight", (ff, d, 1), d), (p + "feed_forward.w_1.1.bias", (ff,), d)]
+        else:
+            out += [(p + "feed_forward.w_1.weight", (ff, d), d), (p + "feed_forward.w_1.bias", (ff,), d)]
+        out += [(p + "feed_forward.w_2.weight", (d, ff), ff), (p + "feed_forward.w_2.bias", (d,), ff),
                 (p + "norm1.weight", (d,), -1), (p + "norm1.bias", (d,), -2),
                 (p + "norm2.weight", (d,), -1), (p + "norm2.bias", (d,), -2)]
     out += [("enc.1.after_norm.weight", (d,), -1), ("enc.1.after_norm.bias", (d,), -2)]

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FO_ABI_VERSION 1
+#define FO_ABI_VERSION 2
 
 enum { FO_F32 = 0, FO_BF16 = 1, FO_I16 = 2 };     /* compute dtype / PCM sample type */
 enum { FO_OK = 0, FO_ERR_ARG = -1, FO_ERR_CUDA = -2, FO_ERR_STATE = -3, FO_ERR_NOMEM = -4 };
@@ -59,6 +59,10 @@ typedef struct fo_config {
     /* capacity */
     int32_t max_sessions;      /* session slots resident in HBM */
     int32_t max_stream_frames; /* largest fbank-frame count of one streaming call (>= context+frames_per_chunk) */
+    /* positionwise layer: 0 or 1 = PositionwiseFeedForward (models/encoder/attention.py:122-143);
+     * k >= 2 = Conv1dLinear with kernel_size k (models/encoder/attention.py:198-266): causal depthwise conv over
+     * time (left context carried per session and layer) + 1x1 conv + ReLU + Linear */
+    int32_t ffn_conv_kernel;
 } fo_config;
 
 typedef struct fo_stats_t {
@@ -101,6 +105,9 @@ int fo_session_set_frames(fo_ctx* ctx, int32_t id, int64_t n_frames);
 /* adapter cache in the reference layout (models/adapter.py:141-143): (d_model, kernel-1); valid=0 means None */
 int fo_session_export_adapter_cache(fo_ctx* ctx, int32_t id, float* cache, int32_t* valid);
 int fo_session_import_adapter_cache(fo_ctx* ctx, int32_t id, const float* cache, int32_t valid);
+
+/* Conv1dLinear left context of one layer in the reference layout (models/encoder/attention.py:221,258): (d_model, k-1) */
+int fo_session_export_ffn_cache(fo_ctx* ctx, int32_t id, int layer, float* cache);
 
 /* ---- frontend: replaces audioEncoderProcessor.process (bin/inference.py:71-80) /
  * AudioFeatureGating._extract_fbank (models/AudioFeatureGating.py:54-75).

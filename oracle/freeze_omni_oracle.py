@@ -211,6 +211,27 @@ def attention_scores(sd: State, pfx: str, q: Tensor, k: Tensor, pos_emb: Tensor,
     return (torch.matmul(qu, k.transpose(-2, -1)) + torch.matmul(qv, p.transpose(-2, -1))) / math.sqrt(dk)
 
 
+def feed_forward(sd: State, p: str, y: Tensor, cache: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """Positionwise layer of one block.  PositionwiseFeedForward (attention.py:137-143): w_2(relu(w_1 y)); or
+    Conv1dLinear (attention.py:241-266): causal depthwise Conv1d over time (left context = `cache`, the last k-1
+    input frames, zeros at the start -- the left_padding of :251) -> 1x1 Conv1d -> ReLU -> Linear.  The reference's
+    streaming wiring of Conv1dLinear is broken, so the cache carry here is the one that makes chunked
+    evaluation equal to `forward` on the concatenated input.  Returns (out, new_cache (B, C, k-1) or None)."""
+    if p + "feed_forward.w_1.0.weight" in sd:
+        wd, bd = sd[p + "feed_forward.w_1.0.weight"], sd[p + "feed_forward.w_1.0.bias"]
+        k = wd.size(-1)
+        x = y.transpose(1, 2)                                                         # (B, C, T)
+        left = cache if cache is not None else x.new_zeros(x.size(0), x.size(1), k - 1)
+        x = torch.cat([left, x], dim=2)
+        new_cache = x[:, :, -(k - 1):].clone()
+        x = F.conv1d(x, wd, bd, groups=x.size(1))
+        x = F.conv1d(x, sd[p + "feed_forward.w_1.1.weight"], sd[p + "feed_forward.w_1.1.bias"])
+        x = F.relu(x).transpose(1, 2)
+        return F.linear(x, sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"]), new_cache
+    return F.linear(F.relu(F.linear(y, sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_1.bias"])),
+                    sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"]), None
+
+
 def layer_stream(sd: State, i: int, x: Tensor, pos_emb: Tensor, kv: Optional[List[Tensor]], h: int,
                  window: int) -> Tuple[Tensor, List[Tensor]]:
     """TransformerLayer.infer (transformer.py:103-130) + MultiHeadedAttention.infer
@@ -230,8 +251,9 @@ def layer_stream(sd: State, i: int, x: Tensor, pos_emb: Tensor, kv: Optional[Lis
     o = torch.matmul(attn, v).transpose(1, 2).reshape(x.size(0), -1, d)
     x = x + F.linear(o, sd[a + "linear_out.weight"], sd[a + "linear_out.bias"])
     y = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
-    y = F.linear(F.relu(F.linear(y, sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_1.bias"])),
-                 sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"])
+    y, ffn_cache = feed_forward(sd, p, y, kv[2] if (kv is not None and len(kv) > 2) else None)
+    if ffn_cache is not None:
+        new_kv.append(ffn_cache)                      # third entry of the layer's cache: Conv1dLinear left context
     return x + y, new_kv
 
 
@@ -251,8 +273,7 @@ def layer_offline(sd: State, i: int, x: Tensor, pos_emb: Tensor, mask: Tensor, h
     o = torch.matmul(attn, v).transpose(1, 2).reshape(x.size(0), -1, d)
     x = x + F.linear(o, sd[a + "linear_out.weight"], sd[a + "linear_out.bias"])
     y = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
-    y = F.linear(F.relu(F.linear(y, sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_1.bias"])),
-                 sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"])
+    y, _ = feed_forward(sd, p, y)
     return x + y
 
 

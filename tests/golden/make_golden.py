@@ -211,6 +211,27 @@ def main():
              t7_feats=torch.stack(feats32).numpy(), **{"t7_" + k: v for k, v in st7.items()},
              off_feats=xs.numpy(), off_ilens=ilens.numpy(), **{"off_" + k: v for k, v in off.items()})
 
+    # ---------------- conv1d-linear positionwise variant (Conv1dLinear, attention.py:198-266) ----------
+    # Only `forward` can be executed in the reference for this variant (its streaming wiring is broken):
+    # offline goldens here; the streaming carry is pinned by the property "chunked == forward" in the tests.
+    if want("tiny_conv1d"):
+        ycfg = load_yaml("tiny_conv1d")
+        cfg = path_config_from_dict(ycfg)
+        enc, adp = build_reference(mods, ycfg, cfg, seed=3)
+        g = torch.Generator().manual_seed(17)
+        xs = 9.0 + 3.0 * torch.randn(3, 150, 80, generator=g)
+        ilens = torch.tensor([150, 97, 40])
+        off = {}
+        with torch.no_grad():
+            for (c, L) in ((4, 16), (-1, -1)):
+                eo, m = enc(xs, ilens, c, L)
+                eo = eo.clone()
+                y, ym = adp(eo.clone(), m)
+                off["enc_c%d_L%d" % (c, L)] = eo.numpy()
+                off["adp_c%d_L%d" % (c, L)] = y.numpy()
+                off["mask_c%d_L%d" % (c, L)] = m.numpy()
+        save("tiny_conv1d", seed=np.int64(3), off_feats=xs.numpy(), off_ilens=ilens.numpy(), **{"off_" + k: v for k, v in off.items()})
+
     # ---------------- shipped config -------------------------------------------------------
     if want("shipped"):
         ycfg = load_yaml("shipped")

@@ -364,6 +364,46 @@ def test_shipped_offline_fp32(golden, shipped32):
     assert maxabs(y.cpu(), g["adapter_out"]) < FP32_TOL
 
 
+# ---- conv1d-linear positionwise variant (Conv1dLinear, attention.py:198-266) ------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_conv1d_linear_offline(golden, dtype, tol):
+    cfg, eng = make_engine("tiny_conv1d", 3, dtype=dtype, max_sessions=4)
+    g = golden("tiny_conv1d")
+    try:
+        for (c, L) in ((4, 16), (-1, -1)):
+            enc, mask, y, ymask = eng.encode_offline(torch.from_numpy(g["off_feats"]), g["off_ilens"], c, L)
+            tag = "c%d_L%d" % (c, L)
+            assert np.array_equal(mask.cpu().numpy(), g["off_mask_" + tag])
+            valid = torch.from_numpy(g["off_mask_" + tag]).squeeze(1).unsqueeze(-1)
+            assert maxabs((enc.cpu() * valid).numpy(), g["off_enc_" + tag] * valid.numpy()) < tol, tag
+    finally:
+        eng.close()
+
+
+def test_conv1d_linear_stream_vs_oracle():
+    """Streaming with the per-session, per-layer left context of the depthwise conv: against the oracle's
+    StreamSession (whose carry is pinned by chunked == forward in tests/test_oracle_golden.py)."""
+    cfg, eng = make_engine("tiny_conv1d", 3, max_sessions=4)
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    g = torch.Generator().manual_seed(41)
+    sessions = [O.StreamSession(cfg, esd, asd) for _ in range(3)]
+    ids = eng.alloc(3)
+    try:
+        for i in range(6):
+            n = 3 if i != 2 else 2                       # session 2 skips a step: ragged
+            pcm = (0.05 * torch.randn(n, cfg.samples_per_chunk, generator=g) * 32768).round().to(torch.int16)
+            enc, y = eng.stream_step(ids[:n], pcm, 1.0)
+            for b in range(n):
+                _, eo, yo = sessions[b].step_pcm(pcm[b].float(), 1.0)
+                assert maxabs(enc[b].cpu(), eo[0]) < FP32_TOL and maxabs(y[b].cpu(), yo[0]) < FP32_TOL, (i, b)
+        for li in (0, 1):
+            assert maxabs(eng.export_ffn_cache(int(ids[1]), li), sessions[1].buffer[li][2]) < FP32_TOL
+        eng.reset(ids[:1])
+        assert float(eng.export_ffn_cache(int(ids[0]), 0).abs().max()) == 0.0
+    finally:
+        eng.close()
+
+
 def _bf16_weights(sd):
     """What a bf16 context computes with: matrices rounded to bf16, vectors (biases, LayerNorm, pos_bias,
     CMVN, first conv) left in fp32 -- the split autocast applies to the reference."""

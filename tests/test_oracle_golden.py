@@ -167,6 +167,44 @@ def test_tiny_stream_equals_offline_until_saturation(golden, tiny):
     assert float(diff[17:].max()) > 1e-4
 
 
+# ---- conv1d-linear positionwise variant (Conv1dLinear, attention.py:198-266) -------------------------------------
+@pytest.fixture(scope="module")
+def tiny_conv1d():
+    cfg = load_path_config("tiny_conv1d")
+    return cfg, make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+
+
+@pytest.mark.parametrize("c,L", [(4, 16), (-1, -1)])
+def test_conv1d_linear_offline(golden, tiny_conv1d, c, L):
+    """The reference can only run `forward` for this variant; its outputs pin the oracle's Conv1dLinear."""
+    cfg, esd, asd = tiny_conv1d
+    g = golden("tiny_conv1d")
+    xs, m, y, ym = O.offline_path(cfg, esd, asd, torch.from_numpy(g["off_feats"]), torch.from_numpy(g["off_ilens"]), c, L)
+    tag = "c%d_L%d" % (c, L)
+    assert np.array_equal(m.numpy(), g["off_mask_" + tag])
+    assert np.abs(xs.numpy() - g["off_enc_" + tag]).max() < FP32_TOL
+    assert np.abs(y.numpy() - g["off_adp_" + tag]).max() < FP32_TOL
+
+
+def test_conv1d_linear_stream_equals_offline(golden, tiny_conv1d):
+    """Streaming carry of the depthwise conv (last k-1 frames per layer): chunked evaluation must equal `forward`
+    on the whole signal until the KV window saturates (then the positional offset of SURVEY 2.4-1 applies)."""
+    cfg, esd, asd = tiny_conv1d
+    pcm = golden("tiny")["stream_pcm"][0].astype(np.float32)
+    off_feats = O.fbank(torch.cat([torch.zeros(240), torch.from_numpy(pcm)])).unsqueeze(0)
+    off_feats = torch.cat([torch.zeros(1, 3, 80), off_feats], 1)
+    xs, _ = O.EncoderOracle(cfg, esd).forward(off_feats, torch.tensor([off_feats.size(1)]), 4, 16)
+    sess = O.StreamSession(cfg, esd, asd)
+    outs = []
+    for i in range(20):
+        _, eo, _ = sess.step_pcm(torch.from_numpy(pcm[i * 2560:(i + 1) * 2560]), 1.0)
+        outs.append(eo[0])
+    st = torch.stack(outs)
+    diff = (xs[0, :80].reshape(-1, 4, cfg.d_model) - st).abs().amax(dim=(1, 2))
+    assert float(diff[:17].max()) < 1e-4
+    assert sess.buffer[0][2].shape == (1, cfg.d_model, cfg.ffn_conv_kernel - 1)
+
+
 @pytest.fixture(scope="module")
 def shipped():
     cfg = load_path_config("shipped")
