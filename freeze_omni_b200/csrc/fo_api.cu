@@ -53,7 +53,8 @@ struct HostTensor {          // staged fp32 weight on device until finalize
 
 struct LayerW {
     void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
-    float* ptab = nullptr;                    // P_l = pe * Wpos_l^T, fp32 [pos_rows][D]
+    float* ptab = nullptr;                    // P_l = pe * Wpos_l^T, fp32 [pos_rows][D] (offline attention)
+    void* ptab_h = nullptr;                   // the same, [H][pos_rows][64] in the activation type (streaming attention)
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
     float *dw_w = nullptr, *dw_b = nullptr;   // Conv1dLinear depthwise taps [C][k] and bias (fp32); w1 is then the 1x1 conv
     float *pos_u = nullptr, *pos_v = nullptr, *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
@@ -410,6 +411,11 @@ int finalize_t(fo_ctx* c) {
                 ep.ldc = D;
                 r = gemm_simt<float, float>(pe->d, plain_rows(D, c->pos_rows), wpos, c->pos_rows, D, D, ep, RowMap(), 0);
             }
+            if (r == 0) r = dev_alloc(c, &w.ptab_h, (size_t)c->pos_rows * D * (sizeof(TW) == 2 ? 2 : 4));
+            if (r == 0) {
+                if (sizeof(TW) == 2) r = ptab_head_major<act16>(w.ptab, c->pos_rows, H, reinterpret_cast<act16*>(w.ptab_h), 0);
+                else r = ptab_head_major<float>(w.ptab, c->pos_rows, H, reinterpret_cast<float*>(w.ptab_h), 0);
+            }
             cudaDeviceSynchronize();
             cudaFree(wpos);
             FO_TRY(r);
@@ -694,8 +700,8 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
             }
             if (r == 0) r = layer_pre<TA>(c, w, Mg, hg, qkvg, q32g, pfq, sg);
             if (r == 0 && !(c->debug_skip & 1))
-                r = attention_stream<TA>(a, qkvg, q32g, reinterpret_cast<TA*>(c->ring) + l * layer_stride, w.ptab, w.pos_u, w.pos_v,
-                                         attg, sg);
+                r = attention_stream<TA>(a, qkvg, q32g, reinterpret_cast<TA*>(c->ring) + l * layer_stride,
+                                         reinterpret_cast<const TA*>(w.ptab_h), w.pos_u, w.pos_v, attg, sg);
             NextNorm nn{last ? c->after_g : c->layers[l + 1].ln1g, last ? c->after_b : c->layers[l + 1].ln1b,
                         last ? enc_out_dev + r0 * D : nullptr};
             FfnConv fc;

@@ -119,7 +119,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <typename TA>
 __global__ void __launch_bounds__(ATT_THREADS, 7)
 attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* __restrict__ q32, TA* __restrict__ ring,
-                        const float* __restrict__ ptab, const float* __restrict__ pos_u, const float* __restrict__ pos_v,
+                        const TA* __restrict__ ptab_h, const float* __restrict__ pos_u, const float* __restrict__ pos_v,
                         TA* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int EPC = Chunk<TA>::EPC, NCH = Chunk<TA>::NCH;
@@ -148,15 +148,20 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
     TA* ringV = ringK + (long long)a.H * cap * DK;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (cl > 0 && tid == 0) {
+    // rel-pos rows P_l[start .. start+nk) of this head are contiguous in the head-major table: one bulk copy
+    const int np = min(nk, a.pos_rows - start);
+    if (tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const int p0 = first % cap;
         const int len1 = min(cl, cap - p0), len2 = cl - len1;
         const uint32_t rowb = DK * sizeof(TA);
-        mbar_expect_tx(&bar, 2u * cl * rowb);
-        bulk_g2s(Ks, ringK + (long long)p0 * DK, len1 * rowb, &bar);
-        bulk_g2s(Vs, ringV + (long long)p0 * DK, len1 * rowb, &bar);
+        mbar_expect_tx(&bar, (2u * cl + np) * rowb);
+        bulk_g2s(Ps, ptab_h + ((long long)h * a.pos_rows + start) * DK, np * rowb, &bar);
+        if (len1 > 0) {
+            bulk_g2s(Ks, ringK + (long long)p0 * DK, len1 * rowb, &bar);
+            bulk_g2s(Vs, ringV + (long long)p0 * DK, len1 * rowb, &bar);
+        }
         if (len2 > 0) {
             bulk_g2s(Ks + len1 * DK, ringK, len2 * rowb, &bar);
             bulk_g2s(Vs + len1 * DK, ringV, len2 * rowb, &bar);
@@ -173,19 +178,6 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
         new_r = (tid / NCH) % t;
         new_c = tid % NCH;
         newv = *reinterpret_cast<const uint4*>(qkv + (long long)(b * t + new_r) * 3 * D + (new_which + 1) * D + h * DK + new_c * EPC);
-    }
-    // (b) rel-pos rows, 4 floats per item
-    constexpr int PMAX = 9;                          // ceil(68 rows * 16 float4 / 128 threads)
-    float4 pv[PMAX];
-    const int n_p = nk * (DK / 4);
-#pragma unroll
-    for (int k = 0; k < PMAX; ++k) {
-        const int i = tid + k * ATT_THREADS;
-        if (i < n_p) {
-            const int j = i / (DK / 4), c = i % (DK / 4);
-            const int pos = min(start + j, a.pos_rows - 1);
-            pv[k] = *reinterpret_cast<const float4*>(ptab + (long long)pos * D + h * DK + c * 4);
-        }
     }
     // (c) Q + biases: t*64 floats, two per thread when t <= 4
     float qreg[4], ureg[4], vreg[4];
@@ -213,28 +205,12 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
         *reinterpret_cast<uint4*>((which ? Vs : Ks) + (cl + r) * DK + c * EPC) = val;
         *reinterpret_cast<uint4*>((which ? ringV : ringK) + (long long)((nf + r) % cap) * DK + c * EPC) = val;
     }
+    // positions past the end of the table repeat its last row (unreachable with the reference's pe_index wrap)
+    for (int i = tid + np * (DK / 8); i < nk * (DK / 8); i += ATT_THREADS) {
+        const int j = i / (DK / 8), c = i % (DK / 8);
+        const TA* src = ptab_h + ((long long)h * a.pos_rows + a.pos_rows - 1) * DK + c * 8;
 #pragma unroll
-    for (int k = 0; k < PMAX; ++k) {
-        const int i = tid + k * ATT_THREADS;
-        if (i < n_p) {
-            const int j = i / (DK / 4), c = i % (DK / 4);
-            TA* d = Ps + j * DK + c * 4;
-            if constexpr (sizeof(TA) == 2) {
-                uint2 hh;
-                hh.x = pack2<TA>(pv[k].x, pv[k].y);
-                hh.y = pack2<TA>(pv[k].z, pv[k].w);
-                *reinterpret_cast<uint2*>(d) = hh;
-            } else {
-                *reinterpret_cast<float4*>(d) = pv[k];
-            }
-        }
-    }
-    for (int i = tid + PMAX * ATT_THREADS; i < n_p; i += ATT_THREADS) {   // windows larger than the register budget
-        const int j = i / (DK / 4), c = i % (DK / 4);
-        const int pos = min(start + j, a.pos_rows - 1);
-        const float4 v4 = *reinterpret_cast<const float4*>(ptab + (long long)pos * D + h * DK + c * 4);
-        TA* d = Ps + j * DK + c * 4;
-        d[0] = from_f<TA>(v4.x); d[1] = from_f<TA>(v4.y); d[2] = from_f<TA>(v4.z); d[3] = from_f<TA>(v4.w);
+        for (int e = 0; e < 8; ++e) Ps[j * DK + c * 8 + e] = src[e];
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -248,7 +224,7 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
         qv[i] = q + pos_v[h * DK + d];
     }
     __syncthreads();
-    if (cl > 0) mbar_wait(&bar, 0);
+    mbar_wait(&bar, 0);
 
     // ---- scores + softmax + PV: warp = query row ----
     constexpr int KPL = 4;                                // keys per lane (<= 128 keys per call)
@@ -554,7 +530,7 @@ __global__ void advance_sessions_kernel(const int32_t* __restrict__ ids, int n, 
 }  // namespace
 
 template <typename TA>
-int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* ring, const float* ptab,
+int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* ring, const TA* ptab_h,
                      const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
     if (a.n <= 0) return 0;
     FO_CHECK(a.t <= TQ_MAX, "attention_stream: %d frames per call exceeds %d", a.t, TQ_MAX);
@@ -570,14 +546,33 @@ int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* r
     }
     FO_CHECK(smem <= 160 * 1024, "attention_stream: window too large for shared memory");
     dim3 grid(a.n, a.H);
-    FO_CUDA(launch_pdl(attention_stream_kernel<TA>, grid, dim3(ATT_THREADS), smem, st, a, qkv, q32, ring, ptab, pos_u, pos_v, out));
+    FO_CUDA(launch_pdl(attention_stream_kernel<TA>, grid, dim3(ATT_THREADS), smem, st, a, qkv, q32, ring, ptab_h, pos_u, pos_v, out));
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
 }
 template int attention_stream<float>(const AttnStream&, const float*, const float*, float*, const float*, const float*, const float*, float*, cudaStream_t);
-template int attention_stream<bf16>(const AttnStream&, const bf16*, const float*, bf16*, const float*, const float*, const float*, bf16*, cudaStream_t);
-template int attention_stream<__half>(const AttnStream&, const __half*, const float*, __half*, const float*, const float*, const float*, __half*, cudaStream_t);
+// head-major copy of a rel-pos table in the activation type: out[h][pos][64] = (TA) in[pos][h*64 + d]
+template <typename TA>
+__global__ void ptab_head_major_kernel(const float* __restrict__ in, int pos_rows, int H, TA* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)pos_rows * H * DK;
+    if (i >= total) return;
+    const int d = (int)(i % DK);
+    const long long r = i / DK;
+    const int pos = (int)(r % pos_rows), h = (int)(r / pos_rows);
+    out[i] = from_f<TA>(in[((long long)pos * H + h) * DK + d]);
+}
+template <typename TA>
+int ptab_head_major(const float* in, int pos_rows, int H, TA* out, cudaStream_t st) {
+    const long long total = (long long)pos_rows * H * DK;
+    ptab_head_major_kernel<TA><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, pos_rows, H, out);
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int ptab_head_major<float>(const float*, int, int, float*, cudaStream_t);
+template int ptab_head_major<__half>(const float*, int, int, __half*, cudaStream_t);
+template int attention_stream<__half>(const AttnStream&, const __half*, const float*, __half*, const __half*, const float*, const float*, __half*, cudaStream_t);
 
 template <typename TA>
 int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,

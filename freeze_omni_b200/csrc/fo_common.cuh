@@ -266,8 +266,11 @@ struct AttnStream {
 // columns hold Q (the QKV GEMM keeps Q in fp32, Epilogue::split_col); ring = this layer's
 // (slot, 2, H, ring_cap, 64); ptab (pos_rows, D) fp32; out (n*t, D).  Appends the new K/V rows to the ring.
 template <typename TA>
-int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* ring, const float* ptab,
+int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* ring, const TA* ptab_h,
                      const float* pos_u, const float* pos_v, TA* out, cudaStream_t st);
+// ptab_h: the same table as [H][pos_rows][64] in the activation type (rows of one head contiguous -> one bulk copy)
+template <typename TA>
+int ptab_head_major(const float* in, int pos_rows, int H, TA* out, cudaStream_t st);
 // offline: qkv (B*T, 3*D); valid lengths ilens (B); window from (chunk, left); positions 0..T-1.
 template <typename TA>
 int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,

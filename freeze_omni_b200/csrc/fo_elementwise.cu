@@ -80,27 +80,38 @@ cmvn_conv1_kernel(const float* __restrict__ feats, int T, int F, const float* __
 }
 
 // ---- LayerNorm ---------------------------------------------------------------------------------
-// one warp per row; two-pass in registers (mean, then centred variance) like ATen's CPU kernel.
+// one warp per row, 4 rows per CTA (a 256-row streaming step spreads over 64 SMs); two-pass in registers (mean, then
+// centred variance) like ATen's CPU kernel.  The row and gamma/beta are all requested before the first reduction so
+// one memory latency covers them.
 template <typename TA, int MAXV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 layer_norm_kernel(const float* __restrict__ x, int M, int D, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, int act, float out_scale, TA* __restrict__ y_act,
                   float* __restrict__ y_f32) {
     FO_PDL_TRIGGER();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    const int nv = D >> 7;                    // float4 per lane
+    float4 g[MAXV], bt[MAXV];
+    if (MAXV <= 8) {                          // weights do not depend on the previous kernel: fetch them before the wait
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (i < nv) {
+                g[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+                bt[i] = *reinterpret_cast<const float4*>(beta + (i * 32 + lane) * 4);
+            }
+    }
     FO_PDL_WAIT();
     if (row >= M) return;
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
-    const int nv = D >> 7;                    // float4 per lane
     float4 v[MAXV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
-        if (i < nv) {
-            v[i] = xr[i * 32 + lane];
-            s += v[i].x + v[i].y + v[i].z + v[i].w;
-        }
+        if (i < nv) v[i] = xr[i * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
     const float mu = warp_sum(s) / D;
     float q = 0.f;
 #pragma unroll
@@ -114,10 +125,14 @@ layer_norm_kernel(const float* __restrict__ x, int M, int D, const float* __rest
     for (int i = 0; i < MAXV; ++i)
         if (i < nv) {
             const int col = (i * 32 + lane) * 4;
-            float4 g = *reinterpret_cast<const float4*>(gamma + col);
-            float4 bt = *reinterpret_cast<const float4*>(beta + col);
-            float o[4] = {(v[i].x - mu) * rstd * g.x + bt.x, (v[i].y - mu) * rstd * g.y + bt.y,
-                          (v[i].z - mu) * rstd * g.z + bt.z, (v[i].w - mu) * rstd * g.w + bt.w};
+            float4 gg, bb;
+            if (MAXV <= 8) { gg = g[i]; bb = bt[i]; }
+            else {
+                gg = *reinterpret_cast<const float4*>(gamma + col);
+                bb = *reinterpret_cast<const float4*>(beta + col);
+            }
+            float o[4] = {(v[i].x - mu) * rstd * gg.x + bb.x, (v[i].y - mu) * rstd * gg.y + bb.y,
+                          (v[i].z - mu) * rstd * gg.z + bb.z, (v[i].w - mu) * rstd * gg.w + bb.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (act == 1) o[j] = fmaxf(o[j], 0.f);
@@ -372,12 +387,12 @@ int layer_norm(const float* x, int M, int D, const float* gamma, const float* be
                float out_scale, TA* y_act, float* y_f32, cudaStream_t st) {
     if (M <= 0) return 0;
     FO_CHECK(D % 128 == 0 && D <= 4096, "layer_norm: D (%d) must be a multiple of 128 and <= 4096", D);
-    const int rows_per_cta = 8;
+    const int rows_per_cta = 4;
     dim3 grid(cdiv(M, rows_per_cta));
     if (D <= 1024)
-        FO_CUDA(launch_pdl(layer_norm_kernel<TA, 8>, grid, dim3(256), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
+        FO_CUDA(launch_pdl(layer_norm_kernel<TA, 8>, grid, dim3(128), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
     else
-        FO_CUDA(launch_pdl(layer_norm_kernel<TA, 32>, grid, dim3(256), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
+        FO_CUDA(launch_pdl(layer_norm_kernel<TA, 32>, grid, dim3(128), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
