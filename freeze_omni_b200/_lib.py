@@ -7,7 +7,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfo_b200.so")
+LIB_PATH = os.environ.get("FO_B200_LIB", os.path.join(HERE, "libfo_b200.so"))   # override: A/B runs of two builds
 
 FO_F32, FO_BF16, FO_I16 = 0, 1, 2
 
