@@ -32,7 +32,8 @@ namespace fo {
 
 namespace {
 
-constexpr int TC_THREADS = 352;   // warp 1 MMA, warps 2..5 epilogue, warps 0 and 6..10 TMA producers (up to 6)
+constexpr int TC_THREADS = 224;   // warp 0 / warp 6: TMA producers of the two operands, warp 1 MMA, warps 2..5 epilogue
+                                  // (more producer warps and 352 threads measured 2-3 % slower per step)
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
@@ -141,10 +142,14 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#ifdef FO_TC_TRACE_BUILD      // development builds only (tools/gemm_trace.py): the stamps cost ~1 % of a step
 #define TC_TRACE(slot)                                                                     \
     do {                                                                                   \
         if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[slot] = gtime(); \
     } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -627,8 +632,8 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     p.bn = pl.bn;
     p.swap = pl.swap;
     p.act_fp16 = act_fp16;
-    p.npa = g_forced_npa > 0 ? g_forced_npa : 4;
-    p.npb = g_forced_npb > 0 ? g_forced_npb : (pl.bn >= 64 ? 2 : 1);
+    p.npa = 1;
+    p.npb = 1;
     if (pl.bn % (8 * p.npb) != 0) p.npb = 1;
     const uint32_t stage = (BM + pl.bn) * BK * 2;
     p.stages = std::max(1, std::min<int>(std::min(MAX_STAGES, kbs), (int)(SMEM_BUDGET / stage)));
@@ -679,6 +684,8 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     dim3 grid(ta, tb, pl.split);
     const size_t tile_stage = pl.swap ? (size_t)pl.bn * (BM + 4) * 4 : (size_t)BM * (pl.bn + 4) * 4;
     const size_t smem = std::max((size_t)p.stages * stage, tile_stage) + 1024;
+    // (a compile-time "lean" variant without the split-K / fused-LayerNorm paths measured slower: two alternating GEMM
+    // kernels cost more in kernel switches than the dead code does)
     FO_CUDA(launch_pdl(gemm_tc_kernel, grid, dim3(TC_THREADS), smem, st, pl.swap ? map_w : map_act, pl.swap ? map_act : map_w, p));
     FO_LAUNCHED();
     ++g_tc_launches;

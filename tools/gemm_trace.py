@@ -10,7 +10,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["FO_TC_TRACE"] = "1"
+os.environ["FO_TC_TRACE"] = "1"      # needs a library built with FO_TC_TRACE_BUILD=1 python -m freeze_omni_b200.build --force
 from freeze_omni_b200.config import load_path_config  # noqa: E402
 from freeze_omni_b200.engine import Engine  # noqa: E402
 from freeze_omni_b200.weights import make_adapter_state, make_encoder_state  # noqa: E402
