@@ -122,6 +122,35 @@ def cpu_reference_step_rate(cfg, n_sessions, steps, warmup, threads=None):
     return n_sessions * CHUNK_SEC / t, t, torch.get_num_threads()
 
 
+def gpu_torch_reference_latency(cfg, steps, warmup):
+    """The reference's GPU PyTorch path for one session: the oracle port of its modules moved to the
+    GPU, eager, under torch.autocast(bf16) as models/pipeline.py:67-68 runs them, batch 1 per call, including the
+    per-chunk CPU sin/cos table + H2D copy of transformer.py:278-279.  CUDA-event time per chunk (ms)."""
+    from oracle import freeze_omni_oracle as O
+    dev = torch.device("cuda")
+    esd = {k: v.to(dev) for k, v in make_encoder_state(cfg, 0).items()}
+    asd = {k: v.to(dev) for k, v in make_adapter_state(cfg, 0).items()}
+    enc = O.EncoderOracle(cfg, esd)
+    g = torch.Generator().manual_seed(3)
+    buf, cache, pe = enc.new_buffer(), None, 0
+    lat = []
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for i in range(steps + warmup):
+            feats = (9.0 + 3.0 * torch.randn(1, cfg.chunk_feat_frames, cfg.feat_dim, generator=g)).to(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eo, buf, pe = enc.infer(feats, buf, pe)
+            mask = torch.ones(1, 1, eo.size(1), dtype=torch.bool, device=dev)
+            y, _, cache = O.adapter_forward(cfg, asd, eo.float(), mask, cache)
+            b.record()
+            b.synchronize()
+            if i >= warmup:
+                lat.append(a.elapsed_time(b))
+    lat = np.asarray(lat)
+    return {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "chunks": int(len(lat)),
+            "what": "oracle port of the reference modules on the GPU, eager, autocast bf16, 1 session per call"}
+
+
 def workload_text(S):
     return ("%d concurrent sessions per GPU, streaming 160 ms chunks with KV/CNN caches (windows full), shipped config "
             "(24x1024, adapter 3584), random-init weights" % S)
@@ -190,13 +219,73 @@ def bench_offline(args, eng, cfg, rank, world):
                           "gemm_ms_per_pass": sum(x["ms_total"] for x in shapes), "gemm_shapes": shapes}))
 
 
+def bench_ragged(args, eng, cfg, rank, world, dist):
+    """BASELINE.json config 3: ragged sessions (lengths U[5 s, 120 s], seed 7, arrivals spread over the first 16 s),
+    `--sessions` per GPU, every rank its own partition.  Each step advances the sessions that are active; the active set
+    is padded to a multiple of 16 with scratch sessions so that one captured graph serves each batch-size bucket."""
+    S, bucket = args.sessions, 16
+    rng = np.random.RandomState(7 + 1000 * rank)
+    length = np.round(rng.uniform(5.0, 120.0, S) / CHUNK_SEC).astype(np.int64)
+    if args.steps < 750:                                    # bounded run: scale the lengths down with --steps
+        length = np.maximum(8, (length * args.steps) // 750)
+    arrive = rng.randint(0, max(1, min(100, args.steps // 4)), S)
+    end = arrive + length
+    total_steps = int(end.max())
+    ids_all = eng.alloc(S + bucket)
+    real, scratch = ids_all[:S], ids_all[S:]
+    eng.set_option("l2_prefetch", 0)                        # the prefetch range would make every active set its own graph
+    n_pcm = 16
+    pcm_dev = torch.from_numpy(synth_pcm(S + bucket, n_pcm, cfg.samples_per_chunk, seed0=5000 + 4096 * rank)).cuda()
+    t_enc, t_out = eng.out_frames(cfg.chunk_feat_frames)
+    y_dev = torch.empty(S + bucket, t_out, cfg.llm_dim, device="cuda")
+
+    def step(k):
+        act = np.nonzero((arrive <= k) & (k < end))[0]
+        if len(act) == 0:
+            return 0
+        pad = (-len(act)) % bucket
+        ids = np.concatenate([real[act], scratch[:pad]]).astype(np.int32)
+        rows = torch.from_numpy(np.concatenate([act, np.arange(S, S + pad)])).cuda()
+        eng.stream_step(ids, pcm_dev[k % n_pcm].index_select(0, rows), 1.0, adapter_out=y_dev[:len(ids)], want_enc=False)
+        return len(act)
+
+    # warm every bucket (eager + capture), then reset the sessions and time the whole trace
+    for n in range(bucket, S + bucket, bucket):
+        ids = np.concatenate([real[:min(n, S)], scratch[:n - min(n, S)]]).astype(np.int32)
+        for _ in range(3):
+            eng.stream_step(ids, pcm_dev[0][:n].contiguous(), 1.0, adapter_out=y_dev[:n], want_enc=False)
+    eng.reset(ids_all)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    chunks = 0
+    for k in range(total_steps):
+        chunks += step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    tot = torch.tensor([float(chunks)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"workload": "ragged: %d sessions per GPU, lengths U[5,120] s (scaled by steps/750), staggered arrivals; "
+                                      "active set padded to multiples of %d" % (S, bucket),
+                          "metric": METRIC, "value": float(tot.item()) * CHUNK_SEC / (float(ms.item()) * 1e-3), "unit": UNIT,
+                          "n_gpus": world, "steps": total_steps, "session_chunks": float(tot.item()), "ms_total": float(ms.item()),
+                          "mean_active_per_gpu": float(tot.item()) / world / max(1, total_steps), "scaling": "weak",
+                          "dtype": "bf16", "dtype_note": DTYPE_NOTE}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="stream", choices=["stream", "latency", "offline"])
+    ap.add_argument("--workload", default="stream", choices=["stream", "latency", "offline", "ragged"])
     ap.add_argument("--sessions", type=int, default=64, help="concurrent sessions per GPU")
     ap.add_argument("--ref-sessions", type=int, default=64)
     ap.add_argument("--offline-batch", type=int, default=256)
@@ -238,7 +327,7 @@ def main():
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     S, K, W = args.sessions, args.steps, args.warmup
     eng = Engine(cfg, make_encoder_state(cfg, 0), make_adapter_state(cfg, 0), dtype=dtype, device=local_rank,
-                 max_sessions=S, max_stream_frames=cfg.chunk_feat_frames)
+                 max_sessions=S + (16 if args.workload == "ragged" else 0), max_stream_frames=cfg.chunk_feat_frames)
     if args.graph >= 0:
         eng.set_option("use_graph", args.graph)
     if args.backend >= 0:
@@ -250,6 +339,12 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, int(v))
+    if args.workload == "ragged":
+        bench_ragged(args, eng, cfg, rank, world, dist)
+        eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     if args.workload == "offline":
         bench_offline(args, eng, cfg, rank, world)
         eng.close()
@@ -331,36 +426,45 @@ def main():
         lat.append(a.elapsed_time(b))
     lat = np.asarray(lat)
 
-    # ---- roofline of the dominant kernel class: every tcgen05 GEMM launch of a step, timed with a CUDA event pair on
-    # the launching stream inside the library (eager launches for this pass; tensor maps are cached so the host stays
-    # ahead of the device)
+    # ---- roofline of the dominant kernel class (the tcgen05 GEMM launches).  Their time inside a step is measured
+    # differentially with CUDA events on the launching stream: K graph-replayed steps with every kernel, minus K steps
+    # with exactly the GEMM launches dropped (library option debug_skip=32; outputs of that pass are discarded).
+    # Per-shape rates come from event pairs around each eager launch (they include ~3 us of event/launch overhead per
+    # launch, so they are lower bounds on the rates).
     hbm_peak, tf_sustained, tf_burst, peak_kind = load_peaks()
     step_ms = ms / K
     roof, shapes = None, []
     try:
+        eng.set_option("debug_skip", 32)
+        run_steps(3, False, 0)
+        ms_nogemm = timed(K, False, 3) / K
+        eng.set_option("debug_skip", args.debug_skip)
+        eng.reset(ids)                                               # the skipped pass left garbage in the session state
+        run_steps(18, False, 0)
+        gemm_ms = max(step_ms - ms_nogemm, 1e-6)
         steps_prof = min(K, 10)
-        run_steps(2, False, 0)
         eng.set_option("profile_gemm", 1)
         run_steps(steps_prof, False, 0)
         torch.cuda.synchronize()
         rows = eng.profile_dump()
         eng.set_option("profile_gemm", 0)
-        gemm_ms = sum(r[4] for r in rows) / 1e3
         gemm_n = sum(r[3] for r in rows)
-        gflop = GFLOP_GEMM_PER_CHUNK * S * steps_prof
+        gflop = GFLOP_GEMM_PER_CHUNK * S
         achieved = gflop / gemm_ms                                  # GFLOP / ms == TFLOP/s
         roof = {"bound": "tensor", "achieved": achieved, "peak": tf_sustained, "unit": "TFLOP/s",
                 "frac": achieved / tf_sustained, "traffic": None, "peak_source": peak_kind + " (sustained bf16 cuBLAS)",
                 "kernel": "gemm_tc_kernel (all %d GEMM launches of a step; algorithmic %.2f GFLOP per session-chunk)"
                           % (gemm_n // steps_prof, GFLOP_GEMM_PER_CHUNK),
-                "launches_per_step": gemm_n / steps_prof, "gemm_ms_per_step": gemm_ms / steps_prof,
-                "share_of_step": (gemm_ms / steps_prof) / step_ms,
-                "note": "M = 4 rows per session puts the layer GEMMs on the weight-streaming / latency side of the ridge; "
-                        "gemm_shapes gives the per-shape rates (conv2, M = sessions*80 padded rows, is the tensor-bound one)"}
+                "launches_per_step": gemm_n / steps_prof, "gemm_ms_per_step": gemm_ms, "ms_per_step_without_gemms": ms_nogemm,
+                "share_of_step": gemm_ms / step_ms,
+                "weights_GBs": 751.6e-3 / gemm_ms * 1e3, "weights_frac_of_hbm": 751.6e-3 / gemm_ms * 1e3 / hbm_peak,
+                "note": "M = 4 rows per session puts the layer GEMMs on the weight-streaming / latency side of the ridge "
+                        "(each launch is 8-16 us of pipeline fill, L2->SM ingest and epilogue); gemm_shapes gives per-shape "
+                        "rates, conv2 (M = sessions*80 padded rows) is the tensor-bound one; ncu capture in profiles/"}
         for (m, n, k, cnt, us) in sorted(rows, key=lambda r: -r[4]):
-            shapes.append({"M": m, "N": n, "K": k, "launches_per_step": cnt / steps_prof, "us_per_launch": us / cnt,
+            shapes.append({"M": m, "N": n, "K": k, "launches_per_step": cnt / steps_prof, "us_per_launch_eager_events": us / cnt,
                            "tflops": 2.0 * m * n * k * cnt / us / 1e6, "weight_GBs": 2.0 * n * k * cnt / us / 1e3})
-    except Exception as ex:  # library built without the profiling option
+    except Exception as ex:  # library built without the profiling options
         roof = {"bound": "tensor", "achieved": None, "peak": tf_sustained, "unit": "TFLOP/s", "frac": None,
                 "traffic": None, "note": "gemm profiling unavailable: %s" % ex}
     step_bytes = 751.6e6 + S * 6.7e6
@@ -375,6 +479,12 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
                "sample": "%d sessions x %d chunks, oracle port of the reference modules (fp32 torch CPU), %.2f s/step" % (S, args.cpu_steps, t)}
 
+    gpu_ref = None
+    if rank == 0 and world == 1 and args.workload == "latency":
+        try:
+            gpu_ref = gpu_torch_reference_latency(cfg, 200, 30)
+        except Exception as ex:
+            gpu_ref = {"error": str(ex)[:200]}
     if rank == 0:
         h2d = S * cfg.samples_per_chunk * 2 + S * 4
         d2h = S * t_out * cfg.llm_dim * 4
@@ -391,6 +501,7 @@ def main():
                 "gpu_launches": int(launches),
                 "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "sessions": S},
                 "roofline": roof, "gemm_shapes": shapes[:12], "step_roofline": whole, "cpu_baseline": cpu,
+                "gpu_torch_baseline": gpu_ref,
                 "clocks": sampler.summary(),
                 "options": {"gemm_backend": eng.get_option("gemm_backend"), "use_graph": eng.get_option("use_graph"),
                             "session_groups": eng.get_option("session_groups")}}

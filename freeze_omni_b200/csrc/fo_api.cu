@@ -115,7 +115,7 @@ struct fo_ctx {
     TcWorkspace tc_wsg[MAX_GROUPS];           // split-K partials + tile counters of the tcgen05 GEMM, one per session group
     TcWorkspace* tc_cur = &tc_wsg[0];
     int debug_skip = 0;                       // timing attribution only (results invalid): bit0 attention, bit1 LayerNorm,
-                                              // bit2 QKV/out GEMMs, bit3 FFN GEMMs, bit4 subsampling GEMMs
+                                              // bit2 QKV/out GEMMs, bit3 FFN GEMMs, bit4 subsampling/adapter GEMMs, bit5 EVERY GEMM launch (nothing else)
     int use_prefetch = 1;                     // next-kernel L2 prefetch of weights / KV rings (L2Prefetch)
     int pf_slot_lo = 0, pf_slot_hi = 0;       // slot range of the sessions of the current step
     int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
@@ -255,7 +255,9 @@ int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N,
          const RowMap& rm, cudaStream_t st) {
     bool fused = false;
     int r;
-    if (!c->profile_gemm) {
+    if (c->debug_skip & 32) {
+        r = 0;                                    // timing attribution: every GEMM launch dropped, the rest of the step kept
+    } else if (!c->profile_gemm) {
         r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st, &fused);
     } else {
         cudaEvent_t e0, e1;
@@ -499,14 +501,14 @@ int adapter_program(fo_ctx* c, const float* enc, const uint8_t* mask, int B, int
     e1.bias = c->ad_conv_b;
     e1.c_f32 = reinterpret_cast<float*>(aconv);
     e1.ldc = 2 * D;
-    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xin), ga, c->ad_conv_w, (int)ga.rows, 2 * D, KA * D, e1, rm, st));
+    if (!(c->debug_skip & 16)) FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xin), ga, c->ad_conv_w, (int)ga.rows, 2 * D, KA * D, e1, rm, st));
     FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(aconv), Mo, 2 * D, c->ad_ln_g, c->ad_ln_b, 1e-3f,
                           c->cfg.adapter_gelu ? 2 : 1, 1.0f, reinterpret_cast<TA*>(ah), nullptr, st));
     Epilogue e2;
     e2.bias = c->ad_proj_b;
     e2.c_f32 = y;
     e2.ldc = E;
-    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(ah), c->ad_proj_w, Mo, E, 2 * D, e2, st));
+    if (!(c->debug_skip & 16)) FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(ah), c->ad_proj_w, Mo, E, 2 * D, e2, st));
     return 0;
 }
 
@@ -530,7 +532,7 @@ int subsample_program(fo_ctx* c, const float* feats, int B, int T, float** x_out
     e.relu = 1;
     e.c_act = c2;
     e.ldc = D;
-    FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c1), ga, c->conv2_w, (int)ga.rows, D, 9 * D, e, rm, st));
+    if (!(c->debug_skip & 16)) FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c1), ga, c->conv2_w, (int)ga.rows, D, 9 * D, e, rm, st));
     const float xscale = sqrtf((float)D);
     if (c->cfg.input_layer_linear) {
         FO_TRY(ws_ensure(c, WS_XSUB, (size_t)M * D * sizeof(TA), &xsub));
@@ -539,12 +541,12 @@ int subsample_program(fo_ctx* c, const float* feats, int B, int T, float** x_out
         e2.bias = c->sub_b;
         e2.c_act = xsub;
         e2.ldc = D;
-        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c2), c->sub_w, M, D, F2 * D, e2, st));
+        if (!(c->debug_skip & 16)) FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(c2), c->sub_w, M, D, F2 * D, e2, st));
         Epilogue e3;
         e3.bias = c->emb_b;
         e3.c_f32 = reinterpret_cast<float*>(emb);
         e3.ldc = D;
-        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xsub), c->emb_w, M, D, D, e3, st));
+        if (!(c->debug_skip & 16)) FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xsub), c->emb_w, M, D, D, e3, st));
         FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(emb), M, D, c->emb_g, c->emb_beta, 1e-5f, 1, xscale, nullptr,
                               reinterpret_cast<float*>(x), st));
     } else {

@@ -298,7 +298,7 @@ class EncoderOracle:
         pe_index = pe_index % c.pe_wrap
         x = x * math.sqrt(c.d_model)
         start = max(0, pe_index - c.full_chunk_size)
-        pos_emb = pos_table(start, n_cache + x.size(1), c.d_model).unsqueeze(0)
+        pos_emb = pos_table(start, n_cache + x.size(1), c.d_model).unsqueeze(0).to(x.device)   # transformer.py:278-279
         pe_index = pe_index + c.chunk_size
         for i in range(c.n_layers):
             x, buffer[i] = layer_stream(sd, i, x, pos_emb, buffer[i], c.n_heads, c.kv_window)
@@ -318,7 +318,7 @@ class EncoderOracle:
         valid = valid[:, :, 2::2][:, :, 2::2]                       # subsampling.py:65
         mask = offline_attention_mask(valid, chunk, left)           # transformer.py:253-258
         x = embed(sd, x) * math.sqrt(c.d_model)                     # attention.py:100-102
-        pos_emb = pos_table(0, x.size(1), c.d_model).unsqueeze(0)
+        pos_emb = pos_table(0, x.size(1), c.d_model).unsqueeze(0).to(x.device)
         for i in range(c.n_layers):
             x = layer_offline(sd, i, x, pos_emb, mask, c.n_heads)
         x = F.layer_norm(x, (c.d_model,), sd["enc.1.after_norm.weight"], sd["enc.1.after_norm.bias"])
