@@ -1203,7 +1203,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     memcpy(&sbits, &a.scale, 4);
     snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
              c->gemm_backend, c->groups, (c->debug_skip * 2 + c->fuse_ln) * 2 + c->use_prefetch,
-             c->use_prefetch ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl, c->use_prefetch ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
+             (c->use_prefetch ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), c->use_prefetch ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
     if (c->graphs.size() > 256 && c->graphs.find(key) == c->graphs.end()) {
         for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         c->graphs.clear();

@@ -6,9 +6,14 @@
 // fused QKV GEMM output and are appended to the ring in the same pass.  Offline: one CTA per
 // (utterance, head, 4 query rows); the band [start,end) of models/masks.py:50-56 and the pad mask are
 // evaluated arithmetically, never materialised; key tiles + online softmax cover unbounded left context.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "fo_common.cuh"
 
 namespace fo {
+
 
 namespace {
 
@@ -106,7 +111,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Streaming chunk attention, one CTA per (session, head), 4 warps.  Steady state: 64 cached + 4 new keys, 4 queries.
+// Streaming chunk attention (fp32 contexts; the fp16 variant below runs the contractions on mma.sync), one CTA per
+// (session, head), 4 warps.  Steady state: 64 cached + 4 new keys, 4 queries.
 //   load   thread 0 starts the bulk copies of the ring's K/V rows (HBM -> smem, mbarrier); meanwhile every thread
 //          fetches its share of the chunk's own K/V rows (appended to the ring in the same pass), the rel-pos rows
 //          P_l[start + j] and Q, all issued before the first use so that one memory latency covers them
@@ -307,6 +313,252 @@ attention_stream_kernel(AttnStream a, const TA* __restrict__ qkv, const float* _
             o[1] = from_f<TA>(o1 * inv);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp16 variant of the streaming kernel with the two small contractions on the legacy tensor-core path
+// (mma.sync.m16n8k16, fp32 accumulate; the attention core is 1 % of the FLOPs, far too small for tcgen05):
+//   S^T (keys x queries) = K (keys x 64) . (q+u)^T  +  P (keys x 64) . (q+v)^T     key tiles of 16 over the 4 warps
+//   O^T (64 x queries)   = V^T (64 x keys) . prob^T                                   one 16-dim tile per warp
+// With 4 query rows the scalar kernel spends ~13 k FMA/convert instructions per CTA on these; here they are ~60 MMAs.
+// Loads, ring append, masking, fp32 softmax and the outputs are as in attention_stream_kernel.  (q+u), (q+v) and the
+// normalised probabilities are rounded to fp16 for the MMAs.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t lds32(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
+#ifdef FO_TC_TRACE_BUILD
+__device__ unsigned long long g_attn_trace[16];
+#define AT_TRACE(slot)                                                                                   \
+    do {                                                                                                 \
+        if (threadIdx.x == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) {                        \
+            unsigned long long t_;                                                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                       \
+            g_attn_trace[slot] = t_;                                                                     \
+        }                                                                                                \
+    } while (0)
+#else
+#define AT_TRACE(slot) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(ATT_THREADS, 7)
+attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const float* __restrict__ q32,
+                            __half* __restrict__ ring, const __half* __restrict__ ptab_h, const float* __restrict__ pos_u,
+                            const float* __restrict__ pos_v, __half* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef __half TA;
+    constexpr int EPC = 8, NCH = 8;
+    AT_TRACE(0);
+    FO_PDL_TRIGGER();
+    FO_PDL_WAIT();
+    AT_TRACE(1);
+    const int cap = a.ring_cap;
+    const int t = a.t, D = a.H * DK;
+    const int rows = a.window + t;                  // K / P rows held; a partial last key tile reads on into the next
+    const int vrows = (rows + 15) & ~15;            // array (finite or masked); V is padded with zero rows instead
+    TA* Ks = reinterpret_cast<TA*>(smem_raw);
+    TA* Ps = Ks + rows * DK;
+    TA* Vs = Ps + rows * DK;
+    TA* quh = Vs + vrows * DK;                      // (q+u), (q+v) as fp16, t x 64 each
+    TA* qvh = quh + t * DK;
+    TA* ph = qvh + t * DK;                          // normalised probabilities, t x vrows
+    float* sc = reinterpret_cast<float*>(ph + t * vrows);   // scores t x vrows (fp32); later the output tile t x 64
+    __shared__ __align__(8) uint64_t bar;
+
+    const int b = blockIdx.x, h = blockIdx.y;
+    const int slot = a.ids[b];
+    const int nf = a.n_frames[slot];
+    const int cl = min(nf, a.window);
+    const int first = nf - cl;
+    const int nk = cl + t;
+    const int pe = a.pe_index[slot] % a.pe_wrap;
+    const int start = max(0, pe - a.full_chunk);     // attention.py:112-114
+    TA* ringK = ring + (long long)slot * a.ring_slot_stride + (long long)h * cap * DK;
+    TA* ringV = ringK + (long long)a.H * cap * DK;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int np = min(nk, a.pos_rows - start);
+    AT_TRACE(2);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int p0 = first % cap;
+        const int len1 = min(cl, cap - p0), len2 = cl - len1;
+        const uint32_t rowb = DK * sizeof(TA);
+        mbar_expect_tx(&bar, (2u * cl + np) * rowb);
+        bulk_g2s(Ps, ptab_h + ((long long)h * a.pos_rows + start) * DK, np * rowb, &bar);
+        if (len1 > 0) {
+            bulk_g2s(Ks, ringK + (long long)p0 * DK, len1 * rowb, &bar);
+            bulk_g2s(Vs, ringV + (long long)p0 * DK, len1 * rowb, &bar);
+        }
+        if (len2 > 0) {
+            bulk_g2s(Ks + len1 * DK, ringK, len2 * rowb, &bar);
+            bulk_g2s(Vs + len1 * DK, ringV, len2 * rowb, &bar);
+        }
+    }
+    AT_TRACE(3);
+    // chunk's own K/V rows -> registers
+    const int n_new = t * NCH * 2;
+    uint4 newv = make_uint4(0, 0, 0, 0);
+    int new_which = 0, new_r = 0, new_c = 0;
+    const bool has_new = tid < n_new;
+    if (has_new) {
+        new_which = tid / (t * NCH);
+        new_r = (tid / NCH) % t;
+        new_c = tid % NCH;
+        newv = *reinterpret_cast<const uint4*>(qkv + (long long)(b * t + new_r) * 3 * D + (new_which + 1) * D + h * DK + new_c * EPC);
+    }
+    float qreg[4], ureg[4], vreg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * ATT_THREADS;
+        if (i < t * DK) {
+            const int r = i / DK, d = i % DK;
+            qreg[k] = q32[(long long)(b * t + r) * 3 * D + h * DK + d];
+            ureg[k] = pos_u[h * DK + d];
+            vreg[k] = pos_v[h * DK + d];
+        }
+    }
+    l2_prefetch_slice(a.prefetch, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, tid, ATT_THREADS);
+    // 16-byte chunk c of the row of frame f lives at chunk c ^ (f & 7) (kv_swz): rows that the MMA fragment loads read
+    // together then sit in different banks, although the bulk copies land the rows densely (128 B apart)
+    if (has_new) {
+        const int pc = new_c ^ ((nf + new_r) & 7);
+        *reinterpret_cast<uint4*>((new_which ? Vs : Ks) + (cl + new_r) * DK + pc * EPC) = newv;
+        *reinterpret_cast<uint4*>((new_which ? ringV : ringK) + (long long)((nf + new_r) % cap) * DK + pc * EPC) = newv;
+    }
+    for (int i = tid + ATT_THREADS; i < n_new; i += ATT_THREADS) {      // t > 8 only
+        const int which = i / (t * NCH), r = (i / NCH) % t, c = i % NCH;
+        const uint4 val = *reinterpret_cast<const uint4*>(qkv + (long long)(b * t + r) * 3 * D + (which + 1) * D + h * DK + c * EPC);
+        const int pc = c ^ ((nf + r) & 7);
+        *reinterpret_cast<uint4*>((which ? Vs : Ks) + (cl + r) * DK + pc * EPC) = val;
+        *reinterpret_cast<uint4*>((which ? ringV : ringK) + (long long)((nf + r) % cap) * DK + pc * EPC) = val;
+    }
+    // zero rows of V behind the last key (they enter the PV MMAs with probability 0: they must be finite)
+    for (int i = tid; i < (vrows - nk) * NCH; i += ATT_THREADS)
+        *reinterpret_cast<uint4*>(Vs + (nk + i / NCH) * DK + (i % NCH) * EPC) = make_uint4(0, 0, 0, 0);
+    for (int i = tid + np * NCH; i < nk * NCH; i += ATT_THREADS) {       // positions past the table end repeat its last row
+        const int j = i / NCH, c = i % NCH;
+        *reinterpret_cast<uint4*>(Ps + j * DK + (c ^ ((start + j) & 7)) * EPC) =
+            *reinterpret_cast<const uint4*>(ptab_h + ((long long)h * a.pos_rows + a.pos_rows - 1) * DK + (c ^ ((a.pos_rows - 1) & 7)) * EPC);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * ATT_THREADS;
+        if (i < t * DK) {
+            const int r = i / DK, d = i % DK;
+            const int o = r * DK + (((d >> 3) ^ (r & 7)) << 3) + (d & 7);      // same chunk swizzle, keyed by the query row
+            quh[o] = from_f<TA>(qreg[k] + ureg[k]);
+            qvh[o] = from_f<TA>(qreg[k] + vreg[k]);
+        }
+    }
+    for (int i = tid + 4 * ATT_THREADS; i < t * DK; i += ATT_THREADS) {
+        const int r = i / DK, d = i % DK;
+        const float q = q32[(long long)(b * t + r) * 3 * D + h * DK + d];
+        const int o = r * DK + (((d >> 3) ^ (r & 7)) << 3) + (d & 7);
+        quh[o] = from_f<TA>(q + pos_u[h * DK + d]);
+        qvh[o] = from_f<TA>(q + pos_v[h * DK + d]);
+    }
+    AT_TRACE(4);
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    AT_TRACE(5);
+
+    const int g = lane >> 2, c = lane & 3;
+    // ---- scores: S^T tile (16 keys x 8 queries) per MMA chain ----
+    for (int k0 = warp * 16; k0 < nk; k0 += 16 * (ATT_THREADS / 32)) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        // swizzle keys of the rows this lane reads: K rows by frame number, P rows by position, q rows by query index
+        const int kk0 = (first + k0 + g) & 7, kk1 = (first + k0 + g + 8) & 7;
+        const int kp0 = (start + k0 + g) & 7, kp1 = (start + k0 + g + 8) & 7;
+        const TA* kr0 = Ks + (k0 + g) * DK + c * 2;
+        const TA* kr1 = Ks + (k0 + g + 8) * DK + c * 2;
+        const TA* pr0 = Ps + (k0 + g) * DK + c * 2;
+        const TA* pr1 = Ps + (k0 + g + 8) * DK + c * 2;
+#pragma unroll
+        for (int ks = 0; ks < DK / 16; ++ks) {
+            const int c0 = ks * 2, c1 = ks * 2 + 1;                 // the two 16-byte chunks of this k step
+            uint32_t af[4], bf[2];
+            af[0] = lds32(kr0 + ((c0 ^ kk0) << 3));
+            af[1] = lds32(kr1 + ((c0 ^ kk1) << 3));
+            af[2] = lds32(kr0 + ((c1 ^ kk0) << 3));
+            af[3] = lds32(kr1 + ((c1 ^ kk1) << 3));
+            bf[0] = g < t ? lds32(quh + g * DK + ((c0 ^ g) << 3) + c * 2) : 0u;
+            bf[1] = g < t ? lds32(quh + g * DK + ((c1 ^ g) << 3) + c * 2) : 0u;
+            mma16816(d, af, bf);
+            af[0] = lds32(pr0 + ((c0 ^ kp0) << 3));
+            af[1] = lds32(pr1 + ((c0 ^ kp1) << 3));
+            af[2] = lds32(pr0 + ((c1 ^ kp0) << 3));
+            af[3] = lds32(pr1 + ((c1 ^ kp1) << 3));
+            bf[0] = g < t ? lds32(qvh + g * DK + ((c0 ^ g) << 3) + c * 2) : 0u;
+            bf[1] = g < t ? lds32(qvh + g * DK + ((c1 ^ g) << 3) + c * 2) : 0u;
+            mma16816(d, af, bf);
+        }
+        const int q0 = c * 2;
+        if (q0 < t) { sc[q0 * vrows + k0 + g] = d[0] * 0.125f; sc[q0 * vrows + k0 + g + 8] = d[2] * 0.125f; }
+        if (q0 + 1 < t) { sc[(q0 + 1) * vrows + k0 + g] = d[1] * 0.125f; sc[(q0 + 1) * vrows + k0 + g + 8] = d[3] * 0.125f; }
+    }
+    __syncthreads();
+    AT_TRACE(6);
+    // ---- softmax (fp32), probabilities normalised and rounded to fp16 ----
+    for (int i = warp; i < t; i += ATT_THREADS / 32) {
+        float sv[4];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = lane + 32 * k;
+            sv[k] = j < nk ? sc[i * vrows + j] : -INFINITY;
+            m = fmaxf(m, sv[k]);
+        }
+        m = warp_max(m);
+        float ssum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sv[k] = (lane + 32 * k < nk) ? __expf(sv[k] - m) : 0.f;
+            ssum += sv[k];
+        }
+        ssum = warp_sum(ssum);
+        const float inv = 1.f / ssum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = lane + 32 * k;
+            if (j < vrows) ph[i * vrows + j] = __float2half_rn(sv[k] * inv);
+        }
+    }
+    __syncthreads();
+    AT_TRACE(7);
+    // ---- PV: O^T tile (16 dims x 8 queries) per warp ----
+    {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        const int dim0 = warp * 16;
+        const int mi = lane >> 3, r = lane & 7;
+        for (int key0 = 0; key0 < nk; key0 += 16) {
+            uint32_t af[4], bf[2];
+            const int vrow = key0 + r + ((mi & 2) ? 8 : 0);
+            const TA* ap = Vs + vrow * DK + ((((dim0 >> 3) + (mi & 1)) ^ ((first + vrow) & 7)) << 3);
+            const uint32_t saddr = smem_u32(ap);
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3])
+                         : "r"(saddr));
+            bf[0] = g < t ? lds32(ph + g * vrows + key0 + c * 2) : 0u;
+            bf[1] = g < t ? lds32(ph + g * vrows + key0 + 8 + c * 2) : 0u;
+            mma16816(d, af, bf);
+        }
+        const int q0 = c * 2;
+        if (q0 < t) { sc[q0 * DK + dim0 + g] = d[0]; sc[q0 * DK + dim0 + g + 8] = d[2]; }
+        if (q0 + 1 < t) { sc[(q0 + 1) * DK + dim0 + g] = d[1]; sc[(q0 + 1) * DK + dim0 + g + 8] = d[3]; }
+    }
+    __syncthreads();
+    AT_TRACE(8);
+    for (int i = tid; i < t * (DK / 2); i += ATT_THREADS) {
+        const int q = i / (DK / 2), pr = i % (DK / 2);
+        *reinterpret_cast<uint32_t*>(out + (long long)(b * t + q) * D + h * DK + 2 * pr) =
+            pack2<__half>(sc[q * DK + 2 * pr], sc[q * DK + 2 * pr + 1]);
+    }
+    AT_TRACE(9);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -546,8 +798,28 @@ int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* r
     }
     FO_CHECK(smem <= 160 * 1024, "attention_stream: window too large for shared memory");
     dim3 grid(a.n, a.H);
-    FO_CUDA(launch_pdl(attention_stream_kernel<TA>, grid, dim3(ATT_THREADS), smem, st, a, qkv, q32, ring, ptab_h, pos_u, pos_v, out));
-    FO_LAUNCHED();
+    if constexpr (sizeof(TA) == 2) {
+            const int vrows = (rows + 15) & ~15;
+            const size_t sm = (size_t)(2 * rows + vrows) * DK * 2 + (size_t)2 * a.t * DK * 2 + (size_t)a.t * vrows * 2 +
+                              (size_t)a.t * std::max(vrows, DK) * 4;
+            FO_CUDA(launch_pdl(attention_stream_mma_kernel, grid, dim3(ATT_THREADS), sm, st, a, reinterpret_cast<const __half*>(qkv), q32,
+                               reinterpret_cast<__half*>(ring), reinterpret_cast<const __half*>(ptab_h), pos_u, pos_v,
+                               reinterpret_cast<__half*>(out)));
+            FO_LAUNCHED();
+#ifdef FO_TC_TRACE_BUILD
+            if (getenv("FO_TC_TRACE") && st == nullptr) {
+                cudaStreamSynchronize(st);
+                unsigned long long hb[16];
+                cudaMemcpyFromSymbol(hb, g_attn_trace, sizeof(hb));
+                fprintf(stderr, "attn_trace n=%d:", a.n);
+                for (int i = 1; i <= 9; ++i) fprintf(stderr, " t%d=%lld", i, (long long)(hb[i] - hb[0]));
+                fprintf(stderr, " ns\n");
+            }
+#endif
+    } else {
+        FO_CUDA(launch_pdl(attention_stream_kernel<TA>, grid, dim3(ATT_THREADS), smem, st, a, qkv, q32, ring, ptab_h, pos_u, pos_v, out));
+        FO_LAUNCHED();
+    }
     FO_CUDA(cudaGetLastError());
     return 0;
 }
@@ -561,7 +833,9 @@ __global__ void ptab_head_major_kernel(const float* __restrict__ in, int pos_row
     const int d = (int)(i % DK);
     const long long r = i / DK;
     const int pos = (int)(r % pos_rows), h = (int)(r / pos_rows);
-    out[i] = from_f<TA>(in[((long long)pos * H + h) * DK + d]);
+    // 16-bit tables carry the chunk swizzle of the fp16 attention kernel (chunk c of the row of position p at c ^ (p & 7))
+    const int dd = sizeof(TA) == 2 ? ((((d >> 3) ^ (pos & 7)) << 3) + (d & 7)) : d;
+    out[r * DK + dd] = from_f<TA>(in[((long long)pos * H + h) * DK + d]);
 }
 template <typename TA>
 int ptab_head_major(const float* in, int pos_rows, int H, TA* out, cudaStream_t st) {

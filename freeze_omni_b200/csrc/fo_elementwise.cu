@@ -330,7 +330,9 @@ __global__ void ring_export_kernel(const TA* __restrict__ ring, int H, int cap, 
     int d = i & 63;
     int j = (i >> 6) % n;
     int h = i / (64LL * n);
-    out[i] = to_f(ring[((long long)h * cap + (first + j) % cap) * 64 + d]);
+    // 16-bit rings carry the chunk swizzle of the fp16 attention kernel: chunk c of frame f at c ^ (f & 7)
+    const int dd = sizeof(TA) == 2 ? ((((d >> 3) ^ (int)((first + j) & 7)) << 3) + (d & 7)) : d;
+    out[i] = to_f(ring[((long long)h * cap + (first + j) % cap) * 64 + dd]);
 }
 template <typename TA>
 __global__ void ring_import_kernel(TA* __restrict__ ring, int H, int cap, long long first, int n,
@@ -340,7 +342,8 @@ __global__ void ring_import_kernel(TA* __restrict__ ring, int H, int cap, long l
     int d = i & 63;
     int j = (i >> 6) % n;
     int h = i / (64LL * n);
-    ring[((long long)h * cap + (first + j) % cap) * 64 + d] = from_f<TA>(in[i]);
+    const int dd = sizeof(TA) == 2 ? ((((d >> 3) ^ (int)((first + j) & 7)) << 3) + (d & 7)) : d;
+    ring[((long long)h * cap + (first + j) % cap) * 64 + dd] = from_f<TA>(in[i]);
 }
 
 inline int blocks_for(long long n, int t) { return (int)((n + t - 1) / t); }
