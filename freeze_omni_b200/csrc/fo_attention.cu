@@ -765,6 +765,217 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
     }
 }
 
+// fp16 variant of the full-utterance kernel on mma.sync.m16n8k16 (same reformulation as attention_stream_mma_kernel):
+// CTA = (32-query block, head, utterance); per 96-key tile K, V and the rel-pos rows are staged once with the XOR chunk
+// swizzle (chunk c of tile row i at c ^ (i & 7)), warp w computes S^T for query group w (8 queries) against the six
+// 16-key tiles, does the masked online softmax of its own queries, and owns output dims [16w, 16w+16) of all 32 queries
+// for the PV MMAs (accumulators rescaled per tile by the queries' correction factors).
+constexpr int OSC = 100;     // score row pitch (fp32): 4 mod 32 -> the MMA fragment stores of 4 query pairs hit 4 bank groups
+constexpr int OPH = 104;     // probability row pitch (fp16): 52 words = 20 mod 32 -> conflict-free B-fragment loads
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_offline_mma_kernel(const __half* __restrict__ qkv, const float* __restrict__ q32, int T, int H,
+                             const int32_t* __restrict__ ilens, int chunk, int left, const float* __restrict__ ptab,
+                             const float* __restrict__ pos_u, const float* __restrict__ pos_v, __half* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef __half TA;
+    constexpr int NCH = 8, EPC = 8;
+    TA* Ks = reinterpret_cast<TA*>(smem_raw);
+    TA* Ps = Ks + KT * DK;
+    TA* Vs = Ps + KT * DK;
+    TA* quh = Vs + KT * DK;                                  // QB x 64
+    TA* qvh = quh + QB * DK;
+    TA* ph = qvh + QB * DK;                                  // QB x OPH
+    float* sc = reinterpret_cast<float*>(ph + QB * OPH);     // QB x OSC scores; at the end the output tile QB x 64
+    float* m_run = sc + QB * OSC;
+    float* l_run = m_run + QB;
+    float* corr = l_run + QB;
+    __shared__ int win[QB][2];
+
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int D = H * DK;
+    const int q0 = qb * QB;
+    const int nq = min(QB, T - q0);
+    const int klen = ilens ? min(ilens[b], T) : T;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, c = lane & 3;
+
+    if (tid < QB) {
+        int s0 = 0, e0 = 0;
+        if (tid < nq) {
+            const int i = q0 + tid;
+            s0 = 0; e0 = T;
+            if (chunk > 0) {
+                s0 = left < 0 ? 0 : max((i / chunk - left) * chunk, 0);
+                e0 = min((i / chunk + 1) * chunk, T);
+            }
+            e0 = min(e0, klen);
+        }
+        win[tid][0] = s0;
+        win[tid][1] = e0;
+        m_run[tid] = -INFINITY;
+        l_run[tid] = 0.f;
+    }
+    for (int i = tid; i < QB * (DK / 4); i += ATT_THREADS) {
+        const int r = i / (DK / 4), d = (i % (DK / 4)) * 4;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nq) q = *reinterpret_cast<const float4*>(q32 + ((long long)b * T + q0 + r) * 3 * D + h * DK + d);
+        const float4 u = *reinterpret_cast<const float4*>(pos_u + h * DK + d);
+        const float4 v = *reinterpret_cast<const float4*>(pos_v + h * DK + d);
+        const int o = r * DK + (((d >> 3) ^ (r & 7)) << 3) + (d & 7);
+        uint2 hu, hv;
+        hu.x = pack2<TA>(q.x + u.x, q.y + u.y); hu.y = pack2<TA>(q.z + u.z, q.w + u.w);
+        hv.x = pack2<TA>(q.x + v.x, q.y + v.y); hv.y = pack2<TA>(q.z + v.z, q.w + v.w);
+        *reinterpret_cast<uint2*>(quh + o) = hu;
+        *reinterpret_cast<uint2*>(qvh + o) = hv;
+    }
+    __syncthreads();
+    int k_lo = T, k_hi = 0;
+    for (int r = 0; r < nq; ++r)
+        if (win[r][1] > win[r][0]) { k_lo = min(k_lo, win[r][0]); k_hi = max(k_hi, win[r][1]); }
+
+    float oacc[QB / 8][4];
+#pragma unroll
+    for (int qg = 0; qg < QB / 8; ++qg) { oacc[qg][0] = 0.f; oacc[qg][1] = 0.f; oacc[qg][2] = 0.f; oacc[qg][3] = 0.f; }
+
+    for (int kt = k_lo; kt < k_hi; kt += KT) {
+        const int nk = min(KT, k_hi - kt);
+        __syncthreads();                                   // previous tile fully consumed
+        for (int i = tid; i < KT * NCH * 2; i += ATT_THREADS) {
+            const int which = i / (KT * NCH);              // 0 K, 1 V
+            const int j = (i / NCH) % KT, cc = i % NCH;
+            uint4 val = make_uint4(0, 0, 0, 0);            // rows behind the last key: zeros (finite in the PV MMAs)
+            if (j < nk) val = *reinterpret_cast<const uint4*>(qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + cc * EPC);
+            *reinterpret_cast<uint4*>((which == 0 ? Ks : Vs) + j * DK + ((cc ^ (j & 7)) << 3)) = val;
+        }
+        for (int i = tid; i < nk * (DK / 4); i += ATT_THREADS) {
+            const int j = i / (DK / 4), d = (i % (DK / 4)) * 4;
+            const float4 v4 = *reinterpret_cast<const float4*>(ptab + (long long)(kt + j) * D + h * DK + d);
+            uint2 hh;
+            hh.x = pack2<TA>(v4.x, v4.y);
+            hh.y = pack2<TA>(v4.z, v4.w);
+            *reinterpret_cast<uint2*>(Ps + j * DK + (((d >> 3) ^ (j & 7)) << 3) + (d & 7)) = hh;
+        }
+        __syncthreads();
+        // ---- scores of query group `warp` against the 16-key tiles ----
+        const int qrow = warp * 8 + g;                     // B-fragment row (query) of this lane
+        for (int k0 = 0; k0 < nk; k0 += 16) {
+            float d4[4] = {0.f, 0.f, 0.f, 0.f};
+            const int s0k = (k0 + g) & 7, s1k = (k0 + g + 8) & 7;
+            const TA* kr0 = Ks + (k0 + g) * DK + c * 2;
+            const TA* kr1 = Ks + (k0 + g + 8) * DK + c * 2;
+            const TA* pr0 = Ps + (k0 + g) * DK + c * 2;
+            const TA* pr1 = Ps + (k0 + g + 8) * DK + c * 2;
+#pragma unroll
+            for (int ks = 0; ks < DK / 16; ++ks) {
+                const int c0 = ks * 2, c1 = ks * 2 + 1;
+                uint32_t af[4], bf[2];
+                af[0] = lds32(kr0 + ((c0 ^ s0k) << 3));
+                af[1] = lds32(kr1 + ((c0 ^ s1k) << 3));
+                af[2] = lds32(kr0 + ((c1 ^ s0k) << 3));
+                af[3] = lds32(kr1 + ((c1 ^ s1k) << 3));
+                bf[0] = lds32(quh + qrow * DK + ((c0 ^ g) << 3) + c * 2);
+                bf[1] = lds32(quh + qrow * DK + ((c1 ^ g) << 3) + c * 2);
+                mma16816(d4, af, bf);
+                af[0] = lds32(pr0 + ((c0 ^ s0k) << 3));
+                af[1] = lds32(pr1 + ((c0 ^ s1k) << 3));
+                af[2] = lds32(pr0 + ((c1 ^ s0k) << 3));
+                af[3] = lds32(pr1 + ((c1 ^ s1k) << 3));
+                bf[0] = lds32(qvh + qrow * DK + ((c0 ^ g) << 3) + c * 2);
+                bf[1] = lds32(qvh + qrow * DK + ((c1 ^ g) << 3) + c * 2);
+                mma16816(d4, af, bf);
+            }
+            const int qa = warp * 8 + c * 2;
+            sc[qa * OSC + k0 + g] = d4[0] * 0.125f;
+            sc[(qa + 1) * OSC + k0 + g] = d4[1] * 0.125f;
+            sc[qa * OSC + k0 + g + 8] = d4[2] * 0.125f;
+            sc[(qa + 1) * OSC + k0 + g + 8] = d4[3] * 0.125f;
+        }
+        __syncwarp();
+        // ---- masked online softmax of this warp's 8 queries; un-normalised probabilities as fp16 ----
+        for (int qi = 0; qi < 8; ++qi) {
+            const int r = warp * 8 + qi;
+            const int lo = win[r][0], hi = win[r][1];
+            float sv[3];
+            float m = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int j = lane + 32 * k, key = kt + j;
+                sv[k] = (j < nk && key >= lo && key < hi) ? sc[r * OSC + j] : -INFINITY;
+                m = fmaxf(m, sv[k]);
+            }
+            m = warp_max(m);
+            const float m_old = m_run[r];
+            const float m_new = fmaxf(m_old, m);
+            float cf = 1.f, ssum = 0.f;
+            if (m_new != -INFINITY) {
+                cf = __expf(m_old - m_new);                // m_old = -inf -> 0
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    sv[k] = __expf(sv[k] - m_new);         // masked keys: exp(-inf) = 0
+                    ssum += sv[k];
+                }
+            } else {
+                sv[0] = sv[1] = sv[2] = 0.f;
+            }
+            ssum = warp_sum(ssum);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ph[r * OPH + lane + 32 * k] = __float2half_rn(sv[k]);
+            if (lane == 0) {
+                m_run[r] = m_new;
+                l_run[r] = l_run[r] * cf + ssum;
+                corr[r] = cf;
+            }
+        }
+        __syncthreads();
+        // ---- PV: this warp's 16 output dims of all 32 queries ----
+        {
+            const int dim0 = warp * 16;
+            const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+            for (int qg = 0; qg < QB / 8; ++qg) {
+                const float f0 = corr[qg * 8 + c * 2], f1 = corr[qg * 8 + c * 2 + 1];
+                oacc[qg][0] *= f0; oacc[qg][1] *= f1; oacc[qg][2] *= f0; oacc[qg][3] *= f1;
+            }
+            for (int key0 = 0; key0 < nk; key0 += 16) {
+                uint32_t af[4];
+                const int vrow = key0 + rr + ((mi & 2) ? 8 : 0);
+                const TA* ap = Vs + vrow * DK + ((((dim0 >> 3) + (mi & 1)) ^ (vrow & 7)) << 3);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3])
+                             : "r"(smem_u32(ap)));
+#pragma unroll
+                for (int qg = 0; qg < QB / 8; ++qg) {
+                    uint32_t bf[2];
+                    bf[0] = lds32(ph + (qg * 8 + g) * OPH + key0 + c * 2);
+                    bf[1] = lds32(ph + (qg * 8 + g) * OPH + key0 + 8 + c * 2);
+                    mma16816(oacc[qg], af, bf);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- normalise, stage the 32 x 64 output tile, coalesced store ----
+    {
+        const int dim0 = warp * 16;
+#pragma unroll
+        for (int qg = 0; qg < QB / 8; ++qg) {
+            const int qa = qg * 8 + c * 2;
+            const float i0 = l_run[qa] > 0.f ? 1.f / l_run[qa] : 0.f;          // fully masked row -> zeros (attention.py:396-397)
+            const float i1 = l_run[qa + 1] > 0.f ? 1.f / l_run[qa + 1] : 0.f;
+            sc[qa * DK + dim0 + g] = oacc[qg][0] * i0;
+            sc[(qa + 1) * DK + dim0 + g] = oacc[qg][1] * i1;
+            sc[qa * DK + dim0 + g + 8] = oacc[qg][2] * i0;
+            sc[(qa + 1) * DK + dim0 + g + 8] = oacc[qg][3] * i1;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nq * (DK / 2); i += ATT_THREADS) {
+        const int q = i / (DK / 2), pr = i % (DK / 2);
+        *reinterpret_cast<uint32_t*>(out + ((long long)b * T + q0 + q) * D + h * DK + 2 * pr) =
+            pack2<__half>(sc[q * DK + 2 * pr], sc[q * DK + 2 * pr + 1]);
+    }
+}
+
 __global__ void advance_sessions_kernel(const int32_t* __restrict__ ids, int n, int t, int chunk_size, int pe_wrap,
                                         int32_t* n_frames, int32_t* pe_index, int32_t* adapter_valid) {
     FO_PDL_TRIGGER();
@@ -860,7 +1071,18 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
         FO_CUDA(cudaFuncSetAttribute(attention_offline_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set[sizeof(TA) == 2] = true;
     }
-    attention_offline_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(qkv, q32, T, H, ilens, chunk, left, ptab, pos_u, pos_v, out);
+    if constexpr (sizeof(TA) == 2) {
+        const size_t sm = (size_t)3 * KT * DK * 2 + (size_t)2 * QB * DK * 2 + (size_t)QB * OPH * 2 + (size_t)QB * OSC * 4 + 3 * QB * 4;
+        static bool attr2 = false;
+        if (!attr2) {
+            FO_CUDA(cudaFuncSetAttribute(attention_offline_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr2 = true;
+        }
+        attention_offline_mma_kernel<<<grid, ATT_THREADS, sm, st>>>(reinterpret_cast<const __half*>(qkv), q32, T, H, ilens, chunk, left,
+                                                                    ptab, pos_u, pos_v, reinterpret_cast<__half*>(out));
+    } else {
+        attention_offline_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(qkv, q32, T, H, ilens, chunk, left, ptab, pos_u, pos_v, out);
+    }
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
