@@ -120,6 +120,10 @@ struct fo_ctx {
     int pf_slot_lo = 0, pf_slot_hi = 0;       // slot range of the sessions of the current step
     int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
                                               // (measured slower than the stand-alone kernel at 64-256 sessions: off)
+    int stack_kernel = 0;                     // 24-layer stack of the streaming step as ONE persistent cooperative kernel (fo_stack.cu)
+    int stack_split_o = 0, stack_split_f2 = 0;   // debugging: force its K splits
+    StackState* stack = nullptr;
+    long long stack_launches = 0;
     int groups = 1;                           // session groups whose layer kernels run on parallel streams
     cudaStream_t grp_stream[MAX_GROUPS] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {nullptr};
@@ -145,7 +149,7 @@ struct fo_ctx {
 namespace {
 
 enum { WS_FEATS = 0, WS_C1, WS_C2, WS_XSUB, WS_EMB, WS_X, WS_H, WS_QKV, WS_ATT, WS_FFH, WS_ENC, WS_XIN, WS_ACONV, WS_AH,
-       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_COUNT };
+       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_PART, WS_COUNT };
 
 int dev_alloc(fo_ctx* c, void** p, size_t bytes) {
     *p = nullptr;
@@ -653,6 +657,41 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
     void* hc = nullptr;
     if (c->KF >= 2) FO_TRY(ws_ensure(c, WS_HC, (size_t)M * D * sizeof(TA), &hc));
+    // fp16 context, plain feed-forward: the whole stack as one persistent kernel
+    bool stack_done = false;
+    if (sizeof(TA) == 2 && c->stack_kernel && c->gemm_backend == 1 && c->KF < 2 && !c->debug_skip && !c->profile_gemm) {
+        const int MAXS = 8;
+        void* part;
+        FO_TRY(ws_ensure(c, WS_PART, (size_t)MAXS * M * D * sizeof(float), &part));
+        if (!c->stack) FO_TRY(stack_state_create(&c->stack));
+        const long long lstride = (long long)c->cfg.max_sessions * 2LL * H * c->ring_cap * 64;
+        std::vector<StackLayerHost> hl(c->L);
+        for (int l = 0; l < c->L; ++l) {
+            const LayerW& w = c->layers[l];
+            hl[l] = StackLayerHost{w.wqkv, w.wo, w.w1, w.w2, w.ln1g, w.ln1b, w.ln2g, w.ln2b, w.bqkv, w.bo, w.b1, w.b2,
+                                   w.pos_u, w.pos_v, w.ptab_h, reinterpret_cast<TA*>(c->ring) + l * lstride};
+        }
+        StackHostArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.layers = hl.data();
+        sa.L = c->L; sa.D = D; sa.FF = FF; sa.H = H;
+        sa.x = x; sa.h = h; sa.qkv = qkv; sa.q32 = q32; sa.att = att; sa.ffh = ffh;
+        sa.partial = reinterpret_cast<float*>(part);
+        sa.max_split = MAXS;
+        sa.force_split_o = c->stack_split_o;
+        sa.force_split_f2 = c->stack_split_f2;
+        sa.fin_g = c->after_g; sa.fin_b = c->after_b;
+        sa.enc_out = enc_out_dev;
+        sa.a.ids = c->ids_dev;
+        sa.a.n_frames = c->n_frames;
+        sa.a.pe_index = c->pe_index;
+        sa.a.n = n; sa.a.t = t; sa.a.H = H; sa.a.ring_cap = c->ring_cap; sa.a.window = c->window; sa.a.full_chunk = c->full_chunk;
+        sa.a.pe_wrap = c->pe_wrap; sa.a.pos_rows = c->pos_rows;
+        sa.a.ring_slot_stride = 2LL * H * c->ring_cap * 64;
+        const int r = stack_stream_launch(c->stack, sa, st);
+        if (r < 0) return r;
+        if (r == 0) { stack_done = true; ++c->stack_launches; }
+    }
     // The 24 layers run per SESSION GROUP on parallel streams (fork/join with events, also under graph capture):
     // sessions are independent, every layer kernel of a 64-session step is latency bound (<= 148 CTAs, 8-16 us), so
     // two groups' kernels overlap each other's pipeline fill, epilogue and launch gaps.  Rows of one group are
@@ -661,12 +700,13 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     if (G > fo_ctx::MAX_GROUPS) G = fo_ctx::MAX_GROUPS;
     while (G > 1 && n < 8 * G) --G;
     const long long layer_stride = (long long)c->cfg.max_sessions * 2LL * H * c->ring_cap * 64;
+    if (stack_done) G = 1;
     if (G > 1) {
         FO_CUDA(cudaEventRecord(c->ev_fork, st));
         for (int g = 1; g < G; ++g) FO_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->ev_fork, 0));
     }
     const int per = (n + G - 1) / G;
-    for (int l = 0; l < c->L; ++l) {
+    for (int l = 0; l < c->L && !stack_done; ++l) {
         const LayerW& w = c->layers[l];
         const bool last = l + 1 == c->L;
         for (int g = 0; g < G; ++g) {
@@ -876,6 +916,7 @@ int fo_destroy(fo_ctx* c) {
     for (auto& kv : c->staged) cudaFree(kv.second.d);
     for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    stack_state_destroy(c->stack);
     for (int g = 1; g < fo_ctx::MAX_GROUPS; ++g) {
         if (c->grp_stream[g]) cudaStreamDestroy(c->grp_stream[g]);
         if (c->ev_join[g]) cudaEventDestroy(c->ev_join[g]);
@@ -1202,7 +1243,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     uint32_t sbits;
     memcpy(&sbits, &a.scale, 4);
     snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
-             c->gemm_backend, c->groups, (c->debug_skip * 2 + c->fuse_ln) * 2 + c->use_prefetch,
+             c->gemm_backend, c->groups, ((c->debug_skip * 2 + c->fuse_ln) * 2 + c->use_prefetch) * 64 + c->stack_kernel * 32 + c->stack_split_o * 4 + c->stack_split_f2 / 2,
              (c->use_prefetch ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), c->use_prefetch ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
     if (c->graphs.size() > 256 && c->graphs.find(key) == c->graphs.end()) {
         for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1386,6 +1427,9 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "split_k")) c->split_k = (int)value;
     else if (!strcmp(name, "debug_skip")) c->debug_skip = (int)value;
     else if (!strcmp(name, "fuse_ln")) c->fuse_ln = value != 0;
+    else if (!strcmp(name, "stack_kernel")) c->stack_kernel = value != 0;
+    else if (!strcmp(name, "stack_split_o")) c->stack_split_o = (int)value;
+    else if (!strcmp(name, "stack_split_f2")) c->stack_split_f2 = (int)value;
     else if (!strcmp(name, "l2_prefetch")) c->use_prefetch = value != 0;
     else if (!strcmp(name, "pdl")) g_want_pdl = value != 0;
     else if (!strcmp(name, "session_groups")) {
@@ -1415,6 +1459,8 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     else if (!strcmp(name, "split_k")) *value = c->split_k;
     else if (!strcmp(name, "session_groups")) *value = c->groups;
     else if (!strcmp(name, "fuse_ln")) *value = c->fuse_ln;
+    else if (!strcmp(name, "stack_kernel")) *value = c->stack_kernel;
+    else if (!strcmp(name, "stack_launches")) *value = c->stack_launches;
     else if (!strcmp(name, "l2_prefetch")) *value = c->use_prefetch;
     else if (!strcmp(name, "pdl")) *value = g_want_pdl;
     else if (!strcmp(name, "profile_gemm_count")) *value = (int64_t)c->prof_events.size();

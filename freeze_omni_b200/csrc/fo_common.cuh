@@ -275,6 +275,30 @@ int ptab_head_major(const float* in, int pos_rows, int H, TA* out, cudaStream_t 
 template <typename TA>
 int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,
                       const float* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st);
+// ---- persistent transformer-stack kernel of the streaming step (fo_stack.cu) ---------------------------
+struct StackLayerHost {
+    const void *wqkv, *wo, *w1, *w2;          // fp16 containers, K-major
+    const float *ln1g, *ln1b, *ln2g, *ln2b, *bqkv, *bo, *b1, *b2, *pos_u, *pos_v;
+    const void* ptab_h;
+    void* ring;                                // this layer's KV ring
+};
+struct StackHostArgs {
+    const StackLayerHost* layers;              // (L); read on the first launch of a context only
+    int L, D, FF, H;
+    float* x; void* h; void* qkv; float* q32; void* att; void* ffh;
+    float* partial;                            // (max_split, M, D) fp32
+    int max_split;
+    int force_split_o, force_split_f2;         // 0: automatic
+    const float *fin_g, *fin_b;
+    float* enc_out;
+    AttnStream a;
+};
+struct StackState;
+int stack_state_create(StackState** out);
+void stack_state_destroy(StackState* s);
+// 0: launched; 1: shape not covered (caller runs the per-kernel chain); < 0: error
+int stack_stream_launch(StackState* s, const StackHostArgs& args, cudaStream_t st);
+
 // end of a streaming step: n_frames += t, pe_index = pe_index % wrap + chunk_size (attention.py:107,120),
 // and flip the live half of the double-buffered adapter cache.  Either group may be null.
 int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,

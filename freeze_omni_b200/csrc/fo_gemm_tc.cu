@@ -587,6 +587,11 @@ int gemm_tc_init() {
     return 0;
 }
 
+int tc_make_map(CUtensorMap* map, const void* base, int seg_len, long long rows, int planes, int box_rows) {
+    FO_TRY(gemm_tc_init());
+    return make_map(map, reinterpret_cast<const bf16*>(base), seg_len, rows, planes, box_rows);
+}
+
 int gemm_tc_workspace(TcWorkspace* ws) {
     FO_CUDA(cudaMalloc(&ws->counters, MAX_TILES * sizeof(int)));
     FO_CUDA(cudaMemset(ws->counters, 0, MAX_TILES * sizeof(int)));
