@@ -1,0 +1,141 @@
+"""Batched session scheduler with the VAD-gated streaming frontend (SURVEY 8 f1 + f3).
+
+The reference runs one feature-gating thread and one predictor thread PER SESSION, hands fbank blocks between them
+as Python lists and calls the encoder with batch 1 (bin/dialog_state_pred.py:600-684 feature gating, :719-775 the
+processing loop, :793-814 the encoder call; bin/pool.py:61-91 the pipeline pool).  Here one scheduler per GPU gathers
+the chunks that arrived during a tick (<= 160 ms), runs ONE batched fbank call for all of them, applies the gating rule
+on the device and drains the per-session feature queues with batched encoder+adapter steps:
+
+  gating rule (models/AudioFeatureGating.py:77-109, process_and_gate):
+    * features are ALWAYS extracted, so the sample carry / context ring stay continuous;
+    * status None (no speech):       the block only enters the session's history ring (last `history_chunks` blocks);
+    * status 'ipu_sl' (speech onset): the last `onset_chunks` history blocks are queued in front of the current one
+      (dialog_state_pred.py:639-670), each of them is one encoder step;
+    * any other status:              the block is queued.
+  Each queued block is one `encoder.infer` + adapter step of that session (dialog_state_pred.py:793-814).
+
+Per drain round the head block of every session with a non-empty queue forms one batch; the batch is padded to a
+multiple of `bucket` with scratch sessions so that a handful of captured CUDA graphs serve every active-set size.
+State (KV rings, adapter cache, sample carry, feature ring, history ring, queued blocks) never leaves the device.
+"""
+from collections import deque
+from typing import Any, Deque, Dict, Hashable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+IPU_START = "ipu_sl"
+
+
+def plan_rounds(queue_lens: Dict[Hashable, int], max_batch: int) -> List[List[Hashable]]:
+    """Drain order for per-session FIFO queues: every round takes the head block of each session that still has one
+    (a session's blocks must run in order, so it appears at most once per round), `max_batch` sessions per batch.
+    Pure function of the queue lengths -> testable without a GPU."""
+    left = dict(queue_lens)
+    rounds: List[List[Hashable]] = []
+    while True:
+        ready = [k for k, n in left.items() if n > 0]
+        if not ready:
+            return rounds
+        for i in range(0, len(ready), max_batch):
+            rounds.append(ready[i:i + max_batch])
+        for k in ready:
+            left[k] -= 1
+
+
+def bucket_size(n: int, bucket: int) -> int:
+    return (n + bucket - 1) // bucket * bucket
+
+
+class StreamScheduler:
+    def __init__(self, engine, history_chunks: int = 10, onset_chunks: int = 6, bucket: int = 16,
+                 max_batch: Optional[int] = None, max_sessions: Optional[int] = None):
+        assert 0 <= onset_chunks <= history_chunks
+        self.eng, self.cfg = engine, engine.cfg
+        self.history_chunks, self.onset_chunks, self.bucket = history_chunks, onset_chunks, max(1, bucket)
+        self.max_batch = max_batch or 1 << 30
+        self.keys: Dict[Hashable, int] = {}                    # session key -> slot
+        self.rows: Dict[Hashable, int] = {}                    # session key -> row of the history tensor
+        self.free_rows: List[int] = []
+        self.pending: Dict[Hashable, Tuple[Any, Optional[str]]] = {}
+        self.queues: Dict[Hashable, Deque[torch.Tensor]] = {}
+        self.scratch = engine.alloc(self.bucket - 1) if self.bucket > 1 else np.zeros(0, np.int32)
+        cap = max_sessions or 64
+        self._hist = torch.zeros(cap, history_chunks, self.cfg.chunk_feat_frames, self.cfg.feat_dim, device=engine.torch_device)
+        self.free_rows = list(range(cap - 1, -1, -1))
+        self.stats = {"ticks": 0, "fbank_calls": 0, "encode_calls": 0, "session_steps": 0, "padded_steps": 0}
+
+    # ---- sessions ---------------------------------------------------------------------------------
+    def open(self, key: Hashable) -> int:
+        """New session == encoder_cache None, adapter_cache None, pe_index 0 (dialog_state_pred.py:221-232) and a
+        zeroed frontend (AudioFeatureGating.reset)."""
+        assert key not in self.keys, "session already open"
+        if not self.free_rows:
+            raise RuntimeError("scheduler is full (max_sessions=%d)" % self._hist.shape[0])
+        slot = int(self.eng.alloc(1)[0])
+        self.keys[key], self.rows[key] = slot, self.free_rows.pop()
+        self._hist[self.rows[key]].zero_()
+        self.queues[key] = deque()
+        return slot
+
+    def close(self, key: Hashable) -> None:
+        self.eng.free([self.keys.pop(key)])
+        self.free_rows.append(self.rows.pop(key))
+        self.queues.pop(key)
+        self.pending.pop(key, None)
+
+    def reset(self, key: Hashable) -> None:
+        self.eng.reset([self.keys[key]])
+        self._hist[self.rows[key]].zero_()
+        self.queues[key].clear()
+        self.pending.pop(key, None)
+
+    # ---- data path ----------------------------------------------------------------------------------
+    def push(self, key: Hashable, pcm, status: Optional[str]) -> None:
+        """One chunk of `samples_per_chunk` samples (int16 or float32, host or device) with its VAD annotation."""
+        assert key in self.keys and key not in self.pending, "one chunk per session per tick"
+        self.pending[key] = (pcm, status)
+
+    def tick(self, scale: Optional[float] = None) -> Dict[Hashable, List[Tuple[torch.Tensor, Optional[torch.Tensor]]]]:
+        """Process everything pushed since the last tick.  Returns, per session that produced output, the list of
+        (encoder frames (t, D), adapter embeddings (t_out, E)) in stream order (one entry per queued block)."""
+        self.stats["ticks"] += 1
+        out: Dict[Hashable, List[Tuple[torch.Tensor, Optional[torch.Tensor]]]] = {}
+        if self.pending:
+            keys = list(self.pending)
+            dev = self.eng.torch_device
+            pcm = torch.stack([torch.as_tensor(self.pending[k][0]).to(dev, non_blocking=True) for k in keys])
+            ids = np.array([self.keys[k] for k in keys], np.int32)
+            feats = self.eng.fbank_stream(ids, pcm, scale)                       # carry + context ring advance for everyone
+            self.stats["fbank_calls"] += 1
+            silent = [i for i, k in enumerate(keys) if self.pending[k][1] is None]
+            if silent:                                                           # history ring: drop the oldest, append
+                rows = torch.tensor([self.rows[keys[i]] for i in silent], device=dev)
+                h = self._hist.index_select(0, rows)
+                h = torch.cat([h[:, 1:], feats.index_select(0, torch.tensor(silent, device=dev)).unsqueeze(1)], dim=1)
+                self._hist.index_copy_(0, rows, h)
+            for i, k in enumerate(keys):
+                status = self.pending[k][1]
+                if status is None:
+                    continue
+                if status == IPU_START and self.onset_chunks > 0:
+                    hist = self._hist[self.rows[k], self.history_chunks - self.onset_chunks:].clone()
+                    self.queues[k].extend(hist.unbind(0))
+                self.queues[k].append(feats[i])
+            self.pending.clear()
+        for batch in plan_rounds({k: len(q) for k, q in self.queues.items()}, self.max_batch):
+            blocks = [self.queues[k].popleft() for k in batch]
+            n = len(batch)
+            pad = bucket_size(n, self.bucket) - n
+            ids = np.concatenate([np.array([self.keys[k] for k in batch], np.int32), self.scratch[:pad]]).astype(np.int32)
+            x = torch.stack(blocks + [blocks[0]] * pad)
+            enc, emb = self.eng.encode_stream(ids, x)
+            self.stats["encode_calls"] += 1
+            self.stats["session_steps"] += n
+            self.stats["padded_steps"] += pad
+            for i, k in enumerate(batch):
+                out.setdefault(k, []).append((enc[i], emb[i] if emb is not None else None))
+        return out
+
+    def history(self, key: Hashable) -> torch.Tensor:
+        return self._hist[self.rows[key]]

@@ -520,6 +520,58 @@ def test_fused_layernorm_matches_standalone(shipped16):
         eng.free(ids)
 
 
+def test_scheduler_vad_gating_vs_oracle():
+    """Batched scheduler + VAD-gated frontend (freeze_omni_b200/scheduler.py) against per-session oracle runs that
+    restate the reference flow: features always extracted (AudioFeatureGating.py:92-93), silent blocks only enter the
+    10-deep history ring (:96-99), speech onset replays the last 6 history blocks before the current one
+    (:109-112, dialog_state_pred.py:639-670), every queued block is one encoder + adapter step (:793-814)."""
+    from freeze_omni_b200.scheduler import StreamScheduler
+    cfg, eng = make_engine("tiny", 3, max_sessions=24)
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    g = torch.Generator().manual_seed(53)
+    S, T = 4, 16
+    pattern = [
+        ["ipu_cl"] * T,                                                                   # always speaking
+        [None] * 8 + ["ipu_sl"] + ["ipu_cl"] * 3 + [None] * 2 + ["ipu_sl", "ipu_cl"],     # two onsets, full history at the first
+        [None] * 3 + ["ipu_sl"] + ["ipu_cl"] * 12,                                        # onset before the history ring is full
+        [None] * T,                                                                       # never speaks
+    ]
+    try:
+        sch = StreamScheduler(eng, history_chunks=10, onset_chunks=6, bucket=4, max_sessions=8)
+        oracle = [O.StreamSession(cfg, esd, asd) for _ in range(S)]
+        hist = [torch.zeros(10, cfg.chunk_feat_frames, cfg.feat_dim) for _ in range(S)]
+        for s in range(S):
+            sch.open(s)
+        expected_steps = 0
+        for tck in range(T):
+            pcm = (0.05 * torch.randn(S, cfg.samples_per_chunk, generator=g) * 32768).round().to(torch.int16)
+            active = [s for s in range(S) if not (s == 0 and tck % 5 == 4)]              # session 0 misses some ticks
+            for s in active:
+                sch.push(s, pcm[s], pattern[s][tck])
+            out = sch.tick(1.0)
+            for s in active:
+                feats = oracle[s].front.process(pcm[s].float(), 1.0)                      # (1, 19, 80)
+                status = pattern[s][tck]
+                if status is None:
+                    hist[s] = torch.cat([hist[s][1:], feats])
+                    assert s not in out
+                    continue
+                blocks = list(hist[s][-6:].unsqueeze(1)) + [feats] if status == "ipu_sl" else [feats]
+                assert len(out[s]) == len(blocks), (tck, s)
+                expected_steps += len(blocks)
+                for (enc, emb), blk in zip(out[s], blocks):
+                    eo, yo = oracle[s].step_feats(blk)
+                    assert maxabs(enc.cpu(), eo[0]) < FP32_TOL and maxabs(emb.cpu(), yo[0]) < FP32_TOL, (tck, s)
+            assert maxabs(sch.history(1).cpu(), hist[1]) < 1e-4 * 20
+        st = sch.stats
+        assert st["fbank_calls"] == T and st["session_steps"] == expected_steps
+        assert st["encode_calls"] < st["session_steps"]                                   # steps were batched
+        for s in range(S):
+            assert eng.state(sch.keys[s])[1] == oracle[s].pe_index
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("n", [1, 5, 24])
 def test_persistent_stack_kernel_matches_chain(n):
     """Option stack_kernel=1 runs the 24 layers of a streaming step as ONE cooperative persistent kernel
