@@ -120,6 +120,8 @@ struct fo_ctx {
     int pf_slot_lo = 0, pf_slot_hi = 0;       // slot range of the sessions of the current step
     int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
                                               // (measured slower than the stand-alone kernel at 64-256 sessions: off)
+    void* handoff = nullptr;                  // fo_stream_step_embeds: fp16 destination of the adapter rows for this call
+    long long handoff_rows = 0, handoff_off = 0;
     int stack_kernel = 0;                     // 24-layer stack of the streaming step as ONE persistent cooperative kernel (fo_stack.cu)
     int stack_split_o = 0, stack_split_f2 = 0;   // debugging: force its K splits
     StackState* stack = nullptr;
@@ -512,7 +514,16 @@ int adapter_program(fo_ctx* c, const float* enc, const uint8_t* mask, int B, int
     e2.bias = c->ad_proj_b;
     e2.c_f32 = y;
     e2.ldc = E;
-    if (!(c->debug_skip & 16)) FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(ah), c->ad_proj_w, Mo, E, 2 * D, e2, st));
+    RowMap rm2;
+    if (c->handoff && ids_dev) {
+        // LLM hand-off (audioLLM.py:404-411): rows of session b go, as fp16, to row  b * rows_per_session + row_offset + j  of
+        // the caller's inputs_embeds buffer, straight from the projection's epilogue (no fp32 copy, no cat, no .half())
+        e2.c_f32 = nullptr;
+        e2.c_act = reinterpret_cast<TA*>(c->handoff) + c->handoff_off * E;
+        rm2.p1 = t_out; rm2.p0 = t_out; rm2.v1 = 1; rm2.v0 = t_out; rm2.q1 = (int)c->handoff_rows; rm2.q0 = 0;
+    }
+    if (!(c->debug_skip & 16))
+        FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(ah), plain_rows(2 * D, Mo), c->ad_proj_w, Mo, E, 2 * D, e2, rm2, st));
     return 0;
 }
 
@@ -760,10 +771,11 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
             FO_CUDA(cudaStreamWaitEvent(st, c->ev_join[g], 0));
         }
     }
-    if (c->cfg.has_adapter && y_dev)
+    const bool run_adapter = c->cfg.has_adapter && (y_dev || c->handoff);
+    if (run_adapter)
         FO_TRY(adapter_program<TA>(c, enc_out_dev, nullptr, n, t, c->ids_dev, nullptr, nullptr, y_dev, st));
     FO_TRY(advance_sessions(c->ids_dev, n, t, c->cfg.chunk_size, c->pe_wrap, c->n_frames, c->pe_index,
-                            (c->cfg.has_adapter && y_dev) ? c->ad_valid : nullptr, st));
+                            run_adapter ? c->ad_valid : nullptr, st));
     return 0;
 }
 
@@ -1239,10 +1251,10 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     // +12 % at 1 session, where the early-resident successor CTAs only get in the way)
     g_use_pdl = g_want_pdl && a.n >= 16;
     if (!c->use_graph || c->profile_gemm) return step_body(c, a, st);
-    char key[128];
+    char key[192];
     uint32_t sbits;
     memcpy(&sbits, &a.scale, 4);
-    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
+    snprintf(key, sizeof(key), "%p/%lld/%lld/%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", c->handoff, c->handoff_rows, c->handoff_off, a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
              c->gemm_backend, c->groups, ((c->debug_skip * 2 + c->fuse_ln) * 2 + c->use_prefetch) * 64 + c->stack_kernel * 32 + c->stack_split_o * 4 + c->stack_split_f2 / 2,
              (c->use_prefetch ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), c->use_prefetch ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
     if (c->graphs.size() > 256 && c->graphs.find(key) == c->graphs.end()) {
@@ -1331,6 +1343,31 @@ int fo_encode_stream(fo_ctx* c, const int32_t* ids, int n, const float* feats, i
     if (feats) FO_CHECK(t_in >= 7, "fo_encode_stream: need at least 7 feature frames");
     else t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
     return stream_common(c, ids, n, nullptr, FO_F32, 1.0f, feats, t_in, enc_out, adapter_out, (cudaStream_t)stream);
+}
+
+int fo_stream_step_embeds(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale, float* enc_out,
+                          void* embeds_f16, int64_t rows_per_session, int64_t row_offset, void* stream) {
+    FO_CHECK(c && c->finalized && c->cfg.has_encoder && c->cfg.has_adapter && c->fb_window,
+             "fo_stream_step_embeds: context needs a finalized frontend + encoder + adapter");
+    FO_CHECK(c->dtype == FO_BF16, "fo_stream_step_embeds: the fp16 hand-off is built for bf16 contexts");
+    FO_CHECK(pcm && (pcm_dtype == FO_F32 || pcm_dtype == FO_I16), "fo_stream_step_embeds: pcm must be FO_F32 or FO_I16");
+    FO_TRY(check_ids(c, ids, n));
+    FO_CUDA(cudaSetDevice(c->device));
+    const int t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
+    const int t = ((t_in - 1) / 2 - 1) / 2, t_out = (t + c->KA - 1 - c->KA) / 2 + 1;
+    FO_CHECK(embeds_f16 && row_offset >= 0 && rows_per_session >= row_offset + t_out && rows_per_session < (1LL << 31),
+             "fo_stream_step_embeds: a session's %d rows at offset %lld do not fit %lld rows per session", t_out,
+             (long long)row_offset, (long long)rows_per_session);
+    cudaPointerAttributes pa;
+    FO_CHECK(cudaPointerGetAttributes(&pa, embeds_f16) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device == c->device,
+             "fo_stream_step_embeds: embeds must be device memory of this context's GPU");
+    c->handoff = embeds_f16;
+    c->handoff_rows = rows_per_session;
+    c->handoff_off = row_offset;
+    const int r = stream_common(c, ids, n, pcm, pcm_dtype, scale, nullptr, t_in, enc_out, nullptr, (cudaStream_t)stream);
+    c->handoff = nullptr;
+    c->handoff_rows = c->handoff_off = 0;
+    return r;
 }
 
 int fo_stream_step(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale, float* enc_out,

@@ -272,6 +272,24 @@ class Engine:
                                            _ptr(adapter_out) if self.has_adapter else None, self._stream()))
         return (enc_out if want_enc else None), (adapter_out if self.has_adapter else None)
 
+    def stream_step_embeds(self, ids, pcm: ArrayLike, embeds: torch.Tensor, row_offset: int = 0,
+                           scale: Optional[float] = None, enc_out: Optional[torch.Tensor] = None, want_enc: bool = False):
+        """stream_step whose adapter rows land, as fp16, in rows [row_offset, row_offset + t_out) of each session's block
+        of `embeds` (n, rows, llm_dim) -- the pre-allocated inputs_embeds of the LLM step (audioLLM.py:404-411)."""
+        ids = _ids(ids)
+        n = len(ids)
+        assert tuple(pcm.shape) == (n, self.cfg.samples_per_chunk)
+        assert embeds.is_cuda and embeds.dtype == torch.float16 and embeds.is_contiguous()
+        assert embeds.dim() == 3 and embeds.shape[0] >= n and embeds.shape[2] == self.cfg.llm_dim
+        t, _ = self.out_frames(self.cfg.chunk_feat_frames)
+        if want_enc:
+            enc_out = self._out(enc_out, (n, t, self.cfg.d_model))
+        _lib.check(self.lib.fo_stream_step_embeds(self._h, _i32p(ids), n, _ptr(pcm), self._pcm_dtype(pcm),
+                                                  float(self.cfg.pcm_scale if scale is None else scale),
+                                                  _ptr(enc_out) if want_enc else None, embeds.data_ptr(),
+                                                  int(embeds.shape[1]), int(row_offset), self._stream()))
+        return (enc_out if want_enc else None), embeds
+
     # ---- offline ----------------------------------------------------------------------------------
     def encode_offline(self, feats: ArrayLike, ilens, chunk: Optional[int] = None, left: Optional[int] = None,
                        want_adapter: Optional[bool] = None):

@@ -131,6 +131,13 @@ int fo_encode_stream(fo_ctx* ctx, const int32_t* ids, int n, const float* feats,
 /* fbank + encode in one call (one captured graph): PCM in, embeddings out */
 int fo_stream_step(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
                    float* enc_out, float* adapter_out, void* stream);
+/* the same with the LLM hand-off fused into the adapter projection: replaces
+ *   inputs_embeds = torch.cat((chat_prefix_embeds, inputs_embeds), 1) ... inputs_embeds.half()   (models/audioLLM.py:404-411).
+ * embeds_f16 is a DEVICE buffer (n, rows_per_session, llm_dim) of IEEE fp16 that the caller pre-fills (chat prefix);
+ * the t_out adapter rows of session i are written to rows [row_offset, row_offset + t_out) of its block, nothing else
+ * is touched.  bf16 contexts only.  enc_out may be NULL. */
+int fo_stream_step_embeds(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
+                          float* enc_out, void* embeds_f16, int64_t rows_per_session, int64_t row_offset, void* stream);
 
 /* ---- full utterance: replaces speechEncoder.forward (models/encoder/encoder.py:104-147) and
  * CNNSubsampling.forward(cache=None).  feats (B, T, feat_dim), ilens (B) int32 valid lengths.

@@ -520,6 +520,29 @@ def test_fused_layernorm_matches_standalone(shipped16):
         eng.free(ids)
 
 
+def test_llm_handoff_fp16_embeds(shipped16):
+    """fo_stream_step_embeds writes the adapter rows as fp16 straight into the caller's inputs_embeds block behind the
+    chat prefix (audioLLM.py:404-411: cat(prefix, embeds).half()): same bits as .half() of the fp32 output, prefix and
+    the rows behind untouched, adapter cache advanced as usual."""
+    cfg, eng = shipped16
+    g = torch.Generator().manual_seed(61)
+    ids = eng.alloc(4)
+    P, R = 5, 9                                                   # 5 prefix rows, 2 adapter rows, 2 spare rows
+    try:
+        buf = torch.full((2, R, cfg.llm_dim), 7.0, dtype=torch.float16, device="cuda")
+        for i in range(4):
+            pcm = (0.05 * torch.randn(2, cfg.samples_per_chunk, generator=g) * 32768).round().to(torch.int16)
+            e0, y0 = eng.stream_step(ids[:2], pcm, 1.0)
+            e1, _ = eng.stream_step_embeds(ids[2:], pcm, buf, row_offset=P, scale=1.0, want_enc=True)
+            assert torch.equal(e0, e1), i
+            assert torch.equal(buf[:, P:P + 2], y0.half()), i
+            assert bool((buf[:, :P] == 7.0).all()) and bool((buf[:, P + 2:] == 7.0).all())
+        with pytest.raises(Exception):
+            eng.stream_step_embeds(ids[2:], pcm, buf, row_offset=R - 1, scale=1.0)      # rows would not fit
+    finally:
+        eng.free(ids)
+
+
 def test_scheduler_vad_gating_vs_oracle():
     """Batched scheduler + VAD-gated frontend (freeze_omni_b200/scheduler.py) against per-session oracle runs that
     restate the reference flow: features always extracted (AudioFeatureGating.py:92-93), silent blocks only enter the
