@@ -126,6 +126,29 @@ def main():
     pcm_pad = np.zeros(n_chunks * 2560, dtype=np.int16)
     pcm_pad[:len(pcm)] = pcm
 
+    # ---------------- cmvn statistics files (models/encoder/cmvn.py:37-107) -------------------
+    if want("cmvn"):
+        import json
+        import tempfile
+        rs = np.random.RandomState(11)
+        d, count = 80, 123457.0
+        x_mean = rs.uniform(-3, 12, d)
+        x_std = rs.uniform(0.5, 4, d)
+        x_std[7] = 0.0                                       # degenerate channel -> variance floor 1e-20
+        sums = (x_mean * count).tolist()
+        sqs = ((x_std ** 2 + x_mean ** 2) * count).tolist()
+        js = json.dumps({"mean_stat": sums, "var_stat": sqs, "frame_num": count})
+        kaldi_txt = " [\n  " + " ".join(repr(v) for v in sums) + " " + repr(count) + "\n  " + \
+            " ".join(repr(v) for v in sqs) + " 0 ]\n"
+        with tempfile.TemporaryDirectory() as td:
+            pj, pk = os.path.join(td, "c.json"), os.path.join(td, "c.txt")
+            open(pj, "w").write(js)
+            open(pk, "w").write(kaldi_txt)
+            mj, ij = ref_cmvn.load_cmvn(pj, True)
+            mk, ik = ref_cmvn.load_cmvn(pk, False)
+        save("cmvn", json_text=np.frombuffer(js.encode(), np.uint8), kaldi_text=np.frombuffer(kaldi_txt.encode(), np.uint8),
+             json_mean=mj, json_istd=ij, kaldi_mean=mk, kaldi_istd=ik)
+
     # ---------------- fbank ----------------------------------------------------------------
     def gating_stream(int16_pcm, fbank_config, chunk):
         g = ref_gating.AudioFeatureGating(16000, fbank_config=fbank_config)
