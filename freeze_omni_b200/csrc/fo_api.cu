@@ -1464,6 +1464,7 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "split_k")) c->split_k = (int)value;
     else if (!strcmp(name, "debug_skip")) c->debug_skip = (int)value;
     else if (!strcmp(name, "fuse_ln")) c->fuse_ln = value != 0;
+    else if (!strcmp(name, "tc_persist")) gemm_tc_set_persist(value != 0);
     else if (!strcmp(name, "stack_kernel")) c->stack_kernel = value != 0;
     else if (!strcmp(name, "stack_split_o")) c->stack_split_o = (int)value;
     else if (!strcmp(name, "stack_split_f2")) c->stack_split_f2 = (int)value;
@@ -1498,6 +1499,7 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     else if (!strcmp(name, "fuse_ln")) *value = c->fuse_ln;
     else if (!strcmp(name, "stack_kernel")) *value = c->stack_kernel;
     else if (!strcmp(name, "stack_launches")) *value = c->stack_launches;
+    else if (!strcmp(name, "tc_persist_launches")) *value = gemm_tc_persist_launches();
     else if (!strcmp(name, "l2_prefetch")) *value = c->use_prefetch;
     else if (!strcmp(name, "pdl")) *value = g_want_pdl;
     else if (!strcmp(name, "profile_gemm_count")) *value = (int64_t)c->prof_events.size();

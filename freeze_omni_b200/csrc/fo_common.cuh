@@ -196,6 +196,8 @@ struct TcTune { int swap, bn, split; };      // -1 / 0 = let the cost model deci
 int gemm_tc_init();
 int gemm_tc_workspace(TcWorkspace* ws);       // allocates; the caller frees the two device pointers
 void gemm_tc_force(const TcTune& t);
+void gemm_tc_set_persist(int on);          // persistent tile loop for fat short-K GEMMs (default on)
+long long gemm_tc_persist_launches();
 void gemm_tc_force_producers(int npa, int npb);   // 0 = default
 long long gemm_tc_launches();                // tcgen05 kernel launches so far (tests check the path taken)
 // A and W: 16-bit operands of ONE format (fp16 when is_fp16, else bf16); c_act / ln_act are written in the same type.

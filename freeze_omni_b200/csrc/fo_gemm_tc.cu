@@ -39,6 +39,7 @@ constexpr int BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+constexpr uint32_t PERSIST_SMEM = 224 * 1024;    // persistent kernel: 4 stages of 48 KB + the epilogue strips
 
 struct TcOperand {
     int seg_blocks;              // k-blocks per segment
@@ -467,6 +468,207 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// ---- persistent variant for fat, short-K GEMMs (offline path: M = B*T' rows, K = 1024..4096) -------------------
+// One CTA per SM walks the output tiles (128 activation rows x BN weight rows, tile_a fastest so that concurrently
+// processed tiles share the weight tile in L2).  The stage ring never drains between tiles and the accumulator is double
+// buffered in TMEM (2 x 256 columns): the MMA warp starts tile i+1 while the epilogue warps drain tile i, which the
+// one-tile-per-CTA kernel can only approximate with two co-resident CTAs that tend to run in lock-step.
+// The epilogue goes straight from TMEM registers to global memory: a thread owns one output row and writes 16
+// consecutive columns per tcgen05.ld (64 B fp32 / 32 B fp16 -- whole sectors), so no staging tile competes with the
+// pipeline stages for shared memory.  Activations on the UMMA-M side only; no split-K, no fused LayerNorm.
+constexpr int PST = 36;           // staging strip pitch (floats): 32 columns + 4, conflict-free float4 rows
+struct TcPersistParams {
+    int rows_a, rows_b, kblocks, bn, stages, act_fp16;
+    int tiles_a, tiles_b;
+    int dbg;                     // development (FO_PERSIST_DBG): 1 no stores, 2 no TMEM loads either (timing only)
+    TcOperand op_a;              // activations (AGather segments)
+    RowMap rmap;
+    Epilogue ep;
+    int n_out;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcPersistParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t acc_full[2];
+    __shared__ __align__(8) uint64_t acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_plane[AGather::MAX_SEG + 1], s_rowoff[AGather::MAX_SEG + 1];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages, bn = p.bn;
+    const int ntiles = p.tiles_a * p.tiles_b;
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)bn * BK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t af0 = smem_u32(&acc_full[0]), ae0 = smem_u32(&acc_empty[0]);
+
+    FO_PDL_TRIGGER();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 2); mbar_init(empty0 + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(af0 + 8 * i, 1); mbar_init(ae0 + 8 * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + AGather::MAX_SEG + 1) {
+        const int sidx = threadIdx.x - 64, sc = min(sidx, AGather::MAX_SEG - 1);
+        s_plane[sidx] = p.op_a.plane[sc];
+        s_rowoff[sidx] = p.op_a.rowoff[sc];
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0 || warp == 6) {
+        if (lane == 0) {
+            const int w = warp == 0 ? 0 : 1;                      // 0: activations (M side), 1: weights (N side)
+            if (w == 0) FO_PDL_WAIT();                            // weights do not depend on the previous kernel
+            const CUtensorMap* map = w ? &map_b : &map_a;
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+            const int segb = w ? p.kblocks : p.op_a.seg_blocks;
+            const uint32_t bytes = w ? b_bytes : a_bytes;
+            int s = 0;
+            uint32_t ph = 1;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int tile_b = tile % p.tiles_b, tile_a = tile / p.tiles_b;
+                const int row0 = w ? tile_b * bn : tile_a * BM;
+                int seg = 0, cblk = 0;
+                int row = row0 + (w ? 0 : s_rowoff[0]), plane = w ? 0 : s_plane[0];
+                for (int i = 0; i < p.kblocks; ++i) {
+                    mbar_wait(empty0 + 8 * s, ph);
+                    mbar_expect_tx(full0 + 8 * s, bytes);
+                    tma_load_3d(base + s * stage_bytes + (w ? a_bytes : 0u), map, full0 + 8 * s, cblk * BK, row, plane);
+                    if (++cblk == segb) {
+                        cblk = 0; ++seg;
+                        if (!w) { row = row0 + s_rowoff[seg]; plane = s_plane[seg]; }
+                    }
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t fmt = p.act_fp16 ? 0u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int s = 0, it = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1;
+                mbar_wait(ae0 + 8 * ab, (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(ab * 256);
+                for (int i = 0; i < p.kblocks; ++i) {
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * stage_bytes;
+                    const uint64_t da = umma_desc(sa), db = umma_desc(sa + a_bytes);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) tc_mma(tacc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(empty0 + 8 * s);
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+                tc_commit(af0 + 8 * ab);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue warps: TMEM lane quarter q = warp % 4 = 32 output rows; 32-column slabs go through a warp-private
+        //      staging strip so that the global accesses are whole 128-byte row segments (4 rows per warp instruction) ----
+        const int q = warp & 3;
+        const Epilogue& ep = p.ep;
+        const float scale = ep.scale;
+        const int relu = ep.relu, ldc = ep.ldc;
+        const float* __restrict__ resid = ep.residual;
+        float* __restrict__ out32 = ep.c_f32;
+        __half* __restrict__ out16 = reinterpret_cast<__half*>(ep.c_act);      // fp16 / bf16 share the 2-byte container
+        float* strip = reinterpret_cast<float*>(smem_dyn + (base - smem_u32(smem_dyn)) + (size_t)stages * stage_bytes) + q * (32 * PST);
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;                    // write-out: 4 rows x 8 float4 per instruction
+        FO_PDL_WAIT();
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int tile_b = tile % p.tiles_b, tile_a = tile / p.tiles_b;
+            const int ab = it & 1;
+            const int ga = tile_a * BM + q * 32 + lane;
+            long long d64 = 0;
+            const bool ok = ga < p.rows_a && row_map(p.rmap, ga, d64);
+            const int drow = ok ? (int)d64 : -1;                                // output row of this lane's tile row
+            const int n0 = tile_b * bn;
+            if (resid && ok) {
+                // the residual rows of this tile do not depend on the MMAs: ask L2 for them now, the mainloop covers the HBM latency
+                const char* rp = reinterpret_cast<const char*>(resid + (long long)drow * ldc + n0);
+                const int nbytes = min(bn, p.n_out - n0) * 4;
+                for (int off = 0; off < nbytes; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+            }
+            mbar_wait(af0 + 8 * ab, ((uint32_t)(it >> 1)) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256);
+            for (int c0 = 0; c0 < bn; c0 += 32) {
+                const int n = n0 + c0;
+                if (n >= p.n_out) break;                               // warp-uniform (n_out is a multiple of 32 here)
+                if (p.dbg & 2) break;
+                float v[32];
+                tc_ld16(taddr + c0, *reinterpret_cast<float(*)[16]>(&v[0]));
+                tc_ld16(taddr + c0 + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+                if (p.dbg & 1) continue;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(strip + lane * PST + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n + sub_c);
+                const bool wf = out32 && (!ep.split_col || n < ep.split_col);
+                const bool wa = out16 && (!ep.split_col || n >= ep.split_col);
+                int dr[8];
+                float4 rv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                          // all residual loads of the slab in flight together
+                    dr[i] = __shfl_sync(0xffffffffu, drow, i * 4 + sub_r);
+                    rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (resid && dr[i] >= 0) rv[i] = __ldcg(reinterpret_cast<const float4*>(resid + (long long)dr[i] * ldc + n + sub_c));
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (dr[i] < 0) continue;
+                    const long long o = (long long)dr[i] * ldc + n + sub_c;
+                    float4 x = *reinterpret_cast<const float4*>(strip + (i * 4 + sub_r) * PST + sub_c);
+                    x.x = (x.x + bv.x) * scale; x.y = (x.y + bv.y) * scale; x.z = (x.z + bv.z) * scale; x.w = (x.w + bv.w) * scale;
+                    if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                    x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w;
+                    if (wf) *reinterpret_cast<float4*>(out32 + o) = x;
+                    if (wa) {
+                        uint2 h;
+                        if (p.act_fp16) { h.x = pack2<__half>(x.x, x.y); h.y = pack2<__half>(x.z, x.w); }
+                        else { h.x = pack2<bf16>(x.x, x.y); h.y = pack2<bf16>(x.z, x.w); }
+                        *reinterpret_cast<uint2*>(out16 + o) = h;
+                    }
+                }
+                __syncwarp();                                          // strip is rewritten by the next slab
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t bar = ae0 + 8 * ab;
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -477,6 +679,8 @@ int g_sm_count = 148;
 TcTune g_forced = {-1, -1, -1};
 long long g_tc_launches = 0;
 int g_forced_npa = 0, g_forced_npb = 0;
+int g_persist = 1;               // fat short-K GEMMs on the persistent kernel (option tc_persist)
+long long g_persist_launches = 0;
 
 // encoded tensor maps are pure functions of (pointer, extents, box): cached so that eager launches stay cheap on the host
 struct MapKey {
@@ -583,6 +787,7 @@ int gemm_tc_init() {
     FO_CUDA(cudaGetDevice(&dev));
     FO_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     FO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));
+    FO_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM));
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     return 0;
 }
@@ -603,6 +808,8 @@ int gemm_tc_workspace(TcWorkspace* ws) {
 }
 
 void gemm_tc_force(const TcTune& t) { g_forced = t; }
+void gemm_tc_set_persist(int on) { g_persist = on; }
+long long gemm_tc_persist_launches() { return g_persist_launches; }
 void gemm_tc_force_producers(int npa, int npb) { g_forced_npa = npa; g_forced_npb = npb; }
 long long gemm_tc_launches() { return g_tc_launches; }
 
@@ -612,6 +819,46 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     if (K % BK != 0 || ga.seg_len % BK != 0 || ep.ldc % 8 != 0 || N % 8 != 0 || ep.split_col % 16 != 0) return 1;
     if (ep.residual && ep.residual != ep.c_f32) { /* residual rows are read at the remapped output row: fine */ }
     if (M <= 0) return 0;
+    // fat, short-K GEMM with several waves of tiles: the persistent kernel (epilogue of tile i under the MMAs of tile i+1)
+    if (g_persist && g_forced.swap < 0 && g_forced.bn <= 0 && g_forced.split <= 0 && M > 384 && K / BK <= 64 && N % 32 == 0 &&
+        ep.split_col % 32 == 0 && !ep.ln_gamma) {
+        const int bn = N % 256 == 0 || N > 1024 ? 256 : (N % 128 == 0 ? 128 : 256);
+        const int ta = (M + BM - 1) / BM, tb = (N + bn - 1) / bn;
+        if ((long long)ta * tb >= 2LL * g_sm_count) {
+            TcPersistParams pp;
+            memset(&pp, 0, sizeof(pp));
+            pp.rows_a = M;
+            pp.rows_b = N;
+            pp.kblocks = K / BK;
+            pp.bn = bn;
+            pp.act_fp16 = act_fp16;
+            pp.tiles_a = ta;
+            pp.tiles_b = tb;
+            const uint32_t stage = (BM + bn) * BK * 2;
+            const size_t strips = 4 * 32 * PST * sizeof(float);              // one staging strip per epilogue warp
+            pp.stages = std::max(2, std::min<int>(MAX_STAGES, (int)((PERSIST_SMEM - 1024 - strips) / stage)));
+            pp.op_a.seg_blocks = ga.seg_len / BK;
+            for (int sgi = 0; sgi < AGather::MAX_SEG; ++sgi) { pp.op_a.plane[sgi] = ga.plane[sgi]; pp.op_a.rowoff[sgi] = ga.rowoff[sgi]; }
+            pp.rmap = rmap;
+            pp.ep = ep;
+            pp.n_out = N;
+            {
+                const char* e = getenv("FO_PERSIST_DBG");
+                pp.dbg = e ? atoi(e) : 0;
+            }
+            CUtensorMap map_act, map_w;
+            FO_TRY(make_map(&map_act, reinterpret_cast<const bf16*>(A), ga.seg_len, ga.rows, ga.planes, BM));
+            FO_TRY(make_map(&map_w, reinterpret_cast<const bf16*>(W), K, N, 1, bn));
+            const size_t smem = (size_t)pp.stages * stage + strips + 1024;
+            const int grid = std::min<long long>(g_sm_count, (long long)ta * tb);
+            FO_CUDA(launch_pdl(gemm_tc_persist_kernel, dim3(grid), dim3(TC_THREADS), smem, st, map_act, map_w, pp));
+            FO_LAUNCHED();
+            ++g_tc_launches;
+            ++g_persist_launches;
+            FO_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     Plan pl = choose_plan(M, N, K);
     if (g_forced.swap >= 0) pl.swap = g_forced.swap;
     if (g_forced.bn > 0) pl.bn = g_forced.bn;

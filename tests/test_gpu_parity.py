@@ -520,6 +520,42 @@ def test_fused_layernorm_matches_standalone(shipped16):
         eng.free(ids)
 
 
+def test_persistent_gemm_matches_tile_per_cta(shipped16):
+    """Fat short-K GEMMs run on the persistent tcgen05 kernel (tile loop per SM, double-buffered TMEM accumulator,
+    epilogue straight from TMEM registers).  Same k order and same fp32 epilogue arithmetic as the one-tile-per-CTA
+    kernel -> bit-identical outputs: plain GEMMs against an fp64 product, and a whole offline pass (bias, ReLU,
+    residual, fp32|fp16 split of the QKV output, ragged lengths) with the option off and on."""
+    cfg, eng = shipped16
+    g = torch.Generator().manual_seed(71)
+    try:
+        for (M, N, K) in [(5000, 4096, 1024), (4100, 3584, 2048), (12000, 1024, 4096)]:
+            A = torch.randn(M, K, generator=g).cuda()
+            W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+            b = torch.randn(N, generator=g).cuda()
+            ref = (A.half().double() @ W.bfloat16().double().T + b.double()).float().cpu()
+            eng.set_option("tc_persist", 1)
+            n0 = eng.get_option("tc_persist_launches")
+            o1, _ = eng.debug_gemm(A, W, b, backend=1)
+            assert eng.get_option("tc_persist_launches") == n0 + 1, "persistent kernel did not launch"
+            eng.set_option("tc_persist", 0)
+            o0, _ = eng.debug_gemm(A, W, b, backend=1)
+            assert eng.get_option("tc_persist_launches") == n0 + 1
+            assert maxabs(o1.cpu(), ref) < 2e-3, (M, N, K)
+            assert torch.equal(o1, o0), (M, N, K)
+        B, T = 5, 2998
+        feats = 9.0 + 3.0 * torch.randn(B, T, cfg.feat_dim, generator=g)
+        ilens = torch.tensor([2998, 2500, 2998, 1203, 2998])
+        eng.set_option("tc_persist", 1)
+        n0 = eng.get_option("tc_persist_launches")
+        e1, m1, y1, _ = eng.encode_offline(feats.cuda(), ilens, 4, 16)
+        assert eng.get_option("tc_persist_launches") > n0
+        eng.set_option("tc_persist", 0)
+        e0, m0, y0, _ = eng.encode_offline(feats.cuda(), ilens, 4, 16)
+        assert torch.equal(m1, m0) and torch.equal(e1, e0) and torch.equal(y1, y0)
+    finally:
+        eng.set_option("tc_persist", 1)
+
+
 def test_llm_handoff_fp16_embeds(shipped16):
     """fo_stream_step_embeds writes the adapter rows as fp16 straight into the caller's inputs_embeds block behind the
     chat prefix (audioLLM.py:404-411: cat(prefix, embeds).half()): same bits as .half() of the fp32 output, prefix and
