@@ -39,7 +39,7 @@ constexpr int BK = 64;           // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t SMEM_BUDGET = 200 * 1024;
-constexpr uint32_t PERSIST_SMEM = 224 * 1024;    // persistent kernel: 4 stages of 48 KB + the epilogue strips
+constexpr uint32_t PERSIST_SMEM = 225 * 1024;    // persistent kernel: 4 stages of 48 KB + the epilogue strips
 
 struct TcOperand {
     int seg_blocks;              // k-blocks per segment
@@ -476,7 +476,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // The epilogue goes straight from TMEM registers to global memory: a thread owns one output row and writes 16
 // consecutive columns per tcgen05.ld (64 B fp32 / 32 B fp16 -- whole sectors), so no staging tile competes with the
 // pipeline stages for shared memory.  Activations on the UMMA-M side only; no split-K, no fused LayerNorm.
-constexpr int PST = 36;           // staging strip pitch (floats): 32 columns + 4, conflict-free float4 rows
+constexpr int PSW = 16;           // epilogue slab width (columns per TMEM load)
+constexpr int PST = PSW + 4;      // staging strip pitch (floats): conflict-free float4 rows
+constexpr int P_EPI = 8;          // epilogue warps: two per TMEM lane quarter, interleaved slabs (12 measured the same; one per quarter is
+                                  // latency bound: ~10 us per 128 x 256 tile against a 6.3 us mainloop)
+constexpr int P_THREADS = (3 + P_EPI) * 32;
 struct TcPersistParams {
     int rows_a, rows_b, kblocks, bn, stages, act_fp16;
     int tiles_a, tiles_b;
@@ -487,7 +491,7 @@ struct TcPersistParams {
     int n_out;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcPersistParams p) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
@@ -509,7 +513,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     FO_PDL_TRIGGER();
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 2); mbar_init(empty0 + 8 * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(af0 + 8 * i, 1); mbar_init(ae0 + 8 * i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(af0 + 8 * i, 1); mbar_init(ae0 + 8 * i, P_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -582,17 +586,20 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         __syncwarp();
     } else {
-        // ---- epilogue warps: TMEM lane quarter q = warp % 4 = 32 output rows; 32-column slabs go through a warp-private
-        //      staging strip so that the global accesses are whole 128-byte row segments (4 rows per warp instruction) ----
+        // ---- epilogue warps: TMEM lane quarter q = warp % 4 = 32 output rows, two warps per quarter on alternating
+        //      16-column slabs; a slab goes through a warp-private staging strip so that the global accesses are contiguous
+        //      row segments (8 rows x 64 B per warp instruction) ----
         const int q = warp & 3;
+        const int e = warp < 6 ? warp - 2 : warp - 3;                           // 0..P_EPI-1
+        const int grp = e >> 2;                                                 // slab parity this warp handles
         const Epilogue& ep = p.ep;
         const float scale = ep.scale;
         const int relu = ep.relu, ldc = ep.ldc;
         const float* __restrict__ resid = ep.residual;
         float* __restrict__ out32 = ep.c_f32;
         __half* __restrict__ out16 = reinterpret_cast<__half*>(ep.c_act);      // fp16 / bf16 share the 2-byte container
-        float* strip = reinterpret_cast<float*>(smem_dyn + (base - smem_u32(smem_dyn)) + (size_t)stages * stage_bytes) + q * (32 * PST);
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;                    // write-out: 4 rows x 8 float4 per instruction
+        float* strip = reinterpret_cast<float*>(smem_dyn + (base - smem_u32(smem_dyn)) + (size_t)stages * stage_bytes) + e * (32 * PST);
+        const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;                    // write-out: 8 rows x 4 float4 per instruction
         FO_PDL_WAIT();
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -607,40 +614,39 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 // the residual rows of this tile do not depend on the MMAs: ask L2 for them now, the mainloop covers the HBM latency
                 const char* rp = reinterpret_cast<const char*>(resid + (long long)drow * ldc + n0);
                 const int nbytes = min(bn, p.n_out - n0) * 4;
-                for (int off = 0; off < nbytes; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
+                for (int off = grp * 128; off < nbytes; off += (P_EPI / 4) * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + off));
             }
             mbar_wait(af0 + 8 * ab, ((uint32_t)(it >> 1)) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256);
-            for (int c0 = 0; c0 < bn; c0 += 32) {
+            for (int c0 = grp * PSW; c0 < bn; c0 += (P_EPI / 4) * PSW) {
                 const int n = n0 + c0;
-                if (n >= p.n_out) break;                               // warp-uniform (n_out is a multiple of 32 here)
+                if (n >= p.n_out) break;                               // warp-uniform (n_out is a multiple of 16)
                 if (p.dbg & 2) break;
-                float v[32];
-                tc_ld16(taddr + c0, *reinterpret_cast<float(*)[16]>(&v[0]));
-                tc_ld16(taddr + c0 + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+                float v[16];
+                tc_ld16(taddr + c0, v);
                 if (p.dbg & 1) continue;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
+                for (int j = 0; j < 16; j += 4)
                     *reinterpret_cast<float4*>(strip + lane * PST + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
                 float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n + sub_c);
                 const bool wf = out32 && (!ep.split_col || n < ep.split_col);
                 const bool wa = out16 && (!ep.split_col || n >= ep.split_col);
-                int dr[8];
-                float4 rv[8];
+                int dr[4];
+                float4 rv[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {                          // all residual loads of the slab in flight together
-                    dr[i] = __shfl_sync(0xffffffffu, drow, i * 4 + sub_r);
+                for (int i = 0; i < 4; ++i) {                          // all residual loads of the slab in flight together
+                    dr[i] = __shfl_sync(0xffffffffu, drow, i * 8 + sub_r);
                     rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (resid && dr[i] >= 0) rv[i] = __ldcg(reinterpret_cast<const float4*>(resid + (long long)dr[i] * ldc + n + sub_c));
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     if (dr[i] < 0) continue;
                     const long long o = (long long)dr[i] * ldc + n + sub_c;
-                    float4 x = *reinterpret_cast<const float4*>(strip + (i * 4 + sub_r) * PST + sub_c);
+                    float4 x = *reinterpret_cast<const float4*>(strip + (i * 8 + sub_r) * PST + sub_c);
                     x.x = (x.x + bv.x) * scale; x.y = (x.y + bv.y) * scale; x.z = (x.z + bv.z) * scale; x.w = (x.w + bv.w) * scale;
                     if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                     x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w;
@@ -820,8 +826,8 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     if (ep.residual && ep.residual != ep.c_f32) { /* residual rows are read at the remapped output row: fine */ }
     if (M <= 0) return 0;
     // fat, short-K GEMM with several waves of tiles: the persistent kernel (epilogue of tile i under the MMAs of tile i+1)
-    if (g_persist && g_forced.swap < 0 && g_forced.bn <= 0 && g_forced.split <= 0 && M > 384 && K / BK <= 64 && N % 32 == 0 &&
-        ep.split_col % 32 == 0 && !ep.ln_gamma) {
+    if (g_persist && g_forced.swap < 0 && g_forced.bn <= 0 && g_forced.split <= 0 && M > 384 && K / BK <= 64 && N % 16 == 0 &&
+        !ep.ln_gamma) {
         const int bn = N % 256 == 0 || N > 1024 ? 256 : (N % 128 == 0 ? 128 : 256);
         const int ta = (M + BM - 1) / BM, tb = (N + bn - 1) / bn;
         if ((long long)ta * tb >= 2LL * g_sm_count) {
@@ -835,7 +841,7 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
             pp.tiles_a = ta;
             pp.tiles_b = tb;
             const uint32_t stage = (BM + bn) * BK * 2;
-            const size_t strips = 4 * 32 * PST * sizeof(float);              // one staging strip per epilogue warp
+            const size_t strips = (size_t)P_EPI * 32 * PST * sizeof(float);     // one staging strip per epilogue warp
             pp.stages = std::max(2, std::min<int>(MAX_STAGES, (int)((PERSIST_SMEM - 1024 - strips) / stage)));
             pp.op_a.seg_blocks = ga.seg_len / BK;
             for (int sgi = 0; sgi < AGather::MAX_SEG; ++sgi) { pp.op_a.plane[sgi] = ga.plane[sgi]; pp.op_a.rowoff[sgi] = ga.rowoff[sgi]; }
@@ -851,7 +857,7 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
             FO_TRY(make_map(&map_w, reinterpret_cast<const bf16*>(W), K, N, 1, bn));
             const size_t smem = (size_t)pp.stages * stage + strips + 1024;
             const int grid = std::min<long long>(g_sm_count, (long long)ta * tb);
-            FO_CUDA(launch_pdl(gemm_tc_persist_kernel, dim3(grid), dim3(TC_THREADS), smem, st, map_act, map_w, pp));
+            FO_CUDA(launch_pdl(gemm_tc_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, map_act, map_w, pp));
             FO_LAUNCHED();
             ++g_tc_launches;
             ++g_persist_launches;
