@@ -802,7 +802,8 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
         const bool last = l + 1 == c->L;
         FO_TRY(layer_pre<TA>(c, w, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), q32, L2Prefetch(), st));
         FO_TRY(attention_offline<TA>(reinterpret_cast<const TA*>(qkv), q32, B, T2, H, ilens2, chunk, left,
-                                     w.ptab, w.pos_u, w.pos_v, reinterpret_cast<TA*>(att), st));
+                                     w.ptab, reinterpret_cast<const TA*>(w.ptab_h), c->pos_rows, w.pos_u, w.pos_v,
+                                     reinterpret_cast<TA*>(att), st));
         NextNorm nn{last ? c->after_g : c->layers[l + 1].ln1g, last ? c->after_b : c->layers[l + 1].ln1b,
                     last ? enc_out_dev : nullptr};
         FfnConv fc;

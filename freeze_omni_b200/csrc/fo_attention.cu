@@ -774,8 +774,9 @@ constexpr int OSC = 100;     // score row pitch (fp32): 4 mod 32 -> the MMA frag
 constexpr int OPH = 104;     // probability row pitch (fp16): 52 words = 20 mod 32 -> conflict-free B-fragment loads
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_offline_mma_kernel(const __half* __restrict__ qkv, const float* __restrict__ q32, int T, int H,
-                             const int32_t* __restrict__ ilens, int chunk, int left, const float* __restrict__ ptab,
-                             const float* __restrict__ pos_u, const float* __restrict__ pos_v, __half* __restrict__ out) {
+                             const int32_t* __restrict__ ilens, int chunk, int left, const __half* __restrict__ ptab_h,
+                             int pos_rows, const float* __restrict__ pos_u, const float* __restrict__ pos_v,
+                             __half* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef __half TA;
     constexpr int NCH = 8, EPC = 8;
@@ -847,13 +848,11 @@ attention_offline_mma_kernel(const __half* __restrict__ qkv, const float* __rest
             if (j < nk) val = *reinterpret_cast<const uint4*>(qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + cc * EPC);
             *reinterpret_cast<uint4*>((which == 0 ? Ks : Vs) + j * DK + ((cc ^ (j & 7)) << 3)) = val;
         }
-        for (int i = tid; i < nk * (DK / 4); i += ATT_THREADS) {
-            const int j = i / (DK / 4), d = (i % (DK / 4)) * 4;
-            const float4 v4 = *reinterpret_cast<const float4*>(ptab + (long long)(kt + j) * D + h * DK + d);
-            uint2 hh;
-            hh.x = pack2<TA>(v4.x, v4.y);
-            hh.y = pack2<TA>(v4.z, v4.w);
-            *reinterpret_cast<uint2*>(Ps + j * DK + (((d >> 3) ^ (j & 7)) << 3) + (d & 7)) = hh;
+        // rel-pos rows from the head-major fp16 table (its 16-byte chunks are swizzled by POSITION, the tile's by tile row)
+        for (int i = tid; i < nk * NCH; i += ATT_THREADS) {
+            const int j = i / NCH, cc = i % NCH, pos = kt + j;
+            *reinterpret_cast<uint4*>(Ps + j * DK + ((cc ^ (j & 7)) << 3)) =
+                *reinterpret_cast<const uint4*>(ptab_h + ((long long)h * pos_rows + pos) * DK + ((cc ^ (pos & 7)) << 3));
         }
         __syncthreads();
         // ---- scores of query group `warp` against the 16-key tiles ----
@@ -1061,7 +1060,8 @@ template int attention_stream<__half>(const AttnStream&, const __half*, const fl
 
 template <typename TA>
 int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,
-                      const float* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st) {
+                      const float* ptab, const TA* ptab_h, int pos_rows, const float* pos_u, const float* pos_v, TA* out,
+                      cudaStream_t st) {
     if (B <= 0 || T <= 0) return 0;
     dim3 grid(cdiv(T, QB), H, B);
     const size_t smem = (size_t)3 * KT * (DK + 16 / sizeof(TA)) * sizeof(TA) + (size_t)2 * QB * DK * sizeof(float) +
@@ -1078,8 +1078,10 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
             FO_CUDA(cudaFuncSetAttribute(attention_offline_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             attr2 = true;
         }
+        if (!ptab_h || T > pos_rows) return 1;
         attention_offline_mma_kernel<<<grid, ATT_THREADS, sm, st>>>(reinterpret_cast<const __half*>(qkv), q32, T, H, ilens, chunk, left,
-                                                                    ptab, pos_u, pos_v, reinterpret_cast<__half*>(out));
+                                                                    reinterpret_cast<const __half*>(ptab_h), pos_rows, pos_u, pos_v,
+                                                                    reinterpret_cast<__half*>(out));
     } else {
         attention_offline_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(qkv, q32, T, H, ilens, chunk, left, ptab, pos_u, pos_v, out);
     }
@@ -1087,9 +1089,9 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
     FO_CUDA(cudaGetLastError());
     return 0;
 }
-template int attention_offline<float>(const float*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, float*, cudaStream_t);
-template int attention_offline<bf16>(const bf16*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, bf16*, cudaStream_t);
-template int attention_offline<__half>(const __half*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, const float*, __half*, cudaStream_t);
+template int attention_offline<float>(const float*, const float*, int, int, int, const int32_t*, int, int, const float*, const float*, int, const float*, const float*, float*, cudaStream_t);
+template int attention_offline<bf16>(const bf16*, const float*, int, int, int, const int32_t*, int, int, const float*, const bf16*, int, const float*, const float*, bf16*, cudaStream_t);
+template int attention_offline<__half>(const __half*, const float*, int, int, int, const int32_t*, int, int, const float*, const __half*, int, const float*, const float*, __half*, cudaStream_t);
 
 int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,
                       int32_t* pe_index, int32_t* adapter_valid, cudaStream_t st) {

@@ -276,7 +276,8 @@ int ptab_head_major(const float* in, int pos_rows, int H, TA* out, cudaStream_t 
 // offline: qkv (B*T, 3*D); valid lengths ilens (B); window from (chunk, left); positions 0..T-1.
 template <typename TA>
 int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,
-                      const float* ptab, const float* pos_u, const float* pos_v, TA* out, cudaStream_t st);
+                      const float* ptab, const TA* ptab_h, int pos_rows, const float* pos_u, const float* pos_v, TA* out,
+                      cudaStream_t st);
 // ---- persistent transformer-stack kernel of the streaming step (fo_stack.cu) ---------------------------
 struct StackLayerHost {
     const void *wqkv, *wo, *w1, *w2;          // fp16 containers, K-major
