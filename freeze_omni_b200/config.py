@@ -119,8 +119,8 @@ class PathConfig:
             raise ValueError("d_model, ffn_dim and llm_dim must be multiples of 64")
         if self.input_layer not in ("linear", "none"):
             raise ValueError("unsupported transformer-input-layer: %s" % self.input_layer)
-        if self.adapter_norm != "layer" or self.adapter_act not in ("gelu", "relu"):
-            raise ValueError("adapter: only norm=layer with gelu/relu is built (adapter.py:100-107)")
+        if self.adapter_norm not in ("layer", "batch") or self.adapter_act not in ("gelu", "relu"):
+            raise ValueError("adapter: norm must be layer|batch and activation gelu|relu (adapter.py:100-107)")
         if self.adapter_kernel < 2:
             raise ValueError("adapter kernel_size must be >= 2")
         if not self.normalize_before:

@@ -463,6 +463,25 @@ int finalize_t(fo_ctx* c) {
         FO_TRY(keep_f32(c, "adapter.conv1d2.bias", {2 * D}, &c->ad_conv_b));
         FO_TRY(keep_f32(c, "adapter.bn2.weight", {2 * D}, &c->ad_ln_g));
         FO_TRY(keep_f32(c, "adapter.bn2.bias", {2 * D}, &c->ad_ln_b));
+        if (g.adapter_batchnorm) {
+            // BatchNorm1d in eval mode (adapter.py:100-101,146) is a per-channel affine map of the running statistics:
+            // y = (x - mean) / sqrt(var + 1e-3) * gamma + beta = x * s + (beta - mean * s); folded once, in double
+            const HostTensor *rm, *rv;
+            FO_TRY(need(c, "adapter.bn2.running_mean", {2 * D}, &rm));
+            FO_TRY(need(c, "adapter.bn2.running_var", {2 * D}, &rv));
+            std::vector<float> gam(2 * D), bet(2 * D), mean(2 * D), var(2 * D);
+            FO_CUDA(cudaMemcpy(gam.data(), c->ad_ln_g, 2 * D * sizeof(float), cudaMemcpyDeviceToHost));
+            FO_CUDA(cudaMemcpy(bet.data(), c->ad_ln_b, 2 * D * sizeof(float), cudaMemcpyDeviceToHost));
+            FO_CUDA(cudaMemcpy(mean.data(), rm->d, 2 * D * sizeof(float), cudaMemcpyDeviceToHost));
+            FO_CUDA(cudaMemcpy(var.data(), rv->d, 2 * D * sizeof(float), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 2 * D; ++i) {
+                const double sc = (double)gam[i] / sqrt((double)var[i] + 1e-3);
+                gam[i] = (float)sc;
+                bet[i] = (float)((double)bet[i] - (double)mean[i] * sc);
+            }
+            FO_CUDA(cudaMemcpy(c->ad_ln_g, gam.data(), 2 * D * sizeof(float), cudaMemcpyHostToDevice));
+            FO_CUDA(cudaMemcpy(c->ad_ln_b, bet.data(), 2 * D * sizeof(float), cudaMemcpyHostToDevice));
+        }
         FO_TRY(keep_w<TW>(c, "adapter.project.weight", {E, 2 * D}, &c->ad_proj_w));
         FO_TRY(keep_f32(c, "adapter.project.bias", {E}, &c->ad_proj_b));
     }
@@ -508,7 +527,8 @@ int adapter_program(fo_ctx* c, const float* enc, const uint8_t* mask, int B, int
     e1.c_f32 = reinterpret_cast<float*>(aconv);
     e1.ldc = 2 * D;
     if (!(c->debug_skip & 16)) FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xin), ga, c->ad_conv_w, (int)ga.rows, 2 * D, KA * D, e1, rm, st));
-    FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(aconv), Mo, 2 * D, c->ad_ln_g, c->ad_ln_b, 1e-3f,
+    FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(aconv), Mo, 2 * D, c->ad_ln_g, c->ad_ln_b,
+                          c->cfg.adapter_batchnorm ? -1.0f : 1e-3f,      // eps < 0: affine only (folded BatchNorm)
                           c->cfg.adapter_gelu ? 2 : 1, 1.0f, reinterpret_cast<TA*>(ah), nullptr, st));
     Epilogue e2;
     e2.bias = c->ad_proj_b;

@@ -112,7 +112,9 @@ layer_norm_kernel(const float* __restrict__ x, int M, int D, const float* __rest
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
         if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
-    const float mu = warp_sum(s) / D;
+    // eps < 0: per-channel affine only (BatchNorm1d in eval mode with the running statistics folded into gamma / beta)
+    const bool affine_only = eps < 0.f;
+    const float mu = affine_only ? 0.f : warp_sum(s) / D;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
@@ -120,7 +122,7 @@ layer_norm_kernel(const float* __restrict__ x, int M, int D, const float* __rest
             float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
             q += a * a + b * b + c * c + d * d;
         }
-    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    const float rstd = affine_only ? 1.f : rsqrtf(warp_sum(q) / D + eps);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
         if (i < nv) {

@@ -242,18 +242,19 @@ class CNNSubsampling(nn.Module):
         super().__init__()
         if enc_out_dim * 4 < llm_embed_dim:
             raise NotImplementedError("two-conv CNNSubsampling branch (adapter.py:84-96) is not built")
-        if norm != 'layer':
-            raise NotImplementedError("adapter norm must be 'layer' (adapter.py:102-103)")
+        if norm not in ('layer', 'batch'):
+            raise NotImplementedError("adapter norm must be 'layer' or 'batch' (adapter.py:100-103)")
         self.kernel_size = kernel_size
         self.left_padding2 = nn.ConstantPad1d((kernel_size - 1, 0), 0.0)
         self.conv1d2 = nn.Conv1d(enc_out_dim, 2 * enc_out_dim, kernel_size, 2, 0)
-        self.bn2 = nn.LayerNorm(2 * enc_out_dim, eps=1e-3)
+        self.bn2 = (nn.LayerNorm(2 * enc_out_dim, eps=1e-3) if norm == 'layer'
+                    else nn.BatchNorm1d(2 * enc_out_dim, eps=1e-3, momentum=0.99))
         self.relu2 = nn.GELU() if activation_func == 'gelu' else nn.ReLU()
         self.project = nn.Linear(2 * enc_out_dim, llm_embed_dim)
         self.cnn_num = 1
         self.path_config = PathConfig(d_model=enc_out_dim, n_heads=enc_out_dim // 64, llm_dim=llm_embed_dim,
                                       adapter_kernel=kernel_size,
-                                      adapter_act='gelu' if activation_func == 'gelu' else 'relu', adapter_norm='layer')
+                                      adapter_act='gelu' if activation_func == 'gelu' else 'relu', adapter_norm=norm)
         self.compute_dtype = torch.float32
 
     def invalidate(self) -> None:

@@ -55,9 +55,11 @@ def encoder_param_shapes(cfg: PathConfig) -> List[Tuple[str, Tuple[int, ...], in
 def adapter_param_shapes(cfg: PathConfig) -> List[Tuple[str, Tuple[int, ...], int]]:
     """CNNSubsampling single-conv branch (adapter.py:97-110)."""
     d, k, e = cfg.d_model, cfg.adapter_kernel, cfg.llm_dim
-    return [("conv1d2.weight", (2 * d, d, k), d * k), ("conv1d2.bias", (2 * d,), d * k),
-            ("bn2.weight", (2 * d,), -1), ("bn2.bias", (2 * d,), -2),
-            ("project.weight", (e, 2 * d), 2 * d), ("project.bias", (e,), 2 * d)]
+    out = [("conv1d2.weight", (2 * d, d, k), d * k), ("conv1d2.bias", (2 * d,), d * k),
+           ("bn2.weight", (2 * d,), -1), ("bn2.bias", (2 * d,), -2)]
+    if cfg.adapter_norm == "batch":            # BatchNorm1d buffers (eval mode uses the running statistics)
+        out += [("bn2.running_mean", (2 * d,), -2), ("bn2.running_var", (2 * d,), -4)]
+    return out + [("project.weight", (e, 2 * d), 2 * d), ("project.bias", (e,), 2 * d)]
 
 
 def _fill(key: str, shape: Tuple[int, ...], fan_in: int, seed: int) -> torch.Tensor:
@@ -71,6 +73,8 @@ def _fill(key: str, shape: Tuple[int, ...], fan_in: int, seed: int) -> torch.Ten
         return 1.0 + 0.1 * torch.randn(shape, generator=g)
     if fan_in == -2:      # LayerNorm shift
         return 0.1 * torch.randn(shape, generator=g)
+    if fan_in == -4:      # BatchNorm running variance: positive
+        return 0.5 + torch.rand(shape, generator=g)
     if fan_in == -3:      # pos_bias_{u,v}: xavier-uniform bound (attention.py:306-307)
         b = math.sqrt(6.0 / (shape[0] + shape[1]))
         return (torch.rand(shape, generator=g) * 2 - 1) * b

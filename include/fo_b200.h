@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FO_ABI_VERSION 2
+#define FO_ABI_VERSION 3
 
 enum { FO_F32 = 0, FO_BF16 = 1, FO_I16 = 2 };     /* compute dtype / PCM sample type */
 enum { FO_OK = 0, FO_ERR_ARG = -1, FO_ERR_CUDA = -2, FO_ERR_STATE = -3, FO_ERR_NOMEM = -4 };
@@ -63,6 +63,9 @@ typedef struct fo_config {
      * k >= 2 = Conv1dLinear with kernel_size k (models/encoder/attention.py:198-266): causal depthwise conv over
      * time (left context carried per session and layer) + 1x1 conv + ReLU + Linear */
     int32_t ffn_conv_kernel;
+    /* adapter norm (models/adapter.py:100-103): 0 = LayerNorm(2C, eps 1e-3); 1 = BatchNorm1d(2C, eps 1e-3) in eval mode
+     * (running statistics; tensors adapter.bn2.{weight,bias,running_mean,running_var}) */
+    int32_t adapter_batchnorm;
 } fo_config;
 
 typedef struct fo_stats_t {

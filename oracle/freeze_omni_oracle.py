@@ -341,7 +341,11 @@ def adapter_forward(cfg, sd: State, x: Tensor, mask: Tensor, cache: Optional[Lis
         xt = torch.cat((cache[0], xt), dim=2)                        # adapter.py:139
     new_cache = [xt[:, :, 1 - k:].contiguous()]                      # adapter.py:141,143
     y = F.conv1d(xt, sd["conv1d2.weight"], sd["conv1d2.bias"], stride=2).transpose(1, 2)
-    y = F.layer_norm(y, (y.size(-1),), sd["bn2.weight"], sd["bn2.bias"], eps=1e-3)
+    if getattr(cfg, "adapter_norm", "layer") == "batch":             # adapter.py:100-101,146: BatchNorm1d(eps=1e-3), eval mode
+        y = F.batch_norm(y.transpose(1, 2), sd["bn2.running_mean"], sd["bn2.running_var"], sd["bn2.weight"], sd["bn2.bias"],
+                         False, 0.0, 1e-3).transpose(1, 2)
+    else:                                                            # adapter.py:102-103,145-149
+        y = F.layer_norm(y, (y.size(-1),), sd["bn2.weight"], sd["bn2.bias"], eps=1e-3)
     y = F.gelu(y) if cfg.adapter_act == "gelu" else F.relu(y)
     y = F.linear(y, sd["project.weight"], sd["project.bias"])
     return y, mask[:, :, 0::2], new_cache

@@ -255,6 +255,30 @@ def main():
                 off["mask_c%d_L%d" % (c, L)] = m.numpy()
         save("tiny_conv1d", seed=np.int64(3), off_feats=xs.numpy(), off_ilens=ilens.numpy(), **{"off_" + k: v for k, v in off.items()})
 
+    # ---------------- adapter with BatchNorm1d + ReLU (adapter.py:100-101,106-107), eval mode ----------------
+    if want("tiny_bn"):
+        ycfg = load_yaml("tiny_bn")
+        cfg = path_config_from_dict(ycfg)
+        mc = ycfg["model_conf"]
+        adp = ref_adapter.CNNSubsampling(mc["enc_out_dim"], mc["llm_embed_dim"], mc["kernel_size"], mc["activation_func"], mc["norm"])
+        sd = make_adapter_state(cfg, 3)
+        missing = adp.load_state_dict(sd, strict=False)
+        assert set(missing.missing_keys) <= {"bn2.num_batches_tracked"} and not missing.unexpected_keys, missing
+        adp.eval()
+        g = torch.Generator().manual_seed(23)
+        xs = [torch.randn(2, 4, cfg.d_model, generator=g) for _ in range(5)]
+        ys, cache = [], None
+        with torch.no_grad():
+            for x in xs:
+                y, _, cache = adp(x.clone(), torch.ones(2, 1, 4, dtype=torch.bool), cache=cache, return_cache=True)
+                ys.append(y.clone())
+            xo = torch.randn(2, 37, cfg.d_model, generator=g)
+            mo = torch.arange(37)[None, None, :] < torch.tensor([37, 20])[:, None, None]
+            yo, mo2 = adp(xo.clone(), mo)
+        save("tiny_bn", seed=np.int64(3), stream_x=torch.stack(xs).numpy(), stream_y=torch.stack(ys).numpy(),
+             stream_cache=cache[0].contiguous().numpy(), off_x=xo.numpy(), off_mask=mo.numpy(), off_y=yo.numpy(),
+             off_mask_out=mo2.numpy())
+
     # ---------------- shipped config -------------------------------------------------------
     if want("shipped"):
         ycfg = load_yaml("shipped")

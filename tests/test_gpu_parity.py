@@ -520,6 +520,28 @@ def test_fused_layernorm_matches_standalone(shipped16):
         eng.free(ids)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_adapter_batchnorm_relu(golden, dtype, tol):
+    """Adapter variant norm='batch' + ReLU (adapter.py:100-101,106-107; BatchNorm1d eval = per-channel affine of the running
+    statistics, folded at fo_finalize_weights) against the reference module's outputs: streaming with the conv cache passed
+    in and out, and a full sequence with a ragged pad mask."""
+    from freeze_omni_b200.engine import Engine
+    cfg = load_path_config("tiny_bn")
+    asd = make_adapter_state(cfg, 3)
+    eng = Engine(cfg, None, asd, dtype=dtype, max_sessions=1)
+    g = golden("tiny_bn")
+    try:
+        cache = None
+        for i in range(g["stream_x"].shape[0]):
+            y, cache = eng.adapter_forward(torch.from_numpy(g["stream_x"][i]).cuda(), None, cache)
+            assert maxabs(y.cpu(), g["stream_y"][i]) < tol, i
+        assert maxabs(cache.cpu(), g["stream_cache"]) < 1e-6
+        y, _ = eng.adapter_forward(torch.from_numpy(g["off_x"]).cuda(), torch.from_numpy(g["off_mask"]).cuda(), None)
+        assert maxabs(y.cpu(), g["off_y"]) < tol
+    finally:
+        eng.close()
+
+
 def test_persistent_gemm_matches_tile_per_cta(shipped16):
     """Fat short-K GEMMs run on the persistent tcgen05 kernel (tile loop per SM, double-buffered TMEM accumulator,
     epilogue straight from TMEM registers).  Same k order and same fp32 epilogue arithmetic as the one-tile-per-CTA

@@ -235,3 +235,20 @@ def test_shipped_offline(golden, shipped):
     assert np.array_equal(m.numpy(), g["mask"]) and np.array_equal(ym.numpy(), g["adapter_mask"])
     assert np.abs(xs.numpy() - g["enc_out"]).max() < FP32_TOL
     assert np.abs(y.numpy() - g["adapter_out"]).max() < FP32_TOL
+
+
+def test_adapter_batchnorm_relu_vs_reference(golden):
+    """CNNSubsampling(norm='batch', activation_func='relu') in eval mode (adapter.py:100-101,106-107): the oracle's folded
+    running-statistics BatchNorm against outputs of the reference module (tests/golden/tiny_bn.npz), streaming with the
+    conv cache and full-sequence with a ragged pad mask."""
+    cfg = load_path_config("tiny_bn")
+    asd = make_adapter_state(cfg, 3)
+    g = golden("tiny_bn")
+    cache = None
+    for i in range(g["stream_x"].shape[0]):
+        y, _, cache = O.adapter_forward(cfg, asd, torch.from_numpy(g["stream_x"][i]), torch.ones(2, 1, 4, dtype=torch.bool), cache)
+        assert float((y - torch.from_numpy(g["stream_y"][i])).abs().max()) < 1e-5, i
+    assert float((cache[0] - torch.from_numpy(g["stream_cache"])).abs().max()) == 0.0
+    y, m, _ = O.adapter_forward(cfg, asd, torch.from_numpy(g["off_x"]), torch.from_numpy(g["off_mask"]))
+    assert float((y - torch.from_numpy(g["off_y"])).abs().max()) < 1e-5
+    assert torch.equal(m, torch.from_numpy(g["off_mask_out"]))
