@@ -452,7 +452,12 @@ def main():
         gflop = GFLOP_GEMM_PER_CHUNK * S
         achieved = gflop / gemm_ms                                  # GFLOP / ms == TFLOP/s
         roof = {"bound": "tensor", "achieved": achieved, "peak": tf_sustained, "unit": "TFLOP/s",
-                "frac": achieved / tf_sustained, "traffic": None, "peak_source": peak_kind + " (sustained bf16 cuBLAS)",
+                "frac": achieved / tf_sustained,
+                # dram__bytes_read+write per GEMM launch at 64 sessions, one ncu pass over two steps' 202 launches
+                # (profiles/r01_i_ncu_gemm_dram_traffic_stream64.csv; cold-cache replays, so it also counts the next-kernel
+                # L2 prefetches these kernels issue: 1.76 GB per step against 0.75 GB of weights + 0.43 GB of KV rings)
+                "traffic": 17.44e6 if S == 64 else None, "traffic_unit": "bytes per launch (ncu)",
+                "peak_source": peak_kind + " (sustained bf16 cuBLAS)",
                 "kernel": "gemm_tc_kernel (all %d GEMM launches of a step; algorithmic %.2f GFLOP per session-chunk)"
                           % (gemm_n // steps_prof, GFLOP_GEMM_PER_CHUNK),
                 "launches_per_step": gemm_n / steps_prof, "gemm_ms_per_step": gemm_ms, "ms_per_step_without_gemms": ms_nogemm,
