@@ -376,6 +376,33 @@ def main():
             else:
                 eng.stream_step(ids, pcm_dev[j], 1.0, adapter_out=y_dev, want_enc=False)
 
+    y_host2 = torch.empty(S, t_out, cfg.llm_dim).pin_memory()
+
+    def run_steps_pipelined(n_steps, first):
+        """fo_stream_step_async: the upload of chunk i+1 and the read-back of chunk i overlap the kernels in between; the
+        host still takes delivery of every chunk's embeddings, one step behind the launch."""
+        prev = None
+        for i in range(n_steps):
+            j = (first + i) % n_pcm
+            tk = eng.stream_step_async(ids, pcm_host[j], y_host if i & 1 else y_host2, 1.0)
+            if prev is not None:
+                eng.stream_wait(prev)
+            prev = tk
+        if prev is not None:
+            eng.stream_wait(prev)
+
+    def timed_pipelined(n_steps, first):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_steps_pipelined(n_steps, first)                  # returns after the last read-back has landed
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
     def timed(n_steps, host_io, first):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -410,10 +437,13 @@ def main():
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     run_steps(W, True, 0)
-    ms_e2e = timed(K, True, W)
+    ms_e2e_sync = timed(K, True, W)                          # every step: upload, kernels, read-back, host synchronisation
+    run_steps_pipelined(max(W, 6), 0)                        # both staging-buffer parities warmed and captured
+    ms_e2e = timed_pipelined(K, W)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     e2e = world * S * CHUNK_SEC * K / (ms_e2e * 1e-3)
+    e2e_sync = world * S * CHUNK_SEC * K / (ms_e2e_sync * 1e-3)
 
     # ---- per-step latency distribution (device timed, one event pair per step) --------------------
     lat = []
@@ -502,7 +532,11 @@ def main():
                            "parallelism": "sessions sharded over ranks, no collective",
                            "l2": "inputs larger than L2: each step streams 752 MB of weights + %.0f MB of KV rings (L2 is 126 MB)" % (S * 6.3)},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / K},
+                        "ms_per_step": ms_e2e / K,
+                        "how": "fo_stream_step_async + fo_stream_wait: pinned-host int16 PCM in, fp32 embeddings back to the host "
+                               "every step, copies on the library's copy stream overlapping the next step's kernels",
+                        "sync_each_step": {"value": e2e_sync, "ms_per_step": ms_e2e_sync / K,
+                                           "how": "fo_stream_step with host buffers + stream synchronisation after every step"}},
                 "gpu_launches": int(launches),
                 "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "sessions": S},
                 "roofline": roof, "gemm_shapes": shapes[:12], "step_roofline": whole, "cpu_baseline": cpu,

@@ -120,6 +120,10 @@ struct fo_ctx {
     int pf_slot_lo = 0, pf_slot_hi = 0;       // slot range of the sessions of the current step
     int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
                                               // (measured slower than the stand-alone kernel at 64-256 sessions: off)
+    // fo_stream_step_async: host <-> device copies on an internal stream, staging buffers double-buffered by ticket parity
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    long long async_ticket = 0;
     void* handoff = nullptr;                  // fo_stream_step_embeds: fp16 destination of the adapter rows for this call
     long long handoff_rows = 0, handoff_off = 0;
     int stack_kernel = 0;                     // 24-layer stack of the streaming step as ONE persistent cooperative kernel (fo_stack.cu)
@@ -151,7 +155,7 @@ struct fo_ctx {
 namespace {
 
 enum { WS_FEATS = 0, WS_C1, WS_C2, WS_XSUB, WS_EMB, WS_X, WS_H, WS_QKV, WS_ATT, WS_FFH, WS_ENC, WS_XIN, WS_ACONV, WS_AH,
-       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_PART, WS_COUNT };
+       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_PART, WS_PCM2, WS_ENC2, WS_Y2, WS_COUNT };
 
 int dev_alloc(fo_ctx* c, void** p, size_t bytes) {
     *p = nullptr;
@@ -950,6 +954,12 @@ int fo_destroy(fo_ctx* c) {
     for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     stack_state_destroy(c->stack);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_compute[i]) cudaEventDestroy(c->ev_compute[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
     for (int g = 1; g < fo_ctx::MAX_GROUPS; ++g) {
         if (c->grp_stream[g]) cudaStreamDestroy(c->grp_stream[g]);
         if (c->ev_join[g]) cudaEventDestroy(c->ev_join[g]);
@@ -1248,18 +1258,22 @@ struct StepArgs {
     bool with_fbank, want_y;
     int pcm_is_i16;
     float scale;
+    int buf;                   // which set of PCM / encoder-output / adapter-output staging buffers (fo_stream_step_async alternates)
 };
+inline int ws_pcm(int buf) { return buf ? WS_PCM2 : WS_PCM; }
+inline int ws_enc(int buf) { return buf ? WS_ENC2 : WS_ENC; }
+inline int ws_y(int buf) { return buf ? WS_Y2 : WS_Y; }
 
 static int step_body(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     void *dfeats, *denc, *dy = nullptr;
     const int T1 = (a.t_in - 1) / 2, t = (T1 - 1) / 2;
     const int km1 = c->KA - 1, t_out = (t + km1 - c->KA) / 2 + 1;
     FO_TRY(ws_ensure(c, WS_FEATS, (size_t)a.n * a.t_in * c->F * sizeof(float), &dfeats));
-    FO_TRY(ws_ensure(c, WS_ENC, (size_t)a.n * t * c->D * sizeof(float), &denc));
-    if (a.want_y) FO_TRY(ws_ensure(c, WS_Y, (size_t)a.n * t_out * c->E * sizeof(float), &dy));
+    FO_TRY(ws_ensure(c, ws_enc(a.buf), (size_t)a.n * t * c->D * sizeof(float), &denc));
+    if (a.want_y) FO_TRY(ws_ensure(c, ws_y(a.buf), (size_t)a.n * t_out * c->E * sizeof(float), &dy));
     if (a.with_fbank) {
         void* dp;
-        FO_TRY(ws_ensure(c, WS_PCM, (size_t)a.n * c->chunk_samples * 4, &dp));
+        FO_TRY(ws_ensure(c, ws_pcm(a.buf), (size_t)a.n * c->chunk_samples * 4, &dp));
         FO_TRY(fbank_stream(fbank_params(c), c->ids_dev, a.n, dp, a.pcm_is_i16, a.scale, c->cfg.frames_per_chunk,
                             c->cfg.context_frames, c->samples, c->feat_ring, (float*)dfeats, st));
     }
@@ -1275,7 +1289,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     char key[192];
     uint32_t sbits;
     memcpy(&sbits, &a.scale, 4);
-    snprintf(key, sizeof(key), "%p/%lld/%lld/%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", c->handoff, c->handoff_rows, c->handoff_off, a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
+    snprintf(key, sizeof(key), "%d/%p/%lld/%lld/%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", a.buf, c->handoff, c->handoff_rows, c->handoff_off, a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
              c->gemm_backend, c->groups, ((c->debug_skip * 2 + c->fuse_ln) * 2 + c->use_prefetch) * 64 + c->stack_kernel * 32 + c->stack_split_o * 4 + c->stack_split_f2 / 2,
              (c->use_prefetch ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), c->use_prefetch ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
     if (c->graphs.size() > 256 && c->graphs.find(key) == c->graphs.end()) {
@@ -1331,7 +1345,7 @@ static int stream_common(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     FO_TRY(upload_ids(c, ids, n, st));
     c->pf_slot_lo = c->pf_slot_hi = ids[0];
     for (int i = 1; i < n; ++i) { c->pf_slot_lo = std::min(c->pf_slot_lo, (int)ids[i]); c->pf_slot_hi = std::max(c->pf_slot_hi, (int)ids[i]); }
-    StepArgs a{n, t_in, pcm != nullptr, adapter_out != nullptr, pcm_dtype == FO_I16, scale};
+    StepArgs a{n, t_in, pcm != nullptr, adapter_out != nullptr, pcm_dtype == FO_I16, scale, 0};
     void* stage;
     if (pcm) {
         const size_t in_bytes = (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4);
@@ -1389,6 +1403,58 @@ int fo_stream_step_embeds(fo_ctx* c, const int32_t* ids, int n, const void* pcm,
     c->handoff = nullptr;
     c->handoff_rows = c->handoff_off = 0;
     return r;
+}
+
+int fo_stream_step_async(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale, float* enc_out,
+                         float* adapter_out, void* stream, int64_t* ticket) {
+    FO_CHECK(c && c->finalized && c->cfg.has_encoder && c->fb_window, "fo_stream_step_async: context has no finalized encoder + frontend");
+    FO_CHECK(pcm && (pcm_dtype == FO_F32 || pcm_dtype == FO_I16) && ticket, "fo_stream_step_async: bad argument");
+    if (adapter_out) FO_CHECK(c->cfg.has_adapter, "adapter_out requested but the context has no adapter");
+    FO_TRY(check_ids(c, ids, n));
+    FO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!c->copy_stream) {
+        FO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            FO_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            FO_CUDA(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
+            FO_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    const int buf = (int)(c->async_ticket & 1);
+    const int t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
+    const int t = ((t_in - 1) / 2 - 1) / 2, t_out = (t + c->KA - 1 - c->KA) / 2 + 1;
+    FO_TRY(upload_ids(c, ids, n, st));
+    c->pf_slot_lo = c->pf_slot_hi = ids[0];
+    for (int i = 1; i < n; ++i) { c->pf_slot_lo = std::min(c->pf_slot_lo, (int)ids[i]); c->pf_slot_hi = std::max(c->pf_slot_hi, (int)ids[i]); }
+    StepArgs a{n, t_in, true, adapter_out != nullptr, pcm_dtype == FO_I16, scale, buf};
+    // inputs: copy stream, once the step that last read this PCM buffer (two tickets ago) is done
+    void* stage;
+    FO_TRY(ws_ensure(c, ws_pcm(buf), (size_t)n * c->chunk_samples * 4, &stage));
+    if (c->async_ticket >= 2) FO_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_compute[buf], 0));
+    FO_CUDA(cudaMemcpyAsync(stage, pcm, (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4), cudaMemcpyDefault, c->copy_stream));
+    FO_CUDA(cudaEventRecord(c->ev_in[buf], c->copy_stream));
+    FO_CUDA(cudaStreamWaitEvent(st, c->ev_in[buf], 0));
+    // outputs of two tickets ago must have left this buffer set before the step overwrites it
+    if (c->async_ticket >= 2) FO_CUDA(cudaStreamWaitEvent(st, c->ev_out[buf], 0));
+    FO_TRY(run_step(c, a, st));
+    FO_CUDA(cudaEventRecord(c->ev_compute[buf], st));
+    FO_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_compute[buf], 0));
+    if (enc_out) FO_CUDA(cudaMemcpyAsync(enc_out, c->ws[ws_enc(buf)].p, (size_t)n * t * c->D * sizeof(float), cudaMemcpyDefault, c->copy_stream));
+    if (adapter_out) FO_CUDA(cudaMemcpyAsync(adapter_out, c->ws[ws_y(buf)].p, (size_t)n * t_out * c->E * sizeof(float), cudaMemcpyDefault, c->copy_stream));
+    FO_CUDA(cudaEventRecord(c->ev_out[buf], c->copy_stream));
+    *ticket = c->async_ticket++;
+    c->stats.stream_steps += 1;
+    c->stats.session_chunks += n;
+    return 0;
+}
+
+int fo_stream_wait(fo_ctx* c, int64_t ticket) {
+    FO_CHECK(c && c->copy_stream && ticket >= 0 && ticket < c->async_ticket, "fo_stream_wait: unknown ticket");
+    FO_CHECK(c->async_ticket - ticket <= 2, "fo_stream_wait: ticket %lld is older than the two steps in flight", (long long)ticket);
+    FO_CUDA(cudaSetDevice(c->device));
+    FO_CUDA(cudaEventSynchronize(c->ev_out[ticket & 1]));
+    return 0;
 }
 
 int fo_stream_step(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale, float* enc_out,

@@ -273,6 +273,26 @@ class Engine:
                                            _ptr(adapter_out) if self.has_adapter else None, self._stream()))
         return (enc_out if want_enc else None), (adapter_out if self.has_adapter else None)
 
+    def stream_step_async(self, ids, pcm: ArrayLike, adapter_out: torch.Tensor, scale: Optional[float] = None,
+                          enc_out: Optional[torch.Tensor] = None) -> int:
+        """Pipelined stream_step for pinned HOST buffers: returns a ticket; `adapter_out` (and `enc_out`) are valid after
+        stream_wait(ticket).  Copies of step i overlap the kernels of step i+1 (at most two steps outstanding)."""
+        ids = _ids(ids)
+        n = len(ids)
+        assert tuple(pcm.shape) == (n, self.cfg.samples_per_chunk)
+        t, t_out = self.out_frames(self.cfg.chunk_feat_frames)
+        assert tuple(adapter_out.shape) == (n, t_out, self.cfg.llm_dim) and adapter_out.dtype == torch.float32 and adapter_out.is_contiguous()
+        if enc_out is not None:
+            assert tuple(enc_out.shape) == (n, t, self.cfg.d_model) and enc_out.dtype == torch.float32 and enc_out.is_contiguous()
+        ticket = C.c_int64()
+        _lib.check(self.lib.fo_stream_step_async(self._h, _i32p(ids), n, _ptr(pcm), self._pcm_dtype(pcm),
+                                                 float(self.cfg.pcm_scale if scale is None else scale), _ptr(enc_out),
+                                                 _ptr(adapter_out), self._stream(), C.byref(ticket)))
+        return int(ticket.value)
+
+    def stream_wait(self, ticket: int) -> None:
+        _lib.check(self.lib.fo_stream_wait(self._h, int(ticket)))
+
     def stream_step_embeds(self, ids, pcm: ArrayLike, embeds: torch.Tensor, row_offset: int = 0,
                            scale: Optional[float] = None, enc_out: Optional[torch.Tensor] = None, want_enc: bool = False):
         """stream_step whose adapter rows land, as fp16, in rows [row_offset, row_offset + t_out) of each session's block

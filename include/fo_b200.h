@@ -134,6 +134,13 @@ int fo_encode_stream(fo_ctx* ctx, const int32_t* ids, int n, const float* feats,
 /* fbank + encode in one call (one captured graph): PCM in, embeddings out */
 int fo_stream_step(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
                    float* enc_out, float* adapter_out, void* stream);
+/* pipelined form for HOST buffers (a server loop that already holds the next chunk): returns once the step is enqueued.
+ * The PCM upload and the read-back of enc_out / adapter_out run on an internal copy stream with double-buffered staging,
+ * so the copies of step i overlap the kernels of step i+1; the outputs of a step are valid after fo_stream_wait(ticket).
+ * At most two steps may be outstanding; the host buffers of a step must stay untouched until its wait returns. */
+int fo_stream_step_async(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
+                         float* enc_out, float* adapter_out, void* stream, int64_t* ticket);
+int fo_stream_wait(fo_ctx* ctx, int64_t ticket);
 /* the same with the LLM hand-off fused into the adapter projection: replaces
  *   inputs_embeds = torch.cat((chat_prefix_embeds, inputs_embeds), 1) ... inputs_embeds.half()   (models/audioLLM.py:404-411).
  * embeds_f16 is a DEVICE buffer (n, rows_per_session, llm_dim) of IEEE fp16 that the caller pre-fills (chat prefix);

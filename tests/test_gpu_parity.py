@@ -578,6 +578,35 @@ def test_persistent_gemm_matches_tile_per_cta(shipped16):
         eng.set_option("tc_persist", 1)
 
 
+def test_async_pipelined_step_matches_sync(shipped16):
+    """fo_stream_step_async / fo_stream_wait (copies on the library's copy stream, double-buffered staging) must deliver the
+    bits of the synchronous call, step after step, with two steps in flight."""
+    cfg, eng = shipped16
+    g = torch.Generator().manual_seed(83)
+    ids = eng.alloc(4)
+    t, t_out = eng.out_frames(cfg.chunk_feat_frames)
+    try:
+        pcm = [(0.05 * torch.randn(2, cfg.samples_per_chunk, generator=g) * 32768).round().to(torch.int16).pin_memory() for _ in range(7)]
+        ref = [eng.stream_step(ids[:2], p, 1.0) for p in pcm]
+        ref = [(e.cpu(), y.cpu()) for e, y in ref]
+        ys = [torch.empty(2, t_out, cfg.llm_dim).pin_memory() for _ in range(7)]
+        es = [torch.empty(2, t, cfg.d_model).pin_memory() for _ in range(7)]
+        prev = None
+        for i in range(7):
+            tk = eng.stream_step_async(ids[2:], pcm[i], ys[i], 1.0, enc_out=es[i])
+            if prev is not None:
+                eng.stream_wait(prev)
+                assert torch.equal(ys[i - 1], ref[i - 1][1]) and torch.equal(es[i - 1], ref[i - 1][0]), i - 1
+            prev = tk
+        eng.stream_wait(prev)
+        assert torch.equal(ys[6], ref[6][1]) and torch.equal(es[6], ref[6][0])
+        with pytest.raises(Exception):
+            eng.stream_wait(prev - 3)                                   # older than the two steps in flight
+        assert eng.state(int(ids[0])) == eng.state(int(ids[2]))
+    finally:
+        eng.free(ids)
+
+
 def test_llm_handoff_fp16_embeds(shipped16):
     """fo_stream_step_embeds writes the adapter rows as fp16 straight into the caller's inputs_embeds block behind the
     chat prefix (audioLLM.py:404-411: cat(prefix, embeds).half()): same bits as .half() of the fp32 output, prefix and
