@@ -116,7 +116,9 @@ struct fo_ctx {
     TcWorkspace* tc_cur = &tc_wsg[0];
     int debug_skip = 0;                       // timing attribution only (results invalid): bit0 attention, bit1 LayerNorm,
                                               // bit2 QKV/out GEMMs, bit3 FFN GEMMs, bit4 subsampling/adapter GEMMs, bit5 EVERY GEMM launch (nothing else)
-    int use_prefetch = 1;                     // next-kernel L2 prefetch of weights / KV rings (L2Prefetch)
+    int use_prefetch = 0;                     // next-kernel L2 prefetch (L2Prefetch): bit0 weights, bit1 this layer's KV rings.
+                                              // Off: it paid 2 % with one GEMM CTA per SM; with two co-resident CTAs hiding
+                                              // each other's cold loads it costs 1-2 % at 16-128 sessions (r75/r76)
     int pf_slot_lo = 0, pf_slot_hi = 0;       // slot range of the sessions of the current step
     int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
                                               // (measured slower than the stand-alone kernel at 64-256 sessions: off)
@@ -639,7 +641,7 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
     const int D = c->D, FF = c->FF;
     const long long wsz = (long long)c->esz;
     Epilogue e;
-    if (c->use_prefetch) e.prefetch = pf1(w.w2, (long long)D * FF * wsz);           // out-proj runs: FFN2's weights
+    if (c->use_prefetch & 1) e.prefetch = pf1(w.w2, (long long)D * FF * wsz);       // out-proj runs: FFN2's weights
     e.bias = w.bo;
     e.residual = x;
     e.c_f32 = x;
@@ -659,7 +661,7 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
         ffn_in = reinterpret_cast<const TA*>(fc.hc);
     }
     Epilogue e1;
-    if (c->use_prefetch && next_wqkv) e1.prefetch = pf1(next_wqkv, 3LL * D * D * wsz);   // FFN1 runs: next layer's QKV weights
+    if ((c->use_prefetch & 1) && next_wqkv) e1.prefetch = pf1(next_wqkv, 3LL * D * D * wsz);   // FFN1 runs: next layer's QKV weights
     e1.bias = w.b1;
     e1.relu = 1;
     e1.c_act = ffh;
@@ -767,10 +769,12 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
             int r = 0;
             if (l == 0) r = layer_norm<TA>(xg, Mg, D, w.ln1g, w.ln1b, 1e-5f, 0, 1.0f, hg, nullptr, sg);
             L2Prefetch pfq;                                   // QKV runs: this layer's KV rings (attention) + out-proj weights
-            if (c->use_prefetch) {
+            if (c->use_prefetch & 2) {
                 const long long slot_bytes = a.ring_slot_stride * (long long)sizeof(TA);
                 pfq.ptr[0] = reinterpret_cast<const char*>(c->ring) + ((long long)l * layer_stride) * sizeof(TA) + (long long)c->pf_slot_lo * slot_bytes;
                 pfq.bytes[0] = (long long)(c->pf_slot_hi - c->pf_slot_lo + 1) * slot_bytes;
+            }
+            if (c->use_prefetch & 1) {
                 pfq.ptr[1] = w.wo;
                 pfq.bytes[1] = (long long)D * D * c->esz;
                 a.prefetch = pf1(w.w1, (long long)D * FF * c->esz);                       // attention runs: FFN1's weights
@@ -1290,8 +1294,8 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     uint32_t sbits;
     memcpy(&sbits, &a.scale, 4);
     snprintf(key, sizeof(key), "%d/%p/%lld/%lld/%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", a.buf, c->handoff, c->handoff_rows, c->handoff_off, a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
-             c->gemm_backend, c->groups, ((c->debug_skip * 2 + c->fuse_ln) * 2 + c->use_prefetch) * 64 + c->stack_kernel * 32 + c->stack_split_o * 4 + c->stack_split_f2 / 2,
-             (c->use_prefetch ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), c->use_prefetch ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
+             c->gemm_backend, c->groups, ((c->debug_skip * 2 + c->fuse_ln) * 4 + c->use_prefetch) * 64 + c->stack_kernel * 32 + c->stack_split_o * 4 + c->stack_split_f2 / 2,
+             ((c->use_prefetch & 2) ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), (c->use_prefetch & 2) ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
     if (c->graphs.size() > 256 && c->graphs.find(key) == c->graphs.end()) {
         for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         c->graphs.clear();
@@ -1555,7 +1559,7 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "stack_kernel")) c->stack_kernel = value != 0;
     else if (!strcmp(name, "stack_split_o")) c->stack_split_o = (int)value;
     else if (!strcmp(name, "stack_split_f2")) c->stack_split_f2 = (int)value;
-    else if (!strcmp(name, "l2_prefetch")) c->use_prefetch = value != 0;
+    else if (!strcmp(name, "l2_prefetch")) c->use_prefetch = (int)(value & 3);
     else if (!strcmp(name, "pdl")) g_want_pdl = value != 0;
     else if (!strcmp(name, "session_groups")) {
         FO_CHECK(value >= 1 && value <= fo_ctx::MAX_GROUPS, "session_groups must be 1..%d", fo_ctx::MAX_GROUPS);

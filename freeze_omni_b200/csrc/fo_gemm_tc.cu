@@ -745,13 +745,22 @@ Plan choose_plan(long long act_rows, int n_out, int K) {
     const int sms = g_sm_count;
     if (act_rows <= 384) {
         const int ta = (n_out + BM - 1) / BM;
-        int split = std::min(4, (kblocks + 31) / 32);
+        // two CTAs fit one SM (<= 100 KB of stages each) and hide each other's fill / epilogue: up to 2 x SMs CTAs, K split
+        // so that a CTA walks ~16 k-blocks (r72 sweep: FFN2 (1,32,4) 11.8 us vs (1,32,2) 15.5 us, QKV (1,32,1) 7.6 vs 8.1)
+        static int occ = 0, kbt = 0;
+        if (!occ) {
+            const char* e1 = getenv("FO_TC_OCC");
+            const char* e2 = getenv("FO_TC_KB");
+            occ = e1 ? atoi(e1) : 2;
+            kbt = e2 ? atoi(e2) : 16;
+        }
+        int split = std::min(4, (kblocks + kbt - 1) / kbt);
         int bn = 256;
         const int cands[5] = {16, 32, 64, 128, 256};
-        for (int ci = 0; ci < 5; ++ci) {                       // smallest slice that keeps the grid within one wave
+        for (int ci = 0; ci < 5; ++ci) {                       // smallest slice that keeps the grid within two CTAs per SM
             const int b = cands[ci];
             const long long tb = (act_rows + b - 1) / b;
-            if ((long long)ta * tb * split <= sms) { bn = b; break; }
+            if ((long long)ta * tb * split <= (long long)occ * sms) { bn = b; break; }
         }
         if (bn > round16((int)act_rows)) bn = round16((int)act_rows);
         const long long tb = (act_rows + bn - 1) / bn;
@@ -898,8 +907,10 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     if (M <= 384) {
         // skinny GEMMs: ~100 KB in flight per CTA covers the L2 latency; staying under half of the shared memory lets a
         // second CTA (another session group's GEMM, or the next kernel's first wave) be resident on the same SM
-        const int cap = (int)((100 * 1024) / stage);
-        if (cap >= 3) p.stages = std::min(p.stages, cap);
+        static int occ_cap = 0;
+        if (!occ_cap) { const char* e1 = getenv("FO_TC_OCC"); occ_cap = e1 ? atoi(e1) : 2; }
+        const int cap = (int)(((occ_cap <= 2 ? 100 : occ_cap == 3 ? 70 : 52) * 1024) / stage);
+        if (cap >= 2) p.stages = std::min(p.stages, std::max(cap, 2));
     } else if ((long long)ta * tb * pl.split > g_sm_count) {
         // more CTAs than SMs: keep two resident per SM (<= ~110 KB each) so one CTA's epilogue overlaps the other's mainloop
         const int cap = (int)((110 * 1024) / stage);

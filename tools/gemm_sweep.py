@@ -23,6 +23,8 @@ def main():
               (128, 3584, 2048), (4, 3072, 1024), (4, 1024, 4096), (512, 4096, 1024), (4096, 4096, 1024), (5120, 1024, 9216)]
     if quick:
         shapes = shapes[:2]
+    if "--layer" in sys.argv:          # the four layer GEMMs of a 64-session streaming step
+        shapes = shapes[:4]
     g = torch.Generator().manual_seed(0)
     for (M, N, K) in shapes:
         A = torch.randn(M, K, generator=g).cuda()
