@@ -353,7 +353,10 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
     constexpr int EPC = 8, NCH = 8;
     AT_TRACE(0);
     FO_PDL_TRIGGER();
-    FO_PDL_WAIT();
+    // Everything up to FO_PDL_WAIT below touches only data that no kernel of THIS step has written before this launch:
+    // the session state (advance_sessions runs at the end of a step, and a step starts with stream copies, which order
+    // it after the previous step completely), the ring rows of earlier frames (appended by this kernel, this layer, in
+    // earlier steps) and constants.  So the ring / rel-pos bulk copies fly while the QKV GEMM is still draining.
     AT_TRACE(1);
     const int cap = a.ring_cap;
     const int t = a.t, D = a.H * DK;
@@ -400,6 +403,16 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
         }
     }
     AT_TRACE(3);
+    float ureg[4], vreg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * ATT_THREADS;
+        if (i < t * DK) {
+            ureg[k] = pos_u[h * DK + i % DK];
+            vreg[k] = pos_v[h * DK + i % DK];
+        }
+    }
+    FO_PDL_WAIT();                                  // from here on: the QKV GEMM's output
     // chunk's own K/V rows -> registers
     const int n_new = t * NCH * 2;
     uint4 newv = make_uint4(0, 0, 0, 0);
@@ -411,15 +424,13 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
         new_c = tid % NCH;
         newv = *reinterpret_cast<const uint4*>(qkv + (long long)(b * t + new_r) * 3 * D + (new_which + 1) * D + h * DK + new_c * EPC);
     }
-    float qreg[4], ureg[4], vreg[4];
+    float qreg[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int i = tid + k * ATT_THREADS;
         if (i < t * DK) {
             const int r = i / DK, d = i % DK;
             qreg[k] = q32[(long long)(b * t + r) * 3 * D + h * DK + d];
-            ureg[k] = pos_u[h * DK + d];
-            vreg[k] = pos_v[h * DK + d];
         }
     }
     l2_prefetch_slice(a.prefetch, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, tid, ATT_THREADS);
