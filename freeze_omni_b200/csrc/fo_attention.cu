@@ -783,6 +783,9 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
 // for the PV MMAs (accumulators rescaled per tile by the queries' correction factors).
 constexpr int OSC = 100;     // score row pitch (fp32): 4 mod 32 -> the MMA fragment stores of 4 query pairs hit 4 bank groups
 constexpr int OPH = 104;     // probability row pitch (fp16): 52 words = 20 mod 32 -> conflict-free B-fragment loads
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_offline_mma_kernel(const __half* __restrict__ qkv, const float* __restrict__ q32, int T, int H,
                              const int32_t* __restrict__ ilens, int chunk, int left, const __half* __restrict__ ptab_h,
@@ -852,19 +855,22 @@ attention_offline_mma_kernel(const __half* __restrict__ qkv, const float* __rest
     for (int kt = k_lo; kt < k_hi; kt += KT) {
         const int nk = min(KT, k_hi - kt);
         __syncthreads();                                   // previous tile fully consumed
+        // global -> shared with cp.async: all 36 16-byte copies of a thread are in flight at once (register staging left
+        // the kernel stalled on the loads: long-scoreboard 3.3 per issue in profiles/r01_h)
         for (int i = tid; i < KT * NCH * 2; i += ATT_THREADS) {
             const int which = i / (KT * NCH);              // 0 K, 1 V
             const int j = (i / NCH) % KT, cc = i % NCH;
-            uint4 val = make_uint4(0, 0, 0, 0);            // rows behind the last key: zeros (finite in the PV MMAs)
-            if (j < nk) val = *reinterpret_cast<const uint4*>(qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + cc * EPC);
-            *reinterpret_cast<uint4*>((which == 0 ? Ks : Vs) + j * DK + ((cc ^ (j & 7)) << 3)) = val;
+            TA* dst = (which == 0 ? Ks : Vs) + j * DK + ((cc ^ (j & 7)) << 3);
+            if (j < nk) cp_async16(dst, qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + cc * EPC);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);    // rows behind the last key: zeros (finite in the PV MMAs)
         }
         // rel-pos rows from the head-major fp16 table (its 16-byte chunks are swizzled by POSITION, the tile's by tile row)
         for (int i = tid; i < nk * NCH; i += ATT_THREADS) {
             const int j = i / NCH, cc = i % NCH, pos = kt + j;
-            *reinterpret_cast<uint4*>(Ps + j * DK + ((cc ^ (j & 7)) << 3)) =
-                *reinterpret_cast<const uint4*>(ptab_h + ((long long)h * pos_rows + pos) * DK + ((cc ^ (pos & 7)) << 3));
+            cp_async16(Ps + j * DK + ((cc ^ (j & 7)) << 3), ptab_h + ((long long)h * pos_rows + pos) * DK + ((cc ^ (pos & 7)) << 3));
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // ---- scores of query group `warp` against the 16-key tiles ----
         const int qrow = warp * 8 + g;                     // B-fragment row (query) of this lane

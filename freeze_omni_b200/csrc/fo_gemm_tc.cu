@@ -909,7 +909,9 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
         // second CTA (another session group's GEMM, or the next kernel's first wave) be resident on the same SM
         static int occ_cap = 0;
         if (!occ_cap) { const char* e1 = getenv("FO_TC_OCC"); occ_cap = e1 ? atoi(e1) : 2; }
-        const int cap = (int)(((occ_cap <= 2 ? 100 : occ_cap == 3 ? 70 : 52) * 1024) / stage);
+        static int cap_kb = 0;
+        if (!cap_kb) { const char* e3 = getenv("FO_TC_CAP"); cap_kb = e3 ? atoi(e3) : (occ_cap <= 2 ? 100 : occ_cap == 3 ? 70 : 52); }
+        const int cap = (int)((cap_kb * 1024) / stage);
         if (cap >= 2) p.stages = std::min(p.stages, std::max(cap, 2));
     } else if ((long long)ta * tb * pl.split > g_sm_count) {
         // more CTAs than SMs: keep two resident per SM (<= ~110 KB each) so one CTA's epilogue overlaps the other's mainloop
