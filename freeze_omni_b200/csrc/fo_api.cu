@@ -1286,9 +1286,12 @@ static int step_body(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
 }
 
 static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
-    // programmatic dependent launch pays off once the kernels have real grids (measured: -2.6 % step time at 64 sessions,
-    // +12 % at 1 session, where the early-resident successor CTAs only get in the way)
-    g_use_pdl = g_want_pdl && a.n >= 16;
+    // programmatic dependent launch along the chain: a kernel's prologue (barrier / TMEM set-up, weight stages, the attention
+    // kernel's ring copies) runs while its predecessor drains.  Pays at every batch size since the prologues carry real work
+    // (r85: -7 % at 1-4 sessions, -6 % at 8, -2.6 % at 64); FO_PDL_MIN raises the threshold for experiments.
+    static int pdl_min = -1;
+    if (pdl_min < 0) { const char* e = getenv("FO_PDL_MIN"); pdl_min = e ? atoi(e) : 1; }
+    g_use_pdl = g_want_pdl && a.n >= pdl_min;
     if (!c->use_graph || c->profile_gemm) return step_body(c, a, st);
     char key[192];
     uint32_t sbits;
