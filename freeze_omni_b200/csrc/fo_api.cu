@@ -120,6 +120,7 @@ struct fo_ctx {
                                               // Off: it paid 2 % with one GEMM CTA per SM; with two co-resident CTAs hiding
                                               // each other's cold loads it costs 1-2 % at 16-128 sessions (r75/r76)
     int pf_slot_lo = 0, pf_slot_hi = 0;       // slot range of the sessions of the current step
+    int defer_reduce = 1;                     // split-K GEMMs of the residual stream leave the reduction to the LayerNorm that follows
     int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
                                               // (measured slower than the stand-alone kernel at 64-256 sessions: off)
     // fo_stream_step_async: host <-> device copies on an internal stream, staging buffers double-buffered by ticket parity
@@ -242,21 +243,26 @@ int upload_ids(fo_ctx* c, const int32_t* ids, int n, cudaStream_t st) {
 // the kernel that ran also did the LayerNorm requested in ep.ln_* (only the tcgen05 kernel does).
 template <typename TA>
 int gemm_raw(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-             const RowMap& rm, cudaStream_t st, bool* fused_ln);
+             const RowMap& rm, cudaStream_t st, bool* fused_ln, int* deferred);
 template <>
 int gemm_raw<float>(fo_ctx* c, const float* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-                    const RowMap& rm, cudaStream_t st, bool* fused_ln) {
+                    const RowMap& rm, cudaStream_t st, bool* fused_ln, int* deferred) {
     *fused_ln = false;
+    *deferred = 0;
     return gemm_simt<float, float>(A, ga, reinterpret_cast<const float*>(W), M, N, K, ep, rm, st);
 }
 template <>
 int gemm_raw<act16>(fo_ctx* c, const act16* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-                    const RowMap& rm, cudaStream_t st, bool* fused_ln) {
+                    const RowMap& rm, cudaStream_t st, bool* fused_ln, int* deferred) {
     *fused_ln = false;
+    *deferred = 0;
     if (c->gemm_backend == 1) {
         Epilogue e = ep;
         if (!c->fuse_ln) e.ln_gamma = nullptr;
-        int r = gemm_tc(A, 1, ga, W, M, N, K, e, rm, *c->tc_cur, st);
+        // the split-K reduction can ride on the LayerNorm that follows (residual stream in place, rows normalised next)
+        e.defer_reduce = c->defer_reduce && ep.ln_gamma && !c->fuse_ln && ep.residual == ep.c_f32 && ep.c_f32 && !ep.c_act &&
+                         !ep.relu && ep.scale == 1.0f && N <= 1024;
+        int r = gemm_tc(A, 1, ga, W, M, N, K, e, rm, *c->tc_cur, st, deferred);
         if (r == 0) *fused_ln = e.ln_gamma != nullptr;
         if (r <= 0) return r;
     }
@@ -266,20 +272,24 @@ template <typename TA>
 int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
          const RowMap& rm, cudaStream_t st) {
     bool fused = false;
+    int deferred = 0;
     int r;
     if (c->debug_skip & 32) {
         r = 0;                                    // timing attribution: every GEMM launch dropped, the rest of the step kept
     } else if (!c->profile_gemm) {
-        r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st, &fused);
+        r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st, &fused, &deferred);
     } else {
         cudaEvent_t e0, e1;
         FO_CUDA(cudaEventCreate(&e0));
         FO_CUDA(cudaEventCreate(&e1));
         FO_CUDA(cudaEventRecord(e0, st));
-        r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st, &fused);
+        r = gemm_raw<TA>(c, A, ga, W, M, N, K, ep, rm, st, &fused, &deferred);
         FO_CUDA(cudaEventRecord(e1, st));
         c->prof_events.push_back(fo_ctx::ProfRec{e0, e1, M, N, K});
     }
+    if (r == 0 && deferred > 0)                   // the GEMM left raw split-K partials: the LayerNorm finishes the sum
+        return layer_norm_reduce<TA>(ep.c_f32, c->tc_cur->partial, deferred, ep.bias, M, N, ep.ln_gamma, ep.ln_beta, ep.ln_eps,
+                                     reinterpret_cast<TA*>(ep.ln_act), ep.ln_f32, st);
     if (r == 0 && ep.ln_gamma && !fused)          // LayerNorm of the finished rows as its own kernel (fp32 / FFMA paths)
         r = layer_norm<TA>(ep.c_f32, M, N, ep.ln_gamma, ep.ln_beta, ep.ln_eps, 0, 1.0f, reinterpret_cast<TA*>(ep.ln_act),
                            ep.ln_f32, st);
@@ -1297,7 +1307,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     uint32_t sbits;
     memcpy(&sbits, &a.scale, 4);
     snprintf(key, sizeof(key), "%d/%p/%lld/%lld/%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", a.buf, c->handoff, c->handoff_rows, c->handoff_off, a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
-             c->gemm_backend, c->groups, ((c->debug_skip * 2 + c->fuse_ln) * 4 + c->use_prefetch) * 64 + c->stack_kernel * 32 + c->stack_split_o * 4 + c->stack_split_f2 / 2,
+             c->gemm_backend, c->groups, (((c->debug_skip * 2 + c->defer_reduce) * 2 + c->fuse_ln) * 4 + c->use_prefetch) * 64 + c->stack_kernel * 32 + c->stack_split_o * 4 + c->stack_split_f2 / 2,
              ((c->use_prefetch & 2) ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), (c->use_prefetch & 2) ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
     if (c->graphs.size() > 256 && c->graphs.find(key) == c->graphs.end()) {
         for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1558,6 +1568,7 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "split_k")) c->split_k = (int)value;
     else if (!strcmp(name, "debug_skip")) c->debug_skip = (int)value;
     else if (!strcmp(name, "fuse_ln")) c->fuse_ln = value != 0;
+    else if (!strcmp(name, "defer_reduce")) c->defer_reduce = value != 0;
     else if (!strcmp(name, "tc_persist")) gemm_tc_set_persist(value != 0);
     else if (!strcmp(name, "stack_kernel")) c->stack_kernel = value != 0;
     else if (!strcmp(name, "stack_split_o")) c->stack_split_o = (int)value;
@@ -1591,6 +1602,7 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     else if (!strcmp(name, "split_k")) *value = c->split_k;
     else if (!strcmp(name, "session_groups")) *value = c->groups;
     else if (!strcmp(name, "fuse_ln")) *value = c->fuse_ln;
+    else if (!strcmp(name, "defer_reduce")) *value = c->defer_reduce;
     else if (!strcmp(name, "stack_kernel")) *value = c->stack_kernel;
     else if (!strcmp(name, "stack_launches")) *value = c->stack_launches;
     else if (!strcmp(name, "tc_persist_launches")) *value = gemm_tc_persist_launches();

@@ -176,6 +176,10 @@ struct Epilogue {
     float* ln_f32 = nullptr;
     int* ln_counters = nullptr;
     L2Prefetch prefetch;              // cold inputs of the kernels that follow (tcgen05 kernel only)
+    // The caller runs a LayerNorm over the finished rows right after this GEMM and lets IT finish a split-K reduction:
+    // every split CTA then just writes its raw accumulators as [split][M][N] fp32 and exits (no tile counters, no
+    // last-CTA pass, no bias / residual here); layer_norm_reduce() folds  x += bias + sum_s partial_s  into its row pass.
+    int defer_reduce = 0;
 };
 
 // C[rowmap(m), n] = A[m, :] . W[n, :]  for m < M (padded GEMM rows), n < N.  A/W are TIn (float or bf16),
@@ -202,7 +206,7 @@ void gemm_tc_force_producers(int npa, int npb);   // 0 = default
 long long gemm_tc_launches();                // tcgen05 kernel launches so far (tests check the path taken)
 // A and W: 16-bit operands of ONE format (fp16 when is_fp16, else bf16); c_act / ln_act are written in the same type.
 int gemm_tc(const void* A, int is_fp16, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-            const RowMap& rmap, const TcWorkspace& ws, cudaStream_t st);
+            const RowMap& rmap, const TcWorkspace& ws, cudaStream_t st, int* deferred_splits = nullptr);
 
 // ---- frontend --------------------------------------------------------------------------------
 struct FbankParams {
@@ -235,6 +239,10 @@ void adapter_gather(int B, int T, int D, int k, AGather* ga, RowMap* rm);
 template <typename TA>
 int layer_norm(const float* x, int M, int D, const float* gamma, const float* beta, float eps, int act,
                float out_scale, TA* y_act, float* y_f32, cudaStream_t st);
+// x (M, D) += bias + sum_{s < nsplit} partial[s] (fixed order), then the row norm of the updated x (D <= 1024)
+template <typename TA>
+int layer_norm_reduce(float* x, const float* partial, int nsplit, const float* bias, int M, int D, const float* gamma,
+                      const float* beta, float eps, TA* y_act, float* y_f32, cudaStream_t st);
 // scale-copy (input-layer "none"): y = x * s
 int scale_rows(const float* x, float* y, long long n, float s, cudaStream_t st);
 // adapter staging: virtual rows x[b][0..k-2] = cache (or 0), x[b][k-1+i] = enc_out[b][i] (zeroed where

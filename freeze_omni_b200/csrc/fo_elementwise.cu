@@ -153,6 +153,84 @@ layer_norm_kernel(const float* __restrict__ x, int M, int D, const float* __rest
         }
 }
 
+// LayerNorm that also finishes a deferred split-K reduction (Epilogue::defer_reduce): x += bias + sum_s partial_s in
+// split order (deterministic), x written back, then the row norm.  One warp per row, D <= 1024.
+template <typename TA>
+__global__ void __launch_bounds__(128)
+layer_norm_reduce_kernel(float* __restrict__ x, const float* __restrict__ partial, int nsplit, const float* __restrict__ bias,
+                         int M, int D, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                         TA* __restrict__ y_act, float* __restrict__ y_f32) {
+    FO_PDL_TRIGGER();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int nv = D >> 7;
+    float4 g[8], bt[8], bs[8], v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) {                            // constants: before the dependency wait
+            g[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+            bt[i] = *reinterpret_cast<const float4*>(beta + (i * 32 + lane) * 4);
+            bs[i] = bias ? *reinterpret_cast<const float4*>(bias + (i * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    FO_PDL_WAIT();
+    if (row >= M) return;
+    float4* xr = reinterpret_cast<float4*>(x + (long long)row * D);
+    const long long split_stride = ((long long)M * D) >> 2;
+    const float4* pr = reinterpret_cast<const float4*>(partial + (long long)row * D);
+    float4 xv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+            xv[i] = xr[i * 32 + lane];
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    // same association as the GEMM's own split-K epilogue: ((sum_s partial_s) + bias) + residual -> bit-identical results
+    for (int s = 0; s < nsplit; ++s) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nv) {
+                const float4 a = __ldcg(pr + s * split_stride + i * 32 + lane);
+                v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+            v[i].x = (v[i].x + bs[i].x) + xv[i].x; v[i].y = (v[i].y + bs[i].y) + xv[i].y;
+            v[i].z = (v[i].z + bs[i].z) + xv[i].z; v[i].w = (v[i].w + bs[i].w) + xv[i].w;
+        }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+            xr[i * 32 + lane] = v[i];
+            sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    const float mu = warp_sum(sum) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+            const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+            q += a * a + b * b + c * c + d * d;
+        }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) {
+            const int col = (i * 32 + lane) * 4;
+            const float o0 = (v[i].x - mu) * rstd * g[i].x + bt[i].x, o1 = (v[i].y - mu) * rstd * g[i].y + bt[i].y;
+            const float o2 = (v[i].z - mu) * rstd * g[i].z + bt[i].z, o3 = (v[i].w - mu) * rstd * g[i].w + bt[i].w;
+            const long long off = (long long)row * D + col;
+            if (y_f32) *reinterpret_cast<float4*>(y_f32 + off) = make_float4(o0, o1, o2, o3);
+            if (y_act) {
+                TA t[4] = {from_f<TA>(o0), from_f<TA>(o1), from_f<TA>(o2), from_f<TA>(o3)};
+                if (sizeof(TA) == 2) *reinterpret_cast<uint2*>(y_act + off) = *reinterpret_cast<uint2*>(t);
+                else *reinterpret_cast<uint4*>(y_act + off) = *reinterpret_cast<uint4*>(t);
+            }
+        }
+}
+
 __global__ void scale_rows_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float s) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = x[i] * s;
@@ -396,6 +474,8 @@ int layer_norm(const float* x, int M, int D, const float* gamma, const float* be
     dim3 grid(cdiv(M, rows_per_cta));
     if (D <= 1024)
         FO_CUDA(launch_pdl(layer_norm_kernel<TA, 8>, grid, dim3(128), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
+    else if (D <= 2048)      // the adapter's norm over 2C: half the registers of the general variant
+        FO_CUDA(launch_pdl(layer_norm_kernel<TA, 16>, grid, dim3(128), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
     else
         FO_CUDA(launch_pdl(layer_norm_kernel<TA, 32>, grid, dim3(128), 0, st, x, M, D, gamma, beta, eps, act, out_scale, y_act, y_f32));
     FO_LAUNCHED();
@@ -405,6 +485,20 @@ int layer_norm(const float* x, int M, int D, const float* gamma, const float* be
 template int layer_norm<float>(const float*, int, int, const float*, const float*, float, int, float, float*, float*, cudaStream_t);
 template int layer_norm<bf16>(const float*, int, int, const float*, const float*, float, int, float, bf16*, float*, cudaStream_t);
 template int layer_norm<__half>(const float*, int, int, const float*, const float*, float, int, float, __half*, float*, cudaStream_t);
+
+template <typename TA>
+int layer_norm_reduce(float* x, const float* partial, int nsplit, const float* bias, int M, int D, const float* gamma,
+                      const float* beta, float eps, TA* y_act, float* y_f32, cudaStream_t st) {
+    if (M <= 0) return 0;
+    FO_CHECK(D % 128 == 0 && D <= 1024, "layer_norm_reduce: D=%d not supported", D);
+    FO_CUDA(launch_pdl(layer_norm_reduce_kernel<TA>, dim3(cdiv(M, 4)), dim3(128), 0, st, x, partial, nsplit, bias, M, D, gamma, beta,
+                       eps, y_act, y_f32));
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int layer_norm_reduce<float>(float*, const float*, int, const float*, int, int, const float*, const float*, float, float*, float*, cudaStream_t);
+template int layer_norm_reduce<__half>(float*, const float*, int, const float*, int, int, const float*, const float*, float, __half*, float*, cudaStream_t);
 
 int scale_rows(const float* x, float* y, long long n, float s, cudaStream_t st) {
     if (n <= 0) return 0;

@@ -55,6 +55,7 @@ struct TcParams {
     int npa, npb;                // TMA producer threads per operand: each loads a 128/npa (bn/npb) row slice of every stage,
                                  // several bulk-tensor copies in flight per SM instead of one large one
     int act_fp16;                // activations (and c_act / ln_act outputs) are IEEE fp16 instead of bf16
+    int defer;                   // split-K partials as [split][rows_b][n_out] fp32 for the LayerNorm that follows (swap = 1 only)
     int stages;
     int tmem_cols;
     TcOperand op_a, op_b;
@@ -291,7 +292,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         if (et == 0) TC_TRACE(8);
         const long long tile_id = (long long)tile_b * gridDim.x + tile_a;
-        if (nsplit > 1) {
+        if (p.defer) {
+            // deferred reduction: this thread owns output column n; a warp's store of one token is one 128-byte line
+            const int n = tile_a * BM + row_l;
+            float* dst = p.partial + ((long long)split * p.rows_b) * p.n_out + n;
+            for (int c0 = 0; c0 < bn; c0 += 16) {
+                float v[16];
+                tc_ld16(taddr + c0, v);
+                const int m0 = tile_b * bn + c0;
+                if (n < p.n_out) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (m0 + j < p.rows_b) __stcg(dst + (long long)(m0 + j) * p.n_out, v[j]);
+                }
+            }
+            if (et == 0) is_last_s = 0;
+        } else if (nsplit > 1) {
             // raw partial tile: [split][tile][col][128 rows] so that a warp's store is one 128-byte line
             float* mine = p.partial + (((long long)split * gridDim.x * gridDim.y + tile_id) * bn) * BM;
             for (int c0 = 0; c0 < bn; c0 += 16) {
@@ -344,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
-        if (nsplit == 1 && et == 0) is_last_s = 1;
+        if (nsplit == 1 && !p.defer && et == 0) is_last_s = 1;
     }
     // ---- coalesced write-out by all 7 warps: consecutive lanes = consecutive output columns, 4 per lane ----
     // swap=0: staging rows are C rows, bn columns starting at n0;  swap=1: staging "columns" are C rows,
@@ -829,7 +845,8 @@ void gemm_tc_force_producers(int npa, int npb) { g_forced_npa = npa; g_forced_np
 long long gemm_tc_launches() { return g_tc_launches; }
 
 int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-            const RowMap& rmap, const TcWorkspace& ws, cudaStream_t st) {
+            const RowMap& rmap, const TcWorkspace& ws, cudaStream_t st, int* deferred_splits) {
+    if (deferred_splits) *deferred_splits = 0;
     if (!g_encode || !ws.partial) return 1;
     if (K % BK != 0 || ga.seg_len % BK != 0 || ep.ldc % 8 != 0 || N % 8 != 0 || ep.split_col % 16 != 0) return 1;
     if (ep.residual && ep.residual != ep.c_f32) { /* residual rows are read at the remapped output row: fine */ }
@@ -948,6 +965,11 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     if (pl.split > 1) {
         const size_t need = (size_t)pl.split * ta * tb * pl.bn * BM * sizeof(float);
         FO_CHECK(need <= ws.partial_bytes, "gemm_tc: split-K workspace too small (%zu bytes needed)", need);
+    }
+    if (ep.defer_reduce && deferred_splits && pl.swap == 1 && pl.split > 1 && rmap.p1 == 0 && !ep.ln_gamma && N == ep.ldc &&
+        (size_t)pl.split * M * N * sizeof(float) <= ws.partial_bytes) {
+        p.defer = 1;
+        *deferred_splits = pl.split;
     }
     CUtensorMap map_act, map_w;
     FO_TRY(make_map(&map_act, reinterpret_cast<const bf16*>(A), ga.seg_len, ga.rows, ga.planes, pl.swap ? pl.bn / p.npb : BM / p.npa));
