@@ -747,7 +747,7 @@ int make_map_uncached(CUtensorMap* map, const bf16* base, int seg_len, long long
 int round16(int x) { return (x + 15) / 16 * 16; }
 
 // Tile plan.  Measured on B200 (profiles/r01_*_gemm_sweep*.jsonl):
-//  * skinny GEMMs (<= 384 activation rows: every streaming-step GEMM at 64 sessions) are latency bound, so the
+//  * skinny GEMMs (<= 1024 activation rows: every layer GEMM of a streaming step up to 256 sessions) are latency bound, so the
 //    weights go on the 128-row UMMA-M side (`swap`), the activation rows are cut into UMMA-N slices as small as
 //    needed to put ~148 CTAs in flight, and K is split only when a CTA would otherwise walk more than 32 k-blocks
 //    (or when the grid would leave most SMs idle);
@@ -756,10 +756,16 @@ int round16(int x) { return (x + 15) / 16 * 16; }
 //    under a multiple of the SM count (wave quantisation), whichever model cost is lower.
 struct Plan { int swap, bn, split; double cost; };
 
-Plan choose_plan(long long act_rows, int n_out, int K) {
+int skinny_rows() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("FO_TC_SKINNY"); v = e ? atoi(e) : 1024; }
+    return v;
+}
+
+Plan choose_plan(long long act_rows, int n_out, int K, bool can_defer = false) {
     const int kblocks = K / BK;
     const int sms = g_sm_count;
-    if (act_rows <= 384) {
+    if (act_rows <= skinny_rows()) {
         const int ta = (n_out + BM - 1) / BM;
         // two CTAs fit one SM (<= 100 KB of stages each) and hide each other's fill / epilogue: up to 2 x SMs CTAs, K split
         // so that a CTA walks ~16 k-blocks (r72 sweep: FFN2 (1,32,4) 11.8 us vs (1,32,2) 15.5 us, QKV (1,32,1) 7.6 vs 8.1)
@@ -770,7 +776,15 @@ Plan choose_plan(long long act_rows, int n_out, int K) {
             occ = e1 ? atoi(e1) : 2;
             kbt = e2 ? atoi(e2) : 16;
         }
-        int split = std::min(4, (kblocks + kbt - 1) / kbt);
+        static int kbd = 0, smax = 0;
+        if (!kbd) {
+            const char* e4 = getenv("FO_TC_KBD");
+            const char* e5 = getenv("FO_TC_SMAX");
+            kbd = e4 ? atoi(e4) : 8;
+            smax = e5 ? atoi(e5) : 4;
+        }
+        // a deferred reduction (Epilogue::defer_reduce) has no serial tail, so K can be cut finer
+        int split = can_defer ? std::min(smax, (kblocks + kbd - 1) / kbd) : std::min(4, (kblocks + kbt - 1) / kbt);
         int bn = 256;
         const int cands[5] = {16, 32, 64, 128, 256};
         for (int ci = 0; ci < 5; ++ci) {                       // smallest slice that keeps the grid within two CTAs per SM
@@ -891,7 +905,8 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
             return 0;
         }
     }
-    Plan pl = choose_plan(M, N, K);
+    const bool can_defer = ep.defer_reduce && deferred_splits && rmap.p1 == 0 && !ep.ln_gamma && N == ep.ldc;
+    Plan pl = choose_plan(M, N, K, can_defer);
     if (g_forced.swap >= 0) pl.swap = g_forced.swap;
     if (g_forced.bn > 0) pl.bn = g_forced.bn;
     if (g_forced.split > 0) pl.split = g_forced.split;
@@ -921,7 +936,7 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     if (pl.bn % (8 * p.npb) != 0) p.npb = 1;
     const uint32_t stage = (BM + pl.bn) * BK * 2;
     p.stages = std::max(1, std::min<int>(std::min(MAX_STAGES, kbs), (int)(SMEM_BUDGET / stage)));
-    if (M <= 384) {
+    if (M <= skinny_rows()) {
         // skinny GEMMs: ~100 KB in flight per CTA covers the L2 latency; staying under half of the shared memory lets a
         // second CTA (another session group's GEMM, or the next kernel's first wave) be resident on the same SM
         static int occ_cap = 0;
