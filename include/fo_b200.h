@@ -167,9 +167,16 @@ int fo_adapter_forward(fo_ctx* ctx, const float* x, const uint8_t* mask, int B, 
 
 /* ---- introspection / tuning ---- */
 int fo_stats(fo_ctx* ctx, fo_stats_t* out);
-/* options: "gemm_backend" 0 = SIMT FFMA, 1 = tcgen05 (bf16 context only); "use_graph" 0/1 (CUDA-graph replay of the streaming
- * step); "session_groups" 1..4 (layer kernels of session groups on parallel streams); "fuse_ln" 0/1; "profile_gemm" 0/1;
- * "tc_swap"/"tc_bn"/"tc_split" force the tile plan of the tcgen05 GEMM (-1 = cost model); "debug_skip" (timing attribution). */
+/* options (value = default):
+ *   "gemm_backend" 0 = SIMT FFMA, 1 = tcgen05 (bf16 contexts; their default)      "use_graph" 1: CUDA-graph replay of the streaming step
+ *   "pdl" 1: programmatic dependent launch along the kernel chain                   "l2_prefetch" 0: next-kernel L2 prefetch, bit0 weights, bit1 KV rings
+ *   "defer_reduce" 1: split-K GEMMs of the residual stream leave the reduction to the LayerNorm that follows
+ *   "tc_persist" 1: persistent tile loop for fat short-K GEMMs (offline path)       "fuse_ln" 0: LayerNorm inside the residual GEMM's epilogue
+ *   "session_groups" 1 (..4): layer kernels of session groups on parallel streams   "stack_kernel" 0: the 24 layers as one cooperative persistent kernel
+ *   "profile_gemm" 0/1, "debug_skip" (timing attribution), "tc_swap"/"tc_bn"/"tc_split" (-1 = cost model): development
+ * get-only: "tc_launches", "tc_persist_launches", "stack_launches", "ring_cap", "max_t", "profile_gemm_us", "profile_gemm_count".
+ * Development environment variables read once per process: FO_TC_OCC, FO_TC_KB, FO_TC_KBD, FO_TC_SMAX, FO_TC_CAP, FO_TC_SKINNY (tile
+ * plan of the skinny GEMMs), FO_PDL_MIN, FO_STACK_TRACE / FO_STACK_DBG, FO_PERSIST_DBG, FO_TC_TRACE. */
 int fo_set_option(fo_ctx* ctx, const char* name, int64_t value);
 int fo_get_option(fo_ctx* ctx, const char* name, int64_t* value);
 /* per-shape totals of the GEMM launches timed while option "profile_gemm" was 1: text lines "M N K launches microseconds"
