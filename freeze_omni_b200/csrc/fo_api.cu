@@ -261,7 +261,7 @@ int gemm_raw<act16>(fo_ctx* c, const act16* A, const AGather& ga, const void* W,
         if (!c->fuse_ln) e.ln_gamma = nullptr;
         // the split-K reduction can ride on the LayerNorm that follows (residual stream in place, rows normalised next)
         e.defer_reduce = c->defer_reduce && ep.ln_gamma && !c->fuse_ln && ep.residual == ep.c_f32 && ep.c_f32 && !ep.c_act &&
-                         !ep.relu && ep.scale == 1.0f && N <= 1024;
+                         !ep.relu && ep.scale == 1.0f && N <= 1024 && N % 256 == 0;
         int r = gemm_tc(A, 1, ga, W, M, N, K, e, rm, *c->tc_cur, st, deferred);
         if (r == 0) *fused_ln = e.ln_gamma != nullptr;
         if (r <= 0) return r;

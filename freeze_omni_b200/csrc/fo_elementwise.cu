@@ -154,71 +154,95 @@ layer_norm_kernel(const float* __restrict__ x, int M, int D, const float* __rest
 }
 
 // LayerNorm that also finishes a deferred split-K reduction (Epilogue::defer_reduce): x += bias + sum_s partial_s in
-// split order (deterministic), x written back, then the row norm.  One warp per row, D <= 1024.
-template <typename TA>
+// split order (deterministic), x written back, then the row norm.  TWO warps per row (each lane holds D/256 float4 of the
+// row), so that x and all NS partial rows are in flight together: with one warp per row the partial loads of the splits
+// went out one after the other (5.1 us per launch in profiles/r01_j, 14 % of the step).  D <= 1024, D % 256 == 0.
+template <typename TA, int NS>
 __global__ void __launch_bounds__(128)
 layer_norm_reduce_kernel(float* __restrict__ x, const float* __restrict__ partial, int nsplit, const float* __restrict__ bias,
                          int M, int D, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                          TA* __restrict__ y_act, float* __restrict__ y_f32) {
+    __shared__ float red[2][2][2];               // [row in CTA][half][sum | sq]
     FO_PDL_TRIGGER();
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    const int nv = D >> 7;
-    float4 g[8], bt[8], bs[8], v[8];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rr = wid >> 1, half = wid & 1;
+    const int row = blockIdx.x * 2 + rr;
+    const int nv = D >> 8;                       // float4 per lane
+    const int f0 = half * (D >> 3) + lane;       // first float4 of this lane within the row (half a row = D/8 float4)
+    float4 g[4], bt[4], bs[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
         if (i < nv) {                            // constants: before the dependency wait
-            g[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
-            bt[i] = *reinterpret_cast<const float4*>(beta + (i * 32 + lane) * 4);
-            bs[i] = bias ? *reinterpret_cast<const float4*>(bias + (i * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g[i] = *(reinterpret_cast<const float4*>(gamma) + f0 + i * 32);
+            bt[i] = *(reinterpret_cast<const float4*>(beta) + f0 + i * 32);
+            bs[i] = bias ? *(reinterpret_cast<const float4*>(bias) + f0 + i * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     FO_PDL_WAIT();
-    if (row >= M) return;
-    float4* xr = reinterpret_cast<float4*>(x + (long long)row * D);
+    const bool live = row < M;
+    float4* xr = reinterpret_cast<float4*>(x + (long long)(live ? row : 0) * D) + f0;
     const long long split_stride = ((long long)M * D) >> 2;
-    const float4* pr = reinterpret_cast<const float4*>(partial + (long long)row * D);
-    float4 xv[8];
+    const float4* pr = reinterpret_cast<const float4*>(partial + (long long)(live ? row : 0) * D) + f0;
+    float4 xv[4], v[4];
+    if (live) {
+        float4 pv[NS > 0 ? NS : 1][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-            xv[i] = xr[i * 32 + lane];
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i)
+            if (i < nv) xv[i] = xr[i * 32];
+        if (NS > 0) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nv) pv[s][i] = __ldcg(pr + s * split_stride + i * 32);
         }
-    // same association as the GEMM's own split-K epilogue: ((sum_s partial_s) + bias) + residual -> bit-identical results
-    for (int s = 0; s < nsplit; ++s) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (i < nv) {
-                const float4 a = __ldcg(pr + s * split_stride + i * 32 + lane);
-                v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
-            }
+        for (int i = 0; i < 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // same association as the GEMM's own split-K epilogue: ((sum_s partial_s) + bias) + residual -> bit-identical results
+        if (NS > 0) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nv) { v[i].x += pv[s][i].x; v[i].y += pv[s][i].y; v[i].z += pv[s][i].z; v[i].w += pv[s][i].w; }
+        } else {
+            for (int s = 0; s < nsplit; ++s)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nv) {
+                        const float4 a = __ldcg(pr + s * split_stride + i * 32);
+                        v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+                    }
+        }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-            v[i].x = (v[i].x + bs[i].x) + xv[i].x; v[i].y = (v[i].y + bs[i].y) + xv[i].y;
-            v[i].z = (v[i].z + bs[i].z) + xv[i].z; v[i].w = (v[i].w + bs[i].w) + xv[i].w;
-        }
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (i < nv) {
-            xr[i * 32 + lane] = v[i];
+    for (int i = 0; i < 4; ++i)
+        if (i < nv && live) {
+            v[i].x = (v[i].x + bs[i].x) + xv[i].x; v[i].y = (v[i].y + bs[i].y) + xv[i].y;
+            v[i].z = (v[i].z + bs[i].z) + xv[i].z; v[i].w = (v[i].w + bs[i].w) + xv[i].w;
+            xr[i * 32] = v[i];
             sum += v[i].x + v[i].y + v[i].z + v[i].w;
         }
-    const float mu = warp_sum(sum) / D;
+    sum = warp_sum(sum);
+    if (lane == 0) red[rr][half][0] = sum;
+    __syncthreads();
+    const float mu = (red[rr][0][0] + red[rr][1][0]) / D;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (i < nv) {
+    for (int i = 0; i < 4; ++i)
+        if (i < nv && live) {
             const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
             q += a * a + b * b + c * c + d * d;
         }
-    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+    q = warp_sum(q);
+    if (lane == 0) red[rr][half][1] = q;
+    __syncthreads();
+    if (!live) return;
+    const float rstd = rsqrtf((red[rr][0][1] + red[rr][1][1]) / D + eps);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
         if (i < nv) {
-            const int col = (i * 32 + lane) * 4;
+            const int col = (f0 + i * 32) * 4;
             const float o0 = (v[i].x - mu) * rstd * g[i].x + bt[i].x, o1 = (v[i].y - mu) * rstd * g[i].y + bt[i].y;
             const float o2 = (v[i].z - mu) * rstd * g[i].z + bt[i].z, o3 = (v[i].w - mu) * rstd * g[i].w + bt[i].w;
             const long long off = (long long)row * D + col;
@@ -490,9 +514,14 @@ template <typename TA>
 int layer_norm_reduce(float* x, const float* partial, int nsplit, const float* bias, int M, int D, const float* gamma,
                       const float* beta, float eps, TA* y_act, float* y_f32, cudaStream_t st) {
     if (M <= 0) return 0;
-    FO_CHECK(D % 128 == 0 && D <= 1024, "layer_norm_reduce: D=%d not supported", D);
-    FO_CUDA(launch_pdl(layer_norm_reduce_kernel<TA>, dim3(cdiv(M, 4)), dim3(128), 0, st, x, partial, nsplit, bias, M, D, gamma, beta,
-                       eps, y_act, y_f32));
+    FO_CHECK(D % 256 == 0 && D <= 1024, "layer_norm_reduce: D=%d not supported", D);
+    const dim3 grid(cdiv(M, 2));
+    if (nsplit == 2)
+        FO_CUDA(launch_pdl(layer_norm_reduce_kernel<TA, 2>, grid, dim3(128), 0, st, x, partial, nsplit, bias, M, D, gamma, beta, eps, y_act, y_f32));
+    else if (nsplit == 4)
+        FO_CUDA(launch_pdl(layer_norm_reduce_kernel<TA, 4>, grid, dim3(128), 0, st, x, partial, nsplit, bias, M, D, gamma, beta, eps, y_act, y_f32));
+    else
+        FO_CUDA(launch_pdl(layer_norm_reduce_kernel<TA, 0>, grid, dim3(128), 0, st, x, partial, nsplit, bias, M, D, gamma, beta, eps, y_act, y_f32));
     FO_LAUNCHED();
     FO_CUDA(cudaGetLastError());
     return 0;
