@@ -262,6 +262,8 @@ int gemm_raw<act16>(fo_ctx* c, const act16* A, const AGather& ga, const void* W,
         // the split-K reduction can ride on the LayerNorm that follows (residual stream in place, rows normalised next)
         e.defer_reduce = c->defer_reduce && ep.ln_gamma && !c->fuse_ln && ep.residual == ep.c_f32 && ep.c_f32 && !ep.c_act &&
                          !ep.relu && ep.scale == 1.0f && N <= 1024 && N % 256 == 0;
+        // ... or on a consumer kernel that asked for it (QKV -> streaming attention): bias only, no residual / activation
+        if (ep.defer_reduce == 2 && c->defer_reduce && !ep.relu && ep.scale == 1.0f && !ep.residual && !ep.ln_gamma) e.defer_reduce = 2;
         int r = gemm_tc(A, 1, ga, W, M, N, K, e, rm, *c->tc_cur, st, deferred);
         if (r == 0) *fused_ln = e.ln_gamma != nullptr;
         if (r <= 0) return r;
@@ -270,7 +272,7 @@ int gemm_raw<act16>(fo_ctx* c, const act16* A, const AGather& ga, const void* W,
 }
 template <typename TA>
 int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
-         const RowMap& rm, cudaStream_t st) {
+         const RowMap& rm, cudaStream_t st, int* deferred_out = nullptr) {
     bool fused = false;
     int deferred = 0;
     int r;
@@ -287,6 +289,7 @@ int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N,
         FO_CUDA(cudaEventRecord(e1, st));
         c->prof_events.push_back(fo_ctx::ProfRec{e0, e1, M, N, K});
     }
+    if (deferred_out) { *deferred_out = deferred; return r; }      // the caller's next kernel finishes the sum
     if (r == 0 && deferred > 0)                   // the GEMM left raw split-K partials: the LayerNorm finishes the sum
         return layer_norm_reduce<TA>(ep.c_f32, c->tc_cur->partial, deferred, ep.bias, M, N, ep.ln_gamma, ep.ln_beta, ep.ln_eps,
                                      reinterpret_cast<TA*>(ep.ln_act), ep.ln_f32, st);
@@ -625,8 +628,10 @@ inline L2Prefetch pf1(const void* p, long long bytes) {
     return f;
 }
 template <typename TA>
-int layer_pre(fo_ctx* c, const LayerW& w, int M, TA* h, TA* qkv, float* q32, const L2Prefetch& pf, cudaStream_t st) {
+int layer_pre(fo_ctx* c, const LayerW& w, int M, TA* h, TA* qkv, float* q32, const L2Prefetch& pf, cudaStream_t st,
+              int* deferred = nullptr) {
     const int D = c->D;
+    if (deferred) *deferred = 0;
     if (c->debug_skip & 4) return 0;
     Epilogue e;
     e.prefetch = pf;
@@ -636,6 +641,14 @@ int layer_pre(fo_ctx* c, const LayerW& w, int M, TA* h, TA* qkv, float* q32, con
     if (sizeof(TA) == 2) {            // bf16 context: Q stays fp32 (columns < D), K|V are written as bf16
         e.c_f32 = q32;
         e.split_col = D;
+    }
+    static int qkv_defer_max_rows = -1;
+    if (qkv_defer_max_rows < 0) { const char* e0 = getenv("FO_QKV_DEFER_MAXM"); qkv_defer_max_rows = e0 ? atoi(e0) : 128; }
+    // streaming, few rows: the attention kernel finishes a split-K sum of the QKV GEMM while it loads its rows (r102: -7 % of
+    // the step at 1 session, -1 % at 32; at 64 sessions the fp32 partial traffic costs more than the finer K split gains: +4 %)
+    if (deferred && sizeof(TA) == 2 && M <= qkv_defer_max_rows) {
+        e.defer_reduce = 2;
+        return gemm<TA>(c, h, plain_rows(D, M), w.wqkv, M, 3 * D, D, e, RowMap(), st, deferred);
     }
     return gemm<TA>(c, h, w.wqkv, M, 3 * D, D, e, st);
 }
@@ -789,7 +802,14 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
                 pfq.bytes[1] = (long long)D * D * c->esz;
                 a.prefetch = pf1(w.w1, (long long)D * FF * c->esz);                       // attention runs: FFN1's weights
             }
-            if (r == 0) r = layer_pre<TA>(c, w, Mg, hg, qkvg, q32g, pfq, sg);
+            int qkv_splits = 0;
+            if (r == 0) r = layer_pre<TA>(c, w, Mg, hg, qkvg, q32g, pfq, sg, &qkv_splits);
+            if (qkv_splits > 0) {
+                a.part = c->tc_cur->partial;
+                a.part_bias = w.bqkv;
+                a.nsplit = qkv_splits;
+                a.part_stride = (long long)Mg * 3 * D;
+            }
             if (r == 0 && !(c->debug_skip & 1))
                 r = attention_stream<TA>(a, qkvg, q32g, reinterpret_cast<TA*>(c->ring) + l * layer_stride,
                                          reinterpret_cast<const TA*>(w.ptab_h), w.pos_u, w.pos_v, attg, sg);

@@ -344,6 +344,7 @@ __device__ unsigned long long g_attn_trace[16];
 #define AT_TRACE(slot) do { } while (0)
 #endif
 
+template <bool DEFER>            // DEFER: q / k / v of the chunk are summed from the QKV GEMM's split-K partials (AttnStream::part)
 __global__ void __launch_bounds__(ATT_THREADS, 7)
 attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const float* __restrict__ q32,
                             __half* __restrict__ ring, const __half* __restrict__ ptab_h, const float* __restrict__ pos_u,
@@ -418,11 +419,35 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
     uint4 newv = make_uint4(0, 0, 0, 0);
     int new_which = 0, new_r = 0, new_c = 0;
     const bool has_new = tid < n_new;
+    // one 16-byte chunk (8 dims) of a new K / V row: from the finished fp16 rows, or summed from the QKV GEMM's split-K partials
+    auto load_new = [&](int which, int r, int cc) -> uint4 {
+        const long long off = (long long)(b * t + r) * 3 * D + (which + 1) * D + h * DK + cc * EPC;
+        if constexpr (!DEFER) return *reinterpret_cast<const uint4*>(qkv + off);
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        for (int sp = 0; sp < a.nsplit; ++sp) {
+            const float4 p0 = __ldcg(reinterpret_cast<const float4*>(a.part + sp * a.part_stride + off));
+            const float4 p1 = __ldcg(reinterpret_cast<const float4*>(a.part + sp * a.part_stride + off + 4));
+            lo.x += p0.x; lo.y += p0.y; lo.z += p0.z; lo.w += p0.w;
+            hi.x += p1.x; hi.y += p1.y; hi.z += p1.z; hi.w += p1.w;
+        }
+        const float* bp = a.part_bias + (which + 1) * D + h * DK + cc * EPC;
+        uint4 o;
+        o.x = pack2<TA>(lo.x + bp[0], lo.y + bp[1]); o.y = pack2<TA>(lo.z + bp[2], lo.w + bp[3]);
+        o.z = pack2<TA>(hi.x + bp[4], hi.y + bp[5]); o.w = pack2<TA>(hi.z + bp[6], hi.w + bp[7]);
+        return o;
+    };
+    auto load_q = [&](int r, int d) -> float {
+        const long long off = (long long)(b * t + r) * 3 * D + h * DK + d;
+        if constexpr (!DEFER) return q32[off];
+        float acc = 0.f;
+        for (int sp = 0; sp < a.nsplit; ++sp) acc += __ldcg(a.part + sp * a.part_stride + off);
+        return acc + a.part_bias[h * DK + d];
+    };
     if (has_new) {
         new_which = tid / (t * NCH);
         new_r = (tid / NCH) % t;
         new_c = tid % NCH;
-        newv = *reinterpret_cast<const uint4*>(qkv + (long long)(b * t + new_r) * 3 * D + (new_which + 1) * D + h * DK + new_c * EPC);
+        newv = load_new(new_which, new_r, new_c);
     }
     float qreg[4];
 #pragma unroll
@@ -430,7 +455,7 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
         const int i = tid + k * ATT_THREADS;
         if (i < t * DK) {
             const int r = i / DK, d = i % DK;
-            qreg[k] = q32[(long long)(b * t + r) * 3 * D + h * DK + d];
+            qreg[k] = load_q(r, d);
         }
     }
     l2_prefetch_slice(a.prefetch, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, tid, ATT_THREADS);
@@ -443,7 +468,7 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
     }
     for (int i = tid + ATT_THREADS; i < n_new; i += ATT_THREADS) {      // t > 8 only
         const int which = i / (t * NCH), r = (i / NCH) % t, c = i % NCH;
-        const uint4 val = *reinterpret_cast<const uint4*>(qkv + (long long)(b * t + r) * 3 * D + (which + 1) * D + h * DK + c * EPC);
+        const uint4 val = load_new(which, r, c);
         const int pc = c ^ ((nf + r) & 7);
         *reinterpret_cast<uint4*>((which ? Vs : Ks) + (cl + r) * DK + pc * EPC) = val;
         *reinterpret_cast<uint4*>((which ? ringV : ringK) + (long long)((nf + r) % cap) * DK + pc * EPC) = val;
@@ -468,7 +493,7 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
     }
     for (int i = tid + 4 * ATT_THREADS; i < t * DK; i += ATT_THREADS) {
         const int r = i / DK, d = i % DK;
-        const float q = q32[(long long)(b * t + r) * 3 * D + h * DK + d];
+        const float q = load_q(r, d);
         const int o = r * DK + (((d >> 3) ^ (r & 7)) << 3) + (d & 7);
         quh[o] = from_f<TA>(q + pos_u[h * DK + d]);
         qvh[o] = from_f<TA>(q + pos_v[h * DK + d]);
@@ -1029,9 +1054,14 @@ int attention_stream(const AttnStream& a, const TA* qkv, const float* q32, TA* r
             const int vrows = (rows + 15) & ~15;
             const size_t sm = (size_t)(2 * rows + vrows) * DK * 2 + (size_t)2 * a.t * DK * 2 + (size_t)a.t * vrows * 2 +
                               (size_t)a.t * std::max(vrows, DK) * 4;
-            FO_CUDA(launch_pdl(attention_stream_mma_kernel, grid, dim3(ATT_THREADS), sm, st, a, reinterpret_cast<const __half*>(qkv), q32,
-                               reinterpret_cast<__half*>(ring), reinterpret_cast<const __half*>(ptab_h), pos_u, pos_v,
-                               reinterpret_cast<__half*>(out)));
+            if (a.nsplit > 0)
+                FO_CUDA(launch_pdl(attention_stream_mma_kernel<true>, grid, dim3(ATT_THREADS), sm, st, a, reinterpret_cast<const __half*>(qkv), q32,
+                                   reinterpret_cast<__half*>(ring), reinterpret_cast<const __half*>(ptab_h), pos_u, pos_v,
+                                   reinterpret_cast<__half*>(out)));
+            else
+                FO_CUDA(launch_pdl(attention_stream_mma_kernel<false>, grid, dim3(ATT_THREADS), sm, st, a, reinterpret_cast<const __half*>(qkv), q32,
+                                   reinterpret_cast<__half*>(ring), reinterpret_cast<const __half*>(ptab_h), pos_u, pos_v,
+                                   reinterpret_cast<__half*>(out)));
             FO_LAUNCHED();
 #ifdef FO_TC_TRACE_BUILD
             if (getenv("FO_TC_TRACE") && st == nullptr) {

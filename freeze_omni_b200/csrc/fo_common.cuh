@@ -271,6 +271,12 @@ struct AttnStream {
     int n, t, H, ring_cap, window, full_chunk, pe_wrap, pos_rows;
     long long ring_slot_stride;   // elements between sessions of one layer: 2*H*ring_cap*64
     L2Prefetch prefetch;          // cold inputs of the kernels that follow
+    // the QKV GEMM may have left raw split-K partials [nsplit][n*t][3D] fp32 (Epilogue::defer_reduce): the kernel then forms
+    // q / k / v = sum_s partial_s + bias itself instead of reading the finished qkv / q32 rows
+    const float* part = nullptr;
+    const float* part_bias = nullptr;
+    int nsplit = 0;
+    long long part_stride = 0;
 };
 // qkv (n*t, 3*D) activation type (K and V columns are read from it); q32 (n*t, 3*D) fp32 whose first D
 // columns hold Q (the QKV GEMM keeps Q in fp32, Epilogue::split_col); ring = this layer's
