@@ -1379,6 +1379,12 @@ static int stream_common(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     const int km1 = c->KA - 1, t_out = (t + km1 - c->KA) / 2 + 1;
     const size_t enc_bytes = (size_t)n * t * c->D * sizeof(float);
     const size_t y_bytes = (size_t)n * t_out * c->E * sizeof(float);
+    if (c->copy_stream && c->async_ticket > 0) {
+        // a synchronous call after pipelined ones reuses staging set 0 (and the shared intermediates): let the read-backs of
+        // the steps still in flight on the copy stream finish first
+        FO_CUDA(cudaStreamWaitEvent(st, c->ev_out[0], 0));
+        if (c->async_ticket > 1) FO_CUDA(cudaStreamWaitEvent(st, c->ev_out[1], 0));
+    }
     FO_TRY(upload_ids(c, ids, n, st));
     c->pf_slot_lo = c->pf_slot_hi = ids[0];
     for (int i = 1; i < n; ++i) { c->pf_slot_lo = std::min(c->pf_slot_lo, (int)ids[i]); c->pf_slot_hi = std::max(c->pf_slot_hi, (int)ids[i]); }

@@ -604,6 +604,13 @@ def test_async_pipelined_step_matches_sync(shipped16):
         assert torch.equal(ys[6], ref[6][1]) and torch.equal(es[6], ref[6][0])
         with pytest.raises(Exception):
             eng.stream_wait(prev - 3)                                   # older than the two steps in flight
+        # a synchronous call right behind pipelined ones (same staging buffers) without waiting for the last ticket
+        tk = eng.stream_step_async(ids[2:], pcm[0], ys[0], 1.0, enc_out=es[0])
+        e_s, y_s = eng.stream_step(ids[2:], pcm[1], 1.0)
+        eng.stream_wait(tk)
+        e_a = eng.stream_step(ids[:2], pcm[0], 1.0)
+        e_b, y_b = eng.stream_step(ids[:2], pcm[1], 1.0)
+        assert torch.equal(ys[0], e_a[1].cpu()) and torch.equal(y_s, y_b) and torch.equal(e_s, e_b)
         assert eng.state(int(ids[0])) == eng.state(int(ids[2]))
     finally:
         eng.free(ids)
