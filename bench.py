@@ -494,7 +494,8 @@ def main():
                 "share_of_step": gemm_ms / step_ms,
                 "weights_GBs": 751.6e-3 / gemm_ms * 1e3, "weights_frac_of_hbm": 751.6e-3 / gemm_ms * 1e3 / hbm_peak,
                 "note": "M = 4 rows per session puts the layer GEMMs on the weight-streaming / latency side of the ridge "
-                        "(each launch is 8-16 us of pipeline fill, L2->SM ingest and epilogue); gemm_shapes gives per-shape "
+                        "(each launch is 6-12 us of pipeline fill, L2->SM ingest and epilogue, two CTAs per SM overlapping each other; the "
+                        "split-K sums of out-proj / FFN2 are finished by the LayerNorm that follows); gemm_shapes gives per-shape "
                         "rates, conv2 (M = sessions*80 padded rows) is the tensor-bound one; ncu capture in profiles/"}
         for (m, n, k, cnt, us) in sorted(rows, key=lambda r: -r[4]):
             shapes.append({"M": m, "N": n, "K": k, "launches_per_step": cnt / steps_prof, "us_per_launch_eager_events": us / cnt,
