@@ -825,10 +825,10 @@ attention_offline_mma_kernel(const __half* __restrict__ qkv, const float* __rest
     TA* quh = Vs + KT * DK;                                  // QB x 64
     TA* qvh = quh + QB * DK;
     TA* ph = qvh + QB * DK;                                  // QB x OPH
-    float* sc = reinterpret_cast<float*>(ph + QB * OPH);     // QB x OSC scores; at the end the output tile QB x 64
-    float* m_run = sc + QB * OSC;
+    float* m_run = reinterpret_cast<float*>(ph + QB * OPH);
     float* l_run = m_run + QB;
     float* corr = l_run + QB;
+    float* sc = reinterpret_cast<float*>(Ks);                // after the last tile: the output tile QB x 64 (K is dead by then)
     __shared__ int win[QB][2];
 
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -897,74 +897,91 @@ attention_offline_mma_kernel(const __half* __restrict__ qkv, const float* __rest
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        // ---- scores of query group `warp` against the 16-key tiles ----
+        // ---- scores of query group `warp` against the six 16-key tiles, kept in registers: lane (g, c) holds, per tile,
+        //      keys k0+g and k0+g+8 of queries 8w+2c and 8w+2c+1 ----
         const int qrow = warp * 8 + g;                     // B-fragment row (query) of this lane
-        for (int k0 = 0; k0 < nk; k0 += 16) {
+        const int qa = warp * 8 + c * 2;                   // the two queries whose scores this lane holds
+        float sreg[KT / 16][4];
+#pragma unroll
+        for (int kti = 0; kti < KT / 16; ++kti) {
+            const int k0 = kti * 16;
             float d4[4] = {0.f, 0.f, 0.f, 0.f};
-            const int s0k = (k0 + g) & 7, s1k = (k0 + g + 8) & 7;
-            const TA* kr0 = Ks + (k0 + g) * DK + c * 2;
-            const TA* kr1 = Ks + (k0 + g + 8) * DK + c * 2;
-            const TA* pr0 = Ps + (k0 + g) * DK + c * 2;
-            const TA* pr1 = Ps + (k0 + g + 8) * DK + c * 2;
+            if (k0 < nk) {
+                const int s0k = (k0 + g) & 7, s1k = (k0 + g + 8) & 7;
+                const TA* kr0 = Ks + (k0 + g) * DK + c * 2;
+                const TA* kr1 = Ks + (k0 + g + 8) * DK + c * 2;
+                const TA* pr0 = Ps + (k0 + g) * DK + c * 2;
+                const TA* pr1 = Ps + (k0 + g + 8) * DK + c * 2;
 #pragma unroll
-            for (int ks = 0; ks < DK / 16; ++ks) {
-                const int c0 = ks * 2, c1 = ks * 2 + 1;
-                uint32_t af[4], bf[2];
-                af[0] = lds32(kr0 + ((c0 ^ s0k) << 3));
-                af[1] = lds32(kr1 + ((c0 ^ s1k) << 3));
-                af[2] = lds32(kr0 + ((c1 ^ s0k) << 3));
-                af[3] = lds32(kr1 + ((c1 ^ s1k) << 3));
-                bf[0] = lds32(quh + qrow * DK + ((c0 ^ g) << 3) + c * 2);
-                bf[1] = lds32(quh + qrow * DK + ((c1 ^ g) << 3) + c * 2);
-                mma16816(d4, af, bf);
-                af[0] = lds32(pr0 + ((c0 ^ s0k) << 3));
-                af[1] = lds32(pr1 + ((c0 ^ s1k) << 3));
-                af[2] = lds32(pr0 + ((c1 ^ s0k) << 3));
-                af[3] = lds32(pr1 + ((c1 ^ s1k) << 3));
-                bf[0] = lds32(qvh + qrow * DK + ((c0 ^ g) << 3) + c * 2);
-                bf[1] = lds32(qvh + qrow * DK + ((c1 ^ g) << 3) + c * 2);
-                mma16816(d4, af, bf);
-            }
-            const int qa = warp * 8 + c * 2;
-            sc[qa * OSC + k0 + g] = d4[0] * 0.125f;
-            sc[(qa + 1) * OSC + k0 + g] = d4[1] * 0.125f;
-            sc[qa * OSC + k0 + g + 8] = d4[2] * 0.125f;
-            sc[(qa + 1) * OSC + k0 + g + 8] = d4[3] * 0.125f;
-        }
-        __syncwarp();
-        // ---- masked online softmax of this warp's 8 queries; un-normalised probabilities as fp16 ----
-        for (int qi = 0; qi < 8; ++qi) {
-            const int r = warp * 8 + qi;
-            const int lo = win[r][0], hi = win[r][1];
-            float sv[3];
-            float m = -INFINITY;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int j = lane + 32 * k, key = kt + j;
-                sv[k] = (j < nk && key >= lo && key < hi) ? sc[r * OSC + j] : -INFINITY;
-                m = fmaxf(m, sv[k]);
-            }
-            m = warp_max(m);
-            const float m_old = m_run[r];
-            const float m_new = fmaxf(m_old, m);
-            float cf = 1.f, ssum = 0.f;
-            if (m_new != -INFINITY) {
-                cf = __expf(m_old - m_new);                // m_old = -inf -> 0
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    sv[k] = __expf(sv[k] - m_new);         // masked keys: exp(-inf) = 0
-                    ssum += sv[k];
+                for (int ks = 0; ks < DK / 16; ++ks) {
+                    const int c0 = ks * 2, c1 = ks * 2 + 1;
+                    uint32_t af[4], bf[2];
+                    af[0] = lds32(kr0 + ((c0 ^ s0k) << 3));
+                    af[1] = lds32(kr1 + ((c0 ^ s1k) << 3));
+                    af[2] = lds32(kr0 + ((c1 ^ s0k) << 3));
+                    af[3] = lds32(kr1 + ((c1 ^ s1k) << 3));
+                    bf[0] = lds32(quh + qrow * DK + ((c0 ^ g) << 3) + c * 2);
+                    bf[1] = lds32(quh + qrow * DK + ((c1 ^ g) << 3) + c * 2);
+                    mma16816(d4, af, bf);
+                    af[0] = lds32(pr0 + ((c0 ^ s0k) << 3));
+                    af[1] = lds32(pr1 + ((c0 ^ s1k) << 3));
+                    af[2] = lds32(pr0 + ((c1 ^ s0k) << 3));
+                    af[3] = lds32(pr1 + ((c1 ^ s1k) << 3));
+                    bf[0] = lds32(qvh + qrow * DK + ((c0 ^ g) << 3) + c * 2);
+                    bf[1] = lds32(qvh + qrow * DK + ((c1 ^ g) << 3) + c * 2);
+                    mma16816(d4, af, bf);
                 }
-            } else {
-                sv[0] = sv[1] = sv[2] = 0.f;
             }
-            ssum = warp_sum(ssum);
+            sreg[kti][0] = d4[0]; sreg[kti][1] = d4[1]; sreg[kti][2] = d4[2]; sreg[kti][3] = d4[3];
+        }
+        // ---- masked online softmax in registers (reduction over the 8 lanes that share c); un-normalised probabilities as fp16 ----
+        {
+            const int lo0 = win[qa][0], hi0 = win[qa][1], lo1 = win[qa + 1][0], hi1 = win[qa + 1][1];
+            float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) ph[r * OPH + lane + 32 * k] = __float2half_rn(sv[k]);
-            if (lane == 0) {
-                m_run[r] = m_new;
-                l_run[r] = l_run[r] * cf + ssum;
-                corr[r] = cf;
+            for (int kti = 0; kti < KT / 16; ++kti) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int j = kti * 16 + g + hh * 8, key = kt + j;
+                    const bool v0 = j < nk && key >= lo0 && key < hi0, v1 = j < nk && key >= lo1 && key < hi1;
+                    sreg[kti][hh * 2] = v0 ? sreg[kti][hh * 2] * 0.125f : -INFINITY;
+                    sreg[kti][hh * 2 + 1] = v1 ? sreg[kti][hh * 2 + 1] * 0.125f : -INFINITY;
+                    m0 = fmaxf(m0, sreg[kti][hh * 2]);
+                    m1 = fmaxf(m1, sreg[kti][hh * 2 + 1]);
+                }
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+            }
+            const float mo0 = m_run[qa], mo1 = m_run[qa + 1];
+            const float mn0 = fmaxf(mo0, m0), mn1 = fmaxf(mo1, m1);
+            const float cf0 = mn0 == -INFINITY ? 1.f : __expf(mo0 - mn0), cf1 = mn1 == -INFINITY ? 1.f : __expf(mo1 - mn1);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int kti = 0; kti < KT / 16; ++kti) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int j = kti * 16 + g + hh * 8;
+                    const float e0 = mn0 == -INFINITY ? 0.f : __expf(sreg[kti][hh * 2] - mn0);         // masked: exp(-inf) = 0
+                    const float e1 = mn1 == -INFINITY ? 0.f : __expf(sreg[kti][hh * 2 + 1] - mn1);
+                    s0 += e0;
+                    s1 += e1;
+                    ph[qa * OPH + j] = __float2half_rn(e0);
+                    ph[(qa + 1) * OPH + j] = __float2half_rn(e1);
+                }
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            __syncwarp();                                  // every lane has read m_run / l_run of its queries
+            if (g == 0) {
+                m_run[qa] = mn0; m_run[qa + 1] = mn1;
+                l_run[qa] = l_run[qa] * cf0 + s0; l_run[qa + 1] = l_run[qa + 1] * cf1 + s1;
+                corr[qa] = cf0; corr[qa + 1] = cf1;
             }
         }
         __syncthreads();
@@ -1119,7 +1136,7 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
         attr_set[sizeof(TA) == 2] = true;
     }
     if constexpr (sizeof(TA) == 2) {
-        const size_t sm = (size_t)3 * KT * DK * 2 + (size_t)2 * QB * DK * 2 + (size_t)QB * OPH * 2 + (size_t)QB * OSC * 4 + 3 * QB * 4;
+        const size_t sm = (size_t)3 * KT * DK * 2 + (size_t)2 * QB * DK * 2 + (size_t)QB * OPH * 2 + 3 * QB * 4;   // 51 KB: 4 CTAs per SM
         static bool attr2 = false;
         if (!attr2) {
             FO_CUDA(cudaFuncSetAttribute(attention_offline_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
