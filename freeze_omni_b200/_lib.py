@@ -17,7 +17,7 @@ class FoConfig(C.Structure):
         "feat_dim", "d_model", "n_heads", "ffn_dim", "n_layers", "chunk_size", "left_chunks",
         "input_layer_linear", "pos_max_len", "llm_dim", "adapter_kernel", "adapter_gelu",
         "has_encoder", "has_adapter", "sample_rate", "frame_len", "frame_shift", "frames_per_chunk",
-        "context_frames", "max_sessions", "max_stream_frames", "ffn_conv_kernel", "adapter_batchnorm")]
+        "context_frames", "max_sessions", "max_stream_frames", "ffn_conv_kernel", "adapter_batchnorm", "adapter_type")]
 
 
 class FoStats(C.Structure):
@@ -82,7 +82,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.fo_abi_version() != 3:
+    if lib.fo_abi_version() != 4:
         raise RuntimeError("libfo_b200.so ABI version mismatch")
     _lib = lib
     return lib

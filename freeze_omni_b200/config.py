@@ -53,6 +53,7 @@ class PathConfig:
     adapter_kernel: int = 5
     adapter_act: str = "gelu"
     adapter_norm: str = "layer"
+    adapter_type: str = "subsampling"       # 'subsampling' (CNNSubsampling, adapter.py:72-157) | 'linear' (LinearAdapter, :59-70)
     # streaming frontend (bin/inference.py:43-56)
     sample_rate: int = 16000
     frame_length_ms: int = 25
@@ -170,11 +171,12 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
     mc = dict(configs.get("model_conf", {}))
     if encoder_only:
         mc = {"enc_out_dim": d, "llm_embed_dim": d}
-    if mc.get("adpter_type", "subsampling") != "subsampling":
-        raise ValueError("only adpter_type 'subsampling' carries a cache (adapter.py:112)")
+    adpter_type = str(mc.get("adpter_type", "subsampling"))
+    if adpter_type not in ("subsampling", "linear"):
+        raise ValueError("adpter_type 'cnn' (CNNAdapter, adapter.py:10-57) is not built; use 'subsampling' or 'linear'")
     if int(mc.get("enc_out_dim", d)) != d:
         raise ValueError("model_conf.enc_out_dim must equal the encoder output dim")
-    if d * 4 < int(mc.get("llm_embed_dim", 3584)):
+    if adpter_type == "subsampling" and d * 4 < int(mc.get("llm_embed_dim", 3584)):
         raise ValueError("two-conv CNNSubsampling branch (adapter.py:84-96) is not built")
     fe = configs.get("frontend", {})
     cfg = PathConfig(
@@ -188,6 +190,7 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
         ffn_conv_kernel=int(tr["transformer-positionwise-conv-kernel_size"]) if tr["transformer-positionwise-layer-type"] == "conv1d-linear" else 1,
         llm_dim=int(mc.get("llm_embed_dim", 3584)), adapter_kernel=int(mc.get("kernel_size", 5)),
         adapter_act=str(mc.get("activation_func", "gelu")), adapter_norm=str(mc.get("norm", "layer")),
+        adapter_type=adpter_type,
         sample_rate=int(fe.get("sample_rate", 16000)), frame_length_ms=int(fe.get("frame_length_ms", 25)),
         frame_shift_ms=int(fe.get("frame_shift_ms", 10)), frames_per_chunk=int(fe.get("frames_per_chunk", 16)),
         context_frames=int(fe.get("context_frames", 3)), pcm_scale=float(fe.get("pcm_scale", 32768.0)),

@@ -474,7 +474,10 @@ int finalize_t(fo_ctx* c) {
             c->fb_hi = reinterpret_cast<int*>(dhi);
         }
     }
-    if (g.has_adapter) {
+    if (g.has_adapter && g.adapter_type == 1) {
+        FO_TRY(keep_w<TW>(c, "adapter.adpter.weight", {E, D}, &c->ad_proj_w));
+        FO_TRY(keep_f32(c, "adapter.adpter.bias", {E}, &c->ad_proj_b));
+    } else if (g.has_adapter) {
         const HostTensor* t;
         FO_TRY(need(c, "adapter.conv1d2.weight", {2 * D, D, KA}, &t));
         FO_TRY(dev_alloc(c, &c->ad_conv_w, (size_t)2 * D * D * KA * sizeof(TW)));
@@ -524,12 +527,43 @@ FbankParams fbank_params(fo_ctx* c) {
     return p;
 }
 
+// frames the adapter emits for T encoder frames: CNNSubsampling = causal conv(k, stride 2) over k-1 cached / padded frames
+// (adapter.py:137-144); LinearAdapter keeps the frame rate (adapter.py:69-70)
+inline int ad_frames(const fo_ctx* c, int T) {
+    return c->cfg.adapter_type == 1 ? T : (T + c->KA - 1 - c->KA) / 2 + 1;
+}
+
 // ---- adapter program on device buffers -----------------------------------------------------------
 // enc (B, T, D) fp32 -> y (B, t_out, E) fp32.  Slot-resident cache when ids != null.
 template <typename TA>
 int adapter_program(fo_ctx* c, const float* enc, const uint8_t* mask, int B, int T, const int32_t* ids_dev,
                     const float* cache_in, float* cache_out, float* y, cudaStream_t st) {
     const int D = c->D, E = c->E, KA = c->KA, km1 = KA - 1;
+    if (c->cfg.adapter_type == 1) {
+        // LinearAdapter: one GEMM over the encoder frames as they are (the reference does not even apply the pad mask)
+        const int M = B * T;
+        void* xin;
+        FO_TRY(ws_ensure(c, WS_XIN, (size_t)M * D * sizeof(TA), &xin));
+        const TA* a_in;
+        if (sizeof(TA) == 2) {
+            FO_TRY(f32_to_act16(enc, reinterpret_cast<act16*>(xin), (long long)M * D, st));
+            a_in = reinterpret_cast<const TA*>(xin);
+        } else {
+            a_in = reinterpret_cast<const TA*>(enc);
+        }
+        Epilogue e;
+        e.bias = c->ad_proj_b;
+        e.c_f32 = y;
+        e.ldc = E;
+        RowMap rml;
+        if (c->handoff && ids_dev) {
+            e.c_f32 = nullptr;
+            e.c_act = reinterpret_cast<TA*>(c->handoff) + c->handoff_off * E;
+            rml.p1 = T; rml.p0 = T; rml.v1 = 1; rml.v0 = T; rml.q1 = (int)c->handoff_rows; rml.q0 = 0;
+        }
+        if (!(c->debug_skip & 16)) FO_TRY(gemm<TA>(c, a_in, plain_rows(D, M), c->ad_proj_w, M, E, D, e, rml, st));
+        return 0;
+    }
     const int t_out = (T + km1 - KA) / 2 + 1;
     const int Mo = B * t_out;
     void *xin, *aconv, *ah;
@@ -833,7 +867,7 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     if (run_adapter)
         FO_TRY(adapter_program<TA>(c, enc_out_dev, nullptr, n, t, c->ids_dev, nullptr, nullptr, y_dev, st));
     FO_TRY(advance_sessions(c->ids_dev, n, t, c->cfg.chunk_size, c->pe_wrap, c->n_frames, c->pe_index,
-                            run_adapter ? c->ad_valid : nullptr, st));
+                            (run_adapter && c->cfg.adapter_type == 0) ? c->ad_valid : nullptr, st));
     return 0;
 }
 
@@ -1301,7 +1335,7 @@ inline int ws_y(int buf) { return buf ? WS_Y2 : WS_Y; }
 static int step_body(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     void *dfeats, *denc, *dy = nullptr;
     const int T1 = (a.t_in - 1) / 2, t = (T1 - 1) / 2;
-    const int km1 = c->KA - 1, t_out = (t + km1 - c->KA) / 2 + 1;
+    const int km1 = c->KA - 1, t_out = ad_frames(c, t);
     FO_TRY(ws_ensure(c, WS_FEATS, (size_t)a.n * a.t_in * c->F * sizeof(float), &dfeats));
     FO_TRY(ws_ensure(c, ws_enc(a.buf), (size_t)a.n * t * c->D * sizeof(float), &denc));
     if (a.want_y) FO_TRY(ws_ensure(c, ws_y(a.buf), (size_t)a.n * t_out * c->E * sizeof(float), &dy));
@@ -1376,7 +1410,7 @@ static int stream_common(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     FO_CHECK(t >= 1 && t <= c->max_t, "streaming call of %d feature frames gives %d encoder frames; context allows 1..%d",
              t_in, t, c->max_t);
     if (adapter_out) FO_CHECK(c->cfg.has_adapter, "adapter_out requested but the context has no adapter");
-    const int km1 = c->KA - 1, t_out = (t + km1 - c->KA) / 2 + 1;
+    const int km1 = c->KA - 1, t_out = ad_frames(c, t);
     const size_t enc_bytes = (size_t)n * t * c->D * sizeof(float);
     const size_t y_bytes = (size_t)n * t_out * c->E * sizeof(float);
     if (c->copy_stream && c->async_ticket > 0) {
@@ -1432,7 +1466,7 @@ int fo_stream_step_embeds(fo_ctx* c, const int32_t* ids, int n, const void* pcm,
     FO_TRY(check_ids(c, ids, n));
     FO_CUDA(cudaSetDevice(c->device));
     const int t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
-    const int t = ((t_in - 1) / 2 - 1) / 2, t_out = (t + c->KA - 1 - c->KA) / 2 + 1;
+    const int t = ((t_in - 1) / 2 - 1) / 2, t_out = ad_frames(c, t);
     FO_CHECK(embeds_f16 && row_offset >= 0 && rows_per_session >= row_offset + t_out && rows_per_session < (1LL << 31),
              "fo_stream_step_embeds: a session's %d rows at offset %lld do not fit %lld rows per session", t_out,
              (long long)row_offset, (long long)rows_per_session);
@@ -1466,7 +1500,7 @@ int fo_stream_step_async(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     }
     const int buf = (int)(c->async_ticket & 1);
     const int t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
-    const int t = ((t_in - 1) / 2 - 1) / 2, t_out = (t + c->KA - 1 - c->KA) / 2 + 1;
+    const int t = ((t_in - 1) / 2 - 1) / 2, t_out = ad_frames(c, t);
     FO_TRY(upload_ids(c, ids, n, st));
     c->pf_slot_lo = c->pf_slot_hi = ids[0];
     for (int i = 1; i < n; ++i) { c->pf_slot_lo = std::min(c->pf_slot_lo, (int)ids[i]); c->pf_slot_hi = std::max(c->pf_slot_hi, (int)ids[i]); }
@@ -1522,7 +1556,7 @@ int fo_encode_offline(fo_ctx* c, const float* feats, const int32_t* ilens, int B
     const void *dfeats, *dil;
     FO_TRY(in_dev(c, feats, (size_t)B * T * c->F * sizeof(float), WS_FEATS, st, &dfeats));
     FO_TRY(in_dev(c, ilens, (size_t)B * sizeof(int32_t), WS_ILENS, st, &dil));
-    const int km1 = c->KA - 1, t_out = (T2 + km1 - c->KA) / 2 + 1;
+    const int km1 = c->KA - 1, t_out = ad_frames(c, T2);
     const size_t enc_bytes = (size_t)B * T2 * c->D * sizeof(float), y_bytes = (size_t)B * t_out * c->E * sizeof(float);
     void *denc, *dy = nullptr, *dmask, *dil2, *damask = nullptr;
     FO_TRY(out_dev(c, enc_out, enc_bytes, WS_ENC, &denc));
@@ -1538,7 +1572,8 @@ int fo_encode_offline(fo_ctx* c, const float* feats, const int32_t* ilens, int B
     FO_TRY(r);
     if (adapter_mask_out) {
         FO_TRY(out_dev(c, adapter_mask_out, (size_t)B * t_out, WS_AMASK, &damask));
-        FO_TRY(stride2_mask((const uint8_t*)dmask, B, T2, t_out, (uint8_t*)damask, st));
+        if (c->cfg.adapter_type == 1) FO_CUDA(cudaMemcpyAsync(damask, dmask, (size_t)B * T2, cudaMemcpyDeviceToDevice, st));   // mask unchanged
+        else FO_TRY(stride2_mask((const uint8_t*)dmask, B, T2, t_out, (uint8_t*)damask, st));
         FO_TRY(out_done(adapter_mask_out, damask, (size_t)B * t_out, st));
     }
     if (enc_out) FO_TRY(out_done(enc_out, denc, enc_bytes, st));
@@ -1555,8 +1590,9 @@ int fo_adapter_forward(fo_ctx* c, const float* x, const uint8_t* mask, int B, in
     FO_CHECK(x && y && B > 0 && T > 0, "fo_adapter_forward: bad argument");
     FO_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int km1 = c->KA - 1, t_out = (T + km1 - c->KA) / 2 + 1;
+    const int km1 = c->KA - 1, t_out = ad_frames(c, T);
     FO_CHECK(t_out >= 1, "fo_adapter_forward: input too short");
+    if (c->cfg.adapter_type == 1) FO_CHECK(!cache_in && !cache_out, "fo_adapter_forward: LinearAdapter carries no cache");
     const void *dx, *dm = nullptr, *dci = nullptr;
     FO_TRY(in_dev(c, x, (size_t)B * T * c->D * sizeof(float), WS_ENC, st, &dx));
     if (mask) FO_TRY(in_dev(c, mask, (size_t)B * T, WS_MASK2, st, &dm));

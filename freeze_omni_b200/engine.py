@@ -65,7 +65,7 @@ class Engine:
             frame_len=cfg.frame_len, frame_shift=cfg.frame_shift, frames_per_chunk=cfg.frames_per_chunk,
             context_frames=cfg.context_frames, max_sessions=int(max_sessions), max_stream_frames=int(msf),
             ffn_conv_kernel=int(cfg.ffn_conv_kernel) if cfg.ffn_type == "conv1d-linear" else 0,
-            adapter_batchnorm=int(cfg.adapter_norm == "batch"))
+            adapter_batchnorm=int(cfg.adapter_norm == "batch"), adapter_type=int(cfg.adapter_type == "linear"))
         h = C.c_void_p()
         _lib.check(self.lib.fo_create(C.byref(c), self.device, _lib.FO_BF16 if dtype == torch.bfloat16 else _lib.FO_F32,
                                       C.byref(h)))
@@ -236,8 +236,15 @@ class Engine:
     # ---- streaming --------------------------------------------------------------------------------
     def out_frames(self, t_in: int) -> Tuple[int, int]:
         t = PathConfig.sub_len(t_in)
+        return t, self.adapter_frames(t)
+
+    def adapter_frames(self, t: int) -> int:
+        """Frames the adapter emits for t encoder frames: CNNSubsampling halves (stride-2 conv over k-1 cached frames),
+        LinearAdapter keeps the rate."""
+        if self.cfg.adapter_type == "linear":
+            return t
         k = self.cfg.adapter_kernel
-        return t, (t + k - 1 - k) // 2 + 1
+        return (t + k - 1 - k) // 2 + 1
 
     def encode_stream(self, ids, feats: Optional[ArrayLike], want_adapter: Optional[bool] = None,
                       enc_out: Optional[torch.Tensor] = None, adapter_out: Optional[torch.Tensor] = None):
@@ -334,13 +341,17 @@ class Engine:
         Returns (y, new_cache)."""
         B, T, D = x.shape
         k = self.cfg.adapter_kernel
-        t_out = (T + k - 1 - k) // 2 + 1
+        t_out = self.adapter_frames(T)
         x = x.detach().float().contiguous()
         m8 = None
         if mask is not None:
             m8 = mask.reshape(B, T).to(torch.uint8).contiguous()
         ci = None if cache is None else cache.detach().float().contiguous()
         y = torch.empty(B, t_out, self.cfg.llm_dim, device=self.torch_device)
+        if self.cfg.adapter_type == "linear":                  # no cache to carry
+            assert cache is None
+            _lib.check(self.lib.fo_adapter_forward(self._h, _ptr(x), _ptr(m8), B, T, None, None, _ptr(y), self._stream()))
+            return y, None
         co = torch.empty(B, D, k - 1, device=self.torch_device)
         _lib.check(self.lib.fo_adapter_forward(self._h, _ptr(x), _ptr(m8), B, T, _ptr(ci), _ptr(co), _ptr(y), self._stream()))
         return y, co

@@ -289,3 +289,37 @@ class CNNSubsampling(nn.Module):
         if return_cache:
             return y, mask_pad[:, :, 0::2], [new_cache]
         return y, mask_pad[:, :, 0::2]
+
+
+class LinearAdapter(nn.Module):
+    """models/adapter.py:59-70 (adpter_type == 'linear', audioLLM.py:161-162): y = Linear(enc_out_dim -> llm_embed_dim)(x),
+    mask passed through; same state-dict keys (adpter.weight / adpter.bias)."""
+
+    def __init__(self, enc_out_dim: int = 512, llm_embed_dim: int = 4096):
+        super().__init__()
+        self.adpter = nn.Linear(enc_out_dim, llm_embed_dim)
+        self.path_config = PathConfig(d_model=enc_out_dim, n_heads=max(1, enc_out_dim // 64), llm_dim=llm_embed_dim,
+                                      adapter_type='linear')
+        self.compute_dtype = torch.float32
+
+    invalidate = CNNSubsampling.invalidate
+    load_state_dict = CNNSubsampling.load_state_dict
+    _apply = CNNSubsampling._apply
+
+    def engine(self, dtype: Optional[torch.dtype] = None) -> Engine:
+        dtype = dtype or _compute_dtype(self)
+        engines = _ENGINES.setdefault(self, {})
+        if dtype not in engines:
+            p = next(self.parameters())
+            if p.device.type != "cuda":
+                raise RuntimeError("LinearAdapter: move the module to a CUDA device first; there is no CPU path")
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            engines[dtype] = Engine(self.path_config, enc_state=None, adp_state=sd, dtype=dtype,
+                                    device=p.device.index or 0, max_sessions=1)
+        return engines[dtype]
+
+    @torch.compiler.disable
+    @torch.no_grad()
+    def forward(self, x, mask_pad):
+        y, _ = self.engine().adapter_forward(x, None, None)
+        return y, mask_pad

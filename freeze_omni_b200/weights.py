@@ -55,6 +55,8 @@ def encoder_param_shapes(cfg: PathConfig) -> List[Tuple[str, Tuple[int, ...], in
 def adapter_param_shapes(cfg: PathConfig) -> List[Tuple[str, Tuple[int, ...], int]]:
     """CNNSubsampling single-conv branch (adapter.py:97-110)."""
     d, k, e = cfg.d_model, cfg.adapter_kernel, cfg.llm_dim
+    if getattr(cfg, "adapter_type", "subsampling") == "linear":      # LinearAdapter (adapter.py:59-70): self.adpter = Linear
+        return [("adpter.weight", (e, d), d), ("adpter.bias", (e,), d)]
     out = [("conv1d2.weight", (2 * d, d, k), d * k), ("conv1d2.bias", (2 * d,), d * k),
            ("bn2.weight", (2 * d,), -1), ("bn2.bias", (2 * d,), -2)]
     if cfg.adapter_norm == "batch":            # BatchNorm1d buffers (eval mode uses the running statistics)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FO_ABI_VERSION 3
+#define FO_ABI_VERSION 4
 
 enum { FO_F32 = 0, FO_BF16 = 1, FO_I16 = 2 };     /* compute dtype / PCM sample type */
 enum { FO_OK = 0, FO_ERR_ARG = -1, FO_ERR_CUDA = -2, FO_ERR_STATE = -3, FO_ERR_NOMEM = -4 };
@@ -66,6 +66,10 @@ typedef struct fo_config {
     /* adapter norm (models/adapter.py:100-103): 0 = LayerNorm(2C, eps 1e-3); 1 = BatchNorm1d(2C, eps 1e-3) in eval mode
      * (running statistics; tensors adapter.bn2.{weight,bias,running_mean,running_var}) */
     int32_t adapter_batchnorm;
+    /* adapter module (models/audioLLM.py:159-166): 0 = CNNSubsampling (adapter.py:72-157, the shipped 'subsampling');
+     * 1 = LinearAdapter (adapter.py:59-70): y = Linear(d_model -> llm_dim)(x), no cache, no subsampling (t_out = t),
+     * tensors adapter.adpter.{weight,bias} */
+    int32_t adapter_type;
 } fo_config;
 
 typedef struct fo_stats_t {

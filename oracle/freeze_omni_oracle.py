@@ -331,6 +331,8 @@ class EncoderOracle:
 def adapter_forward(cfg, sd: State, x: Tensor, mask: Tensor, cache: Optional[List[Tensor]] = None):
     """x (B,T,D), mask (B,1,T) bool, cache None | [Tensor(B,D,k-1)].
     Returns (y (B,T'',E), mask[:, :, 0::2], [new cache])."""
+    if getattr(cfg, "adapter_type", "subsampling") == "linear":      # LinearAdapter.forward, adapter.py:69-70: no mask fill, no cache
+        return F.linear(x, sd["adpter.weight"], sd["adpter.bias"]), mask, None
     k = cfg.adapter_kernel
     xt = x.transpose(1, 2)
     if mask.size(2) > 0:

@@ -279,6 +279,21 @@ def main():
              stream_cache=cache[0].contiguous().numpy(), off_x=xo.numpy(), off_mask=mo.numpy(), off_y=yo.numpy(),
              off_mask_out=mo2.numpy())
 
+    # ---------------- LinearAdapter (adapter.py:59-70) ------------------------------------------------------
+    if want("tiny_linear"):
+        ycfg = load_yaml("tiny_linear")
+        cfg = path_config_from_dict(ycfg)
+        mc = ycfg["model_conf"]
+        adp = ref_adapter.LinearAdapter(mc["enc_out_dim"], mc["llm_embed_dim"])
+        adp.load_state_dict(make_adapter_state(cfg, 3), strict=True)
+        adp.eval()
+        g = torch.Generator().manual_seed(29)
+        x = torch.randn(3, 11, cfg.d_model, generator=g)
+        m = torch.arange(11)[None, None, :] < torch.tensor([11, 7, 2])[:, None, None]
+        with torch.no_grad():
+            y, m2 = adp(x.clone(), m)
+        save("tiny_linear", seed=np.int64(3), x=x.numpy(), mask=m.numpy(), y=y.numpy(), mask_out=m2.numpy())
+
     # ---------------- shipped config -------------------------------------------------------
     if want("shipped"):
         ycfg = load_yaml("shipped")

@@ -544,6 +544,30 @@ def test_adapter_batchnorm_relu(golden, dtype, tol):
         eng.close()
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_linear_adapter(golden, dtype, tol):
+    """adpter_type 'linear' (LinearAdapter, adapter.py:59-70): stateless call against the reference module's output, then
+    the whole streaming path (t_out == t, no adapter cache) against per-session oracle runs."""
+    cfg, eng = make_engine("tiny_linear", 3, dtype=dtype, max_sessions=4)
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    g = golden("tiny_linear")
+    try:
+        y, cache = eng.adapter_forward(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["mask"]).cuda(), None)
+        assert cache is None and maxabs(y.cpu(), g["y"]) < tol
+        gen = torch.Generator().manual_seed(59)
+        sessions = [O.StreamSession(cfg, esd, asd) for _ in range(2)]
+        ids = eng.alloc(2)
+        for i in range(4):
+            pcm = (0.05 * torch.randn(2, cfg.samples_per_chunk, generator=gen) * 32768).round().to(torch.int16)
+            enc, emb = eng.stream_step(ids, pcm, 1.0)
+            assert emb.shape[1] == enc.shape[1] == 4
+            for b in range(2):
+                _, eo, yo = sessions[b].step_pcm(pcm[b].float(), 1.0)
+                assert maxabs(enc[b].cpu(), eo[0]) < tol * (1 if dtype == torch.float32 else 4) and maxabs(emb[b].cpu(), yo[0]) < tol * (1 if dtype == torch.float32 else 4), (i, b)
+    finally:
+        eng.close()
+
+
 def test_persistent_gemm_matches_tile_per_cta(shipped16):
     """Fat short-K GEMMs run on the persistent tcgen05 kernel (tile loop per SM, double-buffered TMEM accumulator,
     epilogue straight from TMEM registers).  Same k order and same fp32 epilogue arithmetic as the one-tile-per-CTA

@@ -252,3 +252,14 @@ def test_adapter_batchnorm_relu_vs_reference(golden):
     y, m, _ = O.adapter_forward(cfg, asd, torch.from_numpy(g["off_x"]), torch.from_numpy(g["off_mask"]))
     assert float((y - torch.from_numpy(g["off_y"])).abs().max()) < 1e-5
     assert torch.equal(m, torch.from_numpy(g["off_mask_out"]))
+
+
+def test_linear_adapter_vs_reference(golden):
+    """LinearAdapter (adapter.py:59-70, adpter_type 'linear'): oracle against the reference module's output; the mask passes
+    through unchanged and the padded frames are NOT zeroed (the reference applies no mask fill here)."""
+    cfg = load_path_config("tiny_linear")
+    asd = make_adapter_state(cfg, 3)
+    g = golden("tiny_linear")
+    y, m, cache = O.adapter_forward(cfg, asd, torch.from_numpy(g["x"]), torch.from_numpy(g["mask"]))
+    assert cache is None and torch.equal(m, torch.from_numpy(g["mask_out"]))
+    assert float((y - torch.from_numpy(g["y"])).abs().max()) < 1e-5
