@@ -1711,6 +1711,12 @@ int fo_profile_dump(fo_ctx* c, char* buf, int cap) {
     return 0;
 }
 
+int fo_debug_plan(int64_t act_rows, int n_out, int K, int can_defer, int* swap, int* bn, int* split) {
+    FO_CHECK(act_rows > 0 && n_out > 0 && K > 0 && K % 64 == 0 && swap && bn && split, "fo_debug_plan: bad argument");
+    gemm_tc_plan(act_rows, n_out, K, can_defer, swap, bn, split);
+    return 0;
+}
+
 int fo_debug_gemm(fo_ctx* c, const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                   int backend, int relu, int iters, float* ms_out, void* stream) {
     FO_CHECK(c && A && W && C && M > 0 && N > 0 && K > 0, "fo_debug_gemm: bad argument");

@@ -199,6 +199,8 @@ struct TcWorkspace {
 struct TcTune { int swap, bn, split; };      // -1 / 0 = let the cost model decide
 int gemm_tc_init();
 int gemm_tc_workspace(TcWorkspace* ws);       // allocates; the caller frees the two device pointers
+// the tile plan the host would pick (pure host logic; fo_debug_plan exposes it to the CPU tests)
+void gemm_tc_plan(long long act_rows, int n_out, int K, int can_defer, int* swap, int* bn, int* split);
 void gemm_tc_force(const TcTune& t);
 void gemm_tc_set_persist(int on);          // persistent tile loop for fat short-K GEMMs (default on)
 long long gemm_tc_persist_launches();

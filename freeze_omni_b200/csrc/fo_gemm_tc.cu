@@ -852,6 +852,10 @@ int gemm_tc_workspace(TcWorkspace* ws) {
     return 0;
 }
 
+void gemm_tc_plan(long long act_rows, int n_out, int K, int can_defer, int* swap, int* bn, int* split) {
+    const Plan p = choose_plan(act_rows, n_out, K, can_defer != 0);
+    *swap = p.swap; *bn = p.bn; *split = p.split;
+}
 void gemm_tc_force(const TcTune& t) { g_forced = t; }
 void gemm_tc_set_persist(int on) { g_persist = on; }
 long long gemm_tc_persist_launches() { return g_persist_launches; }

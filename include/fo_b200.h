@@ -187,6 +187,9 @@ int fo_get_option(fo_ctx* ctx, const char* name, int64_t* value);
 /* per-shape totals of the GEMM launches timed while option "profile_gemm" was 1: text lines "M N K launches microseconds"
  * (M = GEMM rows incl. the padding rows of the implicit-GEMM convolutions). */
 int fo_profile_dump(fo_ctx* ctx, char* buf, int cap);
+/* host-only: the tile plan of the tcgen05 GEMM for (activation rows, output columns, K) -- swap = weights on the UMMA-M side,
+ * bn = UMMA N, split = K splits; can_defer = a consumer kernel finishes the split-K sum.  Needs no GPU (CPU tests of the plan). */
+int fo_debug_plan(int64_t act_rows, int n_out, int K, int can_defer, int* swap, int* bn, int* split);
 /* one GEMM of the library, exposed for kernel-level parity tests and roofline measurement:
  * C[M,N] = A[M,K] * W[N,K]^T (+bias) in the context's dtype, fp32 in/out on device pointers. */
 int fo_debug_gemm(fo_ctx* ctx, const float* A, const float* W, const float* bias, float* C,
