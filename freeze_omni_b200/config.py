@@ -124,6 +124,10 @@ class PathConfig:
             raise ValueError("adapter: norm must be layer|batch and activation gelu|relu (adapter.py:100-107)")
         if self.adapter_kernel < 2:
             raise ValueError("adapter kernel_size must be >= 2")
+        if self.adapter_type not in ("subsampling", "linear"):
+            raise ValueError("adpter_type %r: CNNAdapter (adapter.py:10-57) is not built (the oracle covers it)" % self.adapter_type)
+        if self.adapter_type == "subsampling" and self.d_model * 4 < self.llm_dim:
+            raise ValueError("two-conv CNNSubsampling branch (adapter.py:84-96) is not built (the oracle covers it)")
         if not self.normalize_before:
             raise ValueError("post-norm layers (normalize_before=False) are not built")
         if self.ffn_type not in ("linear", "conv1d-linear"):

@@ -328,11 +328,57 @@ class EncoderOracle:
 # ------------------------------------------------------------------------------------------------
 # Adapter: CNNSubsampling single-conv branch, models/adapter.py:112-157
 # ------------------------------------------------------------------------------------------------
+def _bn_eval(y: Tensor, sd: State, name: str) -> Tensor:
+    """BatchNorm1d(eps=1e-3) in eval mode over (B, C, T) (adapter.py:25-26,87,92)."""
+    return F.batch_norm(y, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
+                        False, 0.0, 1e-3)
+
+
+def cnn_adapter_forward(cfg, sd: State, x: Tensor, mask: Tensor) -> Tensor:
+    """CNNAdapter (adapter.py:10-57): mask fill, two causal convs (kernel k, stride 1, left zero pad k-1) each with
+    BatchNorm + ReLU, then Linear(4C -> E).  No cache: every call starts from a zero left context."""
+    k = cfg.adapter_kernel
+    xt = x.transpose(1, 2)
+    if mask.size(2) > 0:
+        xt = xt.masked_fill(~mask, 0.0)                              # adapter.py:41-42
+    y = F.relu(_bn_eval(F.conv1d(F.pad(xt, (k - 1, 0)), sd["conv1d1.weight"], sd["conv1d1.bias"]), sd, "bn1"))    # :44-47
+    y = F.relu(_bn_eval(F.conv1d(F.pad(y, (k - 1, 0)), sd["conv1d2.weight"], sd["conv1d2.bias"]), sd, "bn2"))     # :49-52
+    return F.linear(y.transpose(1, 2), sd["project.weight"], sd["project.bias"])                                  # :54-55
+
+
+def two_conv_adapter_forward(cfg, sd: State, x: Tensor, mask: Tensor, cache: Optional[List[Optional[Tensor]]] = None):
+    """CNNSubsampling with enc_out_dim * 4 < llm_embed_dim (adapter.py:84-96): conv(C -> 2C, k, stride 1) + BN + ReLU, then
+    conv(2C -> 4C, k, stride 2) + BN + ReLU, Linear(4C -> E).  cache = [c0 (B, 2C, k-1), c1 (B, C, k-1)] (adapter.py:123-143):
+    c1 is the left context of the first conv's INPUT, c0 of the second conv's input."""
+    k = cfg.adapter_kernel
+    xt = x.transpose(1, 2)
+    if mask.size(2) > 0:
+        xt = xt.masked_fill(~mask, 0.0)
+    if cache is None:
+        xt = F.pad(xt, (k - 1, 0))                                   # :124-125
+        new_cache: List[Optional[Tensor]] = [None, xt[:, :, 1 - k:].contiguous()]
+    else:
+        xt = torch.cat((cache[1], xt), dim=2)                        # :126-127
+        new_cache = [cache[0], xt[:, :, 1 - k:].contiguous()]
+    y = F.relu(_bn_eval(F.conv1d(xt, sd["conv1d1.weight"], sd["conv1d1.bias"]), sd, "bn1"))                       # :132-134
+    if new_cache[0] is None:
+        y = F.pad(y, (k - 1, 0))                                     # :136-137
+    else:
+        y = torch.cat((new_cache[0], y), dim=2)                      # :138-139
+    new_cache[0] = y[:, :, 1 - k:].contiguous()                      # :140-141
+    y = F.relu(_bn_eval(F.conv1d(y, sd["conv1d2.weight"], sd["conv1d2.bias"], stride=2), sd, "bn2"))              # :144-150
+    return F.linear(y.transpose(1, 2), sd["project.weight"], sd["project.bias"]), mask[:, :, 0::2], new_cache
+
+
 def adapter_forward(cfg, sd: State, x: Tensor, mask: Tensor, cache: Optional[List[Tensor]] = None):
     """x (B,T,D), mask (B,1,T) bool, cache None | [Tensor(B,D,k-1)].
     Returns (y (B,T'',E), mask[:, :, 0::2], [new cache])."""
     if getattr(cfg, "adapter_type", "subsampling") == "linear":      # LinearAdapter.forward, adapter.py:69-70: no mask fill, no cache
         return F.linear(x, sd["adpter.weight"], sd["adpter.bias"]), mask, None
+    if getattr(cfg, "adapter_type", "subsampling") == "cnn":         # CNNAdapter.forward, adapter.py:33-57 (not built on the GPU yet)
+        return cnn_adapter_forward(cfg, sd, x, mask), mask, None
+    if cfg.d_model * 4 < cfg.llm_dim:                                # CNNSubsampling two-conv branch, adapter.py:84-96,123-135
+        return two_conv_adapter_forward(cfg, sd, x, mask, cache)
     k = cfg.adapter_kernel
     xt = x.transpose(1, 2)
     if mask.size(2) > 0:

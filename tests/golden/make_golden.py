@@ -294,6 +294,44 @@ def main():
             y, m2 = adp(x.clone(), m)
         save("tiny_linear", seed=np.int64(3), x=x.numpy(), mask=m.numpy(), y=y.numpy(), mask_out=m2.numpy())
 
+    # ---------------- adapter variants that only the ORACLE covers so far: CNNAdapter, two-conv CNNSubsampling ----------
+    if want("tiny_adapter_variants"):
+        import dataclasses
+        base = path_config_from_dict(load_yaml("tiny_bn"))
+        g = torch.Generator().manual_seed(37)
+        out = {}
+        # CNNAdapter (adapter.py:10-57)
+        cfg = dataclasses.replace(base, adapter_type="cnn")
+        adp = ref_adapter.CNNAdapter(cfg.d_model, cfg.llm_dim, cfg.adapter_kernel)
+        miss = adp.load_state_dict(make_adapter_state(cfg, 5), strict=False)
+        assert not miss.unexpected_keys and all(k.endswith("num_batches_tracked") for k in miss.missing_keys), miss
+        adp.eval()
+        x = torch.randn(2, 23, cfg.d_model, generator=g)
+        m = torch.arange(23)[None, None, :] < torch.tensor([23, 9])[:, None, None]
+        with torch.no_grad():
+            y, _ = adp(x.clone(), m)
+        out.update(cnn_x=x.numpy(), cnn_mask=m.numpy(), cnn_y=y.numpy())
+        # CNNSubsampling with 4 * enc_out_dim < llm_embed_dim (adapter.py:84-96): streaming with both caches, then offline
+        cfg2 = dataclasses.replace(base, llm_dim=cfg.d_model * 4 + 64)
+        adp2 = ref_adapter.CNNSubsampling(cfg2.d_model, cfg2.llm_dim, cfg2.adapter_kernel, "relu", "batch")
+        assert adp2.cnn_num == 2
+        miss = adp2.load_state_dict(make_adapter_state(cfg2, 5), strict=False)
+        assert not miss.unexpected_keys and all(k.endswith("num_batches_tracked") for k in miss.missing_keys), miss
+        adp2.eval()
+        xs = [torch.randn(2, 4, cfg2.d_model, generator=g) for _ in range(5)]
+        ys, cache = [], None
+        with torch.no_grad():
+            for xx in xs:
+                yy, _, cache = adp2(xx.clone(), torch.ones(2, 1, 4, dtype=torch.bool), cache=cache, return_cache=True)
+                ys.append(yy.clone())
+            xo = torch.randn(2, 31, cfg2.d_model, generator=g)
+            mo = torch.arange(31)[None, None, :] < torch.tensor([31, 12])[:, None, None]
+            yo, mo2 = adp2(xo.clone(), mo)
+        out.update(two_llm_dim=np.int64(cfg2.llm_dim), two_stream_x=torch.stack(xs).numpy(), two_stream_y=torch.stack(ys).numpy(),
+                   two_cache0=cache[0].contiguous().numpy(), two_cache1=cache[1].contiguous().numpy(),
+                   two_off_x=xo.numpy(), two_off_mask=mo.numpy(), two_off_y=yo.numpy(), two_off_mask_out=mo2.numpy())
+        save("tiny_adapter_variants", seed=np.int64(5), **out)
+
     # ---------------- shipped config -------------------------------------------------------
     if want("shipped"):
         ycfg = load_yaml("shipped")

@@ -263,3 +263,26 @@ def test_linear_adapter_vs_reference(golden):
     y, m, cache = O.adapter_forward(cfg, asd, torch.from_numpy(g["x"]), torch.from_numpy(g["mask"]))
     assert cache is None and torch.equal(m, torch.from_numpy(g["mask_out"]))
     assert float((y - torch.from_numpy(g["y"])).abs().max()) < 1e-5
+
+
+def test_oracle_covers_cnn_adapter_and_two_conv_subsampling(golden):
+    """The two adapter variants the GPU path does not build yet (config.validate refuses them): the oracle's restatement is
+    already pinned to the reference modules (CNNAdapter adapter.py:10-57; CNNSubsampling two-conv branch :84-96,123-143 with
+    its two caches), so the next round starts from a checked checker."""
+    import dataclasses
+    g = golden("tiny_adapter_variants")
+    base = load_path_config("tiny_bn")
+    cfg = dataclasses.replace(base, adapter_type="cnn")
+    y, m, cache = O.adapter_forward(cfg, make_adapter_state(cfg, 5), torch.from_numpy(g["cnn_x"]), torch.from_numpy(g["cnn_mask"]))
+    assert cache is None and float((y - torch.from_numpy(g["cnn_y"])).abs().max()) < 1e-5
+    cfg2 = dataclasses.replace(base, llm_dim=int(g["two_llm_dim"]))
+    asd = make_adapter_state(cfg2, 5)
+    cache = None
+    for i in range(g["two_stream_x"].shape[0]):
+        y, _, cache = O.adapter_forward(cfg2, asd, torch.from_numpy(g["two_stream_x"][i]), torch.ones(2, 1, 4, dtype=torch.bool), cache)
+        assert float((y - torch.from_numpy(g["two_stream_y"][i])).abs().max()) < 1e-5, i
+    assert float((cache[0] - torch.from_numpy(g["two_cache0"])).abs().max()) < 1e-6
+    assert float((cache[1] - torch.from_numpy(g["two_cache1"])).abs().max()) == 0.0
+    y, m, _ = O.adapter_forward(cfg2, asd, torch.from_numpy(g["two_off_x"]), torch.from_numpy(g["two_off_mask"]))
+    assert float((y - torch.from_numpy(g["two_off_y"])).abs().max()) < 1e-5
+    assert torch.equal(m, torch.from_numpy(g["two_off_mask_out"]))
