@@ -23,7 +23,7 @@ class FoConfig(C.Structure):
 class FoStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "stream_steps", "session_chunks", "offline_calls", "offline_frames", "kernel_launches",
-        "sessions_in_use", "device_bytes", "graph_replays")]
+        "sessions_in_use", "device_bytes", "graph_replays", "act_saturations")]
 
 
 # every symbol include/fo_b200.h declares: name -> (restype, argtypes)
@@ -83,7 +83,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.fo_abi_version() != 4:
+    if lib.fo_abi_version() != 5:
         raise RuntimeError("libfo_b200.so ABI version mismatch")
     _lib = lib
     return lib

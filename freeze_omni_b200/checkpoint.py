@@ -87,6 +87,6 @@ def load_trained(model_dir_or_pt: str, yaml_path: Optional[str] = None, role: st
     exp = encoder_param_shapes(cfg)
     if "global_cmvn.mean" not in enc:
         exp = [e for e in exp if not e[0].startswith("global_cmvn.")]
-    audit_state_dict(exp, enc)
-    audit_state_dict(adapter_param_shapes(cfg), adp)
+    audit_state_dict(exp, enc, reject_unexpected=True)
+    audit_state_dict(adapter_param_shapes(cfg), adp, reject_unexpected=True)
     return cfg, enc, adp

@@ -26,6 +26,11 @@ _TRANSFORMER_DEFAULTS = {
     "transformer-positionwise-layer-type": "linear", "transformer-positionwise-conv-kernel_size": 1,
     "transformer-chunk_size": -1, "transformer-left_chunks": -1, "transformer-dynamic-chunks": True,
 }
+# AudioLLM.__init__ defaults (audioLLM.py:27-52) for the model_conf keys this path reads
+_MODEL_CONF_DEFAULTS = {
+    "enc_out_dim": 512, "llm_embed_dim": 4096, "kernel_size": 3, "adpter_type": "cnn",
+    "activation_func": "relu", "norm": "batch",
+}
 _SUBSAMPLING_DEFAULTS = {
     "subsampling-rate": 4, "subsampling-input-dim": 256, "subsampling-output-dim": 256,
 }
@@ -172,16 +177,19 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
             int(tr["transformer-output-dim"]), int(over.get("encoder-output-dim", d))}
     if len(dims) != 1 or int(sub["subsampling-input-dim"]) != feat:
         raise ValueError("WRONG CONFIG: component input/output dims do not chain (encoder.py:82-96)")
-    mc = dict(configs.get("model_conf", {}))
+    # absent model_conf keys take the REFERENCE's constructor defaults (AudioLLM.__init__, audioLLM.py:27-52: enc_out_dim 512,
+    # llm_embed_dim 4096, kernel_size 3, adpter_type 'cnn', activation_func 'relu', norm 'batch'), not the shipped values:
+    # a train.yaml that omits activation_func / norm describes a BatchNorm + ReLU checkpoint
+    mc = dict(_MODEL_CONF_DEFAULTS)
+    mc.update(configs.get("model_conf", {}) or {})
     if encoder_only:
-        mc = {"enc_out_dim": d, "llm_embed_dim": d}
-    adpter_type = str(mc.get("adpter_type", "subsampling"))
-    if adpter_type not in ("subsampling", "linear"):
-        raise ValueError("adpter_type 'cnn' (CNNAdapter, adapter.py:10-57) is not built; use 'subsampling' or 'linear'")
-    if int(mc.get("enc_out_dim", d)) != d:
-        raise ValueError("model_conf.enc_out_dim must equal the encoder output dim")
-    if adpter_type == "subsampling" and d * 4 < int(mc.get("llm_embed_dim", 3584)):
-        raise ValueError("two-conv CNNSubsampling branch (adapter.py:84-96) is not built")
+        mc.update({"enc_out_dim": d, "llm_embed_dim": d, "adpter_type": "linear"})
+    adpter_type = str(mc["adpter_type"])
+    if adpter_type not in ("subsampling", "linear", "cnn"):
+        raise ValueError("adpter_type must be cnn | linear | subsampling (audioLLM.py:159-165); got %r" % adpter_type)
+    if int(mc["enc_out_dim"]) != d:
+        raise ValueError("model_conf.enc_out_dim (%d; the reference's default is 512) must equal the encoder output dim %d"
+                         % (int(mc["enc_out_dim"]), d))
     fe = configs.get("frontend", {})
     cfg = PathConfig(
         feat_dim=feat, d_model=d, n_heads=int(tr["transformer-attention-heads"]),
@@ -192,8 +200,8 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
         dynamic_chunks=bool(tr["transformer-dynamic-chunks"]),
         ffn_type=str(tr["transformer-positionwise-layer-type"]),
         ffn_conv_kernel=int(tr["transformer-positionwise-conv-kernel_size"]) if tr["transformer-positionwise-layer-type"] == "conv1d-linear" else 1,
-        llm_dim=int(mc.get("llm_embed_dim", 3584)), adapter_kernel=int(mc.get("kernel_size", 5)),
-        adapter_act=str(mc.get("activation_func", "gelu")), adapter_norm=str(mc.get("norm", "layer")),
+        llm_dim=int(mc["llm_embed_dim"]), adapter_kernel=int(mc["kernel_size"]),
+        adapter_act=str(mc["activation_func"]), adapter_norm=str(mc["norm"]),
         adapter_type=adpter_type,
         sample_rate=int(fe.get("sample_rate", 16000)), frame_length_ms=int(fe.get("frame_length_ms", 25)),
         frame_shift_ms=int(fe.get("frame_shift_ms", 10)), frames_per_chunk=int(fe.get("frames_per_chunk", 16)),

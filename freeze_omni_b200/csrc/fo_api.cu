@@ -127,12 +127,13 @@ struct fo_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     long long async_ticket = 0;
+    unsigned long long* sat_counter = nullptr; // device: fp16-range saturations counted by the GEMM epilogues (Epilogue::sat)
+    cudaEvent_t ev_sync = nullptr;            // recorded after every synchronous step: the copy stream of a later async step
+                                              // must not overwrite the staging buffers that step still reads
+    std::vector<long long> id_stamp;          // check_ids: call number that last named each slot (duplicate detection)
+    long long id_call = 0;
     void* handoff = nullptr;                  // fo_stream_step_embeds: fp16 destination of the adapter rows for this call
     long long handoff_rows = 0, handoff_off = 0;
-    int stack_kernel = 0;                     // 24-layer stack of the streaming step as ONE persistent cooperative kernel (fo_stack.cu)
-    int stack_split_o = 0, stack_split_f2 = 0;   // debugging: force its K splits
-    StackState* stack = nullptr;
-    long long stack_launches = 0;
     int groups = 1;                           // session groups whose layer kernels run on parallel streams
     cudaStream_t grp_stream[MAX_GROUPS] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {nullptr};
@@ -222,8 +223,13 @@ int out_done(void* user, void* dev, size_t bytes, cudaStream_t st) {
 int check_ids(fo_ctx* c, const int32_t* ids, int n) {
     FO_CHECK(ids != nullptr && n > 0, "ids must be a host array of n > 0 session ids");
     FO_CHECK(n <= c->cfg.max_sessions, "n (%d) exceeds max_sessions (%d)", n, c->cfg.max_sessions);
+    if ((int)c->id_stamp.size() != c->cfg.max_sessions) c->id_stamp.assign(c->cfg.max_sessions, 0);
+    const long long call = ++c->id_call;
     for (int i = 0; i < n; ++i) {
         FO_CHECK(ids[i] >= 0 && ids[i] < c->cfg.max_sessions && c->slot_used[ids[i]], "session id %d is not allocated", ids[i]);
+        // two rows of one batch would append to the same KV ring / adapter cache / fbank carry concurrently
+        FO_CHECK(c->id_stamp[ids[i]] != call, "session id %d appears twice in one batch (ids must be distinct)", ids[i]);
+        c->id_stamp[ids[i]] = call;
     }
     return 0;
 }
@@ -256,8 +262,10 @@ int gemm_raw<act16>(fo_ctx* c, const act16* A, const AGather& ga, const void* W,
                     const RowMap& rm, cudaStream_t st, bool* fused_ln, int* deferred) {
     *fused_ln = false;
     *deferred = 0;
+    Epilogue eps = ep;
+    eps.sat = c->sat_counter;
     if (c->gemm_backend == 1) {
-        Epilogue e = ep;
+        Epilogue e = eps;
         if (!c->fuse_ln) e.ln_gamma = nullptr;
         // the split-K reduction can ride on the LayerNorm that follows (residual stream in place, rows normalised next)
         e.defer_reduce = c->defer_reduce && ep.ln_gamma && !c->fuse_ln && ep.residual == ep.c_f32 && ep.c_f32 && !ep.c_act &&
@@ -268,7 +276,7 @@ int gemm_raw<act16>(fo_ctx* c, const act16* A, const AGather& ga, const void* W,
         if (r == 0) *fused_ln = e.ln_gamma != nullptr;
         if (r <= 0) return r;
     }
-    return gemm_simt<act16, act16>(A, ga, reinterpret_cast<const act16*>(W), M, N, K, ep, rm, st);
+    return gemm_simt<act16, act16>(A, ga, reinterpret_cast<const act16*>(W), M, N, K, eps, rm, st);
 }
 template <typename TA>
 int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N, int K, const Epilogue& ep,
@@ -751,41 +759,6 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
     void* hc = nullptr;
     if (c->KF >= 2) FO_TRY(ws_ensure(c, WS_HC, (size_t)M * D * sizeof(TA), &hc));
-    // fp16 context, plain feed-forward: the whole stack as one persistent kernel
-    bool stack_done = false;
-    if (sizeof(TA) == 2 && c->stack_kernel && c->gemm_backend == 1 && c->KF < 2 && !c->debug_skip && !c->profile_gemm) {
-        const int MAXS = 8;
-        void* part;
-        FO_TRY(ws_ensure(c, WS_PART, (size_t)MAXS * M * D * sizeof(float), &part));
-        if (!c->stack) FO_TRY(stack_state_create(&c->stack));
-        const long long lstride = (long long)c->cfg.max_sessions * 2LL * H * c->ring_cap * 64;
-        std::vector<StackLayerHost> hl(c->L);
-        for (int l = 0; l < c->L; ++l) {
-            const LayerW& w = c->layers[l];
-            hl[l] = StackLayerHost{w.wqkv, w.wo, w.w1, w.w2, w.ln1g, w.ln1b, w.ln2g, w.ln2b, w.bqkv, w.bo, w.b1, w.b2,
-                                   w.pos_u, w.pos_v, w.ptab_h, reinterpret_cast<TA*>(c->ring) + l * lstride};
-        }
-        StackHostArgs sa;
-        memset(&sa, 0, sizeof(sa));
-        sa.layers = hl.data();
-        sa.L = c->L; sa.D = D; sa.FF = FF; sa.H = H;
-        sa.x = x; sa.h = h; sa.qkv = qkv; sa.q32 = q32; sa.att = att; sa.ffh = ffh;
-        sa.partial = reinterpret_cast<float*>(part);
-        sa.max_split = MAXS;
-        sa.force_split_o = c->stack_split_o;
-        sa.force_split_f2 = c->stack_split_f2;
-        sa.fin_g = c->after_g; sa.fin_b = c->after_b;
-        sa.enc_out = enc_out_dev;
-        sa.a.ids = c->ids_dev;
-        sa.a.n_frames = c->n_frames;
-        sa.a.pe_index = c->pe_index;
-        sa.a.n = n; sa.a.t = t; sa.a.H = H; sa.a.ring_cap = c->ring_cap; sa.a.window = c->window; sa.a.full_chunk = c->full_chunk;
-        sa.a.pe_wrap = c->pe_wrap; sa.a.pos_rows = c->pos_rows;
-        sa.a.ring_slot_stride = 2LL * H * c->ring_cap * 64;
-        const int r = stack_stream_launch(c->stack, sa, st);
-        if (r < 0) return r;
-        if (r == 0) { stack_done = true; ++c->stack_launches; }
-    }
     // The 24 layers run per SESSION GROUP on parallel streams (fork/join with events, also under graph capture):
     // sessions are independent, every layer kernel of a 64-session step is latency bound (<= 148 CTAs, 8-16 us), so
     // two groups' kernels overlap each other's pipeline fill, epilogue and launch gaps.  Rows of one group are
@@ -794,13 +767,12 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     if (G > fo_ctx::MAX_GROUPS) G = fo_ctx::MAX_GROUPS;
     while (G > 1 && n < 8 * G) --G;
     const long long layer_stride = (long long)c->cfg.max_sessions * 2LL * H * c->ring_cap * 64;
-    if (stack_done) G = 1;
     if (G > 1) {
         FO_CUDA(cudaEventRecord(c->ev_fork, st));
         for (int g = 1; g < G; ++g) FO_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->ev_fork, 0));
     }
     const int per = (n + G - 1) / G;
-    for (int l = 0; l < c->L && !stack_done; ++l) {
+    for (int l = 0; l < c->L; ++l) {
         const LayerW& w = c->layers[l];
         const bool last = l + 1 == c->L;
         for (int g = 0; g < G; ++g) {
@@ -986,6 +958,8 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
         if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->ad_valid = (int32_t*)p; }
         if (!r) { r = dev_alloc(c, &p, (size_t)S * 2 * (c->KA - 1) * c->D * sizeof(float)); c->ad_cache = (float*)p; }
         if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->ids_dev = (int32_t*)p; }
+        if (!r) { r = dev_alloc(c, &p, sizeof(unsigned long long)); c->sat_counter = (unsigned long long*)p; }
+        if (!r && cudaMemset(c->sat_counter, 0, sizeof(unsigned long long)) != cudaSuccess) r = FO_ERR_CUDA;
     }
     for (int k = 0; k < fo_ctx::NSTAGE && !r; ++k) {
         if (cudaMallocHost((void**)&c->ids_host[k], S * sizeof(int32_t)) != cudaSuccess ||
@@ -1021,7 +995,6 @@ int fo_destroy(fo_ctx* c) {
     for (auto& kv : c->staged) cudaFree(kv.second.d);
     for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-    stack_state_destroy(c->stack);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
@@ -1033,6 +1006,7 @@ int fo_destroy(fo_ctx* c) {
         if (c->ev_join[g]) cudaEventDestroy(c->ev_join[g]);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     for (void* p : c->owned) if (p) cudaFree(p);
     for (int k = 0; k < fo_ctx::NSTAGE; ++k) {
         if (c->ids_host[k]) cudaFreeHost(c->ids_host[k]);
@@ -1361,7 +1335,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     uint32_t sbits;
     memcpy(&sbits, &a.scale, 4);
     snprintf(key, sizeof(key), "%d/%p/%lld/%lld/%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", a.buf, c->handoff, c->handoff_rows, c->handoff_off, a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
-             c->gemm_backend, c->groups, (((c->debug_skip * 2 + c->defer_reduce) * 2 + c->fuse_ln) * 4 + c->use_prefetch) * 64 + c->stack_kernel * 32 + c->stack_split_o * 4 + c->stack_split_f2 / 2,
+             c->gemm_backend, c->groups, (((c->debug_skip * 2 + c->defer_reduce) * 2 + c->fuse_ln) * 4 + c->use_prefetch) * 64,
              ((c->use_prefetch & 2) ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), (c->use_prefetch & 2) ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
     if (c->graphs.size() > 256 && c->graphs.find(key) == c->graphs.end()) {
         for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1442,6 +1416,8 @@ static int stream_common(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     FO_TRY(run_step(c, a, st));
     if (enc_out) FO_CUDA(cudaMemcpyAsync(enc_out, c->ws[WS_ENC].p, enc_bytes, cudaMemcpyDefault, st));
     if (adapter_out) FO_CUDA(cudaMemcpyAsync(adapter_out, c->ws[WS_Y].p, y_bytes, cudaMemcpyDefault, st));
+    if (!c->ev_sync) FO_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
+    FO_CUDA(cudaEventRecord(c->ev_sync, st));
     c->stats.stream_steps += 1;
     c->stats.session_chunks += n;
     return 0;
@@ -1509,6 +1485,8 @@ int fo_stream_step_async(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     void* stage;
     FO_TRY(ws_ensure(c, ws_pcm(buf), (size_t)n * c->chunk_samples * 4, &stage));
     if (c->async_ticket >= 2) FO_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_compute[buf], 0));
+    // a synchronous step still queued on `st` stages its PCM in WS_PCM as well and reads the shared intermediates
+    if (c->ev_sync) FO_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_sync, 0));
     FO_CUDA(cudaMemcpyAsync(stage, pcm, (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4), cudaMemcpyDefault, c->copy_stream));
     FO_CUDA(cudaEventRecord(c->ev_in[buf], c->copy_stream));
     FO_CUDA(cudaStreamWaitEvent(st, c->ev_in[buf], 0));
@@ -1618,6 +1596,14 @@ int fo_stats(fo_ctx* c, fo_stats_t* out) {
     out->kernel_launches = g_launches;
     out->sessions_in_use = c->sessions_in_use;
     out->device_bytes = c->device_bytes;
+    out->act_saturations = 0;
+    if (c->sat_counter) {
+        // counted by kernels that may still be in flight on the caller's streams: a blocking copy orders after them
+        unsigned long long v = 0;
+        FO_CUDA(cudaSetDevice(c->device));
+        FO_CUDA(cudaMemcpy(&v, c->sat_counter, sizeof(v), cudaMemcpyDeviceToHost));
+        out->act_saturations = (int64_t)v;
+    }
     return 0;
 }
 
@@ -1632,9 +1618,6 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
     else if (!strcmp(name, "fuse_ln")) c->fuse_ln = value != 0;
     else if (!strcmp(name, "defer_reduce")) c->defer_reduce = value != 0;
     else if (!strcmp(name, "tc_persist")) gemm_tc_set_persist(value != 0);
-    else if (!strcmp(name, "stack_kernel")) c->stack_kernel = value != 0;
-    else if (!strcmp(name, "stack_split_o")) c->stack_split_o = (int)value;
-    else if (!strcmp(name, "stack_split_f2")) c->stack_split_f2 = (int)value;
     else if (!strcmp(name, "l2_prefetch")) c->use_prefetch = (int)(value & 3);
     else if (!strcmp(name, "pdl")) g_want_pdl = value != 0;
     else if (!strcmp(name, "session_groups")) {
@@ -1665,8 +1648,6 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     else if (!strcmp(name, "session_groups")) *value = c->groups;
     else if (!strcmp(name, "fuse_ln")) *value = c->fuse_ln;
     else if (!strcmp(name, "defer_reduce")) *value = c->defer_reduce;
-    else if (!strcmp(name, "stack_kernel")) *value = c->stack_kernel;
-    else if (!strcmp(name, "stack_launches")) *value = c->stack_launches;
     else if (!strcmp(name, "tc_persist_launches")) *value = gemm_tc_persist_launches();
     else if (!strcmp(name, "l2_prefetch")) *value = c->use_prefetch;
     else if (!strcmp(name, "pdl")) *value = g_want_pdl;

@@ -180,7 +180,18 @@ struct Epilogue {
     // every split CTA then just writes its raw accumulators as [split][M][N] fp32 and exits (no tile counters, no
     // last-CTA pass, no bias / residual here); layer_norm_reduce() folds  x += bias + sum_s partial_s  into its row pass.
     int defer_reduce = 0;
+    // fp16-range guard of a 16-bit context: every value the epilogue stages as fp16 for the tensor cores is
+    // clamped to +-65504; when that clamp actually changes a value the kernel counts it here (fo_stats.act_saturations).
+    // Only GEMM outputs are unbounded (FFN1 ReLU, K|V, conv outputs); LayerNorm / softmax-weighted outputs are bounded by
+    // construction.  nullptr = not counted.
+    unsigned long long* sat = nullptr;
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ void count_sat4(unsigned long long* sat, float a, float b, float c, float d) {
+    if (sat && fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c), fabsf(d))) > 65504.f)
+        atomicAdd(sat, (unsigned long long)((fabsf(a) > 65504.f) + (fabsf(b) > 65504.f) + (fabsf(c) > 65504.f) + (fabsf(d) > 65504.f)));
+}
+#endif
 
 // C[rowmap(m), n] = A[m, :] . W[n, :]  for m < M (padded GEMM rows), n < N.  A/W are TIn (float or bf16),
 // accumulate fp32.
@@ -294,30 +305,6 @@ template <typename TA>
 int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, const int32_t* ilens, int chunk, int left,
                       const float* ptab, const TA* ptab_h, int pos_rows, const float* pos_u, const float* pos_v, TA* out,
                       cudaStream_t st);
-// ---- persistent transformer-stack kernel of the streaming step (fo_stack.cu) ---------------------------
-struct StackLayerHost {
-    const void *wqkv, *wo, *w1, *w2;          // fp16 containers, K-major
-    const float *ln1g, *ln1b, *ln2g, *ln2b, *bqkv, *bo, *b1, *b2, *pos_u, *pos_v;
-    const void* ptab_h;
-    void* ring;                                // this layer's KV ring
-};
-struct StackHostArgs {
-    const StackLayerHost* layers;              // (L); read on the first launch of a context only
-    int L, D, FF, H;
-    float* x; void* h; void* qkv; float* q32; void* att; void* ffh;
-    float* partial;                            // (max_split, M, D) fp32
-    int max_split;
-    int force_split_o, force_split_f2;         // 0: automatic
-    const float *fin_g, *fin_b;
-    float* enc_out;
-    AttnStream a;
-};
-struct StackState;
-int stack_state_create(StackState** out);
-void stack_state_destroy(StackState* s);
-// 0: launched; 1: shape not covered (caller runs the per-kernel chain); < 0: error
-int stack_stream_launch(StackState* s, const StackHostArgs& args, cudaStream_t st);
-
 // end of a streaming step: n_frames += t, pe_index = pe_index % wrap + chunk_size (attention.py:107,120),
 // and flip the live half of the double-buffered adapter cache.  Either group may be null.
 int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,

@@ -119,6 +119,7 @@ gemm_simt_kernel(const TIn* __restrict__ A, AGather ga, const TWt* __restrict__ 
         if (wf) *reinterpret_cast<float4*>(ep.c_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
         if (wa) {
             TAct* c = reinterpret_cast<TAct*>(ep.c_act) + o;
+            if (sizeof(TAct) == 2) count_sat4(ep.sat, v[0], v[1], v[2], v[3]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) c[j] = from_f<TAct>(v[j]);
         }

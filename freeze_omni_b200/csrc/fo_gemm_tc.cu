@@ -402,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (wf && ok) *reinterpret_cast<float4*>(out32 + o) = v;
                 if (wa && ok) {
                     uint2 h;
-                    if (p.act_fp16) { h.x = pack2<__half>(v.x, v.y); h.y = pack2<__half>(v.z, v.w); }
+                    if (p.act_fp16) { count_sat4(ep.sat, v.x, v.y, v.z, v.w); h.x = pack2<__half>(v.x, v.y); h.y = pack2<__half>(v.z, v.w); }
                     else { h.x = pack2<bf16>(v.x, v.y); h.y = pack2<bf16>(v.z, v.w); }
                     *reinterpret_cast<uint2*>(out16 + o) = h;
                 }
@@ -669,7 +669,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     if (wf) *reinterpret_cast<float4*>(out32 + o) = x;
                     if (wa) {
                         uint2 h;
-                        if (p.act_fp16) { h.x = pack2<__half>(x.x, x.y); h.y = pack2<__half>(x.z, x.w); }
+                        if (p.act_fp16) { count_sat4(ep.sat, x.x, x.y, x.z, x.w); h.x = pack2<__half>(x.x, x.y); h.y = pack2<__half>(x.z, x.w); }
                         else { h.x = pack2<bf16>(x.x, x.y); h.y = pack2<bf16>(x.z, x.w); }
                         *reinterpret_cast<uint2*>(out16 + o) = h;
                     }

@@ -54,6 +54,7 @@ class Engine:
         self.cfg, self.dtype, self.device = cfg, dtype, int(device)
         self.torch_device = torch.device("cuda", self.device)
         self.has_encoder, self.has_adapter = enc_state is not None, adp_state is not None
+        self.max_sessions = int(max_sessions)
         msf = max_stream_frames or max(cfg.chunk_feat_frames, 39)
         self.max_t = PathConfig.sub_len(msf)
         c = _lib.FoConfig(
@@ -214,6 +215,14 @@ class Engine:
             return _lib.FO_F32
         raise TypeError("PCM must be int16 or float32")
 
+    def _scale(self, pcm: ArrayLike, scale: Optional[float]) -> float:
+        """Factor applied to the samples before the fbank ("value used = sample * scale", fo_b200.h).  The reference feeds
+        kaldi.fbank audio in the int16 RANGE: float audio in [-1, 1] is multiplied by 32768 / 32767 (bin/inference.py:74,
+        AudioFeatureGating.py:58), i.e. `cfg.pcm_scale`; int16 PCM is already in that range, so its default is 1.0."""
+        if scale is not None:
+            return float(scale)
+        return 1.0 if self._pcm_dtype(pcm) == _lib.FO_I16 else float(self.cfg.pcm_scale)
+
     def fbank_stream(self, ids, pcm: ArrayLike, scale: Optional[float] = None,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
         ids = _ids(ids)
@@ -221,15 +230,15 @@ class Engine:
         assert tuple(pcm.shape) == (n, self.cfg.samples_per_chunk), "pcm must be (n, samples_per_chunk)"
         out = self._out(out, (n, self.cfg.chunk_feat_frames, self.cfg.feat_dim))
         _lib.check(self.lib.fo_fbank_stream(self._h, _i32p(ids), n, _ptr(pcm), self._pcm_dtype(pcm),
-                                            float(self.cfg.pcm_scale if scale is None else scale), _ptr(out),
+                                            self._scale(pcm, scale), _ptr(out),
                                             self._stream()))
         return out
 
-    def fbank_offline(self, pcm: ArrayLike, scale: float = 1.0) -> torch.Tensor:
+    def fbank_offline(self, pcm: ArrayLike, scale: Optional[float] = None) -> torch.Tensor:
         B, N = pcm.shape
         m = 1 + (N - self.cfg.frame_len) // self.cfg.frame_shift
         out = torch.empty(B, m, self.cfg.feat_dim, device=self.torch_device)
-        _lib.check(self.lib.fo_fbank_offline(self._h, _ptr(pcm), self._pcm_dtype(pcm), B, N, float(scale), _ptr(out),
+        _lib.check(self.lib.fo_fbank_offline(self._h, _ptr(pcm), self._pcm_dtype(pcm), B, N, self._scale(pcm, scale), _ptr(out),
                                              self._stream()))
         return out
 
@@ -275,7 +284,7 @@ class Engine:
         if self.has_adapter:
             adapter_out = self._out(adapter_out, (n, t_out, self.cfg.llm_dim))
         _lib.check(self.lib.fo_stream_step(self._h, _i32p(ids), n, _ptr(pcm), self._pcm_dtype(pcm),
-                                           float(self.cfg.pcm_scale if scale is None else scale),
+                                           self._scale(pcm, scale),
                                            _ptr(enc_out) if want_enc else None,
                                            _ptr(adapter_out) if self.has_adapter else None, self._stream()))
         return (enc_out if want_enc else None), (adapter_out if self.has_adapter else None)
@@ -293,7 +302,7 @@ class Engine:
             assert tuple(enc_out.shape) == (n, t, self.cfg.d_model) and enc_out.dtype == torch.float32 and enc_out.is_contiguous()
         ticket = C.c_int64()
         _lib.check(self.lib.fo_stream_step_async(self._h, _i32p(ids), n, _ptr(pcm), self._pcm_dtype(pcm),
-                                                 float(self.cfg.pcm_scale if scale is None else scale), _ptr(enc_out),
+                                                 self._scale(pcm, scale), _ptr(enc_out),
                                                  _ptr(adapter_out), self._stream(), C.byref(ticket)))
         return int(ticket.value)
 
@@ -313,7 +322,7 @@ class Engine:
         if want_enc:
             enc_out = self._out(enc_out, (n, t, self.cfg.d_model))
         _lib.check(self.lib.fo_stream_step_embeds(self._h, _i32p(ids), n, _ptr(pcm), self._pcm_dtype(pcm),
-                                                  float(self.cfg.pcm_scale if scale is None else scale),
+                                                  self._scale(pcm, scale),
                                                   _ptr(enc_out) if want_enc else None, embeds.data_ptr(),
                                                   int(embeds.shape[1]), int(row_offset), self._stream()))
         return (enc_out if want_enc else None), embeds

@@ -19,12 +19,30 @@ multiple of `bucket` with scratch sessions so that a handful of captured CUDA gr
 State (KV rings, adapter cache, sample carry, feature ring, history ring, queued blocks) never leaves the device.
 """
 from collections import deque
-from typing import Any, Deque, Dict, Hashable, List, Optional, Tuple
+from typing import Any, Deque, Dict, Hashable, List, NamedTuple, Optional, Tuple
 
 import numpy as np
 import torch
 
 IPU_START = "ipu_sl"
+IPU_CONT = "ipu_cl"
+
+
+class Block(NamedTuple):
+    """One encoder + adapter step of one session, as `tick` hands it to the LLM stage.  `status` is the label the reference's
+    feature-gating thread gives the block (bin/dialog_state_pred.py:639-670): the FIRST block of a speech onset carries
+    'ipu_sl' -- which is where AudioLLM.recognize puts the chat prefix (models/audioLLM.py:404-406) -- every other one 'ipu_cl'."""
+    enc: torch.Tensor                 # (t, D) encoder frames
+    emb: Optional[torch.Tensor]       # (t_out, E) adapter embeddings
+    status: str
+
+
+def onset_statuses(n_history: int, status: str) -> List[str]:
+    """Labels of the blocks one pushed chunk turns into (bin/dialog_state_pred.py:639-670): the replayed history blocks are
+    'ipu_sl', 'ipu_cl', 'ipu_cl', ... and the current block is 'ipu_cl' when history was replayed, else keeps its status."""
+    if status != IPU_START or n_history == 0:
+        return [status]
+    return [IPU_START] + [IPU_CONT] * n_history
 
 
 def plan_rounds(queue_lens: Dict[Hashable, int], max_batch: int) -> List[List[Hashable]]:
@@ -58,12 +76,23 @@ class StreamScheduler:
         self.rows: Dict[Hashable, int] = {}                    # session key -> row of the history tensor
         self.free_rows: List[int] = []
         self.pending: Dict[Hashable, Tuple[Any, Optional[str]]] = {}
-        self.queues: Dict[Hashable, Deque[torch.Tensor]] = {}
+        self.queues: Dict[Hashable, Deque[Tuple[torch.Tensor, str]]] = {}
+        # the scratch sessions that pad a batch to its bucket come out of the engine's slot pool: the scheduler can only
+        # promise what is left of it
+        free = engine.max_sessions - engine.stats()["sessions_in_use"] - (self.bucket - 1)
+        if free < 1:
+            raise ValueError("engine has %d session slots, %d in use: no room for bucket=%d (needs bucket-1 scratch sessions + 1)"
+                             % (engine.max_sessions, engine.stats()["sessions_in_use"], self.bucket))
+        cap = free if max_sessions is None else int(max_sessions)
+        if cap > free:
+            raise ValueError("max_sessions=%d exceeds the engine's free slots (%d of %d) minus %d scratch sessions"
+                             % (cap, free + self.bucket - 1, engine.max_sessions, self.bucket - 1))
         self.scratch = engine.alloc(self.bucket - 1) if self.bucket > 1 else np.zeros(0, np.int32)
-        cap = max_sessions or 64
         self._hist = torch.zeros(cap, history_chunks, self.cfg.chunk_feat_frames, self.cfg.feat_dim, device=engine.torch_device)
         self.free_rows = list(range(cap - 1, -1, -1))
         self.stats = {"ticks": 0, "fbank_calls": 0, "encode_calls": 0, "session_steps": 0, "padded_steps": 0}
+        # tests: when a list, every block the gating rule queues is appended as (key, feature block, status)
+        self.block_log: Optional[List[Tuple[Hashable, torch.Tensor, str]]] = None
 
     # ---- sessions ---------------------------------------------------------------------------------
     def open(self, key: Hashable) -> int:
@@ -96,11 +125,12 @@ class StreamScheduler:
         assert key in self.keys and key not in self.pending, "one chunk per session per tick"
         self.pending[key] = (pcm, status)
 
-    def tick(self, scale: Optional[float] = None) -> Dict[Hashable, List[Tuple[torch.Tensor, Optional[torch.Tensor]]]]:
+    def tick(self, scale: Optional[float] = None) -> Dict[Hashable, List[Block]]:
         """Process everything pushed since the last tick.  Returns, per session that produced output, the list of
-        (encoder frames (t, D), adapter embeddings (t_out, E)) in stream order (one entry per queued block)."""
+        Block(encoder frames (t, D), adapter embeddings (t_out, E), status) in stream order (one entry per queued block).
+        `scale` None = the engine's rule: 1.0 for int16 PCM, cfg.pcm_scale for float audio in [-1, 1]."""
         self.stats["ticks"] += 1
-        out: Dict[Hashable, List[Tuple[torch.Tensor, Optional[torch.Tensor]]]] = {}
+        out: Dict[Hashable, List[Block]] = {}
         if self.pending:
             keys = list(self.pending)
             dev = self.eng.torch_device
@@ -118,13 +148,18 @@ class StreamScheduler:
                 status = self.pending[k][1]
                 if status is None:
                     continue
+                blocks = [feats[i]]
                 if status == IPU_START and self.onset_chunks > 0:
                     hist = self._hist[self.rows[k], self.history_chunks - self.onset_chunks:].clone()
-                    self.queues[k].extend(hist.unbind(0))
-                self.queues[k].append(feats[i])
+                    blocks = list(hist.unbind(0)) + blocks
+                labelled = list(zip(blocks, onset_statuses(len(blocks) - 1, status)))
+                self.queues[k].extend(labelled)
+                if self.block_log is not None:
+                    self.block_log.extend((k, b, lab) for b, lab in labelled)
             self.pending.clear()
         for batch in plan_rounds({k: len(q) for k, q in self.queues.items()}, self.max_batch):
-            blocks = [self.queues[k].popleft() for k in batch]
+            heads = [self.queues[k].popleft() for k in batch]
+            blocks = [h[0] for h in heads]
             n = len(batch)
             pad = bucket_size(n, self.bucket) - n
             ids = np.concatenate([np.array([self.keys[k] for k in batch], np.int32), self.scratch[:pad]]).astype(np.int32)
@@ -134,7 +169,7 @@ class StreamScheduler:
             self.stats["session_steps"] += n
             self.stats["padded_steps"] += pad
             for i, k in enumerate(batch):
-                out.setdefault(k, []).append((enc[i], emb[i] if emb is not None else None))
+                out.setdefault(k, []).append(Block(enc[i], emb[i] if emb is not None else None, heads[i][1]))
         return out
 
     def history(self, key: Hashable) -> torch.Tensor:

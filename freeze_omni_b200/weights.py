@@ -100,12 +100,23 @@ def make_adapter_state(cfg: PathConfig, seed: int = 0) -> Dict[str, torch.Tensor
     return {k: _fill("adapter." + k, s, f, seed).float().contiguous() for k, s, f in adapter_param_shapes(cfg)}
 
 
-def audit_state_dict(expected: List[Tuple[str, Tuple[int, ...], int]], sd: Dict[str, torch.Tensor]) -> None:
+def audit_state_dict(expected: List[Tuple[str, Tuple[int, ...], int]], sd: Dict[str, torch.Tensor],
+                     reject_unexpected: bool = False) -> None:
     """``load_state_dict(strict=False)`` (models/utils.py:20) silently drops renamed keys; the
-    drop-in refuses to run on a partial or mis-shaped state dict instead."""
+    drop-in refuses to run on a partial or mis-shaped state dict instead.  With ``reject_unexpected`` (checkpoint ingest)
+    a tensor the configured variant does not own is an error too: ``bn2.running_mean`` under norm='layer' or
+    ``conv1d1.*`` under the single-conv adapter mean the yaml describes a different module than the checkpoint holds."""
     missing = [k for k, _, _ in expected if k not in sd]
     if missing:
         raise KeyError("state dict is missing %d tensors, e.g. %s" % (len(missing), missing[:3]))
     for k, shp, _ in expected:
         if tuple(sd[k].shape) != tuple(shp):
             raise ValueError("tensor %s has shape %s, expected %s" % (k, tuple(sd[k].shape), shp))
+    if reject_unexpected:
+        names = {k for k, _, _ in expected}
+        has_bn = {k.rsplit(".", 1)[0] for k in names if k.endswith(".running_mean")}
+        extra = [k for k in sd if k not in names
+                 and not (k.endswith(".num_batches_tracked") and k.rsplit(".", 1)[0] in has_bn)]
+        if extra:
+            raise ValueError("state dict holds %d tensors the configured variant does not use, e.g. %s -- the yaml's "
+                             "model_conf / encoder_conf does not describe this checkpoint" % (len(extra), sorted(extra)[:3]))

@@ -15,6 +15,7 @@
  *     context must be serialised by the caller (the reference serialises per pipeline object,
  *     bin/dialog_state_pred.py:279-283).
  *   - floating-point tensors cross the boundary as fp32, row-major, innermost dimension last.
+ *   - the session ids of one call must be distinct (a duplicate is FO_ERR_ARG: two rows would advance one session's state).
  */
 #ifndef FO_B200_H
 #define FO_B200_H
@@ -25,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FO_ABI_VERSION 4
+#define FO_ABI_VERSION 5
 
 enum { FO_F32 = 0, FO_BF16 = 1, FO_I16 = 2 };     /* compute dtype / PCM sample type */
 enum { FO_OK = 0, FO_ERR_ARG = -1, FO_ERR_CUDA = -2, FO_ERR_STATE = -3, FO_ERR_NOMEM = -4 };
@@ -81,6 +82,10 @@ typedef struct fo_stats_t {
     int64_t sessions_in_use;
     int64_t device_bytes;      /* HBM held by the context */
     int64_t graph_replays;
+    /* 16-bit contexts stage GEMM outputs that feed the tensor cores as IEEE fp16 (weights are bf16-rounded); a value beyond
+     * +-65504 is clamped AND counted here.  Non-zero means the model's activations left the fp16 range: results are no longer
+     * within the parity bound; run the context in FO_F32.  (The reference's autocast bf16 has fp32 range.) */
+    int64_t act_saturations;
 } fo_stats_t;
 
 int         fo_abi_version(void);
@@ -177,11 +182,11 @@ int fo_stats(fo_ctx* ctx, fo_stats_t* out);
  *   "pdl" 1: programmatic dependent launch along the kernel chain                   "l2_prefetch" 0: next-kernel L2 prefetch, bit0 weights, bit1 KV rings
  *   "defer_reduce" 1: split-K GEMMs of the residual stream leave the reduction to the LayerNorm that follows
  *   "tc_persist" 1: persistent tile loop for fat short-K GEMMs (offline path)       "fuse_ln" 0: LayerNorm inside the residual GEMM's epilogue
- *   "session_groups" 1 (..4): layer kernels of session groups on parallel streams   "stack_kernel" 0: the 24 layers as one cooperative persistent kernel
+ *   "session_groups" 1 (..4): layer kernels of session groups on parallel streams
  *   "profile_gemm" 0/1, "debug_skip" (timing attribution), "tc_swap"/"tc_bn"/"tc_split" (-1 = cost model): development
- * get-only: "tc_launches", "tc_persist_launches", "stack_launches", "ring_cap", "max_t", "profile_gemm_us", "profile_gemm_count".
+ * get-only: "tc_launches", "tc_persist_launches", "ring_cap", "max_t", "profile_gemm_us", "profile_gemm_count".
  * Development environment variables read once per process: FO_TC_OCC, FO_TC_KB, FO_TC_KBD, FO_TC_SMAX, FO_TC_CAP, FO_TC_SKINNY (tile
- * plan of the skinny GEMMs), FO_PDL_MIN, FO_STACK_TRACE / FO_STACK_DBG, FO_PERSIST_DBG, FO_TC_TRACE. */
+ * plan of the skinny GEMMs), FO_PDL_MIN, FO_PERSIST_DBG, FO_TC_TRACE. */
 int fo_set_option(fo_ctx* ctx, const char* name, int64_t value);
 int fo_get_option(fo_ctx* ctx, const char* name, int64_t* value);
 /* per-shape totals of the GEMM launches timed while option "profile_gemm" was 1: text lines "M N K launches microseconds"

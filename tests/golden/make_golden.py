@@ -179,6 +179,34 @@ def main():
              window=kaldi._feature_window_function("povey", 400, 0.42, torch.device("cpu"), torch.float32).numpy(),
              mel=kaldi.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)[0].numpy())
 
+    # ---------------- VAD gating rule (models/AudioFeatureGating.py:77-109 + the relabelling loop of
+    # bin/dialog_state_pred.py:626-670, restated here because that file imports the service stack) ----------
+    if want("gating"):
+        statuses = [None] * 3 + ["ipu_sl"] + ["ipu_cl"] * 2 + [None] * 9 + ["ipu_sl", "ipu_cl", None, "ipu_sl"]
+        audio = synth_audio(77, 2560 * len(statuses)).numpy()
+        g = ref_gating.AudioFeatureGating(16000)                       # defaults: history 10, onset 6, 25/10 ms, 16+3 frames
+        blocks, labels, owner = [], [], []
+        for i, st_ in enumerate(statuses):
+            a = audio[i * 2560:(i + 1) * 2560].astype(np.float32) / 32768.0
+            res = g.process_and_gate({"audio": a, "status": st_, "ipu_id": 0})
+            if not res:
+                continue
+            if res["status"] == "ipu_sl":                              # dialog_state_pred.py:639-663
+                for j, feat in enumerate(res["feature_last_chunk"]):
+                    blocks.append(np.asarray(feat, np.float32).reshape(19, 80))
+                    labels.append("ipu_sl" if j == 0 else "ipu_cl")
+                    owner.append(i)
+                blocks.append(np.asarray(res["feature"], np.float32).reshape(19, 80))
+                labels.append("ipu_cl" if len(res["feature_last_chunk"]) > 0 else "ipu_sl")
+                owner.append(i)
+            else:                                                      # :665-670
+                blocks.append(np.asarray(res["feature"], np.float32).reshape(19, 80))
+                labels.append(res["status"])
+                owner.append(i)
+        save("gating", pcm=audio, statuses=np.array(["" if s_ is None else s_ for s_ in statuses]),
+             blocks=np.stack(blocks), labels=np.array(labels), owner=np.asarray(owner, np.int64),
+             history=g.history.numpy().copy(), scale=np.float64(32767.0))
+
     # ---------------- masks ----------------------------------------------------------------
     if want("masks"):
         arrs = {}

@@ -57,3 +57,36 @@ def test_checkpoint_split_and_audit(tmp_path):
     with pytest.raises(KeyError):
         load_trained(str(tmp_path), role="user")
     assert load_yaml(str(tmp_path / "final.yaml")) and yaml is not None
+
+
+def test_absent_model_conf_keys_take_the_reference_defaults(tmp_path):
+    """AudioLLM.__init__ defaults (models/audioLLM.py:27-52): kernel_size 3, activation_func 'relu', norm 'batch',
+    llm_embed_dim 4096, enc_out_dim 512, adpter_type 'cnn' -- NOT the shipped values: a train.yaml that omits
+    activation_func / norm describes a BatchNorm + ReLU adapter."""
+    import copy
+    from freeze_omni_b200.config import load_yaml, path_config_from_dict
+    y = load_yaml("tiny")
+    y2 = copy.deepcopy(y)
+    for k in ("activation_func", "norm", "kernel_size"):
+        y2["model_conf"].pop(k)
+    cfg = path_config_from_dict(y2)
+    assert (cfg.adapter_act, cfg.adapter_norm, cfg.adapter_kernel) == ("relu", "batch", 3)
+    y3 = copy.deepcopy(y)
+    y3["model_conf"].pop("enc_out_dim")                                    # default 512 != tiny's 128
+    with pytest.raises(ValueError, match="enc_out_dim"):
+        path_config_from_dict(y3)
+    # a LayerNorm yaml on a BatchNorm checkpoint (extra bn2.running_*) is refused, not silently mis-loaded
+    cfg_ln = load_path_config("tiny")
+    cfg_bn = load_path_config("tiny_bn")
+    enc, adp_bn = make_encoder_state(cfg_ln, 1), make_adapter_state(cfg_bn, 1)
+    ckpt = {"encoder.%s" % k: v for k, v in enc.items()}
+    ckpt.update({"adpter.%s" % k: v for k, v in adp_bn.items()})
+    ckpt["adpter.bn2.num_batches_tracked"] = torch.tensor(7)
+    import shutil
+    torch.save(ckpt, tmp_path / "final.pt")
+    shutil.copy(os.path.join(os.path.dirname(__file__), "..", "configs", "tiny.yaml"), tmp_path / "final.yaml")
+    with pytest.raises(ValueError, match="does not use"):
+        load_trained(str(tmp_path))
+    shutil.copy(os.path.join(os.path.dirname(__file__), "..", "configs", "tiny_bn.yaml"), tmp_path / "final.yaml")
+    cfg2, _, a2 = load_trained(str(tmp_path))                              # num_batches_tracked rides along with a BatchNorm
+    assert cfg2.adapter_norm == "batch" and "bn2.running_var" in a2

@@ -30,6 +30,10 @@ class FakeEngine:
     def __init__(self):
         self.cfg, self.torch_device = FakeCfg(), torch.device("cpu")
         self.next_slot, self.fbank_calls, self.encode_calls = 0, [], []
+        self.max_sessions = 64
+
+    def stats(self):
+        return {"sessions_in_use": self.next_slot}
 
     def alloc(self, n):
         ids = np.arange(self.next_slot, self.next_slot + n, dtype=np.int32)
@@ -69,7 +73,9 @@ def test_gating_rule_and_queue_order():
     sch.push("b", pcm, "ipu_cl")
     out = sch.tick()
     assert [float(e[0][0, 0]) for e in out["a"]] == [100.0 * a + 2, 100.0 * a + 3, 100.0 * a + 4]
-    assert len(out["b"]) == 1
+    # labels of the replayed blocks (bin/dialog_state_pred.py:639-670): the first carries the onset, the rest continue
+    assert [e.status for e in out["a"]] == ["ipu_sl", "ipu_cl", "ipu_cl"]
+    assert len(out["b"]) == 1 and out["b"][0].status == "ipu_cl"
     # every fbank call covered both sessions (features are always extracted); batches were padded to the bucket
     assert all(c == [a, b] for c in eng.fbank_calls)
     assert all(len(ids) % 4 == 0 for ids, _ in eng.encode_calls)
@@ -81,3 +87,68 @@ def test_gating_rule_and_queue_order():
     assert sch.stats["session_steps"] == 3 + 4 and sch.stats["ticks"] == 4
     sch.close("a")
     sch.close("b")
+
+
+def test_onset_without_history_keeps_its_label_and_capacity_is_checked():
+    from freeze_omni_b200.scheduler import onset_statuses
+    assert onset_statuses(0, "ipu_sl") == ["ipu_sl"] and onset_statuses(3, "ipu_cl") == ["ipu_cl"]
+    assert onset_statuses(6, "ipu_sl") == ["ipu_sl"] + ["ipu_cl"] * 6
+    eng = FakeEngine()
+    sch = StreamScheduler(eng, history_chunks=4, onset_chunks=0, bucket=4)
+    sch.open("a")
+    sch.push("a", np.zeros(2560, np.int16), "ipu_sl")
+    assert [b.status for b in sch.tick()["a"]] == ["ipu_sl"]
+    # default capacity = the engine's free slots minus the scratch sessions (open() used to fail at the 50th session)
+    eng2 = FakeEngine()
+    eng2.max_sessions = 8
+    sch2 = StreamScheduler(eng2, bucket=4)
+    assert sch2._hist.shape[0] == 8 - 3
+    import pytest
+    with pytest.raises(ValueError):
+        StreamScheduler(FakeEngine(), bucket=4, max_sessions=64)
+
+
+class OracleFrontEngine(FakeEngine):
+    """FakeEngine whose frontend is the CPU oracle's stateful fbank, one per slot: the scheduler's gating logic runs on the
+    same feature blocks the reference's AudioFeatureGating produced for the golden."""
+
+    def __init__(self):
+        super().__init__()
+        from oracle import freeze_omni_oracle as O
+        self.O, self.front = O, {}
+
+    def fbank_stream(self, ids, pcm, scale=None):
+        self.fbank_calls.append(list(ids))
+        out = []
+        for i, s in enumerate(ids):
+            fr = self.front.setdefault(int(s), self.O.StreamingFrontend())
+            out.append(fr.process(torch.as_tensor(pcm[i]).float(), 1.0 if scale is None else scale))
+        return torch.cat(out, 0)
+
+
+def test_gating_rule_pinned_to_reference_process_and_gate():
+    """tests/golden/gating.npz holds what models/AudioFeatureGating.process_and_gate + the relabelling loop of
+    bin/dialog_state_pred.py:626-670 queued for a seeded stream (generated by tests/golden/make_golden.py from the reference
+    module itself): same blocks, same order, same labels, same history ring."""
+    from conftest import load_golden
+    g = load_golden("gating")
+    eng = OracleFrontEngine()
+    sch = StreamScheduler(eng, history_chunks=10, onset_chunks=6, bucket=1, max_sessions=4)
+    sch.open("u")
+    sch.block_log = []
+    per_tick = []
+    for i, st in enumerate(g["statuses"]):
+        a = g["pcm"][i * 2560:(i + 1) * 2560].astype(np.float32) / 32768.0
+        sch.push("u", a, str(st) if str(st) else None)
+        out = sch.tick(float(g["scale"]))
+        per_tick.append(len(out.get("u", [])))
+    assert len(sch.block_log) == len(g["labels"])
+    assert [lab for _, _, lab in sch.block_log] == [str(x) for x in g["labels"]]
+    got = torch.stack([b for _, b, _ in sch.block_log]).numpy()
+    err = np.abs(got - g["blocks"]) / np.maximum(np.abs(g["blocks"]), 1.0)
+    assert err.max() < 1e-5, err.max()
+    herr = np.abs(sch.history("u").numpy() - g["history"]) / np.maximum(np.abs(g["history"]), 1.0)
+    assert herr.max() < 1e-5
+    # blocks per tick: the reference emits 1 + 6 at an onset, 1 while speaking, 0 when silent
+    want = [int((g["owner"] == i).sum()) for i in range(len(g["statuses"]))]
+    assert per_tick == want
