@@ -20,6 +20,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 if os.environ.get("FO_TC_TRACE_BUILD") == "1":        # in-kernel timeline stamps for tools/gemm_trace.py
     NVCC_FLAGS.append("-DFO_TC_TRACE_BUILD")
+if os.environ.get("FO_TRACE_BUILD") == "1":           # whole-step CTA timeline (tools/step_timeline.py): a SEPARATE library
+    NVCC_FLAGS.append("-DFO_TRACE_BUILD")
+    OBJ = os.path.join(HERE, "csrc", "build_trace")
+    LIB = os.path.join(HERE, "libfo_b200_trace.so")
 
 
 def _nvcc() -> str:

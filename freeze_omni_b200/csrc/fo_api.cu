@@ -127,6 +127,9 @@ struct fo_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     long long async_ticket = 0;
+    unsigned long long* trace_buf = nullptr;  // development (FO_TRACE_BUILD): CTA timeline records, 8 x u64 each
+    unsigned int* trace_cnt = nullptr;
+    unsigned int trace_cap = 0;
     unsigned long long* sat_counter = nullptr; // device: fp16-range saturations counted by the GEMM epilogues (Epilogue::sat)
     cudaEvent_t ev_sync = nullptr;            // recorded after every synchronous step: the copy stream of a later async step
                                               // must not overwrite the staging buffers that step still reads
@@ -1615,6 +1618,32 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
     } else if (!strcmp(name, "use_graph")) c->use_graph = value != 0;
     else if (!strcmp(name, "split_k")) c->split_k = (int)value;
     else if (!strcmp(name, "debug_skip")) c->debug_skip = (int)value;
+    else if (!strcmp(name, "trace")) {
+        // development builds (FO_TRACE_BUILD): value > 0 allocates room for `value` CTA records and binds the kernels to it,
+        // 0 unbinds.  fo_debug_trace_read copies the records out.
+        FO_CUDA(cudaSetDevice(c->device));
+        FO_CUDA(cudaDeviceSynchronize());
+        if (value > 0 && (unsigned int)value > c->trace_cap) {
+            void* p = nullptr;
+            FO_TRY(dev_alloc(c, &p, (size_t)value * 8 * sizeof(unsigned long long)));
+            c->trace_buf = (unsigned long long*)p;
+            c->trace_cap = (unsigned int)value;
+            if (!c->trace_cnt) { FO_TRY(dev_alloc(c, &p, sizeof(unsigned int))); c->trace_cnt = (unsigned int*)p; }
+        }
+        if (c->trace_cnt) FO_CUDA(cudaMemset(c->trace_cnt, 0, sizeof(unsigned int)));
+        unsigned long long* b = value > 0 ? c->trace_buf : nullptr;
+        trace_bind_gemm(b, c->trace_cnt, c->trace_cap);
+        trace_bind_attention(b, c->trace_cnt, c->trace_cap);
+        trace_bind_elementwise(b, c->trace_cnt, c->trace_cap);
+        trace_bind_fbank(b, c->trace_cnt, c->trace_cap);
+    }
+    else if (!strcmp(name, "tc_plan")) {
+        // development: plan of the skinny GEMM with (N, K): N | K << 16 | swap << 32 | bn << 33 | split << 42 | cap_kb << 48; 0 clears
+        const uint64_t v = (uint64_t)value;
+        gemm_tc_plan_override((int)(v & 0xFFFF), (int)((v >> 16) & 0xFFFF), (int)((v >> 32) & 1), (int)((v >> 33) & 0x1FF),
+                              (int)((v >> 42) & 0x3F), (int)((v >> 48) & 0xFF));
+        c->ws_epoch += 1;                       // captured graphs hold the old plans
+    }
     else if (!strcmp(name, "fuse_ln")) c->fuse_ln = value != 0;
     else if (!strcmp(name, "defer_reduce")) c->defer_reduce = value != 0;
     else if (!strcmp(name, "tc_persist")) gemm_tc_set_persist(value != 0);
@@ -1689,6 +1718,22 @@ int fo_profile_dump(fo_ctx* c, char* buf, int cap) {
         off += w;
     }
     buf[off < cap ? off : cap - 1] = 0;
+    return 0;
+}
+
+int fo_debug_trace_read(fo_ctx* c, uint64_t* out, int64_t cap_records, int64_t* n_records) {
+    FO_CHECK(c && out && n_records, "fo_debug_trace_read: null argument");
+    *n_records = 0;
+    if (!c->trace_cnt) return 0;
+    FO_CUDA(cudaSetDevice(c->device));
+    FO_CUDA(cudaDeviceSynchronize());
+    unsigned int n = 0;
+    FO_CUDA(cudaMemcpy(&n, c->trace_cnt, sizeof(n), cudaMemcpyDeviceToHost));
+    if (n > c->trace_cap) n = c->trace_cap;
+    if ((int64_t)n > cap_records) n = (unsigned int)cap_records;
+    FO_CUDA(cudaMemcpy(out, c->trace_buf, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    FO_CUDA(cudaMemset(c->trace_cnt, 0, sizeof(unsigned int)));
+    *n_records = n;
     return 0;
 }
 

@@ -353,6 +353,8 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
     typedef __half TA;
     constexpr int EPC = 8, NCH = 8;
     AT_TRACE(0);
+    FO_TR_DECL();
+    if (threadIdx.x == 0) FO_TR_STAMP(0);
     FO_PDL_TRIGGER();
     // Everything up to FO_PDL_WAIT below touches only data that no kernel of THIS step has written before this launch:
     // the session state (advance_sessions runs at the end of a step, and a step starts with stream copies, which order
@@ -414,6 +416,7 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
         }
     }
     FO_PDL_WAIT();                                  // from here on: the QKV GEMM's output
+    if (threadIdx.x == 0) FO_TR_STAMP(1);
     // chunk's own K/V rows -> registers
     const int n_new = t * NCH * 2;
     uint4 newv = make_uint4(0, 0, 0, 0);
@@ -502,6 +505,7 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
     __syncthreads();
     mbar_wait(&bar, 0);
     AT_TRACE(5);
+    if (threadIdx.x == 0) FO_TR_STAMP(2);
 
     const int g = lane >> 2, c = lane & 3;
     // ---- scores: S^T tile (16 keys x 8 queries) per MMA chain ----
@@ -595,6 +599,7 @@ attention_stream_mma_kernel(AttnStream a, const __half* __restrict__ qkv, const 
             pack2<__half>(sc[q * DK + 2 * pr], sc[q * DK + 2 * pr + 1]);
     }
     AT_TRACE(9);
+    if (threadIdx.x == 0) { FO_TR_STAMP(3); FO_TR_STAMP(4); FO_TR_FLUSH(2, 0); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1165,5 +1170,7 @@ int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wr
     FO_CUDA(cudaGetLastError());
     return 0;
 }
+
+FO_TR_BIND_DEF(trace_bind_attention)
 
 }  // namespace fo

@@ -64,6 +64,56 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- whole-step CTA timeline (development builds: FO_TRACE_BUILD=1 python -m freeze_omni_b200.build) ----------------
+// Every CTA of the traced kernels appends one record {id word, 6 x %globaltimer} to a device buffer; tools/step_timeline.py
+// replays ONE captured step and reconstructs the in-chain timeline (kernel spans, gaps, overlap under PDL).  Each
+// translation unit owns its copy of the three device symbols (no relocatable device code); fo_set_option("trace", n) binds them.
+#ifdef FO_TRACE_BUILD
+#ifdef __CUDACC__
+static __device__ unsigned long long* g_tr_buf = nullptr;
+static __device__ unsigned int* g_tr_cnt = nullptr;
+static __device__ unsigned int g_tr_cap = 0;
+__device__ __forceinline__ unsigned long long fo_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FO_TR_DECL() __shared__ unsigned long long s_tr[6]
+#define FO_TR_STAMP(i) do { s_tr[i] = fo_gtime(); } while (0)
+// one thread, after the CTA's work is done; kid = kernel id, aux = free 16 bits (e.g. split / tile info)
+#define FO_TR_FLUSH(kid, aux)                                                                                     \
+    do {                                                                                                          \
+        if (g_tr_buf) {                                                                                           \
+            s_tr[5] = fo_gtime();                                                                                 \
+            const unsigned int slot_ = atomicAdd(g_tr_cnt, 1u);                                                   \
+            if (slot_ < g_tr_cap) {                                                                               \
+                unsigned int smid_;                                                                               \
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));                                                \
+                unsigned long long* r_ = g_tr_buf + (unsigned long long)slot_ * 8;                                \
+                const unsigned long long lin_ = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; \
+                r_[0] = (unsigned long long)(kid) | ((unsigned long long)smid_ << 8) | ((unsigned long long)((aux) & 0xFFFF) << 16) | (lin_ << 32); \
+                r_[1] = (unsigned long long)gridDim.x | ((unsigned long long)gridDim.y << 20) | ((unsigned long long)gridDim.z << 40); \
+                for (int i_ = 0; i_ < 6; ++i_) r_[2 + i_] = s_tr[i_];                                             \
+            }                                                                                                     \
+        }                                                                                                         \
+    } while (0)
+#define FO_TR_BIND_DEF(fn)                                                                                        \
+    void fn(unsigned long long* buf, unsigned int* cnt, unsigned int cap) {                                       \
+        cudaMemcpyToSymbol(g_tr_buf, &buf, sizeof(buf));                                                          \
+        cudaMemcpyToSymbol(g_tr_cnt, &cnt, sizeof(cnt));                                                          \
+        cudaMemcpyToSymbol(g_tr_cap, &cap, sizeof(cap));                                                          \
+    }
+#endif
+#else
+#define FO_TR_DECL() do { } while (0)
+#define FO_TR_STAMP(i) do { } while (0)
+#define FO_TR_FLUSH(kid, aux) do { } while (0)
+#define FO_TR_BIND_DEF(fn) void fn(unsigned long long*, unsigned int*, unsigned int) {}
+#endif
+void trace_bind_gemm(unsigned long long* buf, unsigned int* cnt, unsigned int cap);
+void trace_bind_attention(unsigned long long* buf, unsigned int* cnt, unsigned int cap);
+void trace_bind_elementwise(unsigned long long* buf, unsigned int* cnt, unsigned int cap);
+void trace_bind_fbank(unsigned long long* buf, unsigned int* cnt, unsigned int cap);
 // ---- dtype helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
@@ -213,6 +263,7 @@ int gemm_tc_workspace(TcWorkspace* ws);       // allocates; the caller frees the
 // the tile plan the host would pick (pure host logic; fo_debug_plan exposes it to the CPU tests)
 void gemm_tc_plan(long long act_rows, int n_out, int K, int can_defer, int* swap, int* bn, int* split);
 void gemm_tc_force(const TcTune& t);
+void gemm_tc_plan_override(int N, int K, int swap, int bn, int split, int cap_kb);   // N <= 0 clears (development)
 void gemm_tc_set_persist(int on);          // persistent tile loop for fat short-K GEMMs (default on)
 long long gemm_tc_persist_launches();
 void gemm_tc_force_producers(int npa, int npb);   // 0 = default

@@ -163,6 +163,8 @@ layer_norm_reduce_kernel(float* __restrict__ x, const float* __restrict__ partia
                          int M, int D, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                          TA* __restrict__ y_act, float* __restrict__ y_f32) {
     __shared__ float red[2][2][2];               // [row in CTA][half][sum | sq]
+    FO_TR_DECL();
+    if (threadIdx.x == 0) FO_TR_STAMP(0);
     FO_PDL_TRIGGER();
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rr = wid >> 1, half = wid & 1;
@@ -178,6 +180,7 @@ layer_norm_reduce_kernel(float* __restrict__ x, const float* __restrict__ partia
             bs[i] = bias ? *(reinterpret_cast<const float4*>(bias) + f0 + i * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     FO_PDL_WAIT();
+    if (threadIdx.x == 0) FO_TR_STAMP(1);
     const bool live = row < M;
     float4* xr = reinterpret_cast<float4*>(x + (long long)(live ? row : 0) * D) + f0;
     const long long split_stride = ((long long)M * D) >> 2;
@@ -237,6 +240,7 @@ layer_norm_reduce_kernel(float* __restrict__ x, const float* __restrict__ partia
     q = warp_sum(q);
     if (lane == 0) red[rr][half][1] = q;
     __syncthreads();
+    if (threadIdx.x == 0) { FO_TR_STAMP(2); FO_TR_STAMP(3); FO_TR_STAMP(4); FO_TR_FLUSH(3, 0); }
     if (!live) return;
     const float rstd = rsqrtf((red[rr][0][1] + red[rr][1][1]) / D + eps);
 #pragma unroll
@@ -668,5 +672,7 @@ template int ring_export<__half>(const __half*, int, int, long long, int, float*
 template int ring_import<float>(float*, int, int, long long, int, const float*, cudaStream_t);
 template int ring_import<bf16>(bf16*, int, int, long long, int, const float*, cudaStream_t);
 template int ring_import<__half>(__half*, int, int, long long, int, const float*, cudaStream_t);
+
+FO_TR_BIND_DEF(trace_bind_elementwise)
 
 }  // namespace fo

@@ -217,4 +217,6 @@ int fbank_offline(const FbankParams& p, const void* pcm, int pcm_is_i16, int B, 
     return 0;
 }
 
+FO_TR_BIND_DEF(trace_bind_fbank)
+
 }  // namespace fo

@@ -183,8 +183,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), accb = smem_u32(&acc_bar);
 
     FO_PDL_TRIGGER();
+    FO_TR_DECL();
     if (threadIdx.x == 0) TC_TRACE(0);
     if (threadIdx.x == 0) {
+        FO_TR_STAMP(0);
         for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, p.npa + p.npb); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(accb, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -218,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0 && pi < p.npa + p.npb) {
             const int w = pi < p.npa ? 0 : 1;
             // the weight operand does not depend on the previous kernel: its stages fill while that kernel drains
-            if ((w == 0) != (p.swap != 0)) FO_PDL_WAIT();
+            if ((w == 0) != (p.swap != 0)) { FO_PDL_WAIT(); FO_TR_STAMP(1); }
             const int sub = w ? pi - p.npa : pi;                 // row slice of the operand tile this thread loads
             const int sub_rows = w ? p.bn / p.npb : BM / p.npa;
             const CUtensorMap* map = w ? &map_b : &map_a;
@@ -253,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
-                if (i == 0) TC_TRACE(5);
+                if (i == 0) { TC_TRACE(5); FO_TR_STAMP(2); }
                 const uint64_t da = umma_desc(sa), db = umma_desc(sa + a_bytes);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k)          // +32 B per K step inside the swizzle atom (>>4 = 2)
@@ -290,9 +292,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                           gridDim.x * gridDim.y * gridDim.z, et, 128);
         mbar_wait(accb, 0);
         tc_fence_after();
-        if (et == 0) TC_TRACE(8);
+        if (et == 0) { TC_TRACE(8); FO_TR_STAMP(3); }
         const long long tile_id = (long long)tile_b * gridDim.x + tile_a;
-        if (p.defer) {
+        if (p.defer && !p.swap) {
+            // deferred reduction, activations on the M side: this thread owns token row m and writes 16 consecutive columns per load
+            const int m = tile_a * BM + row_l;
+            float* dst = p.partial + ((long long)split * p.rows_a + m) * p.n_out + tile_b * bn;
+            for (int c0 = 0; c0 < bn; c0 += 16) {
+                float v[16];
+                tc_ld16(taddr + c0, v);
+                if (m < p.rows_a) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (tile_b * bn + c0 + j < p.n_out) __stcg(reinterpret_cast<float4*>(dst + c0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+            }
+            if (et == 0) is_last_s = 0;
+        } else if (p.defer) {
             // deferred reduction: this thread owns output column n; a warp's store of one token is one 128-byte line
             const int n = tile_a * BM + row_l;
             float* dst = p.partial + ((long long)split * p.rows_b) * p.n_out + n;
@@ -368,7 +384,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // rows are unrolled so that several independent load/store chains are in flight per warp.
     FO_PDL_WAIT();                                             // producer / MMA warps: before their first global access
     __syncthreads();                                           // staging tile (or nothing, for a non-final split) complete
-    if (threadIdx.x == 64) TC_TRACE(9);
+    if (threadIdx.x == 64) { TC_TRACE(9); FO_TR_STAMP(4); }
     if (is_last_s) {
         const Epilogue& ep = p.ep;
         const int n_rows = p.swap ? bn : BM;
@@ -482,6 +498,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                      : "memory");
     }
+    if (threadIdx.x == 0) FO_TR_FLUSH(1, p.n_out >> 6);
 }
 
 // ---- persistent variant for fat, short-K GEMMs (offline path: M = B*T' rows, K = 1024..4096) -------------------
@@ -754,7 +771,11 @@ int round16(int x) { return (x + 15) / 16 * 16; }
 //  * fat GEMMs (offline, conv2) are MMA / L2 bound: activations on the M side, N = 256 when that still fills the
 //    machine, else 128; or weights on the M side with the UMMA-N extent chosen so that the CTA count lands just
 //    under a multiple of the SM count (wave quantisation), whichever model cost is lower.
-struct Plan { int swap, bn, split; double cost; };
+struct Plan { int swap, bn, split; double cost; int cap_kb = 0; };
+
+// development: per-shape plan overrides (option "tc_plan"), consulted before the cost model for skinny GEMMs
+struct PlanKey { int N, K; bool operator<(const PlanKey& o) const { return N != o.N ? N < o.N : K < o.K; } };
+std::map<PlanKey, Plan> g_plan_override;
 
 int skinny_rows() {
     static int v = 0;
@@ -785,12 +806,17 @@ Plan choose_plan(long long act_rows, int n_out, int K, bool can_defer = false) {
         }
         // a deferred reduction (Epilogue::defer_reduce) has no serial tail, so K can be cut finer
         int split = can_defer ? std::min(smax, (kblocks + kbd - 1) / kbd) : std::min(4, (kblocks + kbt - 1) / kbt);
+        // short-K deferred GEMM (out-proj, K = 1024) at >= 128 rows: with K cut in four a CTA walks 4 k-blocks -- nothing for a
+        // second resident CTA to overlap -- so ONE fat CTA per SM with a quarter of the weight re-reads wins
+        // (in-chain sweep profiles/r02_b_plan_sweep.jsonl: (bn 64, split 4) 1.2526 ms per step vs (16, 2) 1.2694)
+        int occ_here = occ;
+        if (can_defer && kblocks <= 16 && kblocks >= 8 && act_rows >= 128) { split = std::min(4, kblocks / 4); occ_here = 1; }
         int bn = 256;
         const int cands[5] = {16, 32, 64, 128, 256};
         for (int ci = 0; ci < 5; ++ci) {                       // smallest slice that keeps the grid within two CTAs per SM
             const int b = cands[ci];
             const long long tb = (act_rows + b - 1) / b;
-            if ((long long)ta * tb * split <= (long long)occ * sms) { bn = b; break; }
+            if ((long long)ta * tb * split <= (long long)occ_here * sms) { bn = b; break; }
         }
         if (bn > round16((int)act_rows)) bn = round16((int)act_rows);
         const long long tb = (act_rows + bn - 1) / bn;
@@ -819,6 +845,8 @@ Plan choose_plan(long long act_rows, int n_out, int K, bool can_defer = false) {
 }
 
 }  // namespace
+
+FO_TR_BIND_DEF(trace_bind_gemm)
 
 int gemm_tc_init() {
     static std::mutex mu;
@@ -857,6 +885,12 @@ void gemm_tc_plan(long long act_rows, int n_out, int K, int can_defer, int* swap
     *swap = p.swap; *bn = p.bn; *split = p.split;
 }
 void gemm_tc_force(const TcTune& t) { g_forced = t; }
+void gemm_tc_plan_override(int N, int K, int swap, int bn, int split, int cap_kb) {
+    if (N <= 0) { g_plan_override.clear(); return; }
+    Plan p{swap, bn, split, 0.0};
+    p.cap_kb = cap_kb;
+    g_plan_override[PlanKey{N, K}] = p;
+}
 void gemm_tc_set_persist(int on) { g_persist = on; }
 long long gemm_tc_persist_launches() { return g_persist_launches; }
 void gemm_tc_force_producers(int npa, int npb) { g_forced_npa = npa; g_forced_npb = npb; }
@@ -911,6 +945,10 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     }
     const bool can_defer = ep.defer_reduce && deferred_splits && rmap.p1 == 0 && !ep.ln_gamma && N == ep.ldc;
     Plan pl = choose_plan(M, N, K, can_defer);
+    if (!g_plan_override.empty() && M <= skinny_rows()) {
+        auto it = g_plan_override.find(PlanKey{N, K});
+        if (it != g_plan_override.end()) pl = it->second;
+    }
     if (g_forced.swap >= 0) pl.swap = g_forced.swap;
     if (g_forced.bn > 0) pl.bn = g_forced.bn;
     if (g_forced.split > 0) pl.split = g_forced.split;
@@ -947,7 +985,7 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
         if (!occ_cap) { const char* e1 = getenv("FO_TC_OCC"); occ_cap = e1 ? atoi(e1) : 2; }
         static int cap_kb = 0;
         if (!cap_kb) { const char* e3 = getenv("FO_TC_CAP"); cap_kb = e3 ? atoi(e3) : (occ_cap <= 2 ? 100 : occ_cap == 3 ? 70 : 52); }
-        const int cap = (int)((cap_kb * 1024) / stage);
+        const int cap = (int)(((pl.cap_kb > 0 ? pl.cap_kb : cap_kb) * 1024) / stage);
         if (cap >= 2) p.stages = std::min(p.stages, std::max(cap, 2));
     } else if ((long long)ta * tb * pl.split > g_sm_count) {
         // more CTAs than SMs: keep two resident per SM (<= ~110 KB each) so one CTA's epilogue overlaps the other's mainloop
@@ -985,7 +1023,7 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
         const size_t need = (size_t)pl.split * ta * tb * pl.bn * BM * sizeof(float);
         FO_CHECK(need <= ws.partial_bytes, "gemm_tc: split-K workspace too small (%zu bytes needed)", need);
     }
-    if (ep.defer_reduce && deferred_splits && pl.swap == 1 && pl.split > 1 && rmap.p1 == 0 && !ep.ln_gamma && N == ep.ldc &&
+    if (ep.defer_reduce && deferred_splits && pl.split > 1 && rmap.p1 == 0 && !ep.ln_gamma && N == ep.ldc &&
         (size_t)pl.split * M * N * sizeof(float) <= ws.partial_bytes) {
         p.defer = 1;
         *deferred_splits = pl.split;

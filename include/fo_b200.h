@@ -192,6 +192,10 @@ int fo_get_option(fo_ctx* ctx, const char* name, int64_t* value);
 /* per-shape totals of the GEMM launches timed while option "profile_gemm" was 1: text lines "M N K launches microseconds"
  * (M = GEMM rows incl. the padding rows of the implicit-GEMM convolutions). */
 int fo_profile_dump(fo_ctx* ctx, char* buf, int cap);
+/* development builds only (FO_TRACE_BUILD=1): after fo_set_option("trace", n) every CTA of the step's main kernels appends one
+ * record of 8 uint64 {kernel id | smid << 8 | aux << 16 | linear block id << 32, grid dims, 6 x %globaltimer ns}; this copies up to
+ * cap_records of them out and restarts the log.  A regular build records nothing (n_records = 0). */
+int fo_debug_trace_read(fo_ctx* ctx, uint64_t* out, int64_t cap_records, int64_t* n_records);
 /* host-only: the tile plan of the tcgen05 GEMM for (activation rows, output columns, K) -- swap = weights on the UMMA-M side,
  * bn = UMMA N, split = K splits; can_defer = a consumer kernel finishes the split-K sum.  Needs no GPU (CPU tests of the plan). */
 int fo_debug_plan(int64_t act_rows, int n_out, int K, int can_defer, int* swap, int* bn, int* split);

@@ -36,7 +36,7 @@ def test_plans_of_the_measured_step():
     # 64 sessions (256 rows): QKV / FFN1 un-split at 32-token slices; out-proj and FFN2 (reduction deferred to the LayerNorm)
     assert plan(256, 3072, 1024) == (1, 32, 1)
     assert plan(256, 4096, 1024) == (1, 32, 1)
-    assert plan(256, 1024, 1024, 1) == (1, 16, 2)
+    assert plan(256, 1024, 1024, 1) == (1, 64, 4)                # short K: one fat CTA per SM (r02 in-chain sweep)
     assert plan(256, 1024, 4096, 1) == (1, 32, 4)
     # one session: K of the QKV GEMM split for the attention kernel to sum
     s, b, p = plan(4, 3072, 1024, 1)
