@@ -47,6 +47,8 @@ SYMBOLS = {
     "fo_session_import_kv": (C.c_int, [_P, C.c_int32, C.c_int, _P, _P, C.c_int32]),
     "fo_session_export_adapter_cache": (C.c_int, [_P, C.c_int32, _P, _I32P]),
     "fo_session_import_adapter_cache": (C.c_int, [_P, C.c_int32, _P, C.c_int32]),
+    "fo_session_export_adapter_cache_n": (C.c_int, [_P, C.c_int32, C.c_int, _P, _I32P]),
+    "fo_session_import_adapter_cache_n": (C.c_int, [_P, C.c_int32, C.c_int, _P, C.c_int32]),
     "fo_session_export_ffn_cache": (C.c_int, [_P, C.c_int32, C.c_int, _P]),
     "fo_fbank_stream": (C.c_int, [_P, _I32P, C.c_int, _P, C.c_int, C.c_float, _P, _P]),
     "fo_fbank_offline": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_float, _P, _P]),
@@ -59,6 +61,7 @@ SYMBOLS = {
     "fo_stream_step_embeds": (C.c_int, [_P, _I32P, C.c_int, _P, C.c_int, C.c_float, _P, _P, C.c_int64, C.c_int64, _P]),
     "fo_encode_offline": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "fo_adapter_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "fo_adapter_forward2": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "fo_stats": (C.c_int, [_P, C.POINTER(FoStats)]),
     "fo_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "fo_get_option": (C.c_int, [_P, C.c_char_p, _I64P]),

@@ -58,7 +58,7 @@ class PathConfig:
     adapter_kernel: int = 5
     adapter_act: str = "gelu"
     adapter_norm: str = "layer"
-    adapter_type: str = "subsampling"       # 'subsampling' (CNNSubsampling, adapter.py:72-157) | 'linear' (LinearAdapter, :59-70)
+    adapter_type: str = "subsampling"       # 'subsampling' (CNNSubsampling, adapter.py:72-157) | 'linear' (LinearAdapter, :59-70) | 'cnn' (CNNAdapter, :10-57)
     # streaming frontend (bin/inference.py:43-56)
     sample_rate: int = 16000
     frame_length_ms: int = 25
@@ -68,6 +68,12 @@ class PathConfig:
     pcm_scale: float = 32768.0
 
     # ---- derived quantities (attention.py:83,88,291; subsampling.py:34) -----------------------
+    @property
+    def adapter_two_conv(self) -> bool:
+        """CNNAdapter (adapter.py:10-57) and CNNSubsampling with enc_out_dim * 4 < llm_embed_dim (adapter.py:83-96) run two
+        convolutions (C -> 2C -> 4C) with BatchNorm1d + ReLU each, whatever activation_func / norm say."""
+        return self.adapter_type == "cnn" or (self.adapter_type == "subsampling" and self.d_model * 4 < self.llm_dim)
+
     @property
     def d_k(self) -> int:
         return self.d_model // self.n_heads
@@ -129,10 +135,10 @@ class PathConfig:
             raise ValueError("adapter: norm must be layer|batch and activation gelu|relu (adapter.py:100-107)")
         if self.adapter_kernel < 2:
             raise ValueError("adapter kernel_size must be >= 2")
-        if self.adapter_type not in ("subsampling", "linear"):
-            raise ValueError("adpter_type %r: CNNAdapter (adapter.py:10-57) is not built (the oracle covers it)" % self.adapter_type)
-        if self.adapter_type == "subsampling" and self.d_model * 4 < self.llm_dim:
-            raise ValueError("two-conv CNNSubsampling branch (adapter.py:84-96) is not built (the oracle covers it)")
+        if self.adapter_type not in ("subsampling", "linear", "cnn"):
+            raise ValueError("adpter_type must be cnn | linear | subsampling (audioLLM.py:159-165); got %r" % self.adapter_type)
+        if self.adapter_two_conv and self.d_model * 4 > 4096:
+            raise ValueError("the two-conv adapters normalise 4 * d_model channels; d_model must be <= 1024")
         if not self.normalize_before:
             raise ValueError("post-norm layers (normalize_before=False) are not built")
         if self.ffn_type not in ("linear", "conv1d-linear"):

@@ -89,6 +89,13 @@ struct fo_ctx {
     float *after_g = nullptr, *after_b = nullptr;
     void *ad_conv_w = nullptr, *ad_proj_w = nullptr;
     float *ad_conv_b = nullptr, *ad_ln_g = nullptr, *ad_ln_b = nullptr, *ad_proj_b = nullptr;
+    // two-conv adapters (CNNAdapter, adapter.py:10-57; CNNSubsampling with 4 * enc_out_dim < llm_embed_dim, adapter.py:84-96):
+    // first conv C -> 2C and its folded eval-BatchNorm; the second conv (2C -> 4C) reuses ad_conv_* / ad_ln_* above
+    void* ad_conv1_w = nullptr;
+    float *ad_conv1_b = nullptr, *ad_bn1_s = nullptr, *ad_bn1_t = nullptr;
+    bool ad_two = false;                      // two convolutions
+    int ad_stride2 = 2;                       // stride of the LAST conv (CNNAdapter: 1)
+    float* ad_cache2 = nullptr;               // [slot][2][k-1][2C] fp32: left context of the second conv (reference cache[0])
     float *fb_window = nullptr, *fb_mel = nullptr;
     int *fb_lo = nullptr, *fb_hi = nullptr;
 
@@ -106,7 +113,7 @@ struct fo_ctx {
     cudaEvent_t ids_event[NSTAGE] = {nullptr};
     int ids_cursor = 0;
     int32_t* ids_dev = nullptr;
-    DevBuf ws[32];                            // named workspaces, see enum below
+    DevBuf ws[40];                            // named workspaces, see enum below
     // options
     int gemm_backend = 0, use_graph = 0, split_k = 1;
     int tc_npa = 0, tc_npb = 0;
@@ -162,7 +169,7 @@ struct fo_ctx {
 namespace {
 
 enum { WS_FEATS = 0, WS_C1, WS_C2, WS_XSUB, WS_EMB, WS_X, WS_H, WS_QKV, WS_ATT, WS_FFH, WS_ENC, WS_XIN, WS_ACONV, WS_AH,
-       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_PART, WS_PCM2, WS_ENC2, WS_Y2, WS_COUNT };
+       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_PART, WS_PCM2, WS_ENC2, WS_Y2, WS_AC1, WS_XIN2, WS_TMP4, WS_TMP5, WS_COUNT };
 
 int dev_alloc(fo_ctx* c, void** p, size_t bytes) {
     *p = nullptr;
@@ -489,34 +496,57 @@ int finalize_t(fo_ctx* c) {
         FO_TRY(keep_w<TW>(c, "adapter.adpter.weight", {E, D}, &c->ad_proj_w));
         FO_TRY(keep_f32(c, "adapter.adpter.bias", {E}, &c->ad_proj_b));
     } else if (g.has_adapter) {
-        const HostTensor* t;
-        FO_TRY(need(c, "adapter.conv1d2.weight", {2 * D, D, KA}, &t));
-        FO_TRY(dev_alloc(c, &c->ad_conv_w, (size_t)2 * D * D * KA * sizeof(TW)));
-        FO_TRY(repack_adapter_conv<TW>(t->d, 2 * D, D, KA, reinterpret_cast<TW*>(c->ad_conv_w), 0));
-        FO_TRY(keep_f32(c, "adapter.conv1d2.bias", {2 * D}, &c->ad_conv_b));
-        FO_TRY(keep_f32(c, "adapter.bn2.weight", {2 * D}, &c->ad_ln_g));
-        FO_TRY(keep_f32(c, "adapter.bn2.bias", {2 * D}, &c->ad_ln_b));
-        if (g.adapter_batchnorm) {
-            // BatchNorm1d in eval mode (adapter.py:100-101,146) is a per-channel affine map of the running statistics:
-            // y = (x - mean) / sqrt(var + 1e-3) * gamma + beta = x * s + (beta - mean * s); folded once, in double
+        // eval-mode BatchNorm1d(eps 1e-3) as a per-channel affine map of the running statistics (adapter.py:25-26,87,92,100-101):
+        // y = (x - mean) / sqrt(var + 1e-3) * gamma + beta = x * s + (beta - mean * s); folded once, in double
+        auto fold_bn = [&](const std::string& name, int n, float* gam_d, float* bet_d) -> int {
             const HostTensor *rm, *rv;
-            FO_TRY(need(c, "adapter.bn2.running_mean", {2 * D}, &rm));
-            FO_TRY(need(c, "adapter.bn2.running_var", {2 * D}, &rv));
-            std::vector<float> gam(2 * D), bet(2 * D), mean(2 * D), var(2 * D);
-            FO_CUDA(cudaMemcpy(gam.data(), c->ad_ln_g, 2 * D * sizeof(float), cudaMemcpyDeviceToHost));
-            FO_CUDA(cudaMemcpy(bet.data(), c->ad_ln_b, 2 * D * sizeof(float), cudaMemcpyDeviceToHost));
-            FO_CUDA(cudaMemcpy(mean.data(), rm->d, 2 * D * sizeof(float), cudaMemcpyDeviceToHost));
-            FO_CUDA(cudaMemcpy(var.data(), rv->d, 2 * D * sizeof(float), cudaMemcpyDeviceToHost));
-            for (int i = 0; i < 2 * D; ++i) {
+            FO_TRY(need(c, "adapter." + name + ".running_mean", {n}, &rm));
+            FO_TRY(need(c, "adapter." + name + ".running_var", {n}, &rv));
+            std::vector<float> gam(n), bet(n), mean(n), var(n);
+            FO_CUDA(cudaMemcpy(gam.data(), gam_d, n * sizeof(float), cudaMemcpyDeviceToHost));
+            FO_CUDA(cudaMemcpy(bet.data(), bet_d, n * sizeof(float), cudaMemcpyDeviceToHost));
+            FO_CUDA(cudaMemcpy(mean.data(), rm->d, n * sizeof(float), cudaMemcpyDeviceToHost));
+            FO_CUDA(cudaMemcpy(var.data(), rv->d, n * sizeof(float), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < n; ++i) {
                 const double sc = (double)gam[i] / sqrt((double)var[i] + 1e-3);
                 gam[i] = (float)sc;
                 bet[i] = (float)((double)bet[i] - (double)mean[i] * sc);
             }
-            FO_CUDA(cudaMemcpy(c->ad_ln_g, gam.data(), 2 * D * sizeof(float), cudaMemcpyHostToDevice));
-            FO_CUDA(cudaMemcpy(c->ad_ln_b, bet.data(), 2 * D * sizeof(float), cudaMemcpyHostToDevice));
+            FO_CUDA(cudaMemcpy(gam_d, gam.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+            FO_CUDA(cudaMemcpy(bet_d, bet.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+            return 0;
+        };
+        const HostTensor* t;
+        if (c->ad_two) {
+            // conv1d1 (C -> 2C, stride 1) + bn1 + ReLU; conv1d2 (2C -> 4C) + bn2 + ReLU; project (4C -> E).  This branch ignores
+            // activation_func / norm: the modules are BatchNorm1d and ReLU by construction (adapter.py:20-29, 84-95)
+            FO_TRY(need(c, "adapter.conv1d1.weight", {2 * D, D, KA}, &t));
+            FO_TRY(dev_alloc(c, &c->ad_conv1_w, (size_t)2 * D * D * KA * sizeof(TW)));
+            FO_TRY(repack_adapter_conv<TW>(t->d, 2 * D, D, KA, reinterpret_cast<TW*>(c->ad_conv1_w), 0));
+            FO_TRY(keep_f32(c, "adapter.conv1d1.bias", {2 * D}, &c->ad_conv1_b));
+            FO_TRY(keep_f32(c, "adapter.bn1.weight", {2 * D}, &c->ad_bn1_s));
+            FO_TRY(keep_f32(c, "adapter.bn1.bias", {2 * D}, &c->ad_bn1_t));
+            FO_TRY(fold_bn("bn1", 2 * D, c->ad_bn1_s, c->ad_bn1_t));
+            FO_TRY(need(c, "adapter.conv1d2.weight", {4 * D, 2 * D, KA}, &t));
+            FO_TRY(dev_alloc(c, &c->ad_conv_w, (size_t)4 * D * 2 * D * KA * sizeof(TW)));
+            FO_TRY(repack_adapter_conv<TW>(t->d, 4 * D, 2 * D, KA, reinterpret_cast<TW*>(c->ad_conv_w), 0));
+            FO_TRY(keep_f32(c, "adapter.conv1d2.bias", {4 * D}, &c->ad_conv_b));
+            FO_TRY(keep_f32(c, "adapter.bn2.weight", {4 * D}, &c->ad_ln_g));
+            FO_TRY(keep_f32(c, "adapter.bn2.bias", {4 * D}, &c->ad_ln_b));
+            FO_TRY(fold_bn("bn2", 4 * D, c->ad_ln_g, c->ad_ln_b));
+            FO_TRY(keep_w<TW>(c, "adapter.project.weight", {E, 4 * D}, &c->ad_proj_w));
+            FO_TRY(keep_f32(c, "adapter.project.bias", {E}, &c->ad_proj_b));
+        } else {
+            FO_TRY(need(c, "adapter.conv1d2.weight", {2 * D, D, KA}, &t));
+            FO_TRY(dev_alloc(c, &c->ad_conv_w, (size_t)2 * D * D * KA * sizeof(TW)));
+            FO_TRY(repack_adapter_conv<TW>(t->d, 2 * D, D, KA, reinterpret_cast<TW*>(c->ad_conv_w), 0));
+            FO_TRY(keep_f32(c, "adapter.conv1d2.bias", {2 * D}, &c->ad_conv_b));
+            FO_TRY(keep_f32(c, "adapter.bn2.weight", {2 * D}, &c->ad_ln_g));
+            FO_TRY(keep_f32(c, "adapter.bn2.bias", {2 * D}, &c->ad_ln_b));
+            if (g.adapter_batchnorm) FO_TRY(fold_bn("bn2", 2 * D, c->ad_ln_g, c->ad_ln_b));
+            FO_TRY(keep_w<TW>(c, "adapter.project.weight", {E, 2 * D}, &c->ad_proj_w));
+            FO_TRY(keep_f32(c, "adapter.project.bias", {E}, &c->ad_proj_b));
         }
-        FO_TRY(keep_w<TW>(c, "adapter.project.weight", {E, 2 * D}, &c->ad_proj_w));
-        FO_TRY(keep_f32(c, "adapter.project.bias", {E}, &c->ad_proj_b));
     }
     FO_CUDA(cudaDeviceSynchronize());
     for (auto& kv : c->staged) cudaFree(kv.second.d);
@@ -541,15 +571,70 @@ FbankParams fbank_params(fo_ctx* c) {
 // frames the adapter emits for T encoder frames: CNNSubsampling = causal conv(k, stride 2) over k-1 cached / padded frames
 // (adapter.py:137-144); LinearAdapter keeps the frame rate (adapter.py:69-70)
 inline int ad_frames(const fo_ctx* c, int T) {
-    return c->cfg.adapter_type == 1 ? T : (T + c->KA - 1 - c->KA) / 2 + 1;
+    if (c->cfg.adapter_type == 1 || c->cfg.adapter_type == 2) return T;      // LinearAdapter / CNNAdapter: stride 1 throughout
+    return (T + c->KA - 1 - c->KA) / 2 + 1;
 }
 
 // ---- adapter program on device buffers -----------------------------------------------------------
 // enc (B, T, D) fp32 -> y (B, t_out, E) fp32.  Slot-resident cache when ids != null.
 template <typename TA>
 int adapter_program(fo_ctx* c, const float* enc, const uint8_t* mask, int B, int T, const int32_t* ids_dev,
-                    const float* cache_in, float* cache_out, float* y, cudaStream_t st) {
+                    const float* cache_in, float* cache_out, float* y, cudaStream_t st,
+                    const float* cache2_in = nullptr, float* cache2_out = nullptr) {
     const int D = c->D, E = c->E, KA = c->KA, km1 = KA - 1;
+    if (c->ad_two) {
+        // CNNAdapter (adapter.py:33-57) / two-conv CNNSubsampling (adapter.py:112-157 with cnn_num == 2):
+        //   stage(x | cache1) -> conv1d1 (stride 1) -> [bn1 + ReLU fused into the next staging] -> stage(. | cache0) -> conv1d2
+        //   (stride 1 or 2) -> bn2 + ReLU -> project.  Both convolutions are implicit GEMMs off the staged rows.
+        const bool cached = c->cfg.adapter_type == 0;             // CNNAdapter carries no cache: zero left context every call
+        const int s2 = c->ad_stride2;
+        const int t_out = s2 == 1 ? T : (T - 1) / 2 + 1;
+        const int Mo = B * t_out;
+        void *xin, *c1out, *xin2, *aconv, *ah;
+        AGather ga1, ga2;
+        RowMap rm1, rm2;
+        conv1d_gather(B, T, D, KA, &ga1, &rm1);
+        if (s2 == 1) conv1d_gather(B, T, 2 * D, KA, &ga2, &rm2);
+        else adapter_gather(B, T, 2 * D, KA, &ga2, &rm2);
+        FO_TRY(ws_ensure(c, WS_XIN, (size_t)ga1.rows * D * sizeof(TA), &xin));
+        FO_TRY(ws_ensure(c, WS_AC1, (size_t)B * T * 2 * D * sizeof(float), &c1out));
+        FO_TRY(ws_ensure(c, WS_XIN2, (size_t)ga2.planes * ga2.rows * 2 * D * sizeof(TA), &xin2));
+        FO_TRY(ws_ensure(c, WS_ACONV, (size_t)Mo * 4 * D * sizeof(float), &aconv));
+        FO_TRY(ws_ensure(c, WS_AH, (size_t)Mo * 4 * D * sizeof(TA), &ah));
+        const int32_t* ids1 = cached ? ids_dev : nullptr;
+        FO_TRY(conv_stage<TA>(enc, mask, B, T, D, km1, 1, nullptr, nullptr, ids1, c->ad_cache, c->ad_valid,
+                              cached ? cache_in : nullptr, cached ? cache_out : nullptr, reinterpret_cast<TA*>(xin), st));
+        Epilogue e1;
+        e1.bias = c->ad_conv1_b;
+        e1.c_f32 = reinterpret_cast<float*>(c1out);
+        e1.ldc = 2 * D;
+        if (!(c->debug_skip & 16))
+            FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xin), ga1, c->ad_conv1_w, (int)ga1.rows, 2 * D, KA * D, e1, rm1, st));
+        FO_TRY(conv_stage<TA>(reinterpret_cast<const float*>(c1out), nullptr, B, T, 2 * D, km1, s2, c->ad_bn1_s, c->ad_bn1_t, ids1,
+                              c->ad_cache2, c->ad_valid, cached ? cache2_in : nullptr, cached ? cache2_out : nullptr,
+                              reinterpret_cast<TA*>(xin2), st));
+        Epilogue e2;
+        e2.bias = c->ad_conv_b;
+        e2.c_f32 = reinterpret_cast<float*>(aconv);
+        e2.ldc = 4 * D;
+        if (!(c->debug_skip & 16))
+            FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(xin2), ga2, c->ad_conv_w, (int)ga2.rows, 4 * D, KA * 2 * D, e2, rm2, st));
+        FO_TRY(layer_norm<TA>(reinterpret_cast<const float*>(aconv), Mo, 4 * D, c->ad_ln_g, c->ad_ln_b, -1.0f /* folded BatchNorm */,
+                              1 /* ReLU */, 1.0f, reinterpret_cast<TA*>(ah), nullptr, st));
+        Epilogue e3;
+        e3.bias = c->ad_proj_b;
+        e3.c_f32 = y;
+        e3.ldc = E;
+        RowMap rm3;
+        if (c->handoff && ids_dev) {
+            e3.c_f32 = nullptr;
+            e3.c_act = reinterpret_cast<TA*>(c->handoff) + c->handoff_off * E;
+            rm3.p1 = t_out; rm3.p0 = t_out; rm3.v1 = 1; rm3.v0 = t_out; rm3.q1 = (int)c->handoff_rows; rm3.q0 = 0;
+        }
+        if (!(c->debug_skip & 16))
+            FO_TRY(gemm<TA>(c, reinterpret_cast<const TA*>(ah), plain_rows(4 * D, Mo), c->ad_proj_w, Mo, E, 4 * D, e3, rm3, st));
+        return 0;
+    }
     if (c->cfg.adapter_type == 1) {
         // LinearAdapter: one GEMM over the encoder frames as they are (the reference does not even apply the pad mask)
         const int M = B * T;
@@ -911,6 +996,9 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
     FO_CHECK(cfg->feat_dim >= 11 && cfg->n_layers > 0 && cfg->max_sessions > 0, "fo_create: bad sizes");
     FO_CHECK(cfg->adapter_kernel >= 2 && cfg->adapter_kernel <= AGather::MAX_SEG, "fo_create: adapter kernel must be in 2..9");
     FO_CHECK(cfg->has_encoder || cfg->has_adapter, "fo_create: nothing to build");
+    FO_CHECK(cfg->adapter_type >= 0 && cfg->adapter_type <= 2, "fo_create: adapter_type must be 0 (subsampling), 1 (linear) or 2 (cnn)");
+    FO_CHECK(!(cfg->has_adapter && (cfg->adapter_type == 2 || (cfg->adapter_type == 0 && 4 * cfg->d_model < cfg->llm_dim))) || 4 * cfg->d_model <= 4096,
+             "fo_create: the two-conv adapters normalise 4 * d_model channels; d_model must be <= 1024");
 
     fo_ctx* c = new fo_ctx();
     c->cfg = *cfg;
@@ -921,6 +1009,10 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
     c->F = cfg->feat_dim; c->F1 = (c->F - 1) / 2; c->F2 = (c->F1 - 1) / 2;
     c->D = cfg->d_model; c->H = cfg->n_heads; c->FF = cfg->ffn_dim; c->L = cfg->n_layers; c->E = cfg->llm_dim;
     c->KA = cfg->adapter_kernel;
+    // adapter module: 0 CNNSubsampling (two convolutions when 4 * enc_out_dim < llm_embed_dim, adapter.py:83), 1 LinearAdapter,
+    // 2 CNNAdapter (two stride-1 convolutions, no cache)
+    c->ad_two = cfg->has_adapter && (cfg->adapter_type == 2 || (cfg->adapter_type == 0 && 4 * cfg->d_model < cfg->llm_dim));
+    c->ad_stride2 = cfg->adapter_type == 2 ? 1 : 2;
     c->KF = cfg->ffn_conv_kernel >= 2 ? cfg->ffn_conv_kernel : 0;
     const bool streaming = cfg->chunk_size > 0 && cfg->left_chunks > 0;
     c->window = streaming ? cfg->chunk_size * cfg->left_chunks : 1;                  // attention.py:290-295
@@ -960,6 +1052,10 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
         void* p = nullptr;
         if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->ad_valid = (int32_t*)p; }
         if (!r) { r = dev_alloc(c, &p, (size_t)S * 2 * (c->KA - 1) * c->D * sizeof(float)); c->ad_cache = (float*)p; }
+        if (!r && c->ad_two && cfg->adapter_type == 0) {
+            r = dev_alloc(c, &p, (size_t)S * 2 * (c->KA - 1) * 2 * c->D * sizeof(float));
+            c->ad_cache2 = (float*)p;
+        }
         if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->ids_dev = (int32_t*)p; }
         if (!r) { r = dev_alloc(c, &p, sizeof(unsigned long long)); c->sat_counter = (unsigned long long*)p; }
         if (!r && cudaMemset(c->sat_counter, 0, sizeof(unsigned long long)) != cudaSuccess) r = FO_ERR_CUDA;
@@ -1199,8 +1295,25 @@ int fo_session_import_kv(fo_ctx* c, int32_t id, int layer, const float* K, const
     return 0;
 }
 
-int fo_session_export_adapter_cache(fo_ctx* c, int32_t id, float* cache, int32_t* valid) {
-    FO_CHECK(c && c->ad_cache, "context has no adapter cache");
+// reference cache list entry `which` of the configured adapter: single-conv CNNSubsampling has one entry (d_model channels);
+// the two-conv branch has cache[0] = second conv's input (2 * d_model channels) and cache[1] = first conv's input (d_model)
+static int ad_cache_of(fo_ctx* c, int which, float** base, int* C) {
+    FO_CHECK(c && c->ad_cache && c->cfg.adapter_type == 0, "context's adapter carries no cache");
+    if (!c->ad_two) {
+        FO_CHECK(which == 0, "single-conv CNNSubsampling has one cache entry (which = 0)");
+        *base = c->ad_cache; *C = c->D;
+    } else {
+        FO_CHECK(which == 0 || which == 1, "two-conv CNNSubsampling has cache entries 0 and 1");
+        *base = which == 0 ? c->ad_cache2 : c->ad_cache;
+        *C = which == 0 ? 2 * c->D : c->D;
+    }
+    return 0;
+}
+
+int fo_session_export_adapter_cache_n(fo_ctx* c, int32_t id, int which, float* cache, int32_t* valid) {
+    float* base;
+    int C;
+    FO_TRY(ad_cache_of(c, which, &base, &C));
     FO_TRY(check_ids(c, &id, 1));
     FO_CUDA(cudaSetDevice(c->device));
     FO_CUDA(cudaDeviceSynchronize());
@@ -1208,32 +1321,47 @@ int fo_session_export_adapter_cache(fo_ctx* c, int32_t id, float* cache, int32_t
     FO_CUDA(cudaMemcpy(&live, c->ad_valid + id, 4, cudaMemcpyDeviceToHost));
     if (valid) *valid = live != 0;
     if (!live || !cache) return 0;
-    const int km1 = c->KA - 1, D = c->D;
-    std::vector<float> tm((size_t)km1 * D), out((size_t)km1 * D);
-    FO_CUDA(cudaMemcpy(tm.data(), c->ad_cache + ((size_t)id * 2 + (live == 2 ? 1 : 0)) * km1 * D, tm.size() * 4, cudaMemcpyDeviceToHost));
+    const int km1 = c->KA - 1;
+    std::vector<float> tm((size_t)km1 * C), out((size_t)km1 * C);
+    FO_CUDA(cudaMemcpy(tm.data(), base + ((size_t)id * 2 + (live == 2 ? 1 : 0)) * km1 * C, tm.size() * 4, cudaMemcpyDeviceToHost));
     for (int r = 0; r < km1; ++r)
-        for (int ch = 0; ch < D; ++ch) out[(size_t)ch * km1 + r] = tm[(size_t)r * D + ch];    // (D, k-1) as adapter.py:141
+        for (int ch = 0; ch < C; ++ch) out[(size_t)ch * km1 + r] = tm[(size_t)r * C + ch];    // (C, k-1) as adapter.py:141
     FO_CUDA(cudaMemcpy(cache, out.data(), out.size() * 4, cudaMemcpyDefault));
     return 0;
 }
 
-int fo_session_import_adapter_cache(fo_ctx* c, int32_t id, const float* cache, int32_t valid) {
-    FO_CHECK(c && c->ad_cache, "context has no adapter cache");
+int fo_session_import_adapter_cache_n(fo_ctx* c, int32_t id, int which, const float* cache, int32_t valid) {
+    float* base;
+    int C;
+    FO_TRY(ad_cache_of(c, which, &base, &C));
     FO_TRY(check_ids(c, &id, 1));
     FO_CUDA(cudaSetDevice(c->device));
     FO_CUDA(cudaDeviceSynchronize());
-    int32_t live = valid ? 1 : 0;
+    int32_t live = 0;
+    FO_CUDA(cudaMemcpy(&live, c->ad_valid + id, 4, cudaMemcpyDeviceToHost));
     if (valid) {
         FO_CHECK(cache, "fo_session_import_adapter_cache: null cache");
-        const int km1 = c->KA - 1, D = c->D;
-        std::vector<float> in((size_t)km1 * D), tm((size_t)km1 * D);
+        const int km1 = c->KA - 1;
+        std::vector<float> in((size_t)km1 * C), tm((size_t)km1 * C);
         FO_CUDA(cudaMemcpy(in.data(), cache, in.size() * 4, cudaMemcpyDefault));
         for (int r = 0; r < km1; ++r)
-            for (int ch = 0; ch < D; ++ch) tm[(size_t)r * D + ch] = in[(size_t)ch * km1 + r];
-        FO_CUDA(cudaMemcpy(c->ad_cache + (size_t)id * 2 * km1 * D, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice));
+            for (int ch = 0; ch < C; ++ch) tm[(size_t)r * C + ch] = in[(size_t)ch * km1 + r];
+        // the entries of one session share the live-half flag: write into the half that is (or becomes) live
+        const int half = live == 2 ? 1 : 0;
+        FO_CUDA(cudaMemcpy(base + ((size_t)id * 2 + half) * km1 * C, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice));
+        if (!live) live = 1;
+    } else {
+        live = 0;
     }
     FO_CUDA(cudaMemcpy(c->ad_valid + id, &live, 4, cudaMemcpyHostToDevice));
     return 0;
+}
+
+int fo_session_export_adapter_cache(fo_ctx* c, int32_t id, float* cache, int32_t* valid) {
+    return fo_session_export_adapter_cache_n(c, id, 0, cache, valid);
+}
+int fo_session_import_adapter_cache(fo_ctx* c, int32_t id, const float* cache, int32_t valid) {
+    return fo_session_import_adapter_cache_n(c, id, 0, cache, valid);
 }
 
 int fo_session_export_ffn_cache(fo_ctx* c, int32_t id, int layer, float* cache) {
@@ -1553,7 +1681,7 @@ int fo_encode_offline(fo_ctx* c, const float* feats, const int32_t* ilens, int B
     FO_TRY(r);
     if (adapter_mask_out) {
         FO_TRY(out_dev(c, adapter_mask_out, (size_t)B * t_out, WS_AMASK, &damask));
-        if (c->cfg.adapter_type == 1) FO_CUDA(cudaMemcpyAsync(damask, dmask, (size_t)B * T2, cudaMemcpyDeviceToDevice, st));   // mask unchanged
+        if (c->cfg.adapter_type != 0) FO_CUDA(cudaMemcpyAsync(damask, dmask, (size_t)B * T2, cudaMemcpyDeviceToDevice, st));   // mask unchanged
         else FO_TRY(stride2_mask((const uint8_t*)dmask, B, T2, t_out, (uint8_t*)damask, st));
         FO_TRY(out_done(adapter_mask_out, damask, (size_t)B * t_out, st));
     }
@@ -1565,31 +1693,50 @@ int fo_encode_offline(fo_ctx* c, const float* feats, const int32_t* ilens, int B
     return 0;
 }
 
-int fo_adapter_forward(fo_ctx* c, const float* x, const uint8_t* mask, int B, int T, const float* cache_in,
-                       float* cache_out, float* y, void* stream) {
+int fo_adapter_forward2(fo_ctx* c, const float* x, const uint8_t* mask, int B, int T, const float* cache0_in, const float* cache1_in,
+                        float* cache0_out, float* cache1_out, float* y, void* stream) {
     FO_CHECK(c && c->finalized && c->cfg.has_adapter, "fo_adapter_forward: context has no finalized adapter");
     FO_CHECK(x && y && B > 0 && T > 0, "fo_adapter_forward: bad argument");
     FO_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int km1 = c->KA - 1, t_out = ad_frames(c, T);
     FO_CHECK(t_out >= 1, "fo_adapter_forward: input too short");
-    if (c->cfg.adapter_type == 1) FO_CHECK(!cache_in && !cache_out, "fo_adapter_forward: LinearAdapter carries no cache");
-    const void *dx, *dm = nullptr, *dci = nullptr;
+    const bool cached = c->cfg.adapter_type == 0;
+    if (!cached) FO_CHECK(!cache0_in && !cache0_out && !cache1_in && !cache1_out, "fo_adapter_forward: this adapter carries no cache");
+    if (!c->ad_two) FO_CHECK(!cache1_in && !cache1_out, "fo_adapter_forward: single-conv CNNSubsampling has one cache entry");
+    // entry 0 / 1 of the reference's cache list (adapter.py:123-143): channels 2C / C with two convolutions, C with one
+    const int C0 = c->ad_two ? 2 * c->D : c->D, C1 = c->D;
+    const void *dx, *dm = nullptr, *dc0 = nullptr, *dc1 = nullptr;
     FO_TRY(in_dev(c, x, (size_t)B * T * c->D * sizeof(float), WS_ENC, st, &dx));
     if (mask) FO_TRY(in_dev(c, mask, (size_t)B * T, WS_MASK2, st, &dm));
-    const size_t cbytes = (size_t)B * c->D * km1 * sizeof(float);
-    if (cache_in) FO_TRY(in_dev(c, cache_in, cbytes, WS_TMP0, st, &dci));
-    void *dco = nullptr, *dy;
-    if (cache_out) FO_TRY(out_dev(c, cache_out, cbytes, WS_TMP1, &dco));
+    const size_t b0 = (size_t)B * C0 * km1 * sizeof(float), b1 = (size_t)B * C1 * km1 * sizeof(float);
+    if (cache0_in) FO_TRY(in_dev(c, cache0_in, b0, WS_TMP0, st, &dc0));
+    if (cache1_in) FO_TRY(in_dev(c, cache1_in, b1, WS_TMP4, st, &dc1));
+    void *do0 = nullptr, *do1 = nullptr, *dy;
+    if (cache0_out) FO_TRY(out_dev(c, cache0_out, b0, WS_TMP1, &do0));
+    if (cache1_out) FO_TRY(out_dev(c, cache1_out, b1, WS_TMP5, &do1));
     const size_t y_bytes = (size_t)B * t_out * c->E * sizeof(float);
     FO_TRY(out_dev(c, y, y_bytes, WS_Y, &dy));
+    // adapter_program: (cache_in, cache_out) = the FIRST conv's input cache, (cache2_*) = the second conv's
+    const float* first_in = (const float*)(c->ad_two ? dc1 : dc0);
+    float* first_out = (float*)(c->ad_two ? do1 : do0);
+    const float* second_in = (const float*)(c->ad_two ? dc0 : nullptr);
+    float* second_out = (float*)(c->ad_two ? do0 : nullptr);
     int r = c->dtype == FO_BF16
-                ? adapter_program<act16>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, (const float*)dci, (float*)dco, (float*)dy, st)
-                : adapter_program<float>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, (const float*)dci, (float*)dco, (float*)dy, st);
+                ? adapter_program<act16>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, first_in, first_out, (float*)dy, st, second_in, second_out)
+                : adapter_program<float>(c, (const float*)dx, (const uint8_t*)dm, B, T, nullptr, first_in, first_out, (float*)dy, st, second_in, second_out);
     FO_TRY(r);
-    if (cache_out) FO_TRY(out_done(cache_out, dco, cbytes, st));
+    if (cache0_out) FO_TRY(out_done(cache0_out, do0, b0, st));
+    if (cache1_out) FO_TRY(out_done(cache1_out, do1, b1, st));
     FO_TRY(out_done(y, dy, y_bytes, st));
     return 0;
+}
+
+int fo_adapter_forward(fo_ctx* c, const float* x, const uint8_t* mask, int B, int T, const float* cache_in,
+                       float* cache_out, float* y, void* stream) {
+    FO_CHECK(c && !(c->ad_two && c->cfg.adapter_type == 0 && (cache_in || cache_out)),
+             "fo_adapter_forward: the two-conv CNNSubsampling carries two caches; use fo_adapter_forward2");
+    return fo_adapter_forward2(c, x, mask, B, T, cache_in, nullptr, cache_out, nullptr, y, stream);
 }
 
 // ---- introspection --------------------------------------------------------------------------------------

@@ -317,6 +317,13 @@ int adapter_stage(const float* enc_out, const uint8_t* mask, int B, int T, int D
                   const int32_t* ids, float* slot_cache, int32_t* slot_valid,       // slot-resident (ids != null)
                   const float* cache_in, float* cache_out,                          // explicit (B, D, km1) layout
                   TA* xin, cudaStream_t st);
+// generalised causal-conv staging for CNNAdapter / the two-conv CNNSubsampling branch (see conv_stage_kernel); C channels,
+// stride 1 (conv1d_gather layout) or 2 (adapter_gather layout); scale/shift != null: rows = ReLU(in * scale + shift)
+template <typename TA>
+int conv_stage(const float* in, const uint8_t* mask, int B, int T, int C, int km1, int stride, const float* scale,
+               const float* shift, const int32_t* ids, float* slot_cache, int32_t* slot_valid, const float* cache_in,
+               float* cache_out, TA* xin, cudaStream_t st);
+void conv1d_gather(int B, int T, int C, int k, AGather* ga, RowMap* rm);
 // Conv1dLinear's causal depthwise Conv1d over time (attention.py:217-224,251): y[r][c] = b[c] + sum_tau w[c][tau] *
 // xin[r + tau][c], xin = [left context (k-1 rows) | x].  Streaming (ids != null): x is (n, t, C), the left context of
 // session ids[b] lives in slot_cache (fp32, (k-1, C) per slot, stride slot_stride) and is replaced by the last k-1 rows

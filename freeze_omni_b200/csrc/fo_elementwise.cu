@@ -303,6 +303,50 @@ __global__ void adapter_stage_kernel(const float* __restrict__ enc_out, const ui
     }
 }
 
+// ---- generalised causal-conv staging (CNNAdapter adapter.py:33-52; two-conv CNNSubsampling adapter.py:123-143) ---------
+// Builds the A operand of a causal Conv1d(C -> *, k, stride) run as an implicit GEMM from fp32 rows `in` (B, T, C):
+//   virtual rows [0, km1) = left context (old cache, or zeros), rows [km1, km1 + T) = f(in) with
+//   f(v) = v (masked to 0 where mask == 0)                         when scale == nullptr  (first conv: the module's input)
+//   f(v) = max(v * scale[c] + shift[c], 0)                         otherwise             (second conv: ReLU(BatchNorm_eval(conv1)))
+// stride 1: one plane, xin[b * (km1 + T) + r][C] (conv1d_gather);  stride 2: two planes by row parity (adapter_gather).
+// The new cache = the last km1 virtual rows, fp32, time-major (slot caches double-buffered exactly as in adapter_stage_kernel;
+// explicit caches in the reference layout (B, C, km1)).
+template <typename TA>
+__global__ void conv_stage_kernel(const float* __restrict__ in, const uint8_t* __restrict__ mask, int T, int C, int km1, int stride,
+                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                  const int32_t* __restrict__ ids, float* slot_cache, const int32_t* __restrict__ slot_valid,
+                                  const float* __restrict__ cache_in, float* cache_out, TA* __restrict__ xin) {
+    FO_PDL_TRIGGER();
+    FO_PDL_WAIT();
+    const int b = blockIdx.x, r = blockIdx.y;          // r in [0, km1 + T)
+    const int slot = ids ? ids[b] : -1;
+    const int live = ids ? slot_valid[slot] : 0;
+    const bool have_old = ids ? (live != 0) : (cache_in != nullptr);
+    const float* old_half = ids ? slot_cache + ((long long)slot * 2 + (live == 2 ? 1 : 0)) * km1 * C : nullptr;
+    float* new_half = ids ? slot_cache + ((long long)slot * 2 + (live == 1 ? 1 : 0)) * km1 * C : nullptr;
+    const int R1 = km1 + T, RP = (km1 + T + 1) >> 1;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v;
+        if (r < km1) {
+            if (!have_old) v = 0.f;
+            else if (ids) v = old_half[(long long)r * C + c];
+            else v = cache_in[((long long)b * C + c) * km1 + r];
+        } else {
+            const int t = r - km1;
+            v = in[((long long)b * T + t) * C + c];
+            if (scale) v = fmaxf(v * scale[c] + shift[c], 0.f);
+            else if (mask && !mask[(long long)b * T + t]) v = 0.f;
+        }
+        if (stride == 1) xin[((long long)b * R1 + r) * C + c] = from_f<TA>(v);
+        else xin[(((long long)(r & 1) * gridDim.x + b) * RP + (r >> 1)) * C + c] = from_f<TA>(v);
+        const int cr = r - T;                            // row of the new cache this element becomes
+        if (cr >= 0) {
+            if (ids) new_half[(long long)cr * C + c] = v;
+            else if (cache_out) cache_out[((long long)b * C + c) * km1 + cr] = v;
+        }
+    }
+}
+
 // grid (ceil(T / DW_TB), B), block = channels (strided).  Each thread owns one channel of DW_TB consecutive output rows:
 // it walks the k-1+DW_TB input rows once (sliding window in registers), so every input element is read once per CTA.
 constexpr int DW_TB = 16;
@@ -556,6 +600,30 @@ int adapter_stage(const float* enc_out, const uint8_t* mask, int B, int T, int D
 template int adapter_stage<float>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, float*, cudaStream_t);
 template int adapter_stage<bf16>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, bf16*, cudaStream_t);
 template int adapter_stage<__half>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, __half*, cudaStream_t);
+
+template <typename TA>
+int conv_stage(const float* in, const uint8_t* mask, int B, int T, int C, int km1, int stride, const float* scale,
+               const float* shift, const int32_t* ids, float* slot_cache, int32_t* slot_valid, const float* cache_in,
+               float* cache_out, TA* xin, cudaStream_t st) {
+    if (B <= 0) return 0;
+    FO_CHECK(stride == 1 || stride == 2, "conv_stage: stride must be 1 or 2");
+    dim3 grid(B, km1 + T);
+    FO_CUDA(launch_pdl(conv_stage_kernel<TA>, grid, dim3(256), 0, st, in, mask, T, C, km1, stride, scale, shift, ids, slot_cache,
+                       (const int32_t*)slot_valid, cache_in, cache_out, xin));
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int conv_stage<float>(const float*, const uint8_t*, int, int, int, int, int, const float*, const float*, const int32_t*, float*, int32_t*, const float*, float*, float*, cudaStream_t);
+template int conv_stage<__half>(const float*, const uint8_t*, int, int, int, int, int, const float*, const float*, const int32_t*, float*, int32_t*, const float*, float*, __half*, cudaStream_t);
+
+// stride-1 causal conv (kernel k) over xin[b * (k-1+T) + r][C]: tap tau of output row t reads row t + tau
+void conv1d_gather(int B, int T, int C, int k, AGather* ga, RowMap* rm) {
+    const int R1 = k - 1 + T;
+    ga->seg_len = C; ga->n_seg = k; ga->rows = (long long)B * R1; ga->planes = 1;
+    for (int i = 0; i < AGather::MAX_SEG; ++i) { ga->plane[i] = 0; ga->rowoff[i] = i; }
+    rm->p0 = R1; rm->p1 = R1; rm->v0 = T; rm->v1 = 1; rm->q0 = 0; rm->q1 = T;
+}
 
 template <typename TA>
 int depthwise_conv(const TA* x, int B, int T, int C, int k, const float* w, const float* bias, const int32_t* ids,

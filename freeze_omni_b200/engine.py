@@ -66,7 +66,8 @@ class Engine:
             frame_len=cfg.frame_len, frame_shift=cfg.frame_shift, frames_per_chunk=cfg.frames_per_chunk,
             context_frames=cfg.context_frames, max_sessions=int(max_sessions), max_stream_frames=int(msf),
             ffn_conv_kernel=int(cfg.ffn_conv_kernel) if cfg.ffn_type == "conv1d-linear" else 0,
-            adapter_batchnorm=int(cfg.adapter_norm == "batch"), adapter_type=int(cfg.adapter_type == "linear"))
+            adapter_batchnorm=int(cfg.adapter_norm == "batch"),
+            adapter_type={"subsampling": 0, "linear": 1, "cnn": 2}[cfg.adapter_type])
         h = C.c_void_p()
         _lib.check(self.lib.fo_create(C.byref(c), self.device, _lib.FO_BF16 if dtype == torch.bfloat16 else _lib.FO_F32,
                                       C.byref(h)))
@@ -192,18 +193,26 @@ class Engine:
         _lib.check(self.lib.fo_session_export_ffn_cache(self._h, int(sid), int(layer), buf.data_ptr()))
         return buf
 
-    def export_adapter_cache(self, sid: int) -> Optional[torch.Tensor]:
-        buf = torch.empty(1, self.cfg.d_model, self.cfg.adapter_kernel - 1)
+    def _adapter_cache_channels(self, which: int) -> int:
+        if self.cfg.adapter_two_conv:
+            return 2 * self.cfg.d_model if which == 0 else self.cfg.d_model
+        return self.cfg.d_model
+
+    def export_adapter_cache(self, sid: int, which: int = 0) -> Optional[torch.Tensor]:
+        """Entry `which` of the reference's adapter cache list (adapter.py:123-143), (1, channels, k-1); None == not set.
+        The two-conv CNNSubsampling has entries 0 (second conv's input, 2 * d_model) and 1 (first conv's input, d_model)."""
+        buf = torch.empty(1, self._adapter_cache_channels(which), self.cfg.adapter_kernel - 1)
         valid = C.c_int32()
-        _lib.check(self.lib.fo_session_export_adapter_cache(self._h, int(sid), buf.data_ptr(), C.byref(valid)))
+        _lib.check(self.lib.fo_session_export_adapter_cache_n(self._h, int(sid), int(which), buf.data_ptr(), C.byref(valid)))
         return buf if valid.value else None
 
-    def import_adapter_cache(self, sid: int, cache: Optional[torch.Tensor]) -> None:
+    def import_adapter_cache(self, sid: int, cache: Optional[torch.Tensor], which: int = 0) -> None:
         if cache is None:
-            _lib.check(self.lib.fo_session_import_adapter_cache(self._h, int(sid), None, 0))
+            _lib.check(self.lib.fo_session_import_adapter_cache_n(self._h, int(sid), int(which), None, 0))
         else:
             c = cache.detach().float().cpu().contiguous()
-            _lib.check(self.lib.fo_session_import_adapter_cache(self._h, int(sid), c.data_ptr(), 1))
+            assert c.numel() == self._adapter_cache_channels(which) * (self.cfg.adapter_kernel - 1)
+            _lib.check(self.lib.fo_session_import_adapter_cache_n(self._h, int(sid), int(which), c.data_ptr(), 1))
 
     # ---- frontend ---------------------------------------------------------------------------------
     @staticmethod
@@ -250,7 +259,7 @@ class Engine:
     def adapter_frames(self, t: int) -> int:
         """Frames the adapter emits for t encoder frames: CNNSubsampling halves (stride-2 conv over k-1 cached frames),
         LinearAdapter keeps the rate."""
-        if self.cfg.adapter_type == "linear":
+        if self.cfg.adapter_type in ("linear", "cnn"):
             return t
         k = self.cfg.adapter_kernel
         return (t + k - 1 - k) // 2 + 1
@@ -345,9 +354,10 @@ class Engine:
                                               _ptr(mask), _ptr(y), _ptr(ymask), self._stream()))
         return enc, mask.bool().unsqueeze(1), y, (ymask.bool().unsqueeze(1) if want_adapter else None)
 
-    def adapter_forward(self, x: torch.Tensor, mask: Optional[torch.Tensor], cache: Optional[torch.Tensor]):
-        """Stateless adapter: x (B,T,D), mask (B,1,T)|(B,T) bool or None, cache (B,D,k-1) or None.
-        Returns (y, new_cache)."""
+    def adapter_forward(self, x: torch.Tensor, mask: Optional[torch.Tensor], cache):
+        """Stateless adapter: x (B,T,D), mask (B,1,T)|(B,T) bool or None.  `cache`: None, a tensor (B,D,k-1) (single-conv
+        CNNSubsampling), or the reference's list [c0 (B,2D,k-1), c1 (B,D,k-1)] for the two-conv branch (entries may be None
+        on the first call, adapter.py:123-143).  Returns (y, new cache in the same form; None for cache-less adapters)."""
         B, T, D = x.shape
         k = self.cfg.adapter_kernel
         t_out = self.adapter_frames(T)
@@ -355,12 +365,22 @@ class Engine:
         m8 = None
         if mask is not None:
             m8 = mask.reshape(B, T).to(torch.uint8).contiguous()
-        ci = None if cache is None else cache.detach().float().contiguous()
         y = torch.empty(B, t_out, self.cfg.llm_dim, device=self.torch_device)
-        if self.cfg.adapter_type == "linear":                  # no cache to carry
+        if self.cfg.adapter_type in ("linear", "cnn"):         # no cache to carry
             assert cache is None
-            _lib.check(self.lib.fo_adapter_forward(self._h, _ptr(x), _ptr(m8), B, T, None, None, _ptr(y), self._stream()))
+            _lib.check(self.lib.fo_adapter_forward2(self._h, _ptr(x), _ptr(m8), B, T, None, None, None, None, _ptr(y), self._stream()))
             return y, None
+        if self.cfg.adapter_two_conv:
+            c0, c1 = (None, None) if cache is None else (cache[0], cache[1])
+            c0 = None if c0 is None else c0.detach().float().contiguous()
+            c1 = None if c1 is None else c1.detach().float().contiguous()
+            assert (c0 is None) == (c1 is None), "the two cache entries are set together (adapter.py:128-141)"
+            o0 = torch.empty(B, 2 * D, k - 1, device=self.torch_device)
+            o1 = torch.empty(B, D, k - 1, device=self.torch_device)
+            _lib.check(self.lib.fo_adapter_forward2(self._h, _ptr(x), _ptr(m8), B, T, _ptr(c0), _ptr(c1), _ptr(o0), _ptr(o1), _ptr(y),
+                                                    self._stream()))
+            return y, [o0, o1]
+        ci = None if cache is None else cache.detach().float().contiguous()
         co = torch.empty(B, D, k - 1, device=self.torch_device)
         _lib.check(self.lib.fo_adapter_forward(self._h, _ptr(x), _ptr(m8), B, T, _ptr(ci), _ptr(co), _ptr(y), self._stream()))
         return y, co

@@ -234,28 +234,8 @@ class speechEncoder(nn.Module):
         return cache
 
 
-class CNNSubsampling(nn.Module):
-    """models/adapter.py:72-157, single-conv branch (enc_out_dim * 4 >= llm_embed_dim)."""
-
-    def __init__(self, enc_out_dim: int = 512, llm_embed_dim: int = 4096, kernel_size: int = 5,
-                 activation_func: str = 'relu', norm: str = 'batch'):
-        super().__init__()
-        if enc_out_dim * 4 < llm_embed_dim:
-            raise NotImplementedError("two-conv CNNSubsampling branch (adapter.py:84-96) is not built")
-        if norm not in ('layer', 'batch'):
-            raise NotImplementedError("adapter norm must be 'layer' or 'batch' (adapter.py:100-103)")
-        self.kernel_size = kernel_size
-        self.left_padding2 = nn.ConstantPad1d((kernel_size - 1, 0), 0.0)
-        self.conv1d2 = nn.Conv1d(enc_out_dim, 2 * enc_out_dim, kernel_size, 2, 0)
-        self.bn2 = (nn.LayerNorm(2 * enc_out_dim, eps=1e-3) if norm == 'layer'
-                    else nn.BatchNorm1d(2 * enc_out_dim, eps=1e-3, momentum=0.99))
-        self.relu2 = nn.GELU() if activation_func == 'gelu' else nn.ReLU()
-        self.project = nn.Linear(2 * enc_out_dim, llm_embed_dim)
-        self.cnn_num = 1
-        self.path_config = PathConfig(d_model=enc_out_dim, n_heads=enc_out_dim // 64, llm_dim=llm_embed_dim,
-                                      adapter_kernel=kernel_size,
-                                      adapter_act='gelu' if activation_func == 'gelu' else 'relu', adapter_norm=norm)
-        self.compute_dtype = torch.float32
+class _AdapterBase(nn.Module):
+    """What the adapter drop-ins share: one Engine per compute dtype, rebuilt when the parameters change."""
 
     def invalidate(self) -> None:
         for eng in _ENGINES.pop(self, {}).values():
@@ -275,23 +255,89 @@ class CNNSubsampling(nn.Module):
         if dtype not in engines:
             p = next(self.parameters())
             if p.device.type != "cuda":
-                raise RuntimeError("CNNSubsampling: move the module to a CUDA device first; there is no CPU path")
+                raise RuntimeError("%s: move the module to a CUDA device first; there is no CPU path" % type(self).__name__)
             sd = {k: v.detach() for k, v in self.state_dict().items()}
             engines[dtype] = Engine(self.path_config, enc_state=None, adp_state=sd, dtype=dtype,
                                     device=p.device.index or 0, max_sessions=1)
         return engines[dtype]
 
+
+class CNNSubsampling(_AdapterBase):
+    """models/adapter.py:72-157: the single-conv branch (enc_out_dim * 4 >= llm_embed_dim) and the two-conv branch
+    (:84-96; two BatchNorm1d + ReLU convolutions, two caches)."""
+
+    def __init__(self, enc_out_dim: int = 512, llm_embed_dim: int = 4096, kernel_size: int = 5,
+                 activation_func: str = 'relu', norm: str = 'batch'):
+        super().__init__()
+        self.kernel_size = kernel_size
+        if enc_out_dim * 4 < llm_embed_dim:
+            self.left_padding1 = nn.ConstantPad1d((kernel_size - 1, 0), 0.0)
+            self.conv1d1 = nn.Conv1d(enc_out_dim, 2 * enc_out_dim, kernel_size, 1, 0)
+            self.bn1 = nn.BatchNorm1d(2 * enc_out_dim, eps=1e-3, momentum=0.99)
+            self.relu1 = nn.ReLU()
+            self.left_padding2 = nn.ConstantPad1d((kernel_size - 1, 0), 0.0)
+            self.conv1d2 = nn.Conv1d(2 * enc_out_dim, 4 * enc_out_dim, kernel_size, 2, 0)
+            self.bn2 = nn.BatchNorm1d(4 * enc_out_dim, eps=1e-3, momentum=0.99)
+            self.relu2 = nn.ReLU()
+            self.project = nn.Linear(4 * enc_out_dim, llm_embed_dim)
+            self.cnn_num = 2
+        else:
+            if norm not in ('layer', 'batch'):
+                raise NotImplementedError("adapter norm must be 'layer' or 'batch' (adapter.py:100-103)")
+            self.left_padding2 = nn.ConstantPad1d((kernel_size - 1, 0), 0.0)
+            self.conv1d2 = nn.Conv1d(enc_out_dim, 2 * enc_out_dim, kernel_size, 2, 0)
+            self.bn2 = (nn.LayerNorm(2 * enc_out_dim, eps=1e-3) if norm == 'layer'
+                        else nn.BatchNorm1d(2 * enc_out_dim, eps=1e-3, momentum=0.99))
+            self.relu2 = nn.GELU() if activation_func == 'gelu' else nn.ReLU()
+            self.project = nn.Linear(2 * enc_out_dim, llm_embed_dim)
+            self.cnn_num = 1
+        self.path_config = PathConfig(d_model=enc_out_dim, n_heads=enc_out_dim // 64, llm_dim=llm_embed_dim,
+                                      adapter_kernel=kernel_size,
+                                      adapter_act='gelu' if activation_func == 'gelu' else 'relu',
+                                      adapter_norm=norm if norm in ('layer', 'batch') else 'batch')
+        self.compute_dtype = torch.float32
+
     @torch.compiler.disable
     @torch.no_grad()
     def forward(self, x, mask_pad, cache=None, return_cache=False):
-        old = None if cache is None else cache[0]
-        y, new_cache = self.engine().adapter_forward(x, mask_pad if mask_pad.size(2) > 0 else None, old)
+        m = mask_pad if mask_pad.size(2) > 0 else None
+        if self.cnn_num == 2:
+            y, new_cache = self.engine().adapter_forward(x, m, cache)
+        else:
+            y, nc = self.engine().adapter_forward(x, m, None if cache is None else cache[0])
+            new_cache = [nc]
         if return_cache:
-            return y, mask_pad[:, :, 0::2], [new_cache]
+            return y, mask_pad[:, :, 0::2], new_cache
         return y, mask_pad[:, :, 0::2]
 
 
-class LinearAdapter(nn.Module):
+class CNNAdapter(_AdapterBase):
+    """models/adapter.py:10-57 (adpter_type == 'cnn', the AudioLLM default, audioLLM.py:159-160): two causal stride-1
+    convolutions with BatchNorm1d + ReLU and Linear(4 * enc_out_dim -> llm_embed_dim); no cache, frame rate kept."""
+
+    def __init__(self, enc_out_dim: int = 512, llm_embed_dim: int = 4096, kernel_size: int = 5):
+        super().__init__()
+        self.left_padding1 = nn.ConstantPad1d((kernel_size - 1, 0), 0.0)
+        self.left_padding2 = nn.ConstantPad1d((kernel_size - 1, 0), 0.0)
+        self.conv1d1 = nn.Conv1d(enc_out_dim, 2 * enc_out_dim, kernel_size, 1, 0)
+        self.conv1d2 = nn.Conv1d(2 * enc_out_dim, 4 * enc_out_dim, kernel_size, 1, 0)
+        self.bn1 = nn.BatchNorm1d(2 * enc_out_dim, eps=1e-3, momentum=0.99)
+        self.bn2 = nn.BatchNorm1d(4 * enc_out_dim, eps=1e-3, momentum=0.99)
+        self.relu1 = nn.ReLU()
+        self.relu2 = nn.ReLU()
+        self.project = nn.Linear(4 * enc_out_dim, llm_embed_dim)
+        self.path_config = PathConfig(d_model=enc_out_dim, n_heads=max(1, enc_out_dim // 64), llm_dim=llm_embed_dim,
+                                      adapter_kernel=kernel_size, adapter_act='relu', adapter_norm='batch', adapter_type='cnn')
+        self.compute_dtype = torch.float32
+
+    @torch.compiler.disable
+    @torch.no_grad()
+    def forward(self, x, mask_pad):
+        y, _ = self.engine().adapter_forward(x, mask_pad if mask_pad.size(2) > 0 else None, None)
+        return y, mask_pad
+
+
+class LinearAdapter(_AdapterBase):
     """models/adapter.py:59-70 (adpter_type == 'linear', audioLLM.py:161-162): y = Linear(enc_out_dim -> llm_embed_dim)(x),
     mask passed through; same state-dict keys (adpter.weight / adpter.bias)."""
 
@@ -301,22 +347,6 @@ class LinearAdapter(nn.Module):
         self.path_config = PathConfig(d_model=enc_out_dim, n_heads=max(1, enc_out_dim // 64), llm_dim=llm_embed_dim,
                                       adapter_type='linear')
         self.compute_dtype = torch.float32
-
-    invalidate = CNNSubsampling.invalidate
-    load_state_dict = CNNSubsampling.load_state_dict
-    _apply = CNNSubsampling._apply
-
-    def engine(self, dtype: Optional[torch.dtype] = None) -> Engine:
-        dtype = dtype or _compute_dtype(self)
-        engines = _ENGINES.setdefault(self, {})
-        if dtype not in engines:
-            p = next(self.parameters())
-            if p.device.type != "cuda":
-                raise RuntimeError("LinearAdapter: move the module to a CUDA device first; there is no CPU path")
-            sd = {k: v.detach() for k, v in self.state_dict().items()}
-            engines[dtype] = Engine(self.path_config, enc_state=None, adp_state=sd, dtype=dtype,
-                                    device=p.device.index or 0, max_sessions=1)
-        return engines[dtype]
 
     @torch.compiler.disable
     @torch.no_grad()

@@ -58,8 +58,7 @@ def adapter_param_shapes(cfg: PathConfig) -> List[Tuple[str, Tuple[int, ...], in
     if getattr(cfg, "adapter_type", "subsampling") == "linear":      # LinearAdapter (adapter.py:59-70): self.adpter = Linear
         return [("adpter.weight", (e, d), d), ("adpter.bias", (e,), d)]
     if getattr(cfg, "adapter_type", "subsampling") == "cnn" or d * 4 < e:
-        # CNNAdapter (adapter.py:10-31) and the two-conv CNNSubsampling branch (adapter.py:84-96) share their tensors: not built
-        # on the GPU (config.validate refuses them); the shapes serve the oracle, which is pinned to the reference modules
+        # CNNAdapter (adapter.py:10-31) and the two-conv CNNSubsampling branch (adapter.py:84-96) share their tensors
         return [("conv1d1.weight", (2 * d, d, k), d * k), ("conv1d1.bias", (2 * d,), d * k),
                 ("bn1.weight", (2 * d,), -1), ("bn1.bias", (2 * d,), -2), ("bn1.running_mean", (2 * d,), -2), ("bn1.running_var", (2 * d,), -4),
                 ("conv1d2.weight", (4 * d, 2 * d, k), 2 * d * k), ("conv1d2.bias", (4 * d,), 2 * d * k),

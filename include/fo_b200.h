@@ -67,9 +67,13 @@ typedef struct fo_config {
     /* adapter norm (models/adapter.py:100-103): 0 = LayerNorm(2C, eps 1e-3); 1 = BatchNorm1d(2C, eps 1e-3) in eval mode
      * (running statistics; tensors adapter.bn2.{weight,bias,running_mean,running_var}) */
     int32_t adapter_batchnorm;
-    /* adapter module (models/audioLLM.py:159-166): 0 = CNNSubsampling (adapter.py:72-157, the shipped 'subsampling');
+    /* adapter module (models/audioLLM.py:159-166): 0 = CNNSubsampling (adapter.py:72-157, the shipped 'subsampling'; when
+     * 4 * d_model < llm_dim it has TWO convolutions and two caches, adapter.py:84-96,123-143: tensors adapter.conv1d1 / bn1 /
+     * conv1d2 / bn2 (BatchNorm1d + ReLU by construction) / project);
      * 1 = LinearAdapter (adapter.py:59-70): y = Linear(d_model -> llm_dim)(x), no cache, no subsampling (t_out = t),
-     * tensors adapter.adpter.{weight,bias} */
+     * tensors adapter.adpter.{weight,bias};
+     * 2 = CNNAdapter (adapter.py:10-57): two causal stride-1 convolutions with BatchNorm1d + ReLU, Linear(4 * d_model -> llm_dim),
+     * no cache (zero left context every call), t_out = t */
     int32_t adapter_type;
 } fo_config;
 
@@ -117,6 +121,11 @@ int fo_session_set_frames(fo_ctx* ctx, int32_t id, int64_t n_frames);
 /* adapter cache in the reference layout (models/adapter.py:141-143): (d_model, kernel-1); valid=0 means None */
 int fo_session_export_adapter_cache(fo_ctx* ctx, int32_t id, float* cache, int32_t* valid);
 int fo_session_import_adapter_cache(fo_ctx* ctx, int32_t id, const float* cache, int32_t valid);
+
+/* entry `which` of the reference's cache list for the two-conv CNNSubsampling (adapter.py:123-143): which = 0 is the second
+ * conv's left context (2 * d_model, kernel-1), which = 1 the first conv's (d_model, kernel-1).  Single-conv: which = 0 only. */
+int fo_session_export_adapter_cache_n(fo_ctx* ctx, int32_t id, int which, float* cache, int32_t* valid);
+int fo_session_import_adapter_cache_n(fo_ctx* ctx, int32_t id, int which, const float* cache, int32_t valid);
 
 /* Conv1dLinear left context of one layer in the reference layout (models/encoder/attention.py:221,258): (d_model, k-1) */
 int fo_session_export_ffn_cache(fo_ctx* ctx, int32_t id, int layer, float* cache);
@@ -174,6 +183,11 @@ int fo_encode_offline(fo_ctx* ctx, const float* feats, const int32_t* ilens, int
  * y (B, (T-1)/2+1, llm_dim). */
 int fo_adapter_forward(fo_ctx* ctx, const float* x, const uint8_t* mask, int B, int T,
                        const float* cache_in, float* cache_out, float* y, void* stream);
+/* the same for adapters with two cache entries (two-conv CNNSubsampling): cache0 (B, 2 * d_model, kernel-1), cache1
+ * (B, d_model, kernel-1) in the order of the reference's list; CNNAdapter / LinearAdapter take no caches (all NULL);
+ * y (B, t_out, llm_dim) with t_out = T for CNNAdapter / LinearAdapter. */
+int fo_adapter_forward2(fo_ctx* ctx, const float* x, const uint8_t* mask, int B, int T, const float* cache0_in,
+                        const float* cache1_in, float* cache0_out, float* cache1_out, float* y, void* stream);
 
 /* ---- introspection / tuning ---- */
 int fo_stats(fo_ctx* ctx, fo_stats_t* out);

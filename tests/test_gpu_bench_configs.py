@@ -256,3 +256,125 @@ def test_fp16_range_guard_counts_saturations():
     assert run(8.0) == (0, True)
     n, finite = run(3.0e5)
     assert n > 0 and finite                                   # clamped, counted, never inf/nan
+
+
+# ------------------------------------------------------------------------------------------------
+# adapter variants: CNNAdapter (adapter.py:10-57) and the two-conv CNNSubsampling branch (adapter.py:84-96,123-143)
+# ------------------------------------------------------------------------------------------------
+def _variant_cfgs():
+    import dataclasses
+    base = path_config_from_dict(load_yaml("tiny_bn"))
+    cnn = dataclasses.replace(base, adapter_type="cnn")
+    two = dataclasses.replace(base, llm_dim=base.d_model * 4 + 64)
+    assert cnn.adapter_two_conv and two.adapter_two_conv
+    return cnn, two
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, BF16_TOL)])
+def test_cnn_adapter_vs_reference_golden(golden, dtype, tol):
+    """CNNAdapter: two causal stride-1 convolutions as implicit GEMMs, eval BatchNorm folded, ReLU, Linear(4C -> E); against
+    the reference module's outputs (tests/golden/tiny_adapter_variants.npz), fp32 1e-4; bf16 vs the oracle on bf16 weights."""
+    from freeze_omni_b200.engine import Engine
+    from freeze_omni_b200.modules import CNNAdapter
+    cfg, _ = _variant_cfgs()
+    g = golden("tiny_adapter_variants")
+    asd = make_adapter_state(cfg, 5)
+    x, m = torch.from_numpy(g["cnn_x"]), torch.from_numpy(g["cnn_mask"])
+    eng = Engine(cfg, None, asd, dtype=dtype, max_sessions=2)
+    try:
+        y, cache = eng.adapter_forward(x.cuda(), m.cuda(), None)
+        assert cache is None and tuple(y.shape) == tuple(g["cnn_y"].shape)
+        if dtype == torch.float32:
+            assert maxabs(y.cpu(), g["cnn_y"]) < tol
+        else:
+            yo, _, _ = O.adapter_forward(cfg, bf16_weights(asd), x, m, None)
+            print("CNNAdapter bf16 vs oracle on bf16 weights: %.4g; vs fp32 reference %.4g" % (maxabs(y.cpu(), yo), maxabs(y.cpu(), g["cnn_y"])))
+            assert maxabs(y.cpu(), yo) < tol
+    finally:
+        eng.close()
+    if dtype == torch.float32:                                   # the drop-in module with the reference's constructor / keys
+        mod = CNNAdapter(cfg.d_model, cfg.llm_dim, cfg.adapter_kernel)
+        assert not mod.load_state_dict(asd, strict=False).unexpected_keys
+        mod = mod.cuda().eval()
+        y2, m2 = mod(x.cuda(), m.cuda())
+        assert maxabs(y2.cpu(), g["cnn_y"]) < tol and torch.equal(m2.cpu(), m)
+        mod.invalidate()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, BF16_TOL)])
+def test_two_conv_subsampling_vs_reference_golden(golden, dtype, tol):
+    """CNNSubsampling with 4 * enc_out_dim < llm_embed_dim: streaming with BOTH caches carried by the caller
+    (adapter.py:123-143), then a ragged full-utterance call; outputs and final caches against the reference module."""
+    from freeze_omni_b200.modules import CNNSubsampling
+    _, cfg = _variant_cfgs()
+    g = golden("tiny_adapter_variants")
+    assert int(g["two_llm_dim"]) == cfg.llm_dim
+    asd = make_adapter_state(cfg, 5)
+    mod = CNNSubsampling(cfg.d_model, cfg.llm_dim, cfg.adapter_kernel, "relu", "batch")
+    assert mod.cnn_num == 2 and not mod.load_state_dict(asd, strict=False).unexpected_keys
+    mod = mod.cuda().eval()
+    mod.compute_dtype = dtype
+    ref_sd = bf16_weights(asd) if dtype == torch.bfloat16 else asd
+    cache, ocache, worst = None, None, 0.0
+    ones = torch.ones(2, 1, 4, dtype=torch.bool)
+    for i in range(g["two_stream_x"].shape[0]):
+        x = torch.from_numpy(g["two_stream_x"][i])
+        y, m2, cache = mod(x.cuda(), ones.cuda(), cache=cache, return_cache=True)
+        yo, _, ocache = O.adapter_forward(cfg, ref_sd, x, ones, ocache)
+        worst = max(worst, maxabs(y.cpu(), yo))
+        if dtype == torch.float32:
+            assert maxabs(y.cpu(), g["two_stream_y"][i]) < tol
+    assert worst < tol
+    assert len(cache) == 2 and tuple(cache[0].shape) == (2, 2 * cfg.d_model, 4) and tuple(cache[1].shape) == (2, cfg.d_model, 4)
+    ctol = tol if dtype == torch.float32 else 2e-2
+    assert maxabs(cache[0].cpu(), ocache[0]) < ctol and maxabs(cache[1].cpu(), ocache[1]) < ctol
+    if dtype == torch.float32:
+        assert maxabs(cache[0].cpu(), g["two_cache0"]) < tol and maxabs(cache[1].cpu(), g["two_cache1"]) < tol
+    xo, mo = torch.from_numpy(g["two_off_x"]), torch.from_numpy(g["two_off_mask"])
+    y, m2 = mod(xo.cuda(), mo.cuda())
+    assert np.array_equal(m2.cpu().numpy(), g["two_off_mask_out"])
+    yo, _, _ = O.adapter_forward(cfg, ref_sd, xo, mo, None)
+    assert maxabs(y.cpu(), yo) < tol
+    if dtype == torch.float32:
+        assert maxabs(y.cpu(), g["two_off_y"]) < tol
+    mod.invalidate()
+
+
+@pytest.mark.parametrize("which", ["cnn", "two"])
+def test_adapter_variants_in_the_streaming_step(which):
+    """The variants inside the batched streaming engine (slot-resident caches): every chunk against per-session oracle
+    sessions; for the two-conv branch both caches are exported in the reference layout, re-imported into a fresh session
+    and the stream continues identically."""
+    from freeze_omni_b200.engine import Engine
+    cnn, two = _variant_cfgs()
+    cfg = cnn if which == "cnn" else two
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 5)
+    eng = Engine(cfg, esd, asd, max_sessions=6)
+    try:
+        ids = eng.alloc(3)
+        oracle = [O.StreamSession(cfg, esd, asd) for _ in range(3)]
+        g = torch.Generator().manual_seed(41)
+        t_out = 4 if which == "cnn" else 2
+        for i in range(4):
+            feats = 9.0 + 3.0 * torch.randn(3, cfg.chunk_feat_frames, cfg.feat_dim, generator=g)
+            enc, y = eng.encode_stream(ids, feats)
+            assert tuple(y.shape) == (3, t_out, cfg.llm_dim)
+            for b in range(3):
+                eo, yo = oracle[b].step_feats(feats[b:b + 1])
+                assert maxabs(enc[b].cpu(), eo[0]) < 1e-4 and maxabs(y[b].cpu(), yo[0]) < 1e-4, (i, b)
+        if which == "two":
+            c0, c1 = eng.export_adapter_cache(int(ids[1]), 0), eng.export_adapter_cache(int(ids[1]), 1)
+            assert maxabs(c0, oracle[1].cache[0][0:1]) < 1e-4 and maxabs(c1, oracle[1].cache[1][0:1]) < 1e-4
+            fresh = eng.alloc(1)
+            assert eng.export_adapter_cache(int(fresh[0]), 0) is None
+            eng.import_adapter_cache(int(fresh[0]), c0, 0)
+            eng.import_adapter_cache(int(fresh[0]), c1, 1)
+            x = torch.randn(1, 4, cfg.d_model, generator=g)
+            ya, _ = eng.adapter_forward(x.cuda(), None, [c0.cuda(), c1.cuda()])
+            yo, _, _ = O.adapter_forward(cfg, asd, x, torch.ones(1, 1, 4, dtype=torch.bool), [c0, c1])
+            assert maxabs(ya.cpu(), yo) < 1e-4
+        else:
+            with pytest.raises(Exception):
+                eng.export_adapter_cache(int(ids[0]), 0)          # CNNAdapter carries no cache
+    finally:
+        eng.close()
