@@ -144,6 +144,18 @@ struct fo_ctx {
     long long id_call = 0;
     void* handoff = nullptr;                  // fo_stream_step_embeds: fp16 destination of the adapter rows for this call
     long long handoff_rows = 0, handoff_off = 0;
+    // fo_handoff_arm: the NEXT streaming call writes its adapter rows into `embeds` and the mask / start rows beside them
+    struct Armed {
+        bool on = false;
+        void* embeds = nullptr;
+        long long rows = 0, prefix = 0;
+        int n = 0;
+        std::vector<uint8_t> onset;
+        const uint8_t* prefix_mask = nullptr;     // device (or null)
+        uint8_t* attn_mask = nullptr;
+        int32_t* row_start = nullptr;
+    } armed;
+    uint8_t* onset_dev = nullptr;
     int groups = 1;                           // session groups whose layer kernels run on parallel streams
     cudaStream_t grp_stream[MAX_GROUPS] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {nullptr};
@@ -244,12 +256,17 @@ int check_ids(fo_ctx* c, const int32_t* ids, int n) {
     return 0;
 }
 
-int upload_ids(fo_ctx* c, const int32_t* ids, int n, cudaStream_t st) {
+int upload_ids(fo_ctx* c, const int32_t* ids, int n, cudaStream_t st, const uint8_t* onset = nullptr) {
     const int k = c->ids_cursor;
     c->ids_cursor = (k + 1) % fo_ctx::NSTAGE;
     FO_CUDA(cudaEventSynchronize(c->ids_event[k]));
     memcpy(c->ids_host[k], ids, sizeof(int32_t) * n);
     FO_CUDA(cudaMemcpyAsync(c->ids_dev, c->ids_host[k], sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    if (onset) {                                 // second half of the pinned staging slot: the hand-off's per-session onset flags
+        uint8_t* oh = reinterpret_cast<uint8_t*>(c->ids_host[k] + c->cfg.max_sessions);
+        memcpy(oh, onset, n);
+        FO_CUDA(cudaMemcpyAsync(c->onset_dev, oh, n, cudaMemcpyHostToDevice, st));
+    }
     FO_CUDA(cudaEventRecord(c->ids_event[k], st));
     return 0;
 }
@@ -1057,11 +1074,12 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
             c->ad_cache2 = (float*)p;
         }
         if (!r) { r = dev_alloc(c, &p, S * sizeof(int32_t)); c->ids_dev = (int32_t*)p; }
+        if (!r) { r = dev_alloc(c, &p, S); c->onset_dev = (uint8_t*)p; }
         if (!r) { r = dev_alloc(c, &p, sizeof(unsigned long long)); c->sat_counter = (unsigned long long*)p; }
         if (!r && cudaMemset(c->sat_counter, 0, sizeof(unsigned long long)) != cudaSuccess) r = FO_ERR_CUDA;
     }
     for (int k = 0; k < fo_ctx::NSTAGE && !r; ++k) {
-        if (cudaMallocHost((void**)&c->ids_host[k], S * sizeof(int32_t)) != cudaSuccess ||
+        if (cudaMallocHost((void**)&c->ids_host[k], 2 * S * sizeof(int32_t)) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ids_event[k], cudaEventDisableTiming) != cudaSuccess) {
             set_error("fo_create: pinned staging allocation failed");
             r = FO_ERR_NOMEM;
@@ -1524,7 +1542,19 @@ static int stream_common(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
         FO_CUDA(cudaStreamWaitEvent(st, c->ev_out[0], 0));
         if (c->async_ticket > 1) FO_CUDA(cudaStreamWaitEvent(st, c->ev_out[1], 0));
     }
-    FO_TRY(upload_ids(c, ids, n, st));
+    fo_ctx::Armed armed = c->armed;              // consumed by this call, whatever its outcome
+    c->armed.on = false;
+    if (armed.on) {
+        FO_CHECK(armed.n == n, "fo_handoff_arm was armed for %d sessions, this call advances %d", armed.n, n);
+        FO_CHECK(!adapter_out && !c->handoff, "an armed hand-off replaces adapter_out: pass NULL");
+        FO_CHECK(armed.rows >= armed.prefix + t_out, "hand-off: %d adapter rows behind a %lld-row prefix do not fit %lld rows per session",
+                 t_out, armed.prefix, armed.rows);
+        c->handoff = armed.embeds;
+        c->handoff_rows = armed.rows;
+        c->handoff_off = armed.prefix;
+    }
+    struct HandoffReset { fo_ctx* c; bool on; ~HandoffReset() { if (on) { c->handoff = nullptr; c->handoff_rows = c->handoff_off = 0; } } } hreset{c, armed.on};
+    FO_TRY(upload_ids(c, ids, n, st, armed.on ? armed.onset.data() : nullptr));
     c->pf_slot_lo = c->pf_slot_hi = ids[0];
     for (int i = 1; i < n; ++i) { c->pf_slot_lo = std::min(c->pf_slot_lo, (int)ids[i]); c->pf_slot_hi = std::max(c->pf_slot_hi, (int)ids[i]); }
     StepArgs a{n, t_in, pcm != nullptr, adapter_out != nullptr, pcm_dtype == FO_I16, scale, 0};
@@ -1545,6 +1575,8 @@ static int stream_common(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
                                     (size_t)t_in * c->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     FO_TRY(run_step(c, a, st));
+    if (armed.on && armed.attn_mask)
+        FO_TRY(handoff_mask(c->onset_dev, armed.prefix_mask, n, (int)armed.prefix, t_out, (int)armed.rows, armed.attn_mask, armed.row_start, st));
     if (enc_out) FO_CUDA(cudaMemcpyAsync(enc_out, c->ws[WS_ENC].p, enc_bytes, cudaMemcpyDefault, st));
     if (adapter_out) FO_CUDA(cudaMemcpyAsync(adapter_out, c->ws[WS_Y].p, y_bytes, cudaMemcpyDefault, st));
     if (!c->ev_sync) FO_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
@@ -1562,6 +1594,29 @@ int fo_encode_stream(fo_ctx* c, const int32_t* ids, int n, const float* feats, i
     if (feats) FO_CHECK(t_in >= 7, "fo_encode_stream: need at least 7 feature frames");
     else t_in = c->cfg.context_frames + c->cfg.frames_per_chunk;
     return stream_common(c, ids, n, nullptr, FO_F32, 1.0f, feats, t_in, enc_out, adapter_out, (cudaStream_t)stream);
+}
+
+int fo_handoff_arm(fo_ctx* c, int n, void* embeds_f16, int64_t rows_per_session, int64_t prefix_len, const uint8_t* onset,
+                   const uint8_t* prefix_mask, uint8_t* attn_mask, int32_t* row_start) {
+    FO_CHECK(c && c->finalized && c->cfg.has_encoder && c->cfg.has_adapter, "fo_handoff_arm: context needs a finalized encoder + adapter");
+    FO_CHECK(c->dtype == FO_BF16, "fo_handoff_arm: the fp16 hand-off is built for bf16 contexts");
+    FO_CHECK(n > 0 && n <= c->cfg.max_sessions && embeds_f16 && onset, "fo_handoff_arm: bad argument");
+    FO_CHECK(prefix_len >= 0 && rows_per_session > prefix_len && rows_per_session < (1LL << 31), "fo_handoff_arm: bad row counts");
+    cudaPointerAttributes pa;
+    FO_CHECK(cudaPointerGetAttributes(&pa, embeds_f16) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device == c->device,
+             "fo_handoff_arm: embeds must be device memory of this context's GPU");
+    if (attn_mask) FO_CHECK(is_device_ptr(attn_mask) && (!row_start || is_device_ptr(row_start)) && (!prefix_mask || is_device_ptr(prefix_mask)),
+                            "fo_handoff_arm: attn_mask, row_start and prefix_mask are device pointers");
+    c->armed.on = true;
+    c->armed.embeds = embeds_f16;
+    c->armed.rows = rows_per_session;
+    c->armed.prefix = prefix_len;
+    c->armed.n = n;
+    c->armed.onset.assign(onset, onset + n);
+    c->armed.prefix_mask = prefix_mask;
+    c->armed.attn_mask = attn_mask;
+    c->armed.row_start = row_start;
+    return 0;
 }
 
 int fo_stream_step_embeds(fo_ctx* c, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale, float* enc_out,

@@ -332,6 +332,9 @@ template <typename TA>
 int depthwise_conv(const TA* x, int B, int T, int C, int k, const float* w, const float* bias, const int32_t* ids,
                    float* slot_cache, long long slot_stride, TA* y, cudaStream_t st);
 int subsample_mask(const int32_t* ilens, int B, int T, int T2, uint8_t* mask2, int32_t* ilens2, cudaStream_t st);
+// attention-mask rows + input start rows of the LLM hand-off (audioLLM.py:404-411); device pointers
+int handoff_mask(const uint8_t* onset, const uint8_t* prefix_mask, int n, int P, int t_out, int rows, uint8_t* attn_mask,
+                 int32_t* row_start, cudaStream_t st);
 int stride2_mask(const uint8_t* mask, int B, int T, int To, uint8_t* out, cudaStream_t st);
 
 // ---- attention -----------------------------------------------------------------------------------

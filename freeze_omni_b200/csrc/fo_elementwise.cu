@@ -639,6 +639,30 @@ int depthwise_conv(const TA* x, int B, int T, int C, int k, const float* w, cons
 template int depthwise_conv<float>(const float*, int, int, int, int, const float*, const float*, const int32_t*, float*, long long, float*, cudaStream_t);
 template int depthwise_conv<__half>(const __half*, int, int, int, int, const float*, const float*, const int32_t*, float*, long long, __half*, cudaStream_t);
 
+// LLM hand-off bookkeeping (models/audioLLM.py:404-411): per session the attention-mask row over its block of the inputs_embeds
+// buffer, [prefix_mask | 1 x t_out | 0 ...] when the block opens an IPU (status 'ipu_sl': the chat prefix is part of the input) and
+// [0 x P | 1 x t_out | 0 ...] otherwise, plus the row where the session's input starts (0 / P).
+__global__ void handoff_mask_kernel(const uint8_t* __restrict__ onset, const uint8_t* __restrict__ prefix_mask, int P, int t_out,
+                                    int rows, uint8_t* __restrict__ attn_mask, int32_t* __restrict__ row_start) {
+    const int b = blockIdx.x;
+    const bool on = onset[b] != 0;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        uint8_t v;
+        if (r < P) v = on ? (prefix_mask ? (prefix_mask[r] != 0) : 1) : 0;
+        else v = r < P + t_out ? 1 : 0;
+        attn_mask[(long long)b * rows + r] = v;
+    }
+    if (threadIdx.x == 0 && row_start) row_start[b] = on ? 0 : P;
+}
+int handoff_mask(const uint8_t* onset, const uint8_t* prefix_mask, int n, int P, int t_out, int rows, uint8_t* attn_mask,
+                 int32_t* row_start, cudaStream_t st) {
+    if (n <= 0) return 0;
+    handoff_mask_kernel<<<n, 128, 0, st>>>(onset, prefix_mask, P, t_out, rows, attn_mask, row_start);
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int subsample_mask(const int32_t* ilens, int B, int T, int T2, uint8_t* mask2, int32_t* ilens2, cudaStream_t st) {
     if (B <= 0) return 0;
     subsample_mask_kernel<<<B, 128, 0, st>>>(ilens, T, T2, mask2, ilens2);

@@ -336,6 +336,26 @@ class Engine:
                                                   int(embeds.shape[1]), int(row_offset), self._stream()))
         return (enc_out if want_enc else None), embeds
 
+    def handoff_arm(self, n: int, embeds: torch.Tensor, prefix_len: int, onset, prefix_mask: Optional[torch.Tensor] = None,
+                    attn_mask: Optional[torch.Tensor] = None, row_start: Optional[torch.Tensor] = None) -> None:
+        """Arm the NEXT encode_stream / stream_step call of n sessions (want_adapter=False) with the LLM hand-off of
+        models/audioLLM.py:383-411: adapter rows as fp16 behind the chat prefix of each session's block of `embeds`
+        (>= n, rows, llm_dim), attention-mask rows and input start rows on the device.  `onset`: n flags, status == 'ipu_sl'."""
+        assert embeds.is_cuda and embeds.dtype == torch.float16 and embeds.is_contiguous() and embeds.dim() == 3
+        assert embeds.shape[0] >= n and embeds.shape[2] == self.cfg.llm_dim
+        on = np.ascontiguousarray(np.asarray(onset, dtype=np.uint8).reshape(-1))
+        assert len(on) == n
+        R = int(embeds.shape[1])
+        if attn_mask is not None:
+            assert attn_mask.is_cuda and attn_mask.dtype == torch.uint8 and attn_mask.is_contiguous() and tuple(attn_mask.shape[-1:]) == (R,)
+            assert attn_mask.numel() >= n * R
+        if row_start is not None:
+            assert row_start.is_cuda and row_start.dtype == torch.int32 and row_start.numel() >= n
+        if prefix_mask is not None:
+            assert prefix_mask.is_cuda and prefix_mask.dtype == torch.uint8 and prefix_mask.numel() == prefix_len
+        _lib.check(self.lib.fo_handoff_arm(self._h, n, embeds.data_ptr(), R, int(prefix_len), on.ctypes.data, _ptr(prefix_mask),
+                                           _ptr(attn_mask), _ptr(row_start)))
+
     # ---- offline ----------------------------------------------------------------------------------
     def encode_offline(self, feats: ArrayLike, ilens, chunk: Optional[int] = None, left: Optional[int] = None,
                        want_adapter: Optional[bool] = None):

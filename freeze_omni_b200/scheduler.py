@@ -33,8 +33,26 @@ class Block(NamedTuple):
     feature-gating thread gives the block (bin/dialog_state_pred.py:639-670): the FIRST block of a speech onset carries
     'ipu_sl' -- which is where AudioLLM.recognize puts the chat prefix (models/audioLLM.py:404-406) -- every other one 'ipu_cl'."""
     enc: torch.Tensor                 # (t, D) encoder frames
-    emb: Optional[torch.Tensor]       # (t_out, E) adapter embeddings
-    status: str
+    emb: Optional[torch.Tensor]       # (t_out, E) adapter embeddings; with a Handoff: the fp16 LLM input rows, chat prefix included
+    status: str                       # when status == 'ipu_sl' (views of the Handoff buffers)
+    mask: Optional[torch.Tensor] = None   # with a Handoff: the attention-mask entries of those rows
+
+
+class Handoff:
+    """Pre-allocated LLM-side buffers for `StreamScheduler.tick(handoff=...)` (models/audioLLM.py:383-411): `embeds`
+    (capacity, prefix_len + t_out, E) fp16 whose first prefix_len rows of every block hold the chat-prefix embeddings,
+    `attn_mask` (capacity, prefix_len + t_out) uint8 and `row_start` (capacity) int32.  One block per encoder step of a tick."""
+
+    def __init__(self, engine, capacity: int, prefix_embeds: torch.Tensor, prefix_mask: Optional[torch.Tensor] = None):
+        dev = engine.torch_device
+        self.prefix_len = int(prefix_embeds.shape[-2])
+        _, t_out = engine.out_frames(engine.cfg.chunk_feat_frames)
+        self.rows = self.prefix_len + t_out
+        self.embeds = torch.zeros(capacity, self.rows, engine.cfg.llm_dim, dtype=torch.float16, device=dev)
+        self.embeds[:, :self.prefix_len] = prefix_embeds.reshape(self.prefix_len, -1).to(dev, torch.float16)
+        self.prefix_mask = None if prefix_mask is None else prefix_mask.reshape(-1).to(dev, torch.uint8).contiguous()
+        self.attn_mask = torch.zeros(capacity, self.rows, dtype=torch.uint8, device=dev)
+        self.row_start = torch.zeros(capacity, dtype=torch.int32, device=dev)
 
 
 def onset_statuses(n_history: int, status: str) -> List[str]:
@@ -125,7 +143,7 @@ class StreamScheduler:
         assert key in self.keys and key not in self.pending, "one chunk per session per tick"
         self.pending[key] = (pcm, status)
 
-    def tick(self, scale: Optional[float] = None) -> Dict[Hashable, List[Block]]:
+    def tick(self, scale: Optional[float] = None, handoff: Optional[Handoff] = None) -> Dict[Hashable, List[Block]]:
         """Process everything pushed since the last tick.  Returns, per session that produced output, the list of
         Block(encoder frames (t, D), adapter embeddings (t_out, E), status) in stream order (one entry per queued block).
         `scale` None = the engine's rule: 1.0 for int16 PCM, cfg.pcm_scale for float audio in [-1, 1]."""
@@ -157,6 +175,7 @@ class StreamScheduler:
                 if self.block_log is not None:
                     self.block_log.extend((k, b, lab) for b, lab in labelled)
             self.pending.clear()
+        cursor = 0
         for batch in plan_rounds({k: len(q) for k, q in self.queues.items()}, self.max_batch):
             heads = [self.queues[k].popleft() for k in batch]
             blocks = [h[0] for h in heads]
@@ -164,6 +183,24 @@ class StreamScheduler:
             pad = bucket_size(n, self.bucket) - n
             ids = np.concatenate([np.array([self.keys[k] for k in batch], np.int32), self.scratch[:pad]]).astype(np.int32)
             x = torch.stack(blocks + [blocks[0]] * pad)
+            if handoff is not None:
+                # fused hand-off: rows of this batch land in the next free blocks of the caller's buffers (audioLLM.py:404-411)
+                n_all = n + pad
+                if cursor + n_all > handoff.embeds.shape[0]:
+                    raise RuntimeError("Handoff capacity %d exceeded in one tick" % handoff.embeds.shape[0])
+                onset = [h[1] == IPU_START for h in heads] + [False] * pad
+                self.eng.handoff_arm(n_all, handoff.embeds[cursor:], handoff.prefix_len, onset, handoff.prefix_mask,
+                                     handoff.attn_mask[cursor:], handoff.row_start[cursor:])
+                enc, _ = self.eng.encode_stream(ids, x, want_adapter=False)
+                self.stats["encode_calls"] += 1
+                self.stats["session_steps"] += n
+                self.stats["padded_steps"] += pad
+                for i, k in enumerate(batch):
+                    st0 = 0 if heads[i][1] == IPU_START else handoff.prefix_len
+                    out.setdefault(k, []).append(Block(enc[i], handoff.embeds[cursor + i, st0:], heads[i][1],
+                                                       handoff.attn_mask[cursor + i, st0:]))
+                cursor += n_all
+                continue
             enc, emb = self.eng.encode_stream(ids, x)
             self.stats["encode_calls"] += 1
             self.stats["session_steps"] += n

@@ -168,6 +168,19 @@ int fo_stream_wait(fo_ctx* ctx, int64_t ticket);
 int fo_stream_step_embeds(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
                           float* enc_out, void* embeds_f16, int64_t rows_per_session, int64_t row_offset, void* stream);
 
+/* The hand-off with the status-dependent chat prefix and the attention mask, i.e. all of
+ *   if status == 'ipu_sl': inputs_embeds = cat(chat_prefix_embeds, inputs_embeds); attention_mask = cat(chat_prefix_mask, attention_mask)
+ *   inputs_embeds.half()                                                                          (models/audioLLM.py:383-411)
+ * Arms the NEXT fo_encode_stream / fo_stream_step call of n sessions (its adapter_out must be NULL): the t_out adapter rows of
+ * session i are written as fp16 to rows [prefix_len, prefix_len + t_out) of its block of embeds_f16 (n, rows_per_session, llm_dim),
+ * whose rows [0, prefix_len) the caller filled once with the chat-prefix embeddings.  onset (HOST, n bytes): 1 where the
+ * block's status is 'ipu_sl'.  attn_mask (DEVICE, n x rows_per_session bytes) row i becomes [prefix_mask | 1 x t_out | 0 ..] for an
+ * onset block and [0 x prefix_len | 1 x t_out | 0 ..] otherwise (prefix_mask: DEVICE, prefix_len bytes, NULL = all ones);
+ * row_start (DEVICE, n) = 0 / prefix_len.  The LLM input of session i is rows [row_start[i], prefix_len + t_out) of its block,
+ * with the same slice of attn_mask (the caller prepends the past-KV mask, audioLLM.py:418-420).  bf16 contexts only. */
+int fo_handoff_arm(fo_ctx* ctx, int n, void* embeds_f16, int64_t rows_per_session, int64_t prefix_len, const uint8_t* onset,
+                   const uint8_t* prefix_mask, uint8_t* attn_mask, int32_t* row_start);
+
 /* ---- full utterance: replaces speechEncoder.forward (models/encoder/encoder.py:104-147) and
  * CNNSubsampling.forward(cache=None).  feats (B, T, feat_dim), ilens (B) int32 valid lengths.
  * chunk<=0 means full attention; left<0 means unlimited left context (models/masks.py:50-56,110-122).

@@ -378,3 +378,54 @@ def test_adapter_variants_in_the_streaming_step(which):
                 eng.export_adapter_cache(int(ids[0]), 0)          # CNNAdapter carries no cache
     finally:
         eng.close()
+
+
+def test_llm_handoff_prefix_and_attention_mask(shipped_big):
+    """f2 (models/audioLLM.py:383-411): the scheduler's fused hand-off against the torch sequence it replaces, restated:
+        attention_mask = ones(t_out);  if status == 'ipu_sl': inputs_embeds = cat(prefix, y), attention_mask = cat(prefix_mask, ones)
+        inputs_embeds.half()
+    Bit-exact: the fp16 rows equal .half() of the fp32 adapter output of a twin session, prefix rows are the caller's, the
+    mask rows and start rows match; onset replay blocks carry 'ipu_sl' only on the first block (dialog_state_pred.py:639-670)."""
+    from freeze_omni_b200.scheduler import Handoff, StreamScheduler
+    cfg, eng, _, _ = shipped_big
+    g = torch.Generator().manual_seed(71)
+    P = 6
+    prefix = torch.randn(1, P, cfg.llm_dim, generator=g)
+    pmask = torch.tensor([1, 1, 0, 1, 1, 1], dtype=torch.uint8)             # a chat template with one masked position
+    sch = StreamScheduler(eng, history_chunks=4, onset_chunks=2, bucket=4, max_sessions=4)
+    twin = StreamScheduler(eng, history_chunks=4, onset_chunks=2, bucket=4, max_sessions=4)
+    ho = Handoff(eng, 16, prefix, pmask)
+    pattern = {"a": [None, None, "ipu_sl", "ipu_cl", None, "ipu_sl"], "b": ["ipu_sl", "ipu_cl", "ipu_cl", None, None, "ipu_cl"]}
+    try:
+        for k in pattern:
+            sch.open(k)
+            twin.open(k)
+        seen_onsets = 0
+        for tck in range(6):
+            pcm = (0.05 * torch.randn(2, cfg.samples_per_chunk, generator=g) * 32768).round().to(torch.int16)
+            for i, k in enumerate(pattern):
+                sch.push(k, pcm[i], pattern[k][tck])
+                twin.push(k, pcm[i], pattern[k][tck])
+            out, ref = sch.tick(handoff=ho), twin.tick()
+            assert sorted(out) == sorted(ref)
+            for k in out:
+                assert [b.status for b in out[k]] == [b.status for b in ref[k]]
+                for blk, rb in zip(out[k], ref[k]):
+                    y16 = rb.emb.half()                                               # audioLLM.py:410
+                    ones = torch.ones(y16.shape[0], dtype=torch.uint8, device=y16.device)
+                    if blk.status == "ipu_sl":                                         # audioLLM.py:404-406
+                        want_e = torch.cat((prefix[0].half().to(y16.device), y16), 0)
+                        want_m = torch.cat((pmask.to(y16.device), ones), 0)
+                        seen_onsets += 1
+                    else:
+                        want_e, want_m = y16, ones
+                    assert torch.equal(blk.emb, want_e) and torch.equal(blk.mask, want_m), (tck, k, blk.status)
+                    assert torch.equal(blk.enc, rb.enc)
+        assert seen_onsets == 3
+        rs = ho.row_start[:4].cpu().tolist()
+        assert set(rs) <= {0, P}
+    finally:
+        for s_ in (sch, twin):
+            for k in list(s_.keys):
+                s_.close(k)
+            eng.free(s_.scratch)

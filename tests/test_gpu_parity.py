@@ -704,7 +704,8 @@ def test_scheduler_vad_gating_vs_oracle():
                 expected_steps += len(blocks)
                 want_lab = ["ipu_sl"] + ["ipu_cl"] * 6 if status == "ipu_sl" else [status]
                 assert [b.status for b in out[s]] == want_lab
-                for (enc, emb, _), blk in zip(out[s], blocks):
+                for ob, blk in zip(out[s], blocks):
+                    enc, emb = ob.enc, ob.emb
                     eo, yo = oracle[s].step_feats(blk)
                     assert maxabs(enc.cpu(), eo[0]) < FP32_TOL and maxabs(emb.cpu(), yo[0]) < FP32_TOL, (tck, s)
             assert maxabs(sch.history(1).cpu(), hist[1]) < 1e-4 * 20
