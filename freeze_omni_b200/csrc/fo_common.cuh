@@ -97,6 +97,19 @@ __device__ __forceinline__ unsigned long long fo_gtime() {
             }                                                                                                     \
         }                                                                                                         \
     } while (0)
+// raw record of six caller-supplied stamps (e.g. per-k-block arrival times of one CTA's MMA thread)
+#define FO_TR_RAW(kid, aux, arr)                                                                                  \
+    do {                                                                                                          \
+        if (g_tr_buf) {                                                                                           \
+            const unsigned int slot_ = atomicAdd(g_tr_cnt, 1u);                                                   \
+            if (slot_ < g_tr_cap) {                                                                               \
+                unsigned long long* r_ = g_tr_buf + (unsigned long long)slot_ * 8;                                \
+                r_[0] = (unsigned long long)(kid) | ((unsigned long long)((aux) & 0xFFFF) << 16);                 \
+                r_[1] = (unsigned long long)gridDim.x | ((unsigned long long)gridDim.y << 20) | ((unsigned long long)gridDim.z << 40); \
+                for (int i_ = 0; i_ < 6; ++i_) r_[2 + i_] = (arr)[i_];                                            \
+            }                                                                                                     \
+        }                                                                                                         \
+    } while (0)
 #define FO_TR_BIND_DEF(fn)                                                                                        \
     void fn(unsigned long long* buf, unsigned int* cnt, unsigned int cap) {                                       \
         cudaMemcpyToSymbol(g_tr_buf, &buf, sizeof(buf));                                                          \
@@ -108,6 +121,7 @@ __device__ __forceinline__ unsigned long long fo_gtime() {
 #define FO_TR_DECL() do { } while (0)
 #define FO_TR_STAMP(i) do { } while (0)
 #define FO_TR_FLUSH(kid, aux) do { } while (0)
+#define FO_TR_RAW(kid, aux, arr) do { } while (0)
 #define FO_TR_BIND_DEF(fn) void fn(unsigned long long*, unsigned int*, unsigned int) {}
 #endif
 void trace_bind_gemm(unsigned long long* buf, unsigned int* cnt, unsigned int cap);

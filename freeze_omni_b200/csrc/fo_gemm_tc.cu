@@ -153,6 +153,20 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TC_TRACE(slot) do { } while (0)
 #endif
 
+// One lane of a converged warp.  The producer / MMA loops run warp-uniformly with only the issuing instruction under this
+// predicate: inside an `if (lane == 0)` region nvcc treats the (mathematically uniform) descriptors and coordinates as
+// per-thread values and wraps every UTCHMMA / UTMALDG in an ELECT + 4 x R2UR.BROADCAST + BRA.U.ANY waterfall loop -- measured
+// ~45 ns per tcgen05.mma, which made every skinny GEMM MMA-ISSUE bound (profiles/r02_g_mma_issue_waterfall.md).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // ---- kernel ---------------------------------------------------------------------------------------
@@ -217,14 +231,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int pi = warp == 0 ? 0 : warp - 5;                   // producer index of warps 0, 6, 7, ...
     if (warp == 0 || warp >= 6) {
-        if (lane == 0 && pi < p.npa + p.npb) {
+        if (pi < p.npa + p.npb) {                               // warp-uniform: the whole warp walks the loop, one lane issues
             const int w = pi < p.npa ? 0 : 1;
             // the weight operand does not depend on the previous kernel: its stages fill while that kernel drains
-            if ((w == 0) != (p.swap != 0)) { FO_PDL_WAIT(); FO_TR_STAMP(1); }
+            if ((w == 0) != (p.swap != 0)) { FO_PDL_WAIT(); if (lane == 0) FO_TR_STAMP(1); }
             const int sub = w ? pi - p.npa : pi;                 // row slice of the operand tile this thread loads
             const int sub_rows = w ? p.bn / p.npb : BM / p.npa;
             const CUtensorMap* map = w ? &map_b : &map_a;
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+            if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
             const int segb = w ? p.op_b.seg_blocks : p.op_a.seg_blocks;
             const int row0 = (w ? tile_b * p.bn : tile_a * BM) + sub * sub_rows;
             const uint32_t bytes = (uint32_t)sub_rows * BK * 2;
@@ -235,37 +249,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t ph = 1;                       // a fresh barrier passes a wait on the "previous" phase
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(empty0 + 8 * s, ph);
-                mbar_expect_tx(full0 + 8 * s, bytes);
-                tma_load_3d(dst, map, full0 + 8 * s, cblk * BK, row, plane);
+                if (elect_one()) {
+                    mbar_expect_tx(full0 + 8 * s, bytes);
+                    tma_load_3d(dst, map, full0 + 8 * s, cblk * BK, row, plane);
+                }
+                __syncwarp();
                 if (++cblk == segb) { cblk = 0; ++seg; row = row0 + s_rowoff[w][seg]; plane = s_plane[w][seg]; }
                 dst += stage_bytes;
                 if (++s == stages) { s = 0; ph ^= 1u; dst -= stages * stage_bytes; }
             }
-            if (pi == 0) TC_TRACE(4);
+            if (pi == 0 && lane == 0) TC_TRACE(4);
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
             // operand format (both operands must agree): 0 = fp16, 1 = bf16
             const uint32_t fmt_a = p.act_fp16 ? 0u : 1u, fmt_b = fmt_a;
             const uint32_t idesc = (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int s = 0;
             uint32_t ph = 0, sa = base;
+#ifdef FO_TRACE_BUILD
+            unsigned long long kbt[18], ist[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 18; ++i) kbt[i] = 0;
+#endif
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
-                if (i == 0) { TC_TRACE(5); FO_TR_STAMP(2); }
+#ifdef FO_TRACE_BUILD
+                if (i < 18 && lane == 0) kbt[i] = fo_gtime();
+#endif
+                if (i == 0 && lane == 0) { TC_TRACE(5); FO_TR_STAMP(2); }
                 const uint64_t da = umma_desc(sa), db = umma_desc(sa + a_bytes);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)          // +32 B per K step inside the swizzle atom (>>4 = 2)
-                    tc_mma(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                tc_commit(empty0 + 8 * s);         // frees the stage once these MMAs have read it
+                    for (int k = 0; k < BK / UMMA_K; ++k)          // +32 B per K step inside the swizzle atom (>>4 = 2)
+                        tc_mma(tmem_base, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+#ifdef FO_TRACE_BUILD
+                    if (i == 4 || i == 5) ist[(i - 4) * 3 + 1] = fo_gtime();
+#endif
+                    tc_commit(empty0 + 8 * s);         // frees the stage once these MMAs have read it
+#ifdef FO_TRACE_BUILD
+                    if (i == 4 || i == 5) { ist[(i - 4) * 3 + 2] = fo_gtime(); ist[(i - 4) * 3] = kbt[i]; }
+#endif
+                }
+                __syncwarp();
                 sa += stage_bytes;
                 if (++s == stages) { s = 0; ph ^= 1u; sa = base; }
             }
-            tc_commit(accb);                       // accumulator complete
-            TC_TRACE(7);
+            if (elect_one()) {
+                tc_commit(accb);                       // accumulator complete
+                TC_TRACE(7);
+#ifdef FO_TRACE_BUILD
+                if (lane == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {     // one CTA per launch: k-block arrival times
+                    FO_TR_RAW(9, 0, kbt);
+                    FO_TR_RAW(9, 1, kbt + 6);
+                    FO_TR_RAW(9, 2, kbt + 12);
+                    FO_TR_RAW(10, 0, ist);
+                }
+#endif
+            }
         }
         __syncwarp();
     } else {
@@ -566,11 +609,11 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 0 || warp == 6) {
-        if (lane == 0) {
+        {
             const int w = warp == 0 ? 0 : 1;                      // 0: activations (M side), 1: weights (N side)
             if (w == 0) FO_PDL_WAIT();                            // weights do not depend on the previous kernel
             const CUtensorMap* map = w ? &map_b : &map_a;
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+            if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
             const int segb = w ? p.kblocks : p.op_a.seg_blocks;
             const uint32_t bytes = w ? b_bytes : a_bytes;
             int s = 0;
@@ -582,8 +625,11 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 int row = row0 + (w ? 0 : s_rowoff[0]), plane = w ? 0 : s_plane[0];
                 for (int i = 0; i < p.kblocks; ++i) {
                     mbar_wait(empty0 + 8 * s, ph);
-                    mbar_expect_tx(full0 + 8 * s, bytes);
-                    tma_load_3d(base + s * stage_bytes + (w ? a_bytes : 0u), map, full0 + 8 * s, cblk * BK, row, plane);
+                    if (elect_one()) {
+                        mbar_expect_tx(full0 + 8 * s, bytes);
+                        tma_load_3d(base + s * stage_bytes + (w ? a_bytes : 0u), map, full0 + 8 * s, cblk * BK, row, plane);
+                    }
+                    __syncwarp();
                     if (++cblk == segb) {
                         cblk = 0; ++seg;
                         if (!w) { row = row0 + s_rowoff[seg]; plane = s_plane[seg]; }
@@ -594,7 +640,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t fmt = p.act_fp16 ? 0u : 1u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int s = 0, it = 0;
@@ -609,12 +655,16 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     tc_fence_after();
                     const uint32_t sa = base + s * stage_bytes;
                     const uint64_t da = umma_desc(sa), db = umma_desc(sa + a_bytes);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) tc_mma(tacc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                    tc_commit(empty0 + 8 * s);
+                        for (int k = 0; k < BK / UMMA_K; ++k) tc_mma(tacc, da + 2 * k, db + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        tc_commit(empty0 + 8 * s);
+                    }
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
-                tc_commit(af0 + 8 * ab);
+                if (elect_one()) tc_commit(af0 + 8 * ab);
+                __syncwarp();
             }
         }
         __syncwarp();

@@ -66,6 +66,31 @@ def main():
     rec = buf[:n.value]
     if len(rec) == 0:
         raise SystemExit("no trace records: is FO_B200_LIB a FO_TRACE_BUILD library?")
+    # kid 9: k-block arrival times at the MMA thread of one CTA per GEMM launch (three records of six stamps each)
+    kb = rec[(rec[:, 0] & 0xFF) == 9]
+    iss = rec[(rec[:, 0] & 0xFF) == 10]
+    rec = rec[((rec[:, 0] & 0xFF) != 9) & ((rec[:, 0] & 0xFF) != 10)]
+    if len(iss):
+        v = iss[:, 2:8].astype(np.int64)
+        ok = (v > 0).all(axis=1)
+        v = v[ok]
+        print("MMA thread, k-blocks 4 and 5 of one CTA per launch (ns, median over %d launches): wait-done -> 4 MMAs issued %d / %d, "
+              "-> commit issued %d / %d, commit -> next wait-done %d" % (len(v), np.median(v[:, 1] - v[:, 0]), np.median(v[:, 4] - v[:, 3]),
+              np.median(v[:, 2] - v[:, 1]), np.median(v[:, 5] - v[:, 4]), np.median(v[:, 3] - v[:, 2])))
+    kb_by = {}
+    for r in kb:
+        part = int((r[0] >> 16) & 0xFFFF)
+        grid = (int(r[1] & 0xFFFFF), int((r[1] >> 20) & 0xFFFFF), int(r[1] >> 40))
+        kb_by.setdefault(grid, {}).setdefault(part, []).append(r[2:8].astype(np.int64))
+    print("k-block arrival deltas (ns) at the MMA thread of one CTA, median over the launches of each grid:")
+    for grid, parts in kb_by.items():
+        nl = min(len(v) for v in parts.values())
+        if nl == 0 or len(parts) < 3:
+            continue
+        seqs = np.stack([np.concatenate([parts[p_][i] for p_ in (0, 1, 2)]) for i in range(nl)])
+        valid = (seqs > 0).all(axis=0)
+        d = np.diff(seqs[:, valid], axis=1)
+        print("  grid %-12s launches %3d: %s" % ("x".join(map(str, grid)), nl, " ".join("%d" % x for x in np.median(d, axis=0))))
     kid = (rec[:, 0] & 0xFF).astype(np.int64)
     smid = ((rec[:, 0] >> 8) & 0xFF).astype(np.int64)
     aux = ((rec[:, 0] >> 16) & 0xFFFF).astype(np.int64)
