@@ -127,6 +127,7 @@ struct fo_ctx {
                                               // Off: it paid 2 % with one GEMM CTA per SM; with two co-resident CTAs hiding
                                               // each other's cold loads it costs 1-2 % at 16-128 sessions (r75/r76)
     int pf_slot_lo = 0, pf_slot_hi = 0;       // slot range of the sessions of the current step
+    int step_part = 0;                        // development (timing attribution, results invalid): 1 = front only (fbank .. embed), 2 = layers + adapter only
     int defer_reduce = 1;                     // split-K GEMMs of the residual stream leave the reduction to the LayerNorm that follows
     int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
                                               // (measured slower than the stand-alone kernel at 64-256 sessions: off)
@@ -854,7 +855,14 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     const int D = c->D, FF = c->FF, H = c->H;
     const int T1 = (t_in - 1) / 2, t = (T1 - 1) / 2, M = n * t;
     float* x;
-    FO_TRY(subsample_program<TA>(c, feats, n, t_in, &x, st));
+    if (c->step_part == 2) {
+        void* xp;
+        FO_TRY(ws_ensure(c, WS_X, (size_t)M * D * sizeof(float), &xp));
+        x = reinterpret_cast<float*>(xp);
+    } else {
+        FO_TRY(subsample_program<TA>(c, feats, n, t_in, &x, st));
+        if (c->step_part == 1) return 0;
+    }
     void *h, *qkv, *att, *ffh;
     FO_TRY(ws_ensure(c, WS_H, (size_t)M * D * sizeof(TA), &h));
     FO_TRY(ws_ensure(c, WS_QKV, (size_t)M * 3 * D * sizeof(TA), &qkv));
@@ -1462,7 +1470,7 @@ static int step_body(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     FO_TRY(ws_ensure(c, WS_FEATS, (size_t)a.n * a.t_in * c->F * sizeof(float), &dfeats));
     FO_TRY(ws_ensure(c, ws_enc(a.buf), (size_t)a.n * t * c->D * sizeof(float), &denc));
     if (a.want_y) FO_TRY(ws_ensure(c, ws_y(a.buf), (size_t)a.n * t_out * c->E * sizeof(float), &dy));
-    if (a.with_fbank) {
+    if (a.with_fbank && c->step_part != 2) {
         void* dp;
         FO_TRY(ws_ensure(c, ws_pcm(a.buf), (size_t)a.n * c->chunk_samples * 4, &dp));
         FO_TRY(fbank_stream(fbank_params(c), c->ids_dev, a.n, dp, a.pcm_is_i16, a.scale, c->cfg.frames_per_chunk,
@@ -1820,6 +1828,7 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
     } else if (!strcmp(name, "use_graph")) c->use_graph = value != 0;
     else if (!strcmp(name, "split_k")) c->split_k = (int)value;
     else if (!strcmp(name, "debug_skip")) c->debug_skip = (int)value;
+    else if (!strcmp(name, "step_part")) { c->step_part = (int)value; c->ws_epoch += 1; }
     else if (!strcmp(name, "trace")) {
         // development builds (FO_TRACE_BUILD): value > 0 allocates room for `value` CTA records and binds the kernels to it,
         // 0 unbinds.  fo_debug_trace_read copies the records out.
