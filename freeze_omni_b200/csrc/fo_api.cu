@@ -978,6 +978,7 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
         const LayerW& w = c->layers[l];
         const bool last = l + 1 == c->L;
         FO_TRY(layer_pre<TA>(c, w, M, reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(qkv), q32, L2Prefetch(), st));
+        if (!(c->debug_skip & 1))
         FO_TRY(attention_offline<TA>(reinterpret_cast<const TA*>(qkv), q32, B, T2, H, ilens2, chunk, left,
                                      w.ptab, reinterpret_cast<const TA*>(w.ptab_h), c->pos_rows, w.pos_u, w.pos_v,
                                      reinterpret_cast<TA*>(att), st));

@@ -806,236 +806,239 @@ attention_offline_kernel(const TA* __restrict__ qkv, const float* __restrict__ q
     }
 }
 
-// fp16 variant of the full-utterance kernel on mma.sync.m16n8k16 (same reformulation as attention_stream_mma_kernel):
-// CTA = (32-query block, head, utterance); per 96-key tile K, V and the rel-pos rows are staged once with the XOR chunk
-// swizzle (chunk c of tile row i at c ^ (i & 7)), warp w computes S^T for query group w (8 queries) against the six
-// 16-key tiles, does the masked online softmax of its own queries, and owns output dims [16w, 16w+16) of all 32 queries
-// for the PV MMAs (accumulators rescaled per tile by the queries' correction factors).
-constexpr int OSC = 100;     // score row pitch (fp32): 4 mod 32 -> the MMA fragment stores of 4 query pairs hit 4 bank groups
-constexpr int OPH = 104;     // probability row pitch (fp16): 52 words = 20 mod 32 -> conflict-free B-fragment loads
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
-__global__ void __launch_bounds__(ATT_THREADS)
-attention_offline_mma_kernel(const __half* __restrict__ qkv, const float* __restrict__ q32, int T, int H,
-                             const int32_t* __restrict__ ilens, int chunk, int left, const __half* __restrict__ ptab_h,
-                             int pos_rows, const float* __restrict__ pos_u, const float* __restrict__ pos_v,
-                             __half* __restrict__ out) {
+
+// ---- full-utterance attention, fp16 contexts ------------------------------------------------------------------------
+// Flash-attention style on mma.sync.m16n8k16: CTA = (64-query block, head, utterance), four warps x 16 queries; queries on the
+// MMA-M side, so a warp's (q+u) / (q+v) fragments live in registers for the whole CTA and its probabilities go from the
+// score accumulators straight into the A fragments of the PV MMAs (no score / probability tile in shared memory).  K, V and
+// the rel-pos rows of a 64-key tile are staged by cp.async into a DOUBLE-buffered, XOR-swizzled tile (tile t+1 flies while
+// tile t is multiplied) and read with ldmatrix (K / P rows as B fragments, V transposed).  Arithmetic as in the fp32
+// kernel above: s = ((q+u).k_j + (q+v).p_j) / 8 with p_j the rel-pos row of key POSITION j (attention.py:377-388 without the
+// rel_shift), band [start_i, end_i) of masks.py:50-56 and the pad mask evaluated arithmetically, fp32 online softmax,
+// fully masked rows -> zeros (attention.py:396-397).
+// 16-key groups outside the band of all 16 rows of a warp are skipped (5 of 8 groups remain with the shipped band).  Measured
+// on the 32 x 30 s slice of BASELINE config 4: 147 us per layer launch in the pipeline, against 200 us for the first mma.sync
+// kernel (32-query CTAs, keys on the MMA-M side, score / probability tiles in shared memory), which it replaces.
+constexpr int FQ = 64;           // queries per CTA
+constexpr int FK = 64;           // keys per tile
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __half* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __half* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816_ab(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2_nosat(float a, float b) {      // values in [0, 1]: no clamp needed
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__global__ void __launch_bounds__(ATT_THREADS, 4)
+attention_offline_fa_kernel(const __half* __restrict__ qkv, const float* __restrict__ q32, int T, int H,
+                            const int32_t* __restrict__ ilens, int chunk, int left, const __half* __restrict__ ptab_h,
+                            int pos_rows, const float* __restrict__ pos_u, const float* __restrict__ pos_v,
+                            __half* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef __half TA;
-    constexpr int NCH = 8, EPC = 8;
-    TA* Ks = reinterpret_cast<TA*>(smem_raw);
-    TA* Ps = Ks + KT * DK;
-    TA* Vs = Ps + KT * DK;
-    TA* quh = Vs + KT * DK;                                  // QB x 64
-    TA* qvh = quh + QB * DK;
-    TA* ph = qvh + QB * DK;                                  // QB x OPH
-    float* m_run = reinterpret_cast<float*>(ph + QB * OPH);
-    float* l_run = m_run + QB;
-    float* corr = l_run + QB;
-    float* sc = reinterpret_cast<float*>(Ks);                // after the last tile: the output tile QB x 64 (K is dead by then)
-    __shared__ int win[QB][2];
-
+    constexpr int NCH = 8;                                   // 16-byte chunks per 64-element row
+    TA* tiles = reinterpret_cast<TA*>(smem_raw);             // [2 stages][K | P | V][FK][64]
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int D = H * DK;
-    const int q0 = qb * QB;
-    const int nq = min(QB, T - q0);
+    const int q0 = qb * FQ;
     const int klen = ilens ? min(ilens[b], T) : T;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c = lane & 3;
 
-    if (tid < QB) {
-        int s0 = 0, e0 = 0;
-        if (tid < nq) {
-            const int i = q0 + tid;
-            s0 = 0; e0 = T;
-            if (chunk > 0) {
-                s0 = left < 0 ? 0 : max((i / chunk - left) * chunk, 0);
-                e0 = min((i / chunk + 1) * chunk, T);
+    // band of a query row (masks.py:50-56 + pad mask): keys [s, e)
+    auto win_lo = [&](int i) { return chunk > 0 ? (left < 0 ? 0 : max((i / chunk - left) * chunk, 0)) : 0; };
+    auto win_hi = [&](int i) { return min(chunk > 0 ? min((i / chunk + 1) * chunk, T) : T, klen); };
+    const int last_q = min(q0 + FQ, T) - 1;
+    const int k_lo = win_lo(q0) & ~7;                        // tile rows keep (row & 7) == (position & 7): the rel-pos table is
+    const int k_hi = win_hi(last_q);                         // pre-swizzled by position, so its rows are copied chunk for chunk
+    const int ntiles = k_hi > k_lo ? (k_hi - k_lo + FK - 1) / FK : 0;
+    // this warp's rows and their windows
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    const int s0 = r0 < T ? win_lo(r0) : 0, e0 = r0 < T ? win_hi(r0) : 0;
+    const int s1 = r1 < T ? win_lo(r1) : 0, e1 = r1 < T ? win_hi(r1) : 0;
+    const int wq_first = q0 + warp * 16, wq_last = min(wq_first + 15, T - 1);
+    const int w_lo = wq_first < T ? win_lo(wq_first) : 0, w_hi = wq_first < T ? win_hi(wq_last) : 0;
+
+    auto load_tile = [&](int t, int stage) {
+        const int kt = k_lo + t * FK;
+        TA* Ks = tiles + (size_t)stage * 3 * FK * DK;
+        TA* Ps = Ks + FK * DK;
+        TA* Vs = Ps + FK * DK;
+        for (int i = tid; i < FK * NCH * 3; i += ATT_THREADS) {
+            const int which = i / (FK * NCH);                // 0 K, 1 P, 2 V
+            const int j = (i / NCH) % FK, cc = i % NCH, key = kt + j;
+            TA* dst = (which == 0 ? Ks : which == 1 ? Ps : Vs) + j * DK;
+            if (which == 1) {
+                if (key < pos_rows && key < k_hi) cp_async16(dst + (cc << 3), ptab_h + ((long long)h * pos_rows + key) * DK + (cc << 3));
+                else *reinterpret_cast<uint4*>(dst + (cc << 3)) = make_uint4(0, 0, 0, 0);
+            } else {
+                TA* d2 = dst + ((cc ^ (j & 7)) << 3);
+                if (key < k_hi) cp_async16(d2, qkv + ((long long)b * T + key) * 3 * D + (which == 0 ? 1 : 2) * D + h * DK + cc * 8);
+                else *reinterpret_cast<uint4*>(d2) = make_uint4(0, 0, 0, 0);     // finite operands for the masked columns
             }
-            e0 = min(e0, klen);
-        }
-        win[tid][0] = s0;
-        win[tid][1] = e0;
-        m_run[tid] = -INFINITY;
-        l_run[tid] = 0.f;
-    }
-    for (int i = tid; i < QB * (DK / 4); i += ATT_THREADS) {
-        const int r = i / (DK / 4), d = (i % (DK / 4)) * 4;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nq) q = *reinterpret_cast<const float4*>(q32 + ((long long)b * T + q0 + r) * 3 * D + h * DK + d);
-        const float4 u = *reinterpret_cast<const float4*>(pos_u + h * DK + d);
-        const float4 v = *reinterpret_cast<const float4*>(pos_v + h * DK + d);
-        const int o = r * DK + (((d >> 3) ^ (r & 7)) << 3) + (d & 7);
-        uint2 hu, hv;
-        hu.x = pack2<TA>(q.x + u.x, q.y + u.y); hu.y = pack2<TA>(q.z + u.z, q.w + u.w);
-        hv.x = pack2<TA>(q.x + v.x, q.y + v.y); hv.y = pack2<TA>(q.z + v.z, q.w + v.w);
-        *reinterpret_cast<uint2*>(quh + o) = hu;
-        *reinterpret_cast<uint2*>(qvh + o) = hv;
-    }
-    __syncthreads();
-    int k_lo = T, k_hi = 0;
-    for (int r = 0; r < nq; ++r)
-        if (win[r][1] > win[r][0]) { k_lo = min(k_lo, win[r][0]); k_hi = max(k_hi, win[r][1]); }
-
-    float oacc[QB / 8][4];
-#pragma unroll
-    for (int qg = 0; qg < QB / 8; ++qg) { oacc[qg][0] = 0.f; oacc[qg][1] = 0.f; oacc[qg][2] = 0.f; oacc[qg][3] = 0.f; }
-
-    for (int kt = k_lo; kt < k_hi; kt += KT) {
-        const int nk = min(KT, k_hi - kt);
-        __syncthreads();                                   // previous tile fully consumed
-        // global -> shared with cp.async: all 36 16-byte copies of a thread are in flight at once (register staging left
-        // the kernel stalled on the loads: long-scoreboard 3.3 per issue in profiles/r01_h)
-        for (int i = tid; i < KT * NCH * 2; i += ATT_THREADS) {
-            const int which = i / (KT * NCH);              // 0 K, 1 V
-            const int j = (i / NCH) % KT, cc = i % NCH;
-            TA* dst = (which == 0 ? Ks : Vs) + j * DK + ((cc ^ (j & 7)) << 3);
-            if (j < nk) cp_async16(dst, qkv + ((long long)b * T + kt + j) * 3 * D + (which + 1) * D + h * DK + cc * EPC);
-            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);    // rows behind the last key: zeros (finite in the PV MMAs)
-        }
-        // rel-pos rows from the head-major fp16 table (its 16-byte chunks are swizzled by POSITION, the tile's by tile row)
-        for (int i = tid; i < nk * NCH; i += ATT_THREADS) {
-            const int j = i / NCH, cc = i % NCH, pos = kt + j;
-            cp_async16(Ps + j * DK + ((cc ^ (j & 7)) << 3), ptab_h + ((long long)h * pos_rows + pos) * DK + ((cc ^ (pos & 7)) << 3));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        // ---- scores of query group `warp` against the six 16-key tiles, kept in registers: lane (g, c) holds, per tile,
-        //      keys k0+g and k0+g+8 of queries 8w+2c and 8w+2c+1 ----
-        const int qrow = warp * 8 + g;                     // B-fragment row (query) of this lane
-        const int qa = warp * 8 + c * 2;                   // the two queries whose scores this lane holds
-        float sreg[KT / 16][4];
-#pragma unroll
-        for (int kti = 0; kti < KT / 16; ++kti) {
-            const int k0 = kti * 16;
-            float d4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (k0 < nk) {
-                const int s0k = (k0 + g) & 7, s1k = (k0 + g + 8) & 7;
-                const TA* kr0 = Ks + (k0 + g) * DK + c * 2;
-                const TA* kr1 = Ks + (k0 + g + 8) * DK + c * 2;
-                const TA* pr0 = Ps + (k0 + g) * DK + c * 2;
-                const TA* pr1 = Ps + (k0 + g + 8) * DK + c * 2;
-#pragma unroll
-                for (int ks = 0; ks < DK / 16; ++ks) {
-                    const int c0 = ks * 2, c1 = ks * 2 + 1;
-                    uint32_t af[4], bf[2];
-                    af[0] = lds32(kr0 + ((c0 ^ s0k) << 3));
-                    af[1] = lds32(kr1 + ((c0 ^ s1k) << 3));
-                    af[2] = lds32(kr0 + ((c1 ^ s0k) << 3));
-                    af[3] = lds32(kr1 + ((c1 ^ s1k) << 3));
-                    bf[0] = lds32(quh + qrow * DK + ((c0 ^ g) << 3) + c * 2);
-                    bf[1] = lds32(quh + qrow * DK + ((c1 ^ g) << 3) + c * 2);
-                    mma16816(d4, af, bf);
-                    af[0] = lds32(pr0 + ((c0 ^ s0k) << 3));
-                    af[1] = lds32(pr1 + ((c0 ^ s1k) << 3));
-                    af[2] = lds32(pr0 + ((c1 ^ s0k) << 3));
-                    af[3] = lds32(pr1 + ((c1 ^ s1k) << 3));
-                    bf[0] = lds32(qvh + qrow * DK + ((c0 ^ g) << 3) + c * 2);
-                    bf[1] = lds32(qvh + qrow * DK + ((c1 ^ g) << 3) + c * 2);
-                    mma16816(d4, af, bf);
-                }
-            }
-            sreg[kti][0] = d4[0]; sreg[kti][1] = d4[1]; sreg[kti][2] = d4[2]; sreg[kti][3] = d4[3];
-        }
-        // ---- masked online softmax in registers (reduction over the 8 lanes that share c); un-normalised probabilities as fp16 ----
-        {
-            const int lo0 = win[qa][0], hi0 = win[qa][1], lo1 = win[qa + 1][0], hi1 = win[qa + 1][1];
-            float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-            for (int kti = 0; kti < KT / 16; ++kti) {
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int j = kti * 16 + g + hh * 8, key = kt + j;
-                    const bool v0 = j < nk && key >= lo0 && key < hi0, v1 = j < nk && key >= lo1 && key < hi1;
-                    sreg[kti][hh * 2] = v0 ? sreg[kti][hh * 2] * 0.125f : -INFINITY;
-                    sreg[kti][hh * 2 + 1] = v1 ? sreg[kti][hh * 2 + 1] * 0.125f : -INFINITY;
-                    m0 = fmaxf(m0, sreg[kti][hh * 2]);
-                    m1 = fmaxf(m1, sreg[kti][hh * 2 + 1]);
-                }
-            }
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-                m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-            }
-            const float mo0 = m_run[qa], mo1 = m_run[qa + 1];
-            const float mn0 = fmaxf(mo0, m0), mn1 = fmaxf(mo1, m1);
-            const float cf0 = mn0 == -INFINITY ? 1.f : __expf(mo0 - mn0), cf1 = mn1 == -INFINITY ? 1.f : __expf(mo1 - mn1);
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int kti = 0; kti < KT / 16; ++kti) {
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int j = kti * 16 + g + hh * 8;
-                    const float e0 = mn0 == -INFINITY ? 0.f : __expf(sreg[kti][hh * 2] - mn0);         // masked: exp(-inf) = 0
-                    const float e1 = mn1 == -INFINITY ? 0.f : __expf(sreg[kti][hh * 2 + 1] - mn1);
-                    s0 += e0;
-                    s1 += e1;
-                    ph[qa * OPH + j] = __float2half_rn(e0);
-                    ph[(qa + 1) * OPH + j] = __float2half_rn(e1);
-                }
-            }
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            }
-            __syncwarp();                                  // every lane has read m_run / l_run of its queries
-            if (g == 0) {
-                m_run[qa] = mn0; m_run[qa + 1] = mn1;
-                l_run[qa] = l_run[qa] * cf0 + s0; l_run[qa + 1] = l_run[qa + 1] * cf1 + s1;
-                corr[qa] = cf0; corr[qa + 1] = cf1;
-            }
-        }
-        __syncthreads();
-        // ---- PV: this warp's 16 output dims of all 32 queries ----
-        {
-            const int dim0 = warp * 16;
-            const int mi = lane >> 3, rr = lane & 7;
-#pragma unroll
-            for (int qg = 0; qg < QB / 8; ++qg) {
-                const float f0 = corr[qg * 8 + c * 2], f1 = corr[qg * 8 + c * 2 + 1];
-                oacc[qg][0] *= f0; oacc[qg][1] *= f1; oacc[qg][2] *= f0; oacc[qg][3] *= f1;
-            }
-            for (int key0 = 0; key0 < nk; key0 += 16) {
-                uint32_t af[4];
-                const int vrow = key0 + rr + ((mi & 2) ? 8 : 0);
-                const TA* ap = Vs + vrow * DK + ((((dim0 >> 3) + (mi & 1)) ^ (vrow & 7)) << 3);
-                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(af[0]), "=r"(af[1]), "=r"(af[2]), "=r"(af[3])
-                             : "r"(smem_u32(ap)));
-#pragma unroll
-                for (int qg = 0; qg < QB / 8; ++qg) {
-                    uint32_t bf[2];
-                    bf[0] = lds32(ph + (qg * 8 + g) * OPH + key0 + c * 2);
-                    bf[1] = lds32(ph + (qg * 8 + g) * OPH + key0 + 8 + c * 2);
-                    mma16816(oacc[qg], af, bf);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // ---- normalise, stage the 32 x 64 output tile, coalesced store ----
+    };
+    if (ntiles > 0) load_tile(0, 0);
+
+    // (q+u), (q+v) A fragments of this warp's 16 queries: a0 (row g, k 2c..), a1 (row g+8), a2 (row g, k 2c+8..), a3 (row g+8)
+    uint32_t qu[4][4], qv[4][4];
     {
-        const int dim0 = warp * 16;
+        const float* qr0 = q32 + ((long long)b * T + min(r0, T - 1)) * 3 * D + h * DK;
+        const float* qr1 = q32 + ((long long)b * T + min(r1, T - 1)) * 3 * D + h * DK;
 #pragma unroll
-        for (int qg = 0; qg < QB / 8; ++qg) {
-            const int qa = qg * 8 + c * 2;
-            const float i0 = l_run[qa] > 0.f ? 1.f / l_run[qa] : 0.f;          // fully masked row -> zeros (attention.py:396-397)
-            const float i1 = l_run[qa + 1] > 0.f ? 1.f / l_run[qa + 1] : 0.f;
-            sc[qa * DK + dim0 + g] = oacc[qg][0] * i0;
-            sc[(qa + 1) * DK + dim0 + g] = oacc[qg][1] * i1;
-            sc[qa * DK + dim0 + g + 8] = oacc[qg][2] * i0;
-            sc[(qa + 1) * DK + dim0 + g + 8] = oacc[qg][3] * i1;
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int d = ks * 16 + hf * 8 + c * 2;
+                const float2 u = *reinterpret_cast<const float2*>(pos_u + h * DK + d);
+                const float2 v = *reinterpret_cast<const float2*>(pos_v + h * DK + d);
+                const float2 a = *reinterpret_cast<const float2*>(qr0 + d);
+                const float2 bq = *reinterpret_cast<const float2*>(qr1 + d);
+                qu[ks][hf * 2] = pack2<__half>(a.x + u.x, a.y + u.y);
+                qu[ks][hf * 2 + 1] = pack2<__half>(bq.x + u.x, bq.y + u.y);
+                qv[ks][hf * 2] = pack2<__half>(a.x + v.x, a.y + v.y);
+                qv[ks][hf * 2 + 1] = pack2<__half>(bq.x + v.x, bq.y + v.y);
+            }
         }
     }
-    __syncthreads();
-    for (int i = tid; i < nq * (DK / 2); i += ATT_THREADS) {
-        const int q = i / (DK / 2), pr = i % (DK / 2);
-        *reinterpret_cast<uint32_t*>(out + ((long long)b * T + q0 + q) * D + h * DK + 2 * pr) =
-            pack2<__half>(sc[q * DK + 2 * pr], sc[q * DK + 2 * pr + 1]);
+    float oacc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { oacc[n][0] = 0.f; oacc[n][1] = 0.f; oacc[n][2] = 0.f; oacc[n][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const int mi = lane >> 3, rr = lane & 7;                  // ldmatrix: this lane addresses row rr of matrix mi
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int stage = t & 1;
+        if (t + 1 < ntiles) {
+            load_tile(t + 1, stage ^ 1);                     // (the stage was released by the barrier that ended tile t-1)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int kt = k_lo + t * FK;
+        if (kt < w_hi && kt + FK > w_lo) {                   // warp-uniform: some key of the tile is inside some row's band
+            const TA* Ks = tiles + (size_t)stage * 3 * FK * DK;
+            const TA* Ps = Ks + FK * DK;
+            const TA* Vs = Ps + FK * DK;
+            // 16-key groups of the tile that intersect the band of at least one of this warp's rows (warp-uniform): with the
+            // shipped band (68 keys) a warp needs 5 of the 8 groups of its two tiles
+            bool act[4];
+#pragma unroll
+            for (int np = 0; np < 4; ++np) act[np] = kt + np * 16 < w_hi && kt + np * 16 + 16 > w_lo;
+            float sacc[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) { sacc[n][0] = 0.f; sacc[n][1] = 0.f; sacc[n][2] = 0.f; sacc[n][3] = 0.f; }
+            // ---- S = (q+u) K^T + (q+v) P^T : per k-step one ldmatrix.x4 feeds two 8-key n-tiles ----
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {                 // n-tile pair (16 keys)
+                if (!act[np]) continue;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const int key = np * 16 + (mi >> 1) * 8 + rr;
+                    const int chk = ks * 2 + (mi & 1);
+                    uint32_t kf[4], pf[4];
+                    ldsm_x4(kf, Ks + key * DK + ((chk ^ (key & 7)) << 3));
+                    ldsm_x4(pf, Ps + key * DK + ((chk ^ (key & 7)) << 3));
+                    mma16816_ab(sacc[np * 2], qu[ks], kf[0], kf[1]);
+                    mma16816_ab(sacc[np * 2 + 1], qu[ks], kf[2], kf[3]);
+                    mma16816_ab(sacc[np * 2], qv[ks], pf[0], pf[1]);
+                    mma16816_ab(sacc[np * 2 + 1], qv[ks], pf[2], pf[3]);
+                }
+            }
+            // ---- mask, scale, online softmax in the exp2 domain (rows g and g+8; a row lives in the 4 lanes that share g):
+            //      s2 = s / 8 * log2(e), p = 2^(s2 - m) ----
+            constexpr float SC = 0.125f * 1.4426950408889634f;
+            const int ds0 = s0 - kt - c * 2, de0 = e0 - kt - c * 2, ds1 = s1 - kt - c * 2, de1 = e1 - kt - c * 2;
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                if (!act[n >> 1]) continue;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = n * 8 + e;                 // key = kt + c * 2 + j
+                    sacc[n][e] = (j >= ds0 && j < de0) ? sacc[n][e] * SC : -INFINITY;
+                    sacc[n][2 + e] = (j >= ds1 && j < de1) ? sacc[n][2 + e] * SC : -INFINITY;
+                    mx0 = fmaxf(mx0, sacc[n][e]);
+                    mx1 = fmaxf(mx1, sacc[n][2 + e]);
+                }
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+            // a row with nothing unmasked so far keeps m = -inf; subtracting 0 instead makes every 2^(-inf - 0) an exact 0
+            const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;
+            const float cf0 = fast_exp2(m0 - ms0), cf1 = fast_exp2(m1 - ms1);      // m = -inf -> 0 (and l, o are 0 then)
+            m0 = mn0; m1 = mn1;
+            l0 *= cf0; l1 *= cf1;
+            uint32_t pa[4][4];                               // probabilities as A fragments: k-step kk = keys 16kk .. 16kk+15
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                if (!act[n >> 1]) continue;
+                const float p00 = fast_exp2(sacc[n][0] - ms0), p01 = fast_exp2(sacc[n][1] - ms0);
+                const float p10 = fast_exp2(sacc[n][2] - ms1), p11 = fast_exp2(sacc[n][3] - ms1);
+                l0 += p00 + p01;
+                l1 += p10 + p11;
+                pa[n >> 1][(n & 1) * 2] = pack2_nosat(p00, p01);
+                pa[n >> 1][(n & 1) * 2 + 1] = pack2_nosat(p10, p11);
+            }
+#pragma unroll
+            for (int n = 0; n < 8; ++n) { oacc[n][0] *= cf0; oacc[n][1] *= cf0; oacc[n][2] *= cf1; oacc[n][3] *= cf1; }
+            // ---- O += P V : V transposed by ldmatrix, one x4 = 16 keys x two 8-dim n-tiles ----
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                if (!act[kk]) continue;
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {             // dim n-tile pair
+                    const int key = kk * 16 + (mi & 1) * 8 + rr;
+                    const int chk = dp * 2 + (mi >> 1);
+                    uint32_t vf[4];
+                    ldsm_x4_t(vf, Vs + key * DK + ((chk ^ (key & 7)) << 3));
+                    mma16816_ab(oacc[dp * 2], pa[kk], vf[0], vf[1]);
+                    mma16816_ab(oacc[dp * 2 + 1], pa[kk], vf[2], vf[3]);
+                }
+            }
+        }
+        __syncthreads();                                     // the stage may be refilled
+    }
+    // ---- normalise; a row's partial sums live in its 4 lanes ----
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;      // fully masked row -> zeros
+    // stage the warp's 16 x 64 tile (warp-private region of the tile buffer, all tiles consumed) and store 16-byte chunks
+    TA* ot = tiles + warp * 16 * DK;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        *reinterpret_cast<uint32_t*>(ot + g * DK + n * 8 + c * 2) = pack2<__half>(oacc[n][0] * i0, oacc[n][1] * i0);
+        *reinterpret_cast<uint32_t*>(ot + (g + 8) * DK + n * 8 + c * 2) = pack2<__half>(oacc[n][2] * i1, oacc[n][3] * i1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = lane; i < 16 * NCH; i += 32) {
+        const int r = i >> 3, cc = i & 7, row = q0 + warp * 16 + r;
+        if (row < T)
+            *reinterpret_cast<uint4*>(out + ((long long)b * T + row) * D + h * DK + cc * 8) = *reinterpret_cast<const uint4*>(ot + r * DK + cc * 8);
     }
 }
 
@@ -1141,16 +1144,21 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
         attr_set[sizeof(TA) == 2] = true;
     }
     if constexpr (sizeof(TA) == 2) {
-        const size_t sm = (size_t)3 * KT * DK * 2 + (size_t)2 * QB * DK * 2 + (size_t)QB * OPH * 2 + 3 * QB * 4;   // 51 KB: 4 CTAs per SM
-        static bool attr2 = false;
-        if (!attr2) {
-            FO_CUDA(cudaFuncSetAttribute(attention_offline_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr2 = true;
-        }
         if (!ptab_h || T > pos_rows) return 1;
-        attention_offline_mma_kernel<<<grid, ATT_THREADS, sm, st>>>(reinterpret_cast<const __half*>(qkv), q32, T, H, ilens, chunk, left,
-                                                                    reinterpret_cast<const __half*>(ptab_h), pos_rows, pos_u, pos_v,
-                                                                    reinterpret_cast<__half*>(out));
+        {
+            const size_t smf = (size_t)2 * 3 * FK * DK * 2;      // 48 KB: double-buffered K | P | V tiles
+            static bool attr3 = false;
+            if (!attr3) {
+                FO_CUDA(cudaFuncSetAttribute(attention_offline_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                attr3 = true;
+            }
+            attention_offline_fa_kernel<<<dim3(cdiv(T, FQ), H, B), ATT_THREADS, smf, st>>>(
+                reinterpret_cast<const __half*>(qkv), q32, T, H, ilens, chunk, left, reinterpret_cast<const __half*>(ptab_h), pos_rows,
+                pos_u, pos_v, reinterpret_cast<__half*>(out));
+            FO_LAUNCHED();
+            FO_CUDA(cudaGetLastError());
+            return 0;
+        }
     } else {
         attention_offline_kernel<TA><<<grid, ATT_THREADS, smem, st>>>(qkv, q32, T, H, ilens, chunk, left, ptab, pos_u, pos_v, out);
     }

@@ -42,9 +42,7 @@ class GlobalCMVN(nn.Module):
     def __init__(self, mean: torch.Tensor, istd: torch.Tensor, norm_var: bool = True):
         super().__init__()
         assert mean.shape == istd.shape
-        if not norm_var:
-            raise ValueError("norm_var=False is not built")
-        self.norm_var = norm_var
+        self.norm_var = norm_var          # False: mean removal only (cmvn.py:32-34) -- the engine is then fed istd = 1
         self.register_buffer("mean", mean)
         self.register_buffer("istd", istd)
 
@@ -172,6 +170,8 @@ class speechEncoder(nn.Module):
             if p.device.type != "cuda":
                 raise RuntimeError("speechEncoder: move the module to a CUDA device first; there is no CPU path")
             sd = {k: v.detach() for k, v in self.state_dict().items()}
+            if self.global_cmvn is not None and not self.global_cmvn.norm_var:
+                sd["global_cmvn.istd"] = torch.ones_like(sd["global_cmvn.istd"])      # x - mean only (cmvn.py:32-34)
             engines[dtype] = Engine(self.path_config, enc_state=sd, adp_state=None, dtype=dtype,
                                     device=p.device.index or 0, max_sessions=self.max_sessions,
                                     use_cmvn=self.global_cmvn is not None)

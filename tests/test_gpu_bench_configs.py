@@ -100,7 +100,7 @@ def test_benchmarked_stream_step_bf16_vs_oracle(shipped_big, n, chunks):
 def test_offline_30s_bf16_vs_oracle(shipped_big, chunk, left):
     """BASELINE config 4 at full length: T = 2998 fbank frames -> 748 encoder frames, ragged pair [2998, 1203].  Every
     query block after the third has k_lo > 0 with (4, 16); with left = -1 and with full attention the key loop of
-    attention_offline_mma_kernel walks several 96-key tiles with the online-softmax rescale.
+    attention_offline_fa_kernel walks many 64-key tiles with the online-softmax rescale.
     Reference: encoder/attention.py:350-405, masks.py:23-57, encoder.py:104-147."""
     cfg, eng, esd, asd = shipped_big
     torch.set_num_threads(max(torch.get_num_threads(), 16))
@@ -429,3 +429,97 @@ def test_llm_handoff_prefix_and_attention_mask(shipped_big):
             for k in list(s_.keys):
                 s_.close(k)
             eng.free(s_.scratch)
+
+
+@pytest.mark.parametrize("c,L", [(4, 16), (4, 2), (-1, -1), (4, -1), (3, 1), (4, 0), (7, 3)])
+def test_offline_attention_fa_kernel_edge_cases_bf16(c, L):
+    """attention_offline_fa_kernel (64-query blocks, 64-key double-buffered tiles) on shapes that stress its bookkeeping: T'
+    not a multiple of 64 and shorter than a tile, ragged valid lengths down to a handful of frames, chunk sizes that do not
+    divide 8 (tile start alignment), zero / unlimited left context, full attention; tiny config, bf16 context, vs the oracle
+    on bf16-rounded weights.  Masks bit-exact.  Reference: encoder/attention.py:350-405, masks.py:23-57,110-122."""
+    from freeze_omni_b200.engine import Engine
+    cfg = load_path_config("tiny")
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    eng = Engine(cfg, esd, asd, dtype=torch.bfloat16, max_sessions=2)
+    we, wy = bf16_weights(esd), bf16_weights(asd)
+    g = torch.Generator().manual_seed(100 + 7 * c + L)
+    try:
+        for T, ilens in ((403, [403, 251, 31]), (131, [131, 90, 7]), (1287, [1287, 640, 1100])):
+            feats = 9.0 + 3.0 * torch.randn(3, T, cfg.feat_dim, generator=g)
+            il = torch.tensor(ilens)
+            enc, mask, y, ymask = eng.encode_offline(feats, il.numpy(), c, L)
+            xo, mo, yo, ymo = O.offline_path(cfg, we, wy, feats, il, c, L)
+            assert np.array_equal(mask.cpu().numpy(), mo.numpy())
+            m = mo[:, 0, :].unsqueeze(-1).float().numpy()
+            ym = ymo[:, 0, :].unsqueeze(-1).float().numpy()
+            e, a = maxabs(enc.cpu().numpy() * m, xo.numpy() * m), maxabs(y.cpu().numpy() * ym, yo.numpy() * ym)
+            assert e < BF16_TOL and a < BF16_TOL, (T, c, L, e, a)
+            assert bool(torch.isfinite(enc).all())
+    finally:
+        eng.close()
+
+
+def test_dropin_modules_under_autocast_compile_and_mean_only_cmvn(golden):
+    """The drop-ins as models/pipeline.py and models/audioLLM.py drive them: (1) the whole streaming loop inside
+    torch.autocast('cuda', bfloat16) (pipeline.py:67-68) -> the bf16 context, every chunk within 2e-2 of the oracle on
+    bf16-rounded weights, ONE engine per module; (2) wrapped by torch.compile (audioLLM.py:266-287): forward is a
+    compiler-disabled region, infer is reached through the wrapper, results equal the unwrapped module bit for bit;
+    (3) GlobalCMVN(norm_var=False) (cmvn.py:32-34): mean removal only."""
+    from freeze_omni_b200 import modules as M
+    y, cfg = load_yaml("tiny"), load_path_config("tiny")
+    g = golden("tiny")
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    mc = y["model_conf"]
+
+    def build(norm_var=True):
+        enc = M.speechEncoder(80, global_cmvn=M.GlobalCMVN(esd["global_cmvn.mean"], esd["global_cmvn.istd"], norm_var=norm_var),
+                              **y["encoder_conf"])
+        enc.load_state_dict(esd, strict=True)
+        adp = M.CNNSubsampling(mc["enc_out_dim"], mc["llm_embed_dim"], mc["kernel_size"], mc["activation_func"], mc["norm"])
+        adp.load_state_dict(asd, strict=True)
+        return enc.cuda().eval(), adp.cuda().eval()
+
+    # (1) autocast
+    enc, adp = build()
+    ses = O.StreamSession(cfg, bf16_weights(esd), bf16_weights(asd))
+    buffer, cache, pe = [None] * enc.enc[1].num_blocks, None, 0
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        for i in range(6):
+            speech = torch.from_numpy(g["stream_feats"][i][:1]).cuda()
+            eo, buffer, _, _, pe = enc.infer(speech, buffer, 0, None, pe)
+            emb, _, cache = adp(eo, torch.full(eo.shape[:2], True).unsqueeze(1).to(eo.device), cache=cache, return_cache=True)
+            eo_o, y_o = ses.step_feats(torch.from_numpy(g["stream_feats"][i][:1]))
+            assert maxabs(eo.float().cpu(), eo_o) < BF16_TOL and maxabs(emb.float().cpu(), y_o) < BF16_TOL, i
+    assert pe == ses.pe_index
+    assert list(M._ENGINES[enc]) == [torch.bfloat16] and list(M._ENGINES[adp]) == [torch.bfloat16]
+    del buffer
+    enc.invalidate(); adp.invalidate()
+
+    # (2) torch.compile wrappers
+    enc, adp = build()
+    cenc, cadp = torch.compile(enc), torch.compile(adp)
+    x = torch.from_numpy(g["off_feats"]).cuda()
+    il = torch.from_numpy(g["off_ilens"])
+    xs0, m0 = enc(x, il, 4, 16)
+    xs1, m1 = cenc(x, il, 4, 16)
+    assert torch.equal(xs0, xs1) and torch.equal(m0, m1)
+    y0, _ = adp(xs0, m0)
+    y1, _ = cadp(xs1, m1)
+    assert torch.equal(y0, y1)
+    buf0, buf1 = [None] * cfg.n_layers, [None] * cfg.n_layers
+    sp = torch.from_numpy(g["stream_feats"][0][:1]).cuda()
+    e0, buf0, _, _, p0 = enc.infer(sp, buf0, 0, None, 0)
+    e1, buf1, _, _, p1 = cenc.infer(sp, buf1, 0, None, 0)
+    assert torch.equal(e0, e1) and p0 == p1
+    del buf0, buf1
+    enc.invalidate(); adp.invalidate()
+
+    # (3) mean-only CMVN
+    enc, _ = build(norm_var=False)
+    esd1 = dict(esd)
+    esd1["global_cmvn.istd"] = torch.ones_like(esd["global_cmvn.istd"])
+    xs, m = enc(x, il, 4, 16)
+    xo, mo = O.EncoderOracle(cfg, esd1).forward(torch.from_numpy(g["off_feats"]), il, 4, 16)
+    mm = mo[:, 0, :].unsqueeze(-1).float().numpy()
+    assert np.array_equal(m.cpu().numpy(), mo.numpy()) and maxabs(xs.cpu().numpy() * mm, xo.numpy() * mm) < 1e-4
+    enc.invalidate()
