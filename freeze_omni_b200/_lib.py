@@ -17,7 +17,8 @@ class FoConfig(C.Structure):
         "feat_dim", "d_model", "n_heads", "ffn_dim", "n_layers", "chunk_size", "left_chunks",
         "input_layer_linear", "pos_max_len", "llm_dim", "adapter_kernel", "adapter_gelu",
         "has_encoder", "has_adapter", "sample_rate", "frame_len", "frame_shift", "frames_per_chunk",
-        "context_frames", "max_sessions", "max_stream_frames", "ffn_conv_kernel", "adapter_batchnorm", "adapter_type")]
+        "context_frames", "max_sessions", "max_stream_frames", "ffn_conv_kernel", "adapter_batchnorm", "adapter_type",
+        "post_norm", "concat_after")]
 
 
 class FoStats(C.Structure):
@@ -88,7 +89,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.fo_abi_version() != 5:
+    if lib.fo_abi_version() != 6:
         raise RuntimeError("libfo_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -46,7 +46,8 @@ class PathConfig:
     chunk_size: int = 4           # transformer-chunk_size (encoder frames)
     left_chunks: int = 16         # transformer-left_chunks
     input_layer: str = "linear"   # transformer-input-layer: linear | none
-    normalize_before: bool = True
+    normalize_before: bool = True  # False: post-norm layers (transformer.py:89-90,97-98), no after_norm (:232-233)
+    concat_after: bool = False     # x + concat_linear(cat(layer input, att)) instead of x + att (transformer.py:85-87)
     dynamic_chunks: bool = False
     # positionwise layer (transformer.py:205-217): "linear" = PositionwiseFeedForward (attention.py:122-143);
     # "conv1d-linear" = Conv1dLinear (attention.py:198-266): causal depthwise Conv1d(k) + 1x1 Conv1d + ReLU + Linear
@@ -139,8 +140,6 @@ class PathConfig:
             raise ValueError("adpter_type must be cnn | linear | subsampling (audioLLM.py:159-165); got %r" % self.adapter_type)
         if self.adapter_two_conv and self.d_model * 4 > 4096:
             raise ValueError("the two-conv adapters normalise 4 * d_model channels; d_model must be <= 1024")
-        if not self.normalize_before:
-            raise ValueError("post-norm layers (normalize_before=False) are not built")
         if self.ffn_type not in ("linear", "conv1d-linear"):
             raise ValueError("positionwise-layer-type %r: 'conv1d' (MultiLayeredConv1d, attention.py:145-196) pads "
                              "symmetrically and has no streaming form; only linear / conv1d-linear are built" % self.ffn_type)
@@ -173,8 +172,6 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
     if tr["transformer-positionwise-layer-type"] not in ("linear", "conv1d-linear"):
         raise ValueError("positionwise-layer-type %r is not built (MultiLayeredConv1d has no causal / streaming form, "
                          "attention.py:145-196)" % tr["transformer-positionwise-layer-type"])
-    if tr["transformer-concat-after"]:
-        raise ValueError("transformer-concat-after is not built")
     if sub["subsampling-rate"] != 4:
         raise ValueError("only subsampling-rate 4 exists (subsampling.py:93-96)")
     feat = int(over.get("encoder-input-dim", configs.get("input_dim", 80)))
@@ -202,7 +199,7 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
         ffn_dim=int(tr["transformer-linear-units"]), n_layers=int(tr["transformer-num-blocks"]),
         chunk_size=int(tr["transformer-chunk_size"]), left_chunks=int(tr["transformer-left_chunks"]),
         input_layer=str(tr["transformer-input-layer"]),
-        normalize_before=bool(tr["transformer-normalize-before"]),
+        normalize_before=bool(tr["transformer-normalize-before"]), concat_after=bool(tr["transformer-concat-after"]),
         dynamic_chunks=bool(tr["transformer-dynamic-chunks"]),
         ffn_type=str(tr["transformer-positionwise-layer-type"]),
         ffn_conv_kernel=int(tr["transformer-positionwise-conv-kernel_size"]) if tr["transformer-positionwise-layer-type"] == "conv1d-linear" else 1,

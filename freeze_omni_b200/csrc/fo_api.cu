@@ -53,6 +53,8 @@ struct HostTensor {          // staged fp32 weight on device until finalize
 
 struct LayerW {
     void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    void* wcat = nullptr;                     // concat_linear [D][2D] (transformer-concat-after)
+    float* bcat = nullptr;
     float* ptab = nullptr;                    // P_l = pe * Wpos_l^T, fp32 [pos_rows][D] (offline attention)
     void* ptab_h = nullptr;                   // the same, [H][pos_rows][64] in the activation type (streaming attention)
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
@@ -447,6 +449,10 @@ int finalize_t(fo_ctx* c) {
             FO_TRY(keep_f32(c, p + "norm1.bias", {D}, &w.ln1b));
             FO_TRY(keep_f32(c, p + "norm2.weight", {D}, &w.ln2g));
             FO_TRY(keep_f32(c, p + "norm2.bias", {D}, &w.ln2b));
+            if (g.concat_after) {
+                FO_TRY(keep_w<TW>(c, p + "concat_linear.weight", {D, 2 * D}, &w.wcat));
+                FO_TRY(keep_f32(c, p + "concat_linear.bias", {D}, &w.bcat));
+            }
             // P_l = pe * Wpos^T  (attention.py:433): a function of the weights only, so it is tabulated once
             // instead of per layer per chunk.  fp32 FFMA GEMM over the fp32 sin/cos table and the weights as
             // the context holds them (rounded to bf16 in a bf16 context); the table stays fp32.
@@ -483,8 +489,10 @@ int finalize_t(fo_ctx* c) {
             cudaFree(wpos);
             FO_TRY(r);
         }
-        FO_TRY(keep_f32(c, "enc.1.after_norm.weight", {D}, &c->after_g));
-        FO_TRY(keep_f32(c, "enc.1.after_norm.bias", {D}, &c->after_b));
+        if (!g.post_norm) {                   // transformer.py:232-233: after_norm exists only with normalize_before
+            FO_TRY(keep_f32(c, "enc.1.after_norm.weight", {D}, &c->after_g));
+            FO_TRY(keep_f32(c, "enc.1.after_norm.bias", {D}, &c->after_b));
+        }
         // frontend constants
         if (staged(c, "fbank.window")) {
             FO_TRY(keep_f32(c, "fbank.window", {g.frame_len}, &c->fb_window));
@@ -770,6 +778,10 @@ struct NextNorm {
     const float* beta;
     float* out_f32;          // after_norm of the last layer: fp32 encoder output rows (else null -> h)
 };
+// fp32 rows -> the activation type of the context (post-norm layers feed the un-normalised layer input to the GEMMs)
+template <typename TA> int to_act(const float* x, TA* y, long long n, cudaStream_t st);
+template <> int to_act<float>(const float* x, float* y, long long n, cudaStream_t st) { return scale_rows(x, y, n, 1.0f, st); }
+template <> int to_act<act16>(const float* x, act16* y, long long n, cudaStream_t st) { return f32_to_act16(x, y, n, st); }
 inline L2Prefetch pf1(const void* p, long long bytes) {
     L2Prefetch f;
     f.ptr[0] = p; f.bytes[0] = bytes;
@@ -811,16 +823,35 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
                const void* next_wqkv, const FfnConv& fc, cudaStream_t st) {
     const int D = c->D, FF = c->FF;
     const long long wsz = (long long)c->esz;
+    // transformer-normalize-before: false -> the LayerNorms follow the residual adds (norm1 after attention, norm2 after the
+    // feed-forward, transformer.py:89-90,97-98,117-118,127-128): the normalised rows replace the residual stream AND feed the
+    // next GEMM.  transformer-concat-after -> x + concat_linear(cat(layer input, att)) (transformer.py:85-87,108-113): linear_out
+    // writes its rows behind the layer input (`h` is then a [2][M][D] pair of planes) and concat_linear reads both as ONE K = 2D operand.
+    const bool post = c->cfg.post_norm != 0, cat = c->cfg.concat_after != 0;
     Epilogue e;
     if (c->use_prefetch & 1) e.prefetch = pf1(w.w2, (long long)D * FF * wsz);       // out-proj runs: FFN2's weights
-    e.bias = w.bo;
+    e.bias = cat ? w.bcat : w.bo;
     e.residual = x;
     e.c_f32 = x;
     e.ldc = D;
-    e.ln_gamma = w.ln2g;
-    e.ln_beta = w.ln2b;
+    e.ln_gamma = post ? w.ln1g : w.ln2g;
+    e.ln_beta = post ? w.ln1b : w.ln2b;
     e.ln_act = h;
-    if (!(c->debug_skip & 4)) FO_TRY(gemm<TA>(c, att, w.wo, M, D, D, e, st));
+    if (post) e.ln_f32 = x;
+    if (!(c->debug_skip & 4)) {
+        if (cat) {
+            Epilogue eo;
+            eo.bias = w.bo;
+            eo.c_act = h + (long long)M * D;                      // plane 1 of the concat operand
+            eo.ldc = D;
+            FO_TRY(gemm<TA>(c, att, w.wo, M, D, D, eo, st));
+            AGather ga = plain_rows(D, M);
+            ga.n_seg = 2; ga.planes = 2; ga.plane[1] = 1;
+            FO_TRY(gemm<TA>(c, h, ga, w.wcat, M, D, 2 * D, e, RowMap(), st));
+        } else {
+            FO_TRY(gemm<TA>(c, att, w.wo, M, D, D, e, st));
+        }
+    }
     if (c->debug_skip & 8) return 0;
     const TA* ffn_in = h;
     if (c->KF >= 2) {
@@ -843,10 +874,10 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
     e2.residual = x;
     e2.c_f32 = x;
     e2.ldc = D;
-    e2.ln_gamma = nn.gamma;
-    e2.ln_beta = nn.beta;
-    if (nn.out_f32) e2.ln_f32 = nn.out_f32;
-    else e2.ln_act = h;
+    e2.ln_gamma = post ? w.ln2g : nn.gamma;
+    e2.ln_beta = post ? w.ln2b : nn.beta;
+    if (nn.out_f32) e2.ln_f32 = nn.out_f32;               // last layer: the encoder output rows
+    else { e2.ln_act = h; if (post) e2.ln_f32 = x; }
     return gemm<TA>(c, ffh, w.w2, M, D, FF, e2, st);
 }
 
@@ -864,7 +895,7 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
         if (c->step_part == 1) return 0;
     }
     void *h, *qkv, *att, *ffh;
-    FO_TRY(ws_ensure(c, WS_H, (size_t)M * D * sizeof(TA), &h));
+    FO_TRY(ws_ensure(c, WS_H, (size_t)(c->cfg.concat_after ? 2 : 1) * M * D * sizeof(TA), &h));   // concat_after: [layer input | linear_out rows]
     FO_TRY(ws_ensure(c, WS_QKV, (size_t)M * 3 * D * sizeof(TA), &qkv));
     FO_TRY(ws_ensure(c, WS_ATT, (size_t)M * D * sizeof(TA), &att));
     FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
@@ -879,6 +910,7 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     int G = c->profile_gemm ? 1 : c->groups;
     if (G > fo_ctx::MAX_GROUPS) G = fo_ctx::MAX_GROUPS;
     while (G > 1 && n < 8 * G) --G;
+    if (c->cfg.concat_after) G = 1;                         // the concat operand is a [2][M][D] pair of planes over ALL rows
     const long long layer_stride = (long long)c->cfg.max_sessions * 2LL * H * c->ring_cap * 64;
     if (G > 1) {
         FO_CUDA(cudaEventRecord(c->ev_fork, st));
@@ -909,7 +941,8 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
             float* q32g = q32 + r0 * 3 * D;
             float* xg = x + r0 * D;
             int r = 0;
-            if (l == 0) r = layer_norm<TA>(xg, Mg, D, w.ln1g, w.ln1b, 1e-5f, 0, 1.0f, hg, nullptr, sg);
+            if (l == 0) r = c->cfg.post_norm ? to_act<TA>(xg, hg, (long long)Mg * D, sg)          // post-norm: the layer input as it is
+                                             : layer_norm<TA>(xg, Mg, D, w.ln1g, w.ln1b, 1e-5f, 0, 1.0f, hg, nullptr, sg);
             L2Prefetch pfq;                                   // QKV runs: this layer's KV rings (attention) + out-proj weights
             if (c->use_prefetch & 2) {
                 const long long slot_bytes = a.ring_slot_stride * (long long)sizeof(TA);
@@ -965,7 +998,7 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
     float* x;
     FO_TRY(subsample_program<TA>(c, feats, B, T, &x, st));
     void *h, *qkv, *att, *ffh;
-    FO_TRY(ws_ensure(c, WS_H, (size_t)M * D * sizeof(TA), &h));
+    FO_TRY(ws_ensure(c, WS_H, (size_t)(c->cfg.concat_after ? 2 : 1) * M * D * sizeof(TA), &h));   // concat_after: [layer input | linear_out rows]
     FO_TRY(ws_ensure(c, WS_QKV, (size_t)M * 3 * D * sizeof(TA), &qkv));
     FO_TRY(ws_ensure(c, WS_ATT, (size_t)M * D * sizeof(TA), &att));
     FO_TRY(ws_ensure(c, WS_FFH, (size_t)M * FF * sizeof(TA), &ffh));
@@ -973,7 +1006,8 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
     if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
     void* hc = nullptr;
     if (c->KF >= 2) FO_TRY(ws_ensure(c, WS_HC, (size_t)M * D * sizeof(TA), &hc));
-    FO_TRY(layer_norm<TA>(x, M, D, c->layers[0].ln1g, c->layers[0].ln1b, 1e-5f, 0, 1.0f, reinterpret_cast<TA*>(h), nullptr, st));
+    if (c->cfg.post_norm) FO_TRY(to_act<TA>(x, reinterpret_cast<TA*>(h), (long long)M * D, st));
+    else FO_TRY(layer_norm<TA>(x, M, D, c->layers[0].ln1g, c->layers[0].ln1b, 1e-5f, 0, 1.0f, reinterpret_cast<TA*>(h), nullptr, st));
     for (int l = 0; l < c->L; ++l) {
         const LayerW& w = c->layers[l];
         const bool last = l + 1 == c->L;

@@ -67,7 +67,8 @@ class Engine:
             context_frames=cfg.context_frames, max_sessions=int(max_sessions), max_stream_frames=int(msf),
             ffn_conv_kernel=int(cfg.ffn_conv_kernel) if cfg.ffn_type == "conv1d-linear" else 0,
             adapter_batchnorm=int(cfg.adapter_norm == "batch"),
-            adapter_type={"subsampling": 0, "linear": 1, "cnn": 2}[cfg.adapter_type])
+            adapter_type={"subsampling": 0, "linear": 1, "cnn": 2}[cfg.adapter_type],
+            post_norm=int(not cfg.normalize_before), concat_after=int(cfg.concat_after))
         h = C.c_void_p()
         _lib.check(self.lib.fo_create(C.byref(c), self.device, _lib.FO_BF16 if dtype == torch.bfloat16 else _lib.FO_F32,
                                       C.byref(h)))

@@ -131,9 +131,12 @@ class speechEncoder(nn.Module):
             ff.w_2 = nn.Linear(cfg.ffn_dim, d)
             lay.self_attn, lay.feed_forward = att, ff
             lay.norm1, lay.norm2 = nn.LayerNorm(d), nn.LayerNorm(d)
+            if cfg.concat_after:                       # transformer.py:69-70
+                lay.concat_linear = nn.Linear(2 * d, d)
             layers.append(lay)
         tr.encoders = nn.ModuleList(layers)
-        tr.after_norm = nn.LayerNorm(d)
+        if cfg.normalize_before:                       # transformer.py:232-233
+            tr.after_norm = nn.LayerNorm(d)
         # attributes callers read or set (audioLLM.py:378; encoder.py:132-138)
         tr.num_blocks = cfg.n_layers
         tr.chunk_size, tr.left_chunks = cfg.chunk_size, cfg.left_chunks

@@ -45,10 +45,13 @@ def encoder_param_shapes(cfg: PathConfig) -> List[Tuple[str, Tuple[int, ...], in
                     (p + "feed_forward.w_1.1.weight", (ff, d, 1), d), (p + "feed_forward.w_1.1.bias", (ff,), d)]
         else:
             out += [(p + "feed_forward.w_1.weight", (ff, d), d), (p + "feed_forward.w_1.bias", (ff,), d)]
+        if getattr(cfg, "concat_after", False):            # transformer.py:69-70: Linear(size + size, size)
+            out += [(p + "concat_linear.weight", (d, 2 * d), 2 * d), (p + "concat_linear.bias", (d,), 2 * d)]
         out += [(p + "feed_forward.w_2.weight", (d, ff), ff), (p + "feed_forward.w_2.bias", (d,), ff),
                 (p + "norm1.weight", (d,), -1), (p + "norm1.bias", (d,), -2),
                 (p + "norm2.weight", (d,), -1), (p + "norm2.bias", (d,), -2)]
-    out += [("enc.1.after_norm.weight", (d,), -1), ("enc.1.after_norm.bias", (d,), -2)]
+    if getattr(cfg, "normalize_before", True):             # transformer.py:232-233
+        out += [("enc.1.after_norm.weight", (d,), -1), ("enc.1.after_norm.bias", (d,), -2)]
     return out
 
 

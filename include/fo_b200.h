@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FO_ABI_VERSION 5
+#define FO_ABI_VERSION 6
 
 enum { FO_F32 = 0, FO_BF16 = 1, FO_I16 = 2 };     /* compute dtype / PCM sample type */
 enum { FO_OK = 0, FO_ERR_ARG = -1, FO_ERR_CUDA = -2, FO_ERR_STATE = -3, FO_ERR_NOMEM = -4 };
@@ -75,6 +75,11 @@ typedef struct fo_config {
      * 2 = CNNAdapter (adapter.py:10-57): two causal stride-1 convolutions with BatchNorm1d + ReLU, Linear(4 * d_model -> llm_dim),
      * no cache (zero left context every call), t_out = t */
     int32_t adapter_type;
+    /* TransformerLayer options (models/encoder/transformer.py:56-70): post_norm = 1 is transformer-normalize-before: false
+     * (LayerNorms after the residual adds, :89-90,97-98,117-118,127-128, and no after_norm, :232-233); concat_after = 1 replaces
+     * x + att by x + concat_linear(cat(layer input, att)) (:85-87,108-113; tensor enc.1.encoders.N.concat_linear.{weight,bias}) */
+    int32_t post_norm;
+    int32_t concat_after;
 } fo_config;
 
 typedef struct fo_stats_t {

@@ -232,14 +232,21 @@ def feed_forward(sd: State, p: str, y: Tensor, cache: Optional[Tensor] = None) -
                     sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"]), None
 
 
+def _attn_residual(sd: State, p: str, x: Tensor, y: Tensor, att: Tensor, concat_after: bool) -> Tensor:
+    """x + att, or x + concat_linear(cat(y, att)) with y the (possibly normalised) layer input (transformer.py:85-90,108-116)."""
+    if concat_after:
+        return x + F.linear(torch.cat((y, att), dim=-1), sd[p + "concat_linear.weight"], sd[p + "concat_linear.bias"])
+    return x + att
+
+
 def layer_stream(sd: State, i: int, x: Tensor, pos_emb: Tensor, kv: Optional[List[Tensor]], h: int,
-                 window: int) -> Tuple[Tensor, List[Tensor]]:
+                 window: int, normalize_before: bool = True, concat_after: bool = False) -> Tuple[Tensor, List[Tensor]]:
     """TransformerLayer.infer (transformer.py:103-130) + MultiHeadedAttention.infer
     (attention.py:407-459) + PositionwiseFeedForward.infer (attention.py:141-143)."""
     p = "enc.1.encoders.%d." % i
     a = p + "self_attn."
     d = x.size(-1)
-    y = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+    y = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"]) if normalize_before else x
     q = _split_heads(F.linear(y, sd[a + "linear_q.weight"], sd[a + "linear_q.bias"]), h)
     k = _split_heads(F.linear(y, sd[a + "linear_k.weight"], sd[a + "linear_k.bias"]), h)
     v = _split_heads(F.linear(y, sd[a + "linear_v.weight"], sd[a + "linear_v.bias"]), h)
@@ -249,21 +256,27 @@ def layer_stream(sd: State, i: int, x: Tensor, pos_emb: Tensor, kv: Optional[Lis
     new_kv = [k[:, :, -window:, :], v[:, :, -window:, :]] if k.size(2) > window else [k, v]
     attn = torch.softmax(attention_scores(sd, a, q, k, pos_emb, h), dim=-1)
     o = torch.matmul(attn, v).transpose(1, 2).reshape(x.size(0), -1, d)
-    x = x + F.linear(o, sd[a + "linear_out.weight"], sd[a + "linear_out.bias"])
-    y = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    x = _attn_residual(sd, p, x, y, F.linear(o, sd[a + "linear_out.weight"], sd[a + "linear_out.bias"]), concat_after)
+    if not normalize_before:
+        x = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"])                # transformer.py:117-118
+    y = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"]) if normalize_before else x
     y, ffn_cache = feed_forward(sd, p, y, kv[2] if (kv is not None and len(kv) > 2) else None)
     if ffn_cache is not None:
         new_kv.append(ffn_cache)                      # third entry of the layer's cache: Conv1dLinear left context
-    return x + y, new_kv
+    x = x + y
+    if not normalize_before:
+        x = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"])                # transformer.py:127-128
+    return x, new_kv
 
 
-def layer_offline(sd: State, i: int, x: Tensor, pos_emb: Tensor, mask: Tensor, h: int) -> Tensor:
+def layer_offline(sd: State, i: int, x: Tensor, pos_emb: Tensor, mask: Tensor, h: int, normalize_before: bool = True,
+                  concat_after: bool = False) -> Tensor:
     """TransformerLayer.forward (transformer.py:75-100) + MultiHeadedAttention.forward
     (attention.py:350-405): masked_fill(min) -> softmax -> masked_fill(0)."""
     p = "enc.1.encoders.%d." % i
     a = p + "self_attn."
     d = x.size(-1)
-    y = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+    y = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"]) if normalize_before else x
     q = _split_heads(F.linear(y, sd[a + "linear_q.weight"], sd[a + "linear_q.bias"]), h)
     k = _split_heads(F.linear(y, sd[a + "linear_k.weight"], sd[a + "linear_k.bias"]), h)
     v = _split_heads(F.linear(y, sd[a + "linear_v.weight"], sd[a + "linear_v.bias"]), h)
@@ -271,10 +284,15 @@ def layer_offline(sd: State, i: int, x: Tensor, pos_emb: Tensor, mask: Tensor, h
     dead = mask.unsqueeze(1).eq(0)
     attn = torch.softmax(scores.masked_fill(dead, MIN_VALUE), dim=-1).masked_fill(dead, 0.0)
     o = torch.matmul(attn, v).transpose(1, 2).reshape(x.size(0), -1, d)
-    x = x + F.linear(o, sd[a + "linear_out.weight"], sd[a + "linear_out.bias"])
-    y = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    x = _attn_residual(sd, p, x, y, F.linear(o, sd[a + "linear_out.weight"], sd[a + "linear_out.bias"]), concat_after)
+    if not normalize_before:
+        x = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"])                # transformer.py:89-90
+    y = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"]) if normalize_before else x
     y, _ = feed_forward(sd, p, y)
-    return x + y
+    x = x + y
+    if not normalize_before:
+        x = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"])                # transformer.py:97-98
+    return x
 
 
 class EncoderOracle:
@@ -300,9 +318,11 @@ class EncoderOracle:
         start = max(0, pe_index - c.full_chunk_size)
         pos_emb = pos_table(start, n_cache + x.size(1), c.d_model).unsqueeze(0).to(x.device)   # transformer.py:278-279
         pe_index = pe_index + c.chunk_size
+        nb, ca = getattr(c, "normalize_before", True), getattr(c, "concat_after", False)
         for i in range(c.n_layers):
-            x, buffer[i] = layer_stream(sd, i, x, pos_emb, buffer[i], c.n_heads, c.kv_window)
-        x = F.layer_norm(x, (c.d_model,), sd["enc.1.after_norm.weight"], sd["enc.1.after_norm.bias"])
+            x, buffer[i] = layer_stream(sd, i, x, pos_emb, buffer[i], c.n_heads, c.kv_window, nb, ca)
+        if nb:                                                         # transformer.py:232-233,282-283
+            x = F.layer_norm(x, (c.d_model,), sd["enc.1.after_norm.weight"], sd["enc.1.after_norm.bias"])
         return x, buffer, pe_index
 
     def forward(self, feats: Tensor, ilens: Tensor, chunk: Optional[int] = None,
@@ -319,9 +339,11 @@ class EncoderOracle:
         mask = offline_attention_mask(valid, chunk, left)           # transformer.py:253-258
         x = embed(sd, x) * math.sqrt(c.d_model)                     # attention.py:100-102
         pos_emb = pos_table(0, x.size(1), c.d_model).unsqueeze(0).to(x.device)
+        nb, ca = getattr(c, "normalize_before", True), getattr(c, "concat_after", False)
         for i in range(c.n_layers):
-            x = layer_offline(sd, i, x, pos_emb, mask, c.n_heads)
-        x = F.layer_norm(x, (c.d_model,), sd["enc.1.after_norm.weight"], sd["enc.1.after_norm.bias"])
+            x = layer_offline(sd, i, x, pos_emb, mask, c.n_heads, nb, ca)
+        if nb:
+            x = F.layer_norm(x, (c.d_model,), sd["enc.1.after_norm.weight"], sd["enc.1.after_norm.bias"])
         return x, valid
 
 

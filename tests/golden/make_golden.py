@@ -360,6 +360,25 @@ def main():
                    two_off_x=xo.numpy(), two_off_mask=mo.numpy(), two_off_y=yo.numpy(), two_off_mask_out=mo2.numpy())
         save("tiny_adapter_variants", seed=np.int64(5), **out)
 
+    # ---------------- TransformerLayer options: post-norm (transformer.py:89-90,97-98) and concat_after (:85-87) ------------
+    if want("tiny_layer_variants"):
+        out = {}
+        for name in ("tiny_postnorm_concat", "tiny_concat"):
+            ycfg = load_yaml(name)
+            cfg = path_config_from_dict(ycfg)
+            enc, adp = build_reference(mods, ycfg, cfg, seed=3)
+            g = torch.Generator().manual_seed(59)
+            feats_seq = [9.0 + 3.0 * torch.randn(2, 19, cfg.feat_dim, generator=g) for _ in range(19)]    # past the window saturation
+            st_ = stream_reference(enc, adp, feats_seq, layers_to_keep=(0,))
+            xs = 9.0 + 3.0 * torch.randn(2, 131, cfg.feat_dim, generator=g)
+            ilens = torch.tensor([131, 70])
+            with torch.no_grad():
+                eo, m = enc(xs, ilens, 4, 16)
+            out.update({name + "_feats": torch.stack(feats_seq).numpy(), name + "_enc_out": st_["enc_out"], name + "_adapter_out": st_["adapter_out"],
+                        name + "_pe_index": st_["pe_index"], name + "_off_feats": xs.numpy(), name + "_off_ilens": ilens.numpy(),
+                        name + "_off_enc": eo.numpy(), name + "_off_mask": m.numpy()})
+        save("tiny_layer_variants", seed=np.int64(3), **out)
+
     # ---------------- shipped config -------------------------------------------------------
     if want("shipped"):
         ycfg = load_yaml("shipped")

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported_and_bound(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.fo_abi_version() == 5
+    assert lib.fo_abi_version() == 6
 
 
 def test_struct_layout_matches_header():

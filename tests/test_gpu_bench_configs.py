@@ -523,3 +523,76 @@ def test_dropin_modules_under_autocast_compile_and_mean_only_cmvn(golden):
     mm = mo[:, 0, :].unsqueeze(-1).float().numpy()
     assert np.array_equal(m.cpu().numpy(), mo.numpy()) and maxabs(xs.cpu().numpy() * mm, xo.numpy() * mm) < 1e-4
     enc.invalidate()
+
+
+@pytest.mark.parametrize("name", ["tiny_postnorm_concat", "tiny_concat"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, BF16_TOL)])
+def test_transformer_layer_variants(golden, name, dtype, tol):
+    """transformer-normalize-before: false and transformer-concat-after: true on the GPU (models/encoder/transformer.py:56-70,
+    85-98,108-128,232-233): streaming past the window saturation and a ragged full-utterance pass against the reference
+    modules' outputs (fp32 1e-4); bf16 against the oracle on bf16-rounded weights."""
+    from freeze_omni_b200.engine import Engine
+    cfg = load_path_config(name)
+    g = golden("tiny_layer_variants")
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    eng = Engine(cfg, esd, asd, dtype=dtype, max_sessions=4)
+    try:
+        ids = eng.alloc(2)
+        ses = O.StreamSession(cfg, bf16_weights(esd), bf16_weights(asd)) if dtype == torch.bfloat16 else None
+        for i in range(g[name + "_feats"].shape[0]):
+            f = torch.from_numpy(g[name + "_feats"][i])
+            enc, y = eng.encode_stream(ids, f)
+            if ses is None:
+                assert maxabs(enc.cpu(), g[name + "_enc_out"][i]) < tol and maxabs(y.cpu(), g[name + "_adapter_out"][i]) < tol, i
+            else:
+                eo, yo = ses.step_feats(f)
+                assert maxabs(enc.cpu(), eo) < tol and maxabs(y.cpu(), yo) < tol, i
+        assert eng.state(int(ids[0]))[1] == int(g[name + "_pe_index"][-1])
+        xs, il = torch.from_numpy(g[name + "_off_feats"]), g[name + "_off_ilens"]
+        enc, mask, _, _ = eng.encode_offline(xs, il, 4, 16)
+        assert np.array_equal(mask.cpu().numpy(), g[name + "_off_mask"])
+        m = g[name + "_off_mask"][:, 0, :, None].astype(np.float32)
+        if dtype == torch.float32:
+            assert maxabs(enc.cpu().numpy() * m, g[name + "_off_enc"] * m) < tol
+        else:
+            xo, _ = O.EncoderOracle(cfg, bf16_weights(esd)).forward(xs, torch.from_numpy(il), 4, 16)
+            assert maxabs(enc.cpu().numpy() * m, xo.numpy() * m) < tol
+    finally:
+        eng.close()
+
+
+def test_layer_variants_at_shipped_size_bf16():
+    """Post-norm + concat_after at the shipped dimensions (d_model 1024): the deferred split-K reduction then ends in a
+    LayerNorm that rewrites the residual stream in place, and concat_linear runs as one K = 2048 GEMM over the [layer input |
+    linear_out] planes; 8 sessions x 3 chunks and a short offline pair against the oracle on bf16-rounded weights."""
+    import copy
+    from freeze_omni_b200.engine import Engine
+    y = copy.deepcopy(load_yaml("shipped"))
+    tr = y["encoder_conf"]["para_conf"]["transformer"]
+    tr["transformer-normalize-before"] = False
+    tr["transformer-concat-after"] = True
+    tr["transformer-num-blocks"] = 4                              # keeps the oracle quick; every code path is per layer
+    cfg = path_config_from_dict(y)
+    esd, asd = make_encoder_state(cfg, 2), make_adapter_state(cfg, 2)
+    we, wa = bf16_weights(esd), bf16_weights(asd)
+    eng = Engine(cfg, esd, asd, dtype=torch.bfloat16, max_sessions=8)
+    torch.set_num_threads(max(torch.get_num_threads(), 16))
+    try:
+        ids = eng.alloc(8)
+        orc = O.EncoderOracle(cfg, we)
+        buf, cache, pe = orc.new_buffer(), None, 0
+        g = torch.Generator().manual_seed(77)
+        for i in range(3):
+            f = 9.0 + 3.0 * torch.randn(8, cfg.chunk_feat_frames, cfg.feat_dim, generator=g)
+            enc, yy = eng.encode_stream(ids, f)
+            eo, buf, pe = orc.infer(f, buf, pe)
+            yo, _, cache = O.adapter_forward(cfg, wa, eo, torch.ones(8, 1, 4, dtype=torch.bool), cache)
+            assert maxabs(enc.cpu(), eo) < BF16_TOL and maxabs(yy.cpu(), yo) < BF16_TOL, i
+        xs = 9.0 + 3.0 * torch.randn(2, 263, cfg.feat_dim, generator=g)
+        il = torch.tensor([263, 150])
+        enc, mask, _, _ = eng.encode_offline(xs, il.numpy(), 4, 16)
+        xo, mo = orc.forward(xs, il, 4, 16)
+        m = mo[:, 0, :].unsqueeze(-1).float().numpy()
+        assert np.array_equal(mask.cpu().numpy(), mo.numpy()) and maxabs(enc.cpu().numpy() * m, xo.numpy() * m) < BF16_TOL
+    finally:
+        eng.close()

@@ -286,3 +286,25 @@ def test_oracle_covers_cnn_adapter_and_two_conv_subsampling(golden):
     y, m, _ = O.adapter_forward(cfg2, asd, torch.from_numpy(g["two_off_x"]), torch.from_numpy(g["two_off_mask"]))
     assert float((y - torch.from_numpy(g["two_off_y"])).abs().max()) < 1e-5
     assert torch.equal(m, torch.from_numpy(g["two_off_mask_out"]))
+
+
+@pytest.mark.parametrize("name", ["tiny_postnorm_concat", "tiny_concat"])
+def test_oracle_layer_variants_match_reference(golden, name):
+    """transformer-normalize-before: false (post-norm layers, no after_norm) and transformer-concat-after: true
+    (models/encoder/transformer.py:56-70,85-98,108-128,232-233): the oracle against the reference modules' outputs."""
+    from freeze_omni_b200.config import load_path_config
+    from freeze_omni_b200.weights import make_adapter_state, make_encoder_state
+    cfg = load_path_config(name)
+    g = golden("tiny_layer_variants")
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    assert ("enc.1.after_norm.weight" in esd) == cfg.normalize_before
+    assert ("enc.1.encoders.0.concat_linear.weight" in esd) == cfg.concat_after
+    ses = O.StreamSession(cfg, esd, asd)
+    for i in range(g[name + "_feats"].shape[0]):
+        eo, yo = ses.step_feats(torch.from_numpy(g[name + "_feats"][i]))
+        assert float((eo - torch.from_numpy(g[name + "_enc_out"][i])).abs().max()) < 2e-5, i
+        assert float((yo - torch.from_numpy(g[name + "_adapter_out"][i])).abs().max()) < 2e-5, i
+        assert ses.pe_index == int(g[name + "_pe_index"][i])
+    xo, mo = O.EncoderOracle(cfg, esd).forward(torch.from_numpy(g[name + "_off_feats"]), torch.from_numpy(g[name + "_off_ilens"]), 4, 16)
+    assert np.array_equal(mo.numpy(), g[name + "_off_mask"])
+    assert float((xo - torch.from_numpy(g[name + "_off_enc"])).abs().max()) < 2e-5
