@@ -18,7 +18,7 @@ class FoConfig(C.Structure):
         "input_layer_linear", "pos_max_len", "llm_dim", "adapter_kernel", "adapter_gelu",
         "has_encoder", "has_adapter", "sample_rate", "frame_len", "frame_shift", "frames_per_chunk",
         "context_frames", "max_sessions", "max_stream_frames", "ffn_conv_kernel", "adapter_batchnorm", "adapter_type",
-        "post_norm", "concat_after")]
+        "post_norm", "concat_after", "ffn_multi_conv")]
 
 
 class FoStats(C.Structure):

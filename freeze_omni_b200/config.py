@@ -140,9 +140,11 @@ class PathConfig:
             raise ValueError("adpter_type must be cnn | linear | subsampling (audioLLM.py:159-165); got %r" % self.adapter_type)
         if self.adapter_two_conv and self.d_model * 4 > 4096:
             raise ValueError("the two-conv adapters normalise 4 * d_model channels; d_model must be <= 1024")
-        if self.ffn_type not in ("linear", "conv1d-linear"):
-            raise ValueError("positionwise-layer-type %r: 'conv1d' (MultiLayeredConv1d, attention.py:145-196) pads "
-                             "symmetrically and has no streaming form; only linear / conv1d-linear are built" % self.ffn_type)
+        if self.ffn_type not in ("linear", "conv1d-linear", "conv1d"):
+            raise ValueError("positionwise-layer-type %r: support only linear, conv1d or conv1d-linear" % self.ffn_type)
+        if self.ffn_type == "conv1d" and not (self.ffn_conv_kernel % 2 == 1 and 3 <= self.ffn_conv_kernel <= 9):
+            raise ValueError("conv1d (MultiLayeredConv1d, attention.py:158-196; full-utterance forward only) needs an odd "
+                             "positionwise-conv-kernel_size in 3..9")
         if self.ffn_type == "conv1d-linear" and not (2 <= self.ffn_conv_kernel <= 16):
             raise ValueError("conv1d-linear needs 2 <= positionwise-conv-kernel_size <= 16")
 
@@ -169,9 +171,9 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
     sub.update(para.get("subsampling", {}))
     if tr["transformer-pos-enc-class"] != "rel-enc":
         raise ValueError("only transformer-pos-enc-class 'rel-enc' can stream (attention.py:105)")
-    if tr["transformer-positionwise-layer-type"] not in ("linear", "conv1d-linear"):
-        raise ValueError("positionwise-layer-type %r is not built (MultiLayeredConv1d has no causal / streaming form, "
-                         "attention.py:145-196)" % tr["transformer-positionwise-layer-type"])
+    if tr["transformer-positionwise-layer-type"] not in ("linear", "conv1d-linear", "conv1d"):
+        raise ValueError("positionwise-layer-type %r: support only linear, conv1d or conv1d-linear (transformer.py:205-219)"
+                         % tr["transformer-positionwise-layer-type"])
     if sub["subsampling-rate"] != 4:
         raise ValueError("only subsampling-rate 4 exists (subsampling.py:93-96)")
     feat = int(over.get("encoder-input-dim", configs.get("input_dim", 80)))
@@ -202,7 +204,7 @@ def path_config_from_dict(configs: Dict[str, Any], encoder_only: bool = False) -
         normalize_before=bool(tr["transformer-normalize-before"]), concat_after=bool(tr["transformer-concat-after"]),
         dynamic_chunks=bool(tr["transformer-dynamic-chunks"]),
         ffn_type=str(tr["transformer-positionwise-layer-type"]),
-        ffn_conv_kernel=int(tr["transformer-positionwise-conv-kernel_size"]) if tr["transformer-positionwise-layer-type"] == "conv1d-linear" else 1,
+        ffn_conv_kernel=int(tr["transformer-positionwise-conv-kernel_size"]) if tr["transformer-positionwise-layer-type"] != "linear" else 1,
         llm_dim=int(mc["llm_embed_dim"]), adapter_kernel=int(mc["kernel_size"]),
         adapter_act=str(mc["activation_func"]), adapter_norm=str(mc["norm"]),
         adapter_type=adpter_type,

@@ -79,6 +79,7 @@ struct fo_ctx {
     // derived dims
     int F = 0, F1 = 0, F2 = 0, D = 0, H = 0, FF = 0, L = 0, E = 0, KA = 0;
     int KF = 0;                               // Conv1dLinear kernel size (0: plain feed-forward)
+    int KM = 0;                               // MultiLayeredConv1d kernel size (0: off); full-utterance encode only
     float* ffn_cache = nullptr;               // [slot][L][KF-1][D] fp32: left context of the depthwise conv
     int window = 0, full_chunk = 0, pe_wrap = 0, pos_rows = 0, ring_cap = 0, max_t = 0;
     int carry = 0, chunk_samples = 0, fft = 0;
@@ -184,7 +185,7 @@ struct fo_ctx {
 namespace {
 
 enum { WS_FEATS = 0, WS_C1, WS_C2, WS_XSUB, WS_EMB, WS_X, WS_H, WS_QKV, WS_ATT, WS_FFH, WS_ENC, WS_XIN, WS_ACONV, WS_AH,
-       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_PART, WS_PCM2, WS_ENC2, WS_Y2, WS_AC1, WS_XIN2, WS_TMP4, WS_TMP5, WS_COUNT };
+       WS_Y, WS_MASK2, WS_ILENS, WS_ILENS2, WS_AMASK, WS_PCM, WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_Q32, WS_HC, WS_PART, WS_PCM2, WS_ENC2, WS_Y2, WS_AC1, WS_XIN2, WS_TMP4, WS_TMP5, WS_HP, WS_FP, WS_COUNT };
 
 int dev_alloc(fo_ctx* c, void** p, size_t bytes) {
     *p = nullptr;
@@ -331,8 +332,10 @@ int gemm(fo_ctx* c, const TA* A, const AGather& ga, const void* W, int M, int N,
     if (r == 0 && deferred > 0)                   // the GEMM left raw split-K partials: the LayerNorm finishes the sum
         return layer_norm_reduce<TA>(ep.c_f32, c->tc_cur->partial, deferred, ep.bias, M, N, ep.ln_gamma, ep.ln_beta, ep.ln_eps,
                                      reinterpret_cast<TA*>(ep.ln_act), ep.ln_f32, st);
+    // rows of C: the GEMM rows of an implicit-GEMM convolution run over a padded grid that the row map compacts
+    const int out_rows = rm.p1 ? (M / rm.p1) * rm.q1 : M;
     if (r == 0 && ep.ln_gamma && !fused)          // LayerNorm of the finished rows as its own kernel (fp32 / FFMA paths)
-        r = layer_norm<TA>(ep.c_f32, M, N, ep.ln_gamma, ep.ln_beta, ep.ln_eps, 0, 1.0f, reinterpret_cast<TA*>(ep.ln_act),
+        r = layer_norm<TA>(ep.c_f32, out_rows, N, ep.ln_gamma, ep.ln_beta, ep.ln_eps, 0, 1.0f, reinterpret_cast<TA*>(ep.ln_act),
                            ep.ln_f32, st);
     return r;
 }
@@ -439,11 +442,20 @@ int finalize_t(fo_ctx* c) {
                 FO_TRY(keep_f32(c, p + "feed_forward.w_1.0.bias", {D}, &w.dw_b));
                 FO_TRY(keep_w<TW>(c, p + "feed_forward.w_1.1.weight", {FF, D, 1}, &w.w1));
                 FO_TRY(keep_f32(c, p + "feed_forward.w_1.1.bias", {FF}, &w.b1));
+            } else if (c->KM) {                        // MultiLayeredConv1d: both convolutions as implicit GEMMs, [co][tau * Cin + ci]
+                const HostTensor* t;
+                FO_TRY(need(c, p + "feed_forward.w_1.weight", {FF, D, c->KM}, &t));
+                FO_TRY(dev_alloc(c, &w.w1, (size_t)FF * D * c->KM * sizeof(TW)));
+                FO_TRY(repack_adapter_conv<TW>(t->d, FF, D, c->KM, reinterpret_cast<TW*>(w.w1), 0));
+                FO_TRY(keep_f32(c, p + "feed_forward.w_1.bias", {FF}, &w.b1));
+                FO_TRY(need(c, p + "feed_forward.w_2.weight", {D, FF, c->KM}, &t));
+                FO_TRY(dev_alloc(c, &w.w2, (size_t)FF * D * c->KM * sizeof(TW)));
+                FO_TRY(repack_adapter_conv<TW>(t->d, D, FF, c->KM, reinterpret_cast<TW*>(w.w2), 0));
             } else {
                 FO_TRY(keep_w<TW>(c, p + "feed_forward.w_1.weight", {FF, D}, &w.w1));
                 FO_TRY(keep_f32(c, p + "feed_forward.w_1.bias", {FF}, &w.b1));
             }
-            FO_TRY(keep_w<TW>(c, p + "feed_forward.w_2.weight", {D, FF}, &w.w2));
+            if (!c->KM) FO_TRY(keep_w<TW>(c, p + "feed_forward.w_2.weight", {D, FF}, &w.w2));
             FO_TRY(keep_f32(c, p + "feed_forward.w_2.bias", {D}, &w.b2));
             FO_TRY(keep_f32(c, p + "norm1.weight", {D}, &w.ln1g));
             FO_TRY(keep_f32(c, p + "norm1.bias", {D}, &w.ln1b));
@@ -817,6 +829,8 @@ struct FfnConv {                  // Conv1dLinear only: where the rows come from
     const int32_t* ids = nullptr; // streaming: session slots (left context carried); offline: null (zero padding)
     int layer = 0;
     void* hc = nullptr;           // depthwise output buffer (M, D), activation type
+    void* hp = nullptr;           // MultiLayeredConv1d: zero-padded layer input (B, T + k - 1, D) and hidden rows (B, T + k - 1, FF)
+    void* fp = nullptr;
 };
 template <typename TA>
 int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* ffh, const NextNorm& nn,
@@ -868,7 +882,30 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
     e1.relu = 1;
     e1.c_act = ffh;
     e1.ldc = FF;
-    FO_TRY(gemm<TA>(c, ffn_in, w.w1, M, FF, D, e1, st));
+    AGather ga2 = plain_rows(FF, M);
+    RowMap rm2;
+    const TA* ffn2_in = ffh;
+    int M2 = M, K2 = FF;
+    if (c->KM) {
+        // MultiLayeredConv1d (attention.py:158-196): both Conv1d(k, padding (k-1)/2) as implicit GEMMs over zero-padded rows;
+        // the first writes its ReLU rows at offset (k-1)/2 of the (pre-zeroed) padded hidden buffer, i.e. already padded for the second
+        const int k = c->KM, lead = (k - 1) / 2, R1 = fc.T + k - 1;
+        TA* hp = reinterpret_cast<TA*>(fc.hp);
+        TA* fp = reinterpret_cast<TA*>(fc.fp);
+        FO_TRY(pad_rows<TA>(h, fc.B, fc.T, D, lead, k - 1 - lead, hp, st));
+        AGather ga1;
+        RowMap rm1;
+        conv1d_gather(fc.B, fc.T, D, k, &ga1, &rm1);
+        rm1.q1 = R1;                                           // output rows stay on the padded grid ...
+        e1.c_act = fp + (long long)lead * FF;                  // ... shifted past the leading zero rows
+        FO_TRY(gemm<TA>(c, hp, ga1, w.w1, (int)ga1.rows, FF, k * D, e1, rm1, st));
+        conv1d_gather(fc.B, fc.T, FF, k, &ga2, &rm2);
+        ffn2_in = fp;
+        M2 = (int)ga2.rows;
+        K2 = k * FF;
+    } else {
+        FO_TRY(gemm<TA>(c, ffn_in, w.w1, M, FF, D, e1, st));
+    }
     Epilogue e2;
     e2.bias = w.b2;
     e2.residual = x;
@@ -878,7 +915,7 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
     e2.ln_beta = post ? w.ln2b : nn.beta;
     if (nn.out_f32) e2.ln_f32 = nn.out_f32;               // last layer: the encoder output rows
     else { e2.ln_act = h; if (post) e2.ln_f32 = x; }
-    return gemm<TA>(c, ffh, w.w2, M, D, FF, e2, st);
+    return gemm<TA>(c, ffn2_in, ga2, w.w2, M2, D, K2, e2, rm2, st);
 }
 
 template <typename TA>
@@ -1006,6 +1043,13 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
     if (sizeof(TA) == 2) { void* q; FO_TRY(ws_ensure(c, WS_Q32, (size_t)M * 3 * D * sizeof(float), &q)); q32 = reinterpret_cast<float*>(q); }
     void* hc = nullptr;
     if (c->KF >= 2) FO_TRY(ws_ensure(c, WS_HC, (size_t)M * D * sizeof(TA), &hc));
+    void *hp = nullptr, *fp = nullptr;
+    if (c->KM) {
+        const size_t rows = (size_t)B * (T2 + c->KM - 1);
+        FO_TRY(ws_ensure(c, WS_HP, rows * D * sizeof(TA), &hp));
+        FO_TRY(ws_ensure(c, WS_FP, rows * FF * sizeof(TA), &fp));
+        FO_CUDA(cudaMemsetAsync(fp, 0, rows * FF * sizeof(TA), st));      // the padding rows stay zero: the GEMM only writes the T2 inner rows
+    }
     if (c->cfg.post_norm) FO_TRY(to_act<TA>(x, reinterpret_cast<TA*>(h), (long long)M * D, st));
     else FO_TRY(layer_norm<TA>(x, M, D, c->layers[0].ln1g, c->layers[0].ln1b, 1e-5f, 0, 1.0f, reinterpret_cast<TA*>(h), nullptr, st));
     for (int l = 0; l < c->L; ++l) {
@@ -1019,7 +1063,7 @@ int offline_program(fo_ctx* c, const float* feats, const int32_t* ilens_dev, int
         NextNorm nn{last ? c->after_g : c->layers[l + 1].ln1g, last ? c->after_b : c->layers[l + 1].ln1b,
                     last ? enc_out_dev : nullptr};
         FfnConv fc;
-        fc.B = B; fc.T = T2; fc.ids = nullptr; fc.layer = l; fc.hc = hc;
+        fc.B = B; fc.T = T2; fc.ids = nullptr; fc.layer = l; fc.hc = hc; fc.hp = hp; fc.fp = fp;
         FO_TRY(layer_post<TA>(c, w, x, M, reinterpret_cast<TA*>(att), reinterpret_cast<TA*>(h), reinterpret_cast<TA*>(ffh), nn, nullptr, fc, st));
     }
     if (c->cfg.has_adapter && y_dev)
@@ -1056,6 +1100,8 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
     FO_CHECK(cfg->feat_dim >= 11 && cfg->n_layers > 0 && cfg->max_sessions > 0, "fo_create: bad sizes");
     FO_CHECK(cfg->adapter_kernel >= 2 && cfg->adapter_kernel <= AGather::MAX_SEG, "fo_create: adapter kernel must be in 2..9");
     FO_CHECK(cfg->has_encoder || cfg->has_adapter, "fo_create: nothing to build");
+    FO_CHECK(!cfg->ffn_multi_conv || (cfg->ffn_conv_kernel % 2 == 1 && cfg->ffn_conv_kernel >= 3 && cfg->ffn_conv_kernel <= AGather::MAX_SEG),
+             "fo_create: MultiLayeredConv1d needs an odd ffn_conv_kernel in 3..9");
     FO_CHECK(cfg->adapter_type >= 0 && cfg->adapter_type <= 2, "fo_create: adapter_type must be 0 (subsampling), 1 (linear) or 2 (cnn)");
     FO_CHECK(!(cfg->has_adapter && (cfg->adapter_type == 2 || (cfg->adapter_type == 0 && 4 * cfg->d_model < cfg->llm_dim))) || 4 * cfg->d_model <= 4096,
              "fo_create: the two-conv adapters normalise 4 * d_model channels; d_model must be <= 1024");
@@ -1073,7 +1119,8 @@ int fo_create(const fo_config* cfg, int device, int dtype, fo_ctx** out) {
     // 2 CNNAdapter (two stride-1 convolutions, no cache)
     c->ad_two = cfg->has_adapter && (cfg->adapter_type == 2 || (cfg->adapter_type == 0 && 4 * cfg->d_model < cfg->llm_dim));
     c->ad_stride2 = cfg->adapter_type == 2 ? 1 : 2;
-    c->KF = cfg->ffn_conv_kernel >= 2 ? cfg->ffn_conv_kernel : 0;
+    c->KF = (cfg->ffn_conv_kernel >= 2 && !cfg->ffn_multi_conv) ? cfg->ffn_conv_kernel : 0;
+    c->KM = cfg->ffn_multi_conv ? cfg->ffn_conv_kernel : 0;
     const bool streaming = cfg->chunk_size > 0 && cfg->left_chunks > 0;
     c->window = streaming ? cfg->chunk_size * cfg->left_chunks : 1;                  // attention.py:290-295
     c->full_chunk = (cfg->left_chunks + 1) * cfg->chunk_size;                         // attention.py:83
@@ -1576,6 +1623,8 @@ static int stream_common(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     FO_CHECK(t >= 1 && t <= c->max_t, "streaming call of %d feature frames gives %d encoder frames; context allows 1..%d",
              t_in, t, c->max_t);
     if (adapter_out) FO_CHECK(c->cfg.has_adapter, "adapter_out requested but the context has no adapter");
+    FO_CHECK(!c->KM, "this context's positionwise layer is MultiLayeredConv1d, which has no streaming form (the reference module has no infer(), "
+                     "models/encoder/attention.py:145-196); use fo_encode_offline");
     const int km1 = c->KA - 1, t_out = ad_frames(c, t);
     const size_t enc_bytes = (size_t)n * t * c->D * sizeof(float);
     const size_t y_bytes = (size_t)n * t_out * c->E * sizeof(float);
@@ -1691,6 +1740,7 @@ int fo_stream_step_async(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
                          float* adapter_out, void* stream, int64_t* ticket) {
     FO_CHECK(c && c->finalized && c->cfg.has_encoder && c->fb_window, "fo_stream_step_async: context has no finalized encoder + frontend");
     FO_CHECK(pcm && (pcm_dtype == FO_F32 || pcm_dtype == FO_I16) && ticket, "fo_stream_step_async: bad argument");
+    FO_CHECK(!c->KM, "fo_stream_step_async: MultiLayeredConv1d has no streaming form; use fo_encode_offline");
     if (adapter_out) FO_CHECK(c->cfg.has_adapter, "adapter_out requested but the context has no adapter");
     FO_TRY(check_ids(c, ids, n));
     FO_CUDA(cudaSetDevice(c->device));

@@ -338,6 +338,9 @@ int conv_stage(const float* in, const uint8_t* mask, int B, int T, int C, int km
                const float* shift, const int32_t* ids, float* slot_cache, int32_t* slot_valid, const float* cache_in,
                float* cache_out, TA* xin, cudaStream_t st);
 void conv1d_gather(int B, int T, int C, int k, AGather* ga, RowMap* rm);
+// (B, T, C) -> zero-padded (B, lead + T + trail, C) in the activation type
+template <typename TA>
+int pad_rows(const TA* in, int B, int T, int C, int lead, int trail, TA* out, cudaStream_t st);
 // Conv1dLinear's causal depthwise Conv1d over time (attention.py:217-224,251): y[r][c] = b[c] + sum_tau w[c][tau] *
 // xin[r + tau][c], xin = [left context (k-1 rows) | x].  Streaming (ids != null): x is (n, t, C), the left context of
 // session ids[b] lives in slot_cache (fp32, (k-1, C) per slot, stride slot_stride) and is replaced by the last k-1 rows

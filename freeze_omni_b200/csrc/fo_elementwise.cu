@@ -601,6 +601,31 @@ template int adapter_stage<float>(const float*, const uint8_t*, int, int, int, i
 template int adapter_stage<bf16>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, bf16*, cudaStream_t);
 template int adapter_stage<__half>(const float*, const uint8_t*, int, int, int, int, const int32_t*, float*, int32_t*, const float*, float*, __half*, cudaStream_t);
 
+// rows of B sequences (B, T, C) copied into zero-padded sequences (B, lead + T + trail, C): the A operand of a Conv1d with
+// symmetric padding run as an implicit GEMM (MultiLayeredConv1d, attention.py:171-184); 16-byte chunks
+template <typename TA>
+__global__ void pad_rows_kernel(const TA* __restrict__ in, int T, int C, int lead, int trail, TA* __restrict__ out) {
+    FO_PDL_TRIGGER();
+    FO_PDL_WAIT();
+    const int b = blockIdx.y, r = blockIdx.x;             // r in [0, lead + T + trail)
+    const int R = lead + T + trail;
+    constexpr int EPV = 16 / sizeof(TA);
+    const uint4* src = (r >= lead && r < lead + T) ? reinterpret_cast<const uint4*>(in + ((long long)b * T + (r - lead)) * C) : nullptr;
+    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * R + r) * C);
+    for (int i = threadIdx.x; i < C / EPV; i += blockDim.x) dst[i] = src ? src[i] : make_uint4(0, 0, 0, 0);
+}
+template <typename TA>
+int pad_rows(const TA* in, int B, int T, int C, int lead, int trail, TA* out, cudaStream_t st) {
+    if (B <= 0 || T <= 0) return 0;
+    FO_CHECK(C % (16 / (int)sizeof(TA)) == 0, "pad_rows: C must be a multiple of %d", 16 / (int)sizeof(TA));
+    FO_CUDA(launch_pdl(pad_rows_kernel<TA>, dim3(lead + T + trail, B), dim3(128), 0, st, in, T, C, lead, trail, out));
+    FO_LAUNCHED();
+    FO_CUDA(cudaGetLastError());
+    return 0;
+}
+template int pad_rows<float>(const float*, int, int, int, int, int, float*, cudaStream_t);
+template int pad_rows<__half>(const __half*, int, int, int, int, int, __half*, cudaStream_t);
+
 template <typename TA>
 int conv_stage(const float* in, const uint8_t* mask, int B, int T, int C, int km1, int stride, const float* scale,
                const float* shift, const int32_t* ids, float* slot_cache, int32_t* slot_valid, const float* cache_in,

@@ -65,10 +65,11 @@ class Engine:
             has_encoder=int(self.has_encoder), has_adapter=int(self.has_adapter), sample_rate=cfg.sample_rate,
             frame_len=cfg.frame_len, frame_shift=cfg.frame_shift, frames_per_chunk=cfg.frames_per_chunk,
             context_frames=cfg.context_frames, max_sessions=int(max_sessions), max_stream_frames=int(msf),
-            ffn_conv_kernel=int(cfg.ffn_conv_kernel) if cfg.ffn_type == "conv1d-linear" else 0,
+            ffn_conv_kernel=int(cfg.ffn_conv_kernel) if cfg.ffn_type in ("conv1d-linear", "conv1d") else 0,
             adapter_batchnorm=int(cfg.adapter_norm == "batch"),
             adapter_type={"subsampling": 0, "linear": 1, "cnn": 2}[cfg.adapter_type],
-            post_norm=int(not cfg.normalize_before), concat_after=int(cfg.concat_after))
+            post_norm=int(not cfg.normalize_before), concat_after=int(cfg.concat_after),
+            ffn_multi_conv=int(cfg.ffn_type == "conv1d"))
         h = C.c_void_p()
         _lib.check(self.lib.fo_create(C.byref(c), self.device, _lib.FO_BF16 if dtype == torch.bfloat16 else _lib.FO_F32,
                                       C.byref(h)))

@@ -126,9 +126,15 @@ class speechEncoder(nn.Module):
             ff = _Holder()
             if cfg.ffn_type == "conv1d-linear":        # Conv1dLinear (attention.py:217-234)
                 ff.w_1 = nn.Sequential(nn.Conv1d(d, d, cfg.ffn_conv_kernel, groups=d), nn.Conv1d(d, cfg.ffn_dim, 1))
+            elif cfg.ffn_type == "conv1d":             # MultiLayeredConv1d (attention.py:158-184)
+                kf = cfg.ffn_conv_kernel
+                ff.w_1 = nn.Conv1d(d, cfg.ffn_dim, kf, stride=1, padding=(kf - 1) // 2)
             else:
                 ff.w_1 = nn.Linear(d, cfg.ffn_dim)
-            ff.w_2 = nn.Linear(cfg.ffn_dim, d)
+            if cfg.ffn_type == "conv1d":
+                ff.w_2 = nn.Conv1d(cfg.ffn_dim, d, cfg.ffn_conv_kernel, stride=1, padding=(cfg.ffn_conv_kernel - 1) // 2)
+            else:
+                ff.w_2 = nn.Linear(cfg.ffn_dim, d)
             lay.self_attn, lay.feed_forward = att, ff
             lay.norm1, lay.norm2 = nn.LayerNorm(d), nn.LayerNorm(d)
             if cfg.concat_after:                       # transformer.py:69-70

@@ -43,11 +43,19 @@ def encoder_param_shapes(cfg: PathConfig) -> List[Tuple[str, Tuple[int, ...], in
             kf = cfg.ffn_conv_kernel
             out += [(p + "feed_forward.w_1.0.weight", (d, 1, kf), kf), (p + "feed_forward.w_1.0.bias", (d,), kf),
                     (p + "feed_forward.w_1.1.weight", (ff, d, 1), d), (p + "feed_forward.w_1.1.bias", (ff,), d)]
+        elif cfg.ffn_type == "conv1d":             # MultiLayeredConv1d (attention.py:158-184): Conv1d(d, ff, k), Conv1d(ff, d, k)
+            kf = cfg.ffn_conv_kernel
+            out += [(p + "feed_forward.w_1.weight", (ff, d, kf), d * kf), (p + "feed_forward.w_1.bias", (ff,), d * kf)]
         else:
             out += [(p + "feed_forward.w_1.weight", (ff, d), d), (p + "feed_forward.w_1.bias", (ff,), d)]
         if getattr(cfg, "concat_after", False):            # transformer.py:69-70: Linear(size + size, size)
             out += [(p + "concat_linear.weight", (d, 2 * d), 2 * d), (p + "concat_linear.bias", (d,), 2 * d)]
-        out += [(p + "feed_forward.w_2.weight", (d, ff), ff), (p + "feed_forward.w_2.bias", (d,), ff),
+        if cfg.ffn_type == "conv1d":
+            out += [(p + "feed_forward.w_2.weight", (d, ff, cfg.ffn_conv_kernel), ff * cfg.ffn_conv_kernel),
+                    (p + "feed_forward.w_2.bias", (d,), ff * cfg.ffn_conv_kernel)]
+        else:
+            out += [(p + "feed_forward.w_2.weight", (d, ff), ff), (p + "feed_forward.w_2.bias", (d,), ff)]
+        out += [
                 (p + "norm1.weight", (d,), -1), (p + "norm1.bias", (d,), -2),
                 (p + "norm2.weight", (d,), -1), (p + "norm2.bias", (d,), -2)]
     if getattr(cfg, "normalize_before", True):             # transformer.py:232-233

@@ -80,6 +80,11 @@ typedef struct fo_config {
      * x + att by x + concat_linear(cat(layer input, att)) (:85-87,108-113; tensor enc.1.encoders.N.concat_linear.{weight,bias}) */
     int32_t post_norm;
     int32_t concat_after;
+    /* 1: the positionwise layer is MultiLayeredConv1d (models/encoder/attention.py:145-196, transformer-positionwise-layer-type
+     * "conv1d"): Conv1d(d_model -> ffn_dim, k, padding (k-1)/2) -> ReLU -> Conv1d(ffn_dim -> d_model, k, padding (k-1)/2) over
+     * time with k = ffn_conv_kernel (odd, 3..9); tensors feed_forward.w_1.weight (ffn_dim, d_model, k), w_2.weight (d_model,
+     * ffn_dim, k).  Full-utterance encode only: the reference module has no infer(), the streaming entries refuse such a context. */
+    int32_t ffn_multi_conv;
 } fo_config;
 
 typedef struct fo_stats_t {

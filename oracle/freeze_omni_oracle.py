@@ -228,6 +228,13 @@ def feed_forward(sd: State, p: str, y: Tensor, cache: Optional[Tensor] = None) -
         x = F.conv1d(x, sd[p + "feed_forward.w_1.1.weight"], sd[p + "feed_forward.w_1.1.bias"])
         x = F.relu(x).transpose(1, 2)
         return F.linear(x, sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"]), new_cache
+    if sd[p + "feed_forward.w_1.weight"].dim() == 3:
+        # MultiLayeredConv1d (attention.py:158-196): Conv1d(k, padding (k-1)//2) -> ReLU -> Conv1d(k, padding (k-1)//2) over time;
+        # full-utterance forward only (the module has no infer(), attention.py:145-196)
+        w1, w2 = sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_2.weight"]
+        pad = (w1.size(-1) - 1) // 2
+        x = F.relu(F.conv1d(y.transpose(1, 2), w1, sd[p + "feed_forward.w_1.bias"], padding=pad))
+        return F.conv1d(x, w2, sd[p + "feed_forward.w_2.bias"], padding=pad).transpose(1, 2), None
     return F.linear(F.relu(F.linear(y, sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_1.bias"])),
                     sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"]), None
 

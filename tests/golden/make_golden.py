@@ -379,6 +379,25 @@ def main():
                         name + "_off_enc": eo.numpy(), name + "_off_mask": m.numpy()})
         save("tiny_layer_variants", seed=np.int64(3), **out)
 
+    # ---------------- MultiLayeredConv1d feed-forward (attention.py:145-196): full-utterance forward only ------------------
+    if want("tiny_mlconv"):
+        ycfg = load_yaml("tiny_mlconv")
+        cfg = path_config_from_dict(ycfg)
+        enc, adp = build_reference(mods, ycfg, cfg, seed=3)
+        g = torch.Generator().manual_seed(61)
+        xs = 9.0 + 3.0 * torch.randn(3, 163, cfg.feat_dim, generator=g)
+        ilens = torch.tensor([163, 100, 41])
+        out = {}
+        with torch.no_grad():
+            for (c_, L_) in ((4, 16), (-1, -1)):
+                eo, m = enc(xs, ilens, c_, L_)
+                eo = eo.clone()
+                y, ym = adp(eo.clone(), m)
+                out["enc_c%d_L%d" % (c_, L_)] = eo.numpy()
+                out["adp_c%d_L%d" % (c_, L_)] = y.numpy()
+                out["mask_c%d_L%d" % (c_, L_)] = m.numpy()
+        save("tiny_mlconv", seed=np.int64(3), feats=xs.numpy(), ilens=ilens.numpy(), **out)
+
     # ---------------- shipped config -------------------------------------------------------
     if want("shipped"):
         ycfg = load_yaml("shipped")

@@ -596,3 +596,31 @@ def test_layer_variants_at_shipped_size_bf16():
         assert np.array_equal(mask.cpu().numpy(), mo.numpy()) and maxabs(enc.cpu().numpy() * m, xo.numpy() * m) < BF16_TOL
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, BF16_TOL)])
+def test_multilayered_conv1d_feed_forward_offline(golden, dtype, tol):
+    """transformer-positionwise-layer-type: conv1d (MultiLayeredConv1d, attention.py:145-196): both Conv1d(k, padding (k-1)/2) as
+    implicit GEMMs over zero-padded rows, ragged batch, chunked and full attention, against the reference module's outputs;
+    the streaming entries refuse such a context (the reference module has no infer())."""
+    from freeze_omni_b200.engine import Engine
+    cfg = load_path_config("tiny_mlconv")
+    g = golden("tiny_mlconv")
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    eng = Engine(cfg, esd, asd, dtype=dtype, max_sessions=2)
+    try:
+        feats, il = torch.from_numpy(g["feats"]), g["ilens"]
+        for (c_, L_) in ((4, 16), (-1, -1)):
+            enc, mask, y, _ = eng.encode_offline(feats, il, c_, L_)
+            assert np.array_equal(mask.cpu().numpy(), g["mask_c%d_L%d" % (c_, L_)])
+            m = g["mask_c%d_L%d" % (c_, L_)][:, 0, :, None].astype(np.float32)
+            if dtype == torch.float32:
+                assert maxabs(enc.cpu().numpy() * m, g["enc_c%d_L%d" % (c_, L_)] * m) < tol
+            else:
+                xo, _, _, _ = O.offline_path(cfg, bf16_weights(esd), bf16_weights(asd), feats, torch.from_numpy(il), c_, L_)
+                assert maxabs(enc.cpu().numpy() * m, xo.numpy() * m) < tol
+        ids = eng.alloc(1)
+        with pytest.raises(Exception, match="no streaming form"):
+            eng.encode_stream(ids, torch.zeros(1, cfg.chunk_feat_frames, cfg.feat_dim))
+    finally:
+        eng.close()

@@ -308,3 +308,16 @@ def test_oracle_layer_variants_match_reference(golden, name):
     xo, mo = O.EncoderOracle(cfg, esd).forward(torch.from_numpy(g[name + "_off_feats"]), torch.from_numpy(g[name + "_off_ilens"]), 4, 16)
     assert np.array_equal(mo.numpy(), g[name + "_off_mask"])
     assert float((xo - torch.from_numpy(g[name + "_off_enc"])).abs().max()) < 2e-5
+
+
+def test_oracle_multilayered_conv1d_matches_reference(golden):
+    """transformer-positionwise-layer-type: conv1d (MultiLayeredConv1d, attention.py:145-196), full-utterance forward."""
+    cfg = load_path_config("tiny_mlconv")
+    g = golden("tiny_mlconv")
+    esd, asd = make_encoder_state(cfg, 3), make_adapter_state(cfg, 3)
+    assert tuple(esd["enc.1.encoders.0.feed_forward.w_1.weight"].shape) == (cfg.ffn_dim, cfg.d_model, 3)
+    for (c_, L_) in ((4, 16), (-1, -1)):
+        xo, mo, yo, _ = O.offline_path(cfg, esd, asd, torch.from_numpy(g["feats"]), torch.from_numpy(g["ilens"]), c_, L_)
+        m = torch.from_numpy(g["mask_c%d_L%d" % (c_, L_)])[:, 0, :].unsqueeze(-1).float()
+        assert np.array_equal(mo.numpy(), g["mask_c%d_L%d" % (c_, L_)])
+        assert float(((xo - torch.from_numpy(g["enc_c%d_L%d" % (c_, L_)])) * m).abs().max()) < 2e-5
