@@ -144,6 +144,8 @@ struct fo_ctx {
     unsigned long long* sat_counter = nullptr; // device: fp16-range saturations counted by the GEMM epilogues (Epilogue::sat)
     cudaEvent_t ev_sync = nullptr;            // recorded after every synchronous step: the copy stream of a later async step
                                               // must not overwrite the staging buffers that step still reads
+    std::vector<int32_t> ids_last;            // session ids currently in ids_dev (uploaded on ids_last_stream)
+    cudaStream_t ids_last_stream = nullptr;
     std::vector<long long> id_stamp;          // check_ids: call number that last named each slot (duplicate detection)
     long long id_call = 0;
     void* handoff = nullptr;                  // fo_stream_step_embeds: fp16 destination of the adapter rows for this call
@@ -261,6 +263,10 @@ int check_ids(fo_ctx* c, const int32_t* ids, int n) {
 }
 
 int upload_ids(fo_ctx* c, const int32_t* ids, int n, cudaStream_t st, const uint8_t* onset = nullptr) {
+    // the same sessions as in the previous step (the steady state of a server loop): the device copy is still valid
+    if (!onset && st == c->ids_last_stream && (int)c->ids_last.size() == n && memcmp(c->ids_last.data(), ids, sizeof(int32_t) * n) == 0) return 0;
+    c->ids_last.assign(ids, ids + n);
+    c->ids_last_stream = st;
     const int k = c->ids_cursor;
     c->ids_cursor = (k + 1) % fo_ctx::NSTAGE;
     FO_CUDA(cudaEventSynchronize(c->ids_event[k]));

@@ -561,6 +561,8 @@ struct TcPersistParams {
     int rows_a, rows_b, kblocks, bn, stages, act_fp16;
     int tiles_a, tiles_b;
     int dbg;                     // development (FO_PERSIST_DBG): 1 no stores, 2 no TMEM loads either (timing only)
+    int tma_bufs;                // staging boxes per epilogue warp (1 or 2)
+    int tma_store;               // epilogue through swizzled shared-memory boxes + cp.async.bulk.tensor stores (map_c32 / map_c16)
     TcOperand op_a;              // activations (AGather segments)
     RowMap rmap;
     Epilogue ep;
@@ -568,7 +570,8 @@ struct TcPersistParams {
 };
 
 __global__ void __launch_bounds__(P_THREADS, 1)
-gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcPersistParams p) {
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const __grid_constant__ CUtensorMap map_c32, const __grid_constant__ CUtensorMap map_c16, const TcPersistParams p) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -685,6 +688,103 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;                    // write-out: 8 rows x 4 float4 per instruction
         FO_PDL_WAIT();
         int it = 0;
+        if (p.tma_store) {
+            // ---- epilogue through TMA stores.  Plain st.global from the epilogue warps caps an SM at ~13 GB/s of output (the
+            // store queue drains at the L2 write latency; FO_PERSIST_DBG=1 shows 1500 vs 830 TFLOP/s for FFN1 with / without the
+            // stores): here a lane keeps its ROW, the warp assembles a 32-row x 128-byte box (32 fp32 / 64 fp16 columns) in a
+            // 128B-swizzled staging buffer and one lane hands it to cp.async.bulk.tensor; two buffers per warp, so the copy of
+            // box i drains while box i+1 is assembled.  The residual GEMMs read their residual rows with ordinary loads. ----
+            unsigned char* stg = smem_dyn + (base - smem_u32(smem_dyn)) + (size_t)stages * stage_bytes + (size_t)e * 4096 * p.tma_bufs;
+            int nbox = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int tile_b = tile % p.tiles_b, tile_a = tile / p.tiles_b;
+                const int ab = it & 1;
+                const int row = tile_a * BM + q * 32 + lane;
+                const bool ok = row < p.rows_a;
+                const int n0 = tile_b * bn;
+                const bool f32out = out32 && (!ep.split_col || n0 < ep.split_col);
+                const int cw = f32out ? 32 : 64;                          // columns per box: 128 bytes per row
+                // residual added in place (x += acc + bias): the box goes out as a TMA REDUCE-add, the SM never reads the residual rows
+                const bool red = resid != nullptr && resid == out32 && f32out;
+                mbar_wait(af0 + 8 * ab, ((uint32_t)(it >> 1)) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256);
+                for (int cb = grp * cw; cb < bn; cb += 2 * cw) {          // the two warps of a lane quarter alternate boxes
+                    if (n0 + cb >= p.n_out) break;
+                    unsigned char* buf = stg + (p.tma_bufs == 2 ? (nbox & 1) * 4096 : 0);
+                    if (lane == 0) {                                       // the box that used this buffer has been read out
+                        if (p.tma_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                    for (int c0 = cb; c0 < cb + cw; c0 += 16) {
+                        const int n = n0 + c0;
+                        float v[16];
+                        tc_ld16(taddr + c0, v);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (ep.bias) bv = *reinterpret_cast<const float4*>(ep.bias + n + j);
+                            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (resid && !red && ok) rv = __ldcg(reinterpret_cast<const float4*>(resid + (long long)row * ldc + n + j));
+                            v[j] = (v[j] + bv.x) * scale; v[j + 1] = (v[j + 1] + bv.y) * scale;
+                            v[j + 2] = (v[j + 2] + bv.z) * scale; v[j + 3] = (v[j + 3] + bv.w) * scale;
+                            if (relu) { v[j] = fmaxf(v[j], 0.f); v[j + 1] = fmaxf(v[j + 1], 0.f); v[j + 2] = fmaxf(v[j + 2], 0.f); v[j + 3] = fmaxf(v[j + 3], 0.f); }
+                            v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+                        }
+                        // 16-byte chunk c of row `lane` lives at chunk c ^ (lane & 7) (CU_TENSOR_MAP_SWIZZLE_128B)
+                        unsigned char* rowp = buf + lane * 128;
+                        if (f32out) {
+                            const int ch0 = ((c0 - cb) >> 2);                 // 4 floats per chunk
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(rowp + (((ch0 + j) ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            const int ch0 = ((c0 - cb) >> 3);                 // 8 halves per chunk
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                uint4 h4;
+                                if (p.act_fp16) {
+                                    count_sat4(ep.sat, v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]);
+                                    count_sat4(ep.sat, v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]);
+                                    h4.x = pack2<__half>(v[8 * j], v[8 * j + 1]); h4.y = pack2<__half>(v[8 * j + 2], v[8 * j + 3]);
+                                    h4.z = pack2<__half>(v[8 * j + 4], v[8 * j + 5]); h4.w = pack2<__half>(v[8 * j + 6], v[8 * j + 7]);
+                                } else {
+                                    h4.x = pack2<bf16>(v[8 * j], v[8 * j + 1]); h4.y = pack2<bf16>(v[8 * j + 2], v[8 * j + 3]);
+                                    h4.z = pack2<bf16>(v[8 * j + 4], v[8 * j + 5]); h4.w = pack2<bf16>(v[8 * j + 6], v[8 * j + 7]);
+                                }
+                                *reinterpret_cast<uint4*>(rowp + (((ch0 + j) ^ (lane & 7)) << 4)) = h4;
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the box is read by the async proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        const CUtensorMap* mc = f32out ? &map_c32 : &map_c16;
+                        if (red)
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(mc)),
+                                         "r"(smem_u32(buf)), "r"(n0 + cb), "r"(tile_a * BM + q * 32)
+                                         : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(mc)),
+                                         "r"(smem_u32(buf)), "r"(n0 + cb), "r"(tile_a * BM + q * 32)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++nbox;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t bar = ae0 + 8 * ab;
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // every store of this warp has completed
+            __syncwarp();
+        } else
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int tile_b = tile % p.tiles_b, tile_a = tile / p.tiles_b;
             const int ab = it & 1;
@@ -808,6 +908,36 @@ int make_map_uncached(CUtensorMap* map, const bf16* base, int seg_len, long long
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for seg_len=%d rows=%lld planes=%d box=%d", (int)r,
              seg_len, rows, planes, box_rows);
+    return 0;
+}
+
+// output tensor of an epilogue: rows x cols elements of `esz` bytes, row pitch ldc elements; box = 32 rows x 128 bytes, 128B swizzle
+struct OutKey {
+    const void* base; long long rows; int cols, ldc, esz;
+    bool operator<(const OutKey& o) const {
+        if (base != o.base) return base < o.base;
+        if (rows != o.rows) return rows < o.rows;
+        if (cols != o.cols) return cols < o.cols;
+        if (ldc != o.ldc) return ldc < o.ldc;
+        return esz < o.esz;
+    }
+};
+std::map<OutKey, CUtensorMap> g_out_cache;
+int make_out_map(CUtensorMap* map, const void* base, int esz, long long rows, int cols, int ldc) {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    const OutKey k{base, rows, cols, ldc, esz};
+    auto it = g_out_cache.find(k);
+    if (it != g_out_cache.end()) { *map = it->second; return 0; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ldc * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (output) failed (%d) for rows=%lld cols=%d ldc=%d esz=%d", (int)r, rows, cols, ldc, esz);
+    if (g_out_cache.size() > 4096) g_out_cache.clear();
+    g_out_cache[k] = *map;
     return 0;
 }
 
@@ -969,8 +1099,17 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
             pp.tiles_a = ta;
             pp.tiles_b = tb;
             const uint32_t stage = (BM + bn) * BK * 2;
-            const size_t strips = (size_t)P_EPI * 32 * PST * sizeof(float);     // one staging strip per epilogue warp
-            pp.stages = std::max(2, std::min<int>(MAX_STAGES, (int)((PERSIST_SMEM - 1024 - strips) / stage)));
+            // TMA-store epilogue: identity row map, 16-byte aligned rows, a tile entirely on one side of the fp32 / 16-bit split
+            static int tma_env = -1;
+            if (tma_env < 0) { const char* e = getenv("FO_PERSIST_TMA_STORE"); tma_env = e ? atoi(e) : 1; }
+            pp.tma_store = tma_env && rmap.p1 == 0 && ep.ldc % 8 == 0 && (ep.split_col % bn == 0) && bn % 64 == 0 &&
+                           (ep.c_f32 || ep.c_act) && !(getenv("FO_PERSIST_DBG") && atoi(getenv("FO_PERSIST_DBG")));
+            static int bufs_env = 0;
+            if (!bufs_env) { const char* e = getenv("FO_PERSIST_TMA_BUFS"); bufs_env = e ? std::max(1, std::min(2, atoi(e))) : 2; }
+            pp.tma_bufs = bufs_env;
+            const size_t strips = pp.tma_store ? (size_t)P_EPI * 4096 * pp.tma_bufs           // 4 KB boxes per epilogue warp
+                                               : (size_t)P_EPI * 32 * PST * sizeof(float);    // one staging strip per epilogue warp
+            pp.stages = std::max(2, std::min<int>(MAX_STAGES, (int)((PERSIST_SMEM - 2048 - strips) / stage)));
             pp.op_a.seg_blocks = ga.seg_len / BK;
             for (int sgi = 0; sgi < AGather::MAX_SEG; ++sgi) { pp.op_a.plane[sgi] = ga.plane[sgi]; pp.op_a.rowoff[sgi] = ga.rowoff[sgi]; }
             pp.rmap = rmap;
@@ -985,7 +1124,12 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
             FO_TRY(make_map(&map_w, reinterpret_cast<const bf16*>(W), K, N, 1, bn));
             const size_t smem = (size_t)pp.stages * stage + strips + 1024;
             const int grid = std::min<long long>(g_sm_count, (long long)ta * tb);
-            FO_CUDA(launch_pdl(gemm_tc_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, map_act, map_w, pp));
+            CUtensorMap map_c32 = map_w, map_c16 = map_w;            // (placeholders when an output is absent / the epilogue stores directly)
+            if (pp.tma_store) {
+                if (ep.c_f32) FO_TRY(make_out_map(&map_c32, ep.c_f32, 4, M, N, ep.ldc));
+                if (ep.c_act) FO_TRY(make_out_map(&map_c16, ep.c_act, 2, M, N, ep.ldc));
+            }
+            FO_CUDA(launch_pdl(gemm_tc_persist_kernel, dim3(grid), dim3(P_THREADS), smem, st, map_act, map_w, map_c32, map_c16, pp));
             FO_LAUNCHED();
             ++g_tc_launches;
             ++g_persist_launches;
