@@ -166,6 +166,12 @@ struct fo_ctx {
     cudaStream_t grp_stream[MAX_GROUPS] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {nullptr};
     int profile_gemm = 0;                     // time every GEMM launch with a CUDA event pair (bench roofline)
+    // weight-streaming layer stack (fo_stack.cu): all layers of a step of <= stack_rows token rows in one cooperative launch
+    int stack_rows = 8;                       // option "stack_rows": steps of up to this many token rows take the stack kernel (<= STACK_MAX_ROWS; 0 = never)
+    StackLayer* stack_layers = nullptr;       // device table, built at the first use
+    unsigned int* stack_bar = nullptr;        // grid-barrier words of the kernel
+    unsigned long long* stack_trace = nullptr;
+    long long stack_launches = 0;
     struct ProfRec { cudaEvent_t e0, e1; int M, N, K; };
     std::vector<ProfRec> prof_events;
     // captured step graphs, keyed by the shape of the call; invalidated when a workspace moves
@@ -174,6 +180,7 @@ struct fo_ctx {
         long long epoch = -1;        // ws_epoch the graph was captured at
         long long warm_epoch = -1;   // ws_epoch after the last eager run of this key
         long long launches = 0;      // kernels inside the graph
+        long long stacks = 0;        // stack-kernel launches inside the graph
     };
     std::map<std::string, StepGraph> graphs;
     long long ws_epoch = 0;
@@ -924,6 +931,116 @@ int layer_post(fo_ctx* c, const LayerW& w, float* x, int M, TA* att, TA* h, TA* 
     return gemm<TA>(c, ffn2_in, ga2, w.w2, M2, D, K2, e2, rm2, st);
 }
 
+// All layers of a small streaming step in one cooperative launch (fo_stack.cu).  Returns 1 when the step does not qualify
+// (rows, layer options, dimensions) and the per-kernel chain has to run.
+int stack_program(fo_ctx* c, int n, int t, float* x, void* qkv, float* q32, void* att, void* ffh, float* enc_out_dev,
+                  cudaStream_t st) {
+    const int D = c->D, H = c->H;
+    if (c->dtype != FO_BF16 || c->stack_rows <= 0 || n * t > std::min(c->stack_rows, (int)STACK_MAX_ROWS)) return 1;
+    if (c->cfg.post_norm || c->cfg.concat_after || c->KF >= 2 || c->KM || c->debug_skip || c->profile_gemm) return 1;
+    const long long layer_stride = (long long)c->cfg.max_sessions * 2LL * H * c->ring_cap * 64;
+    if (!c->stack_layers) {
+        // the kernel reads its own copy of the four layer matrices with every row padded by 16 bytes (one bulk copy per
+        // weight slice, bank-conflict-free fragments, fo_stack.cu:load_rows): +604 MB for the shipped model, built at the
+        // first step that qualifies
+        auto padded = [&](const void* src, int rows, int K, const __half** out) -> int {
+            void* d;
+            FO_TRY(dev_alloc(c, &d, (size_t)rows * (K * 2 + 16)));
+            FO_CUDA(cudaMemcpy2D(d, (size_t)K * 2 + 16, src, (size_t)K * 2, (size_t)K * 2, rows, cudaMemcpyDeviceToDevice));
+            *out = reinterpret_cast<const __half*>(d);
+            return 0;
+        };
+        std::vector<StackLayer> tab(c->L);
+        for (int l = 0; l < c->L; ++l) {
+            const LayerW& w = c->layers[l];
+            StackLayer& s = tab[l];
+            FO_TRY(padded(w.wqkv, 3 * D, D, &s.wqkv));
+            FO_TRY(padded(w.wo, D, D, &s.wo));
+            FO_TRY(padded(w.w1, c->FF, D, &s.w1));
+            FO_TRY(padded(w.w2, D, c->FF, &s.w2));
+            s.bqkv = w.bqkv; s.bo = w.bo; s.b1 = w.b1; s.b2 = w.b2;
+            s.ln1g = w.ln1g; s.ln1b = w.ln1b; s.ln2g = w.ln2g; s.ln2b = w.ln2b; s.pos_u = w.pos_u; s.pos_v = w.pos_v;
+            s.ptab_h = reinterpret_cast<const __half*>(w.ptab_h);
+            s.ring = reinterpret_cast<__half*>(c->ring) + l * layer_stride;
+        }
+        void *pt, *pb, *ptr;
+        FO_TRY(dev_alloc(c, &pt, tab.size() * sizeof(StackLayer)));
+        FO_TRY(dev_alloc(c, &pb, 4096));
+        FO_TRY(dev_alloc(c, &ptr, (size_t)(35 * c->L + 8 + 16384) * sizeof(unsigned long long)));
+        FO_CUDA(cudaMemcpy(pt, tab.data(), tab.size() * sizeof(StackLayer), cudaMemcpyHostToDevice));
+        FO_CUDA(cudaMemset(pb, 0, 4096));
+        FO_CUDA(cudaMemset(ptr, 0, (size_t)(35 * c->L + 8 + 16384) * sizeof(unsigned long long)));
+        FO_CUDA(cudaDeviceSynchronize());               // the copies above ran on the default stream
+        c->stack_bar = reinterpret_cast<unsigned int*>(pb);
+        c->stack_trace = reinterpret_cast<unsigned long long*>(ptr);
+        c->stack_layers = reinterpret_cast<StackLayer*>(pt);
+    }
+    StackArgs s;
+    s.layers = c->stack_layers;
+    s.L = c->L; s.D = D; s.FF = c->FF;
+    s.a.ids = c->ids_dev;
+    s.a.n_frames = c->n_frames;
+    s.a.pe_index = c->pe_index;
+    s.a.n = n; s.a.t = t; s.a.H = H; s.a.ring_cap = c->ring_cap; s.a.window = c->window; s.a.full_chunk = c->full_chunk;
+    s.a.pe_wrap = c->pe_wrap; s.a.pos_rows = c->pos_rows;
+    s.a.ring_slot_stride = 2LL * H * c->ring_cap * 64;
+    s.x = x;
+    s.q32 = q32;
+    s.kv = reinterpret_cast<__half*>(qkv);
+    s.att = reinterpret_cast<__half*>(att);
+    s.ffh = reinterpret_cast<__half*>(ffh);
+    s.after_g = c->after_g; s.after_b = c->after_b;
+    s.enc_out = enc_out_dev;
+    s.bar = c->stack_bar;
+    s.sat = c->sat_counter;
+    static int want_trace = -1;
+    if (want_trace < 0) want_trace = getenv("FO_STACK_TRACE") ? 1 : 0;
+    s.trace = want_trace ? c->stack_trace : nullptr;
+    const int r = stream_stack(s, st);
+    if (r != 0) return r;
+    c->stack_launches += 1;
+    if (want_trace) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {
+            std::vector<unsigned long long> hb(35 * c->L + 8 + 16384);
+            FO_CUDA(cudaStreamSynchronize(st));
+            FO_CUDA(cudaMemcpy(hb.data(), c->stack_trace, hb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            const int lm = c->L / 2;
+            fprintf(stderr, "stack_trace n=%d total=%.2f us; layer %d (qkv attn out ffn1 ffn2) ns:", n, (hb[5 * c->L + 1] - hb[0]) * 1e-3, lm);
+            for (int q = 0; q < 5; ++q) fprintf(stderr, " %lld", (long long)(hb[5 * lm + q + 1] - hb[5 * lm + q]));
+            fprintf(stderr, "; first barrier at %lld ns\n  inside (activations ready, weights landed, own MMAs done, all warps done, stored; from the phase start):", (long long)(hb[1] - hb[0]));
+            for (int q = 0; q < 5; ++q) {
+                if (q == 1) continue;
+                const int ph = 5 * lm + q;
+                fprintf(stderr, " [");
+                for (int k : {0, 1, 4, 2, 3}) fprintf(stderr, "%lld ", (long long)(hb[5 * c->L + 2 + 6 * ph + k] - hb[ph]));
+                fprintf(stderr, "]");
+            }
+            fprintf(stderr, "\n  barriers of that layer, over the CTAs (ns from the phase start): ");
+            {
+                int G = 0;
+                cudaDeviceGetAttribute(&G, cudaDevAttrMultiProcessorCount, c->device);
+                for (int q = 0; q < 5; ++q) {
+                    const unsigned long long* a = hb.data() + 35 * c->L + 8 + 2 * G * q;
+                    unsigned long long amin = ~0ULL, amax = 0, rmin = ~0ULL, rmax = 0;
+                    int slow = 0;
+                    for (int g = 0; g < G; ++g) {
+                        if (a[2 * g] > amax) { amax = a[2 * g]; slow = g; }
+                        amin = std::min(amin, a[2 * g]);
+                        rmin = std::min(rmin, a[2 * g + 1]); rmax = std::max(rmax, a[2 * g + 1]);
+                    }
+                    const unsigned long long t0 = hb[5 * lm + q];
+                    fprintf(stderr, "[arrive %lld..%lld (last: cta %d) leave %lld..%lld] ", (long long)(amin - t0), (long long)(amax - t0), slow,
+                            (long long)(rmin - t0), (long long)(rmax - t0));
+                }
+            }
+            fprintf(stderr, "\n");
+        }
+    }
+    return 0;
+}
+
 template <typename TA>
 int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_out_dev, float* y_dev, cudaStream_t st) {
     const int D = c->D, FF = c->FF, H = c->H;
@@ -950,7 +1067,13 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
     // sessions are independent, every layer kernel of a 64-session step is latency bound (<= 148 CTAs, 8-16 us), so
     // two groups' kernels overlap each other's pipeline fill, epilogue and launch gaps.  Rows of one group are
     // contiguous, so the groups just take slices of the same workspaces.
+    int stacked = 1;
+    if (sizeof(TA) == 2) {
+        stacked = stack_program(c, n, t, x, qkv, q32, att, ffh, enc_out_dev, st);
+        if (stacked < 0) return stacked;
+    }
     int G = c->profile_gemm ? 1 : c->groups;
+    if (stacked == 0) G = 1;
     if (G > fo_ctx::MAX_GROUPS) G = fo_ctx::MAX_GROUPS;
     while (G > 1 && n < 8 * G) --G;
     if (c->cfg.concat_after) G = 1;                         // the concat operand is a [2][M][D] pair of planes over ALL rows
@@ -960,7 +1083,7 @@ int stream_program(fo_ctx* c, int n, const float* feats, int t_in, float* enc_ou
         for (int g = 1; g < G; ++g) FO_CUDA(cudaStreamWaitEvent(c->grp_stream[g], c->ev_fork, 0));
     }
     const int per = (n + G - 1) / G;
-    for (int l = 0; l < c->L; ++l) {
+    for (int l = 0; l < c->L && stacked != 0; ++l) {
         const LayerW& w = c->layers[l];
         const bool last = l + 1 == c->L;
         for (int g = 0; g < G; ++g) {
@@ -1580,7 +1703,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     uint32_t sbits;
     memcpy(&sbits, &a.scale, 4);
     snprintf(key, sizeof(key), "%d/%p/%lld/%lld/%d/%d/%d/%d/%d/%08x/%d/%d/%d/%d-%d", a.buf, c->handoff, c->handoff_rows, c->handoff_off, a.n, a.t_in, (int)a.with_fbank, (int)a.want_y, a.pcm_is_i16, sbits,
-             c->gemm_backend, c->groups, (((c->debug_skip * 2 + c->defer_reduce) * 2 + c->fuse_ln) * 4 + c->use_prefetch) * 64,
+             c->gemm_backend, c->groups, (((c->debug_skip * 2 + c->defer_reduce) * 2 + c->fuse_ln) * 4 + c->use_prefetch) * 64 + c->stack_rows,
              ((c->use_prefetch & 2) ? c->pf_slot_lo * 2 + g_use_pdl : g_use_pdl), (c->use_prefetch & 2) ? c->pf_slot_hi : 0);   // the prefetch range is baked into the graph
     if (c->graphs.size() > 256 && c->graphs.find(key) == c->graphs.end()) {
         for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1590,6 +1713,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     if (g.exec && g.epoch == c->ws_epoch) {
         FO_CUDA(cudaGraphLaunch(g.exec, st));
         g_launches += g.launches;
+        c->stack_launches += g.stacks;
         c->stats.graph_replays += 1;
         return 0;
     }
@@ -1599,7 +1723,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
         g.warm_epoch = c->ws_epoch;
         return 0;
     }
-    const long long l0 = g_launches, e0 = c->ws_epoch;
+    const long long l0 = g_launches, e0 = c->ws_epoch, s0 = c->stack_launches;
     FO_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed));
     int r = step_body(c, a, c->cap_stream);
     cudaGraph_t graph = nullptr;
@@ -1616,6 +1740,7 @@ static int run_step(fo_ctx* c, const StepArgs& a, cudaStream_t st) {
     g.epoch = c->ws_epoch;
     g.launches = g_launches - l0;                  // counted while capturing, not yet run
     g_launches = l0;
+    g.stacks = c->stack_launches - s0;
     FO_CUDA(cudaGraphLaunch(g.exec, st));
     g_launches += g.launches;
     c->stats.graph_replays += 1;
@@ -1947,6 +2072,7 @@ int fo_set_option(fo_ctx* c, const char* name, int64_t value) {
         c->ws_epoch += 1;                       // captured graphs hold the old plans
     }
     else if (!strcmp(name, "fuse_ln")) c->fuse_ln = value != 0;
+    else if (!strcmp(name, "stack_rows")) c->stack_rows = (int)value;
     else if (!strcmp(name, "defer_reduce")) c->defer_reduce = value != 0;
     else if (!strcmp(name, "tc_persist")) gemm_tc_set_persist(value != 0);
     else if (!strcmp(name, "l2_prefetch")) c->use_prefetch = (int)(value & 3);
@@ -1978,6 +2104,8 @@ int fo_get_option(fo_ctx* c, const char* name, int64_t* value) {
     else if (!strcmp(name, "split_k")) *value = c->split_k;
     else if (!strcmp(name, "session_groups")) *value = c->groups;
     else if (!strcmp(name, "fuse_ln")) *value = c->fuse_ln;
+    else if (!strcmp(name, "stack_rows")) *value = c->stack_rows;
+    else if (!strcmp(name, "stack_launches")) *value = c->stack_launches;
     else if (!strcmp(name, "defer_reduce")) *value = c->defer_reduce;
     else if (!strcmp(name, "tc_persist_launches")) *value = gemm_tc_persist_launches();
     else if (!strcmp(name, "l2_prefetch")) *value = c->use_prefetch;

@@ -388,6 +388,38 @@ int attention_offline(const TA* qkv, const float* q32, int B, int T, int H, cons
 int advance_sessions(const int32_t* ids, int n, int t, int chunk_size, int pe_wrap, int32_t* n_frames,
                      int32_t* pe_index, int32_t* adapter_valid, cudaStream_t st);
 
+// ---- weight-streaming layer stack for a handful of sessions (fo_stack.cu) ---------------------------
+// All transformer layers of a streaming step in ONE cooperative launch when the step has at most 16 token rows (1-4
+// sessions): at that size a layer is pure weight streaming, and the per-kernel chain spends ~5 us per kernel on
+// dependency latency (181 kernels, 0.94 ms at one session against an HBM floor of 0.12 ms).  See fo_stack.cu.
+struct StackLayer {                 // one entry per layer, device resident
+    const __half *wqkv, *wo, *w1, *w2;            // [3D][D], [D][D], [FF][D], [D][FF], K-major, bf16-rounded in fp16 containers;
+                                                  // the kernel's own copy with every row padded by 16 bytes (row pitch 2K + 16)
+    const float *bqkv, *bo, *b1, *b2;
+    const float *ln1g, *ln1b, *ln2g, *ln2b, *pos_u, *pos_v;
+    const __half* ptab_h;                         // [H][pos_rows][64], chunk-swizzled by position
+    __half* ring;                                 // this layer's (slot, 2, H, ring_cap, 64)
+};
+struct StackArgs {
+    const StackLayer* layers = nullptr;
+    int L = 0, D = 0, FF = 0;
+    AttnStream a;                                 // ids / n_frames / pe_index / n / t / H / ring geometry
+    float* x = nullptr;                           // residual stream (n*t, D) fp32, in place
+    float* q32 = nullptr;                         // (n*t, D) fp32
+    __half* kv = nullptr;                         // (n*t, 2D) the chunk's own K | V rows
+    __half* att = nullptr;                        // (n*t, D)
+    __half* ffh = nullptr;                        // (n*t, FF)
+    const float* after_g = nullptr;               // after_norm -> enc_out (n*t, D) fp32
+    const float* after_b = nullptr;
+    float* enc_out = nullptr;
+    unsigned int* bar = nullptr;                  // grid-barrier flags, one per CTA (<= 1024), all equal between launches
+    unsigned long long* sat = nullptr;            // fp16-range guard counter (Epilogue::sat)
+    unsigned long long* trace = nullptr;          // development: %globaltimer of CTA 0 after every grid barrier, [L*5 + 2]
+};
+constexpr int STACK_MAX_ROWS = 16;
+// 0 = launched; 1 = shape not supported (the caller runs the per-kernel chain); < 0 error
+int stream_stack(const StackArgs& a, cudaStream_t st);
+
 // ---- conversions -----------------------------------------------------------------------------------
 int f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
 int f32_to_act16(const float* src, act16* dst, long long n, cudaStream_t st);

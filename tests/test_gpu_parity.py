@@ -2,6 +2,8 @@
 against the golden vectors produced by the reference modules and against the CPU oracle on seeded inputs.
 Tolerances are the north star's: fbank 1e-5 relative (fp32), encoder/adapter 1e-4 max-abs in fp32 and
 2e-2 max-abs in bf16, masks / cache indexing / position bookkeeping bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -761,3 +763,92 @@ def test_gemm_backends_agree_bf16(shipped16):
         ref = (A.half().double() @ W.bfloat16().double().T + b.double()).float()
         assert maxabs(o0.cpu(), ref.cpu()) < 2e-3, (M, N, K)
         assert maxabs(o1.cpu(), ref.cpu()) < 2e-3, (M, N, K)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight-streaming layer stack (csrc/fo_stack.cu): all layers of a step of <= 16 token rows in one cooperative launch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2])
+def test_stack_kernel_matches_chain_shipped(shipped16, n):
+    """Same PCM through two groups of sessions, one per execution form (option stack_rows): the persistent stack kernel
+    against the per-kernel chain over 22 chunks (past the 17-chunk ring saturation).  Both multiply fp16-staged
+    activations with the same bf16-rounded weights; only the order of summation inside a dot product differs."""
+    cfg, eng = shipped16
+    g = torch.Generator().manual_seed(41)
+    ia, ib = eng.alloc(n), eng.alloc(n)
+    try:
+        l0 = eng.get_option("stack_launches")
+        for i in range(22):
+            pcm = (0.05 * torch.randn(n, cfg.samples_per_chunk, generator=g) * 32768).round().clamp(-32768, 32767).to(torch.int16)
+            eng.set_option("stack_rows", 16)
+            e1, y1 = eng.stream_step(ia, pcm, 1.0)
+            eng.set_option("stack_rows", 0)
+            e0, y0 = eng.stream_step(ib, pcm, 1.0)
+            assert torch.isfinite(e1).all() and torch.isfinite(y1).all(), i
+            assert maxabs(e1.cpu(), e0.cpu()) < 2e-3 and maxabs(y1.cpu(), y0.cpu()) < 2e-3, i
+        assert eng.get_option("stack_launches") - l0 == 22
+        assert eng.state(int(ia[0])) == eng.state(int(ib[0]))
+        assert eng.stats()["act_saturations"] == 0
+    finally:
+        eng.set_option("stack_rows", 8)
+        eng.free(ia)
+        eng.free(ib)
+
+
+def test_stack_kernel_vs_oracle_one_session(shipped16):
+    """One session (the latency configuration, BASELINE config 5) through the stack kernel against the oracle on the same
+    bf16-rounded weights, 20 chunks of PCM through fo_stream_step; bar 2e-2."""
+    cfg, eng = shipped16
+    esd, asd = _bf16_weights(make_encoder_state(cfg, 0)), _bf16_weights(make_adapter_state(cfg, 0))
+    ses = O.StreamSession(cfg, esd, asd)
+    g = torch.Generator().manual_seed(43)
+    ids = eng.alloc(1)
+    we = wy = 0.0
+    try:
+        l0 = eng.get_option("stack_launches")
+        for i in range(20):
+            pcm = (0.05 * torch.randn(1, cfg.samples_per_chunk, generator=g) * 32768).round().clamp(-32768, 32767).to(torch.int16)
+            enc, y = eng.stream_step(ids, pcm, 1.0)
+            _, eo, yo = ses.step_pcm(pcm[0].float(), 1.0)
+            we, wy = max(we, maxabs(enc[0].cpu(), eo[0])), max(wy, maxabs(y[0].cpu(), yo[0]))
+        print("stack kernel, 1 session x 20 chunks, max-abs vs oracle on bf16 weights: encoder %.4g adapter %.4g" % (we, wy))
+        assert eng.get_option("stack_launches") - l0 == 20, "the one-session step must run the stack kernel"
+        assert we < BF16_TOL and wy < BF16_TOL
+    finally:
+        eng.free(ids)
+
+
+def test_stack_kernel_tiny_rows_and_frames():
+    """Toy widths (D = 128, FF = 256, 2 heads: CTAs with zero, one or two weight rows per phase), 12 and 16 token rows
+    (two activation rows per warp pair, FFN2 activations in K chunks) and 7 encoder frames per call (fork frontend)."""
+    cfg, eng = make_engine("tiny", 3, dtype=torch.bfloat16, max_sessions=16)
+    g = torch.Generator().manual_seed(47)
+    try:
+        for n in (3, 4):
+            ia, ib = eng.alloc(n), eng.alloc(n)
+            l0 = eng.get_option("stack_launches")
+            for i in range(20):
+                pcm = (0.05 * torch.randn(n, cfg.samples_per_chunk, generator=g) * 32768).round().clamp(-32768, 32767).to(torch.int16)
+                eng.set_option("stack_rows", 16)
+                e1, y1 = eng.stream_step(ia, pcm, 1.0)
+                eng.set_option("stack_rows", 0)
+                e0, y0 = eng.stream_step(ib, pcm, 1.0)
+                assert maxabs(e1.cpu(), e0.cpu()) < 2e-3 and maxabs(y1.cpu(), y0.cpu()) < 2e-3, (n, i)
+            assert eng.get_option("stack_launches") - l0 == 20
+            eng.free(ia)
+            eng.free(ib)
+        golden7 = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny.npz"))
+        ia, ib = eng.alloc(2), eng.alloc(2)
+        l0 = eng.get_option("stack_launches")
+        for i in range(12):
+            x = torch.from_numpy(golden7["t7_feats"][i]).repeat(2, 1, 1)
+            eng.set_option("stack_rows", 16)
+            e1, y1 = eng.encode_stream(ia, x)
+            eng.set_option("stack_rows", 0)
+            e0, y0 = eng.encode_stream(ib, x)
+            assert e1.shape[1] == 7
+            assert maxabs(e1.cpu(), e0.cpu()) < 2e-3 and maxabs(y1.cpu(), y0.cpu()) < 2e-3, i
+        assert eng.get_option("stack_launches") - l0 == 12
+        assert eng.state(int(ia[1])) == eng.state(int(ib[1]))
+    finally:
+        eng.close()
