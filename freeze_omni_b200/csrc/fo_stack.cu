@@ -1,27 +1,34 @@
 // Weight-streaming layer stack: every transformer layer of a streaming step in ONE cooperative launch, for steps of at
-// most 16 token rows (1-4 sessions of 4 encoder frames).  Reference loop being replaced: Transformer.infer /
-// TransformerLayer.infer (models/encoder/transformer.py:103-130, 273-285) with MultiHeadedAttention.infer
-// (models/encoder/attention.py:407-459) and PositionwiseFeedForward (attention.py:137-143).
+// most 16 token rows (1-4 sessions of 4 encoder frames; taken by default up to 8 rows).  Reference loop being replaced:
+// Transformer.infer / TransformerLayer.infer (models/encoder/transformer.py:103-130, 273-285) with
+// MultiHeadedAttention.infer (models/encoder/attention.py:407-459) and PositionwiseFeedForward (attention.py:137-143).
 //
 // Why a second execution form next to the per-kernel chain of fo_api.cu: with <= 16 rows a layer is pure weight
 // streaming (25 MB of weights against 0.1 GFLOP), and the chain's 7 dependent kernels per layer each cost ~5 us of
-// dependency latency (grid completion -> griddepcontrol.wait -> first load -> ... -> stores drained): 0.94 ms for one
+// dependency latency (grid completion -> griddepcontrol.wait -> first load -> ... -> stores drained): 0.92 ms for one
 // session against an HBM floor of 0.12 ms.  Here
 //   * 148 CTAs (one per SM) stay resident for all layers; a phase boundary is a grid barrier (release add + acquire
-//     poll), five per layer: QKV | attention | out-proj | FFN1 | FFN2;
-//   * every CTA owns a fixed slice of the OUTPUT rows of each weight matrix (3D/G, D/G, FF/G, D/G rows over full K): the
-//     slice is contiguous in HBM, thread 0 streams it row by row with cp.async.bulk into padded shared-memory rows
-//     (conflict-free B fragments) one to four phases AHEAD of its use -- weights never depend on activations, so HBM
-//     streaming runs straight through the barriers; no split-K, no partial sums in global memory;
+//     poll, ~1 us), five per layer: QKV | attention | out-proj | FFN1 | FFN2;
+//   * every CTA owns a fixed slice of the OUTPUT rows of each weight matrix (3D/G, D/G, FF/G, D/G rows over full K).  The
+//     kernel reads its own copy of the four layer matrices whose rows are padded by 16 bytes in HBM, so a slice is ONE
+//     contiguous cp.async.bulk that lands with the row stride that makes the MMA fragment loads bank-conflict free; it is
+//     requested one to four phases AHEAD of its use -- weights never depend on activations, so HBM streaming runs straight
+//     through the barriers; no split-K, no partial sums in global memory;
 //   * the activations of a phase are tiny (<= 16 x 4096 fp16), every CTA re-reads them from L2 and the LayerNorm in
 //     front of QKV / FFN1 is simply recomputed by every CTA (16 KB of fp32 rows) -- no LayerNorm phase;
-//   * the contraction itself is mma.sync.m16n8k16 (tokens on M, 8 weight rows on N, the 8 warps split K and reduce
-//     through shared memory): tcgen05 needs >= 64 rows per operand tile and its 128-lane TMEM epilogue, for 4 rows the
-//     warp-level MMA wastes nothing that matters (0.1 GFLOP per layer);
-//   * attention units (session, head) run on the first n*H CTAs; their ring / rel-pos rows are requested one phase
-//     early (they never depend on this step), the other CTAs prefetch the next layer's small parameters into L2.
+//   * the contraction is mma.sync.m16n8k16 (up to 8 token rows: 16 weight rows on M, the tokens on N; the 8 warps split K
+//     and reduce through shared memory): tcgen05 needs >= 64 rows per operand tile and its 128-lane TMEM epilogue; for
+//     4-8 rows the warp-level MMA wastes nothing that matters (0.1 GFLOP per layer);
+//   * attention units (session, head) run on the first n*H CTAs; their ring / rel-pos rows are requested a phase early
+//     (they never depend on this step), the other CTAs prefetch the next layer's small parameters into L2 meanwhile.
 // Arithmetic matches the chain: fp16-staged activations x bf16-rounded weights in fp16 containers, fp32 accumulation,
 // residual stream / LayerNorm / softmax / Q in fp32; only the summation order inside a dot product differs.
+//
+// Measured (B200, shipped model, graph replay; tools/stack_check.py, FO_STACK_TRACE=1 prints the in-kernel stamps): one
+// session 0.92 -> 0.69 ms per 160 ms chunk (kernel 0.55 ms = 24 x 22.7 us; front 0.07, adapter 0.06 stay on the chain), two
+// sessions 0.95 -> 0.82 ms, four sessions 0.95 -> 1.04 ms (hence the default threshold of 8 rows).  A layer is 5 x
+// (barrier ~1.3 us incl. skew + activation rows ready 1.1-1.6 us + MMAs 0.6-0.9 us + reduce / store 0.35 us) with the
+// attention unit at ~3.4 us: latency of dependent L2 round trips, not bandwidth (25 MB per 22.7 us = 1.1 TB/s).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -34,8 +41,7 @@ namespace {
 constexpr int DK = 64;
 constexpr int ST_THREADS = 256;
 constexpr int ST_WARPS = ST_THREADS / 32;
-constexpr int BAR_COUNTER = 512;          // first counter word of the barrier buffer (the words below are the per-CTA records)
-constexpr int BAR_WAYS = 8;               // counters the arrivals are spread over (128 B apart)
+constexpr int BAR_COUNTER = 512;          // counter word of the barrier buffer (the words below it are the per-CTA records)
 constexpr int MAXG = 4;                    // 8-row weight groups per CTA and phase (<= 32 rows)
 
 #define ST_NOINLINE __device__ __noinline__
@@ -97,16 +103,18 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 
-// Grid barrier.  Every CTA adds one to a counter (release: the CTA's writes of the phase, ordered before it by the CTA
-// barrier, become visible with it) and polls (relaxed loads + acquire fence) until all arrivals of this barrier are in.
-// Arrivals on ONE counter serialise at its L2 slice: with all 148 CTAs arriving within 0.3 us the first CTA left 2.1 us
-// after the last arrival, against 0.9 us when the arrivals are staggered (the attention phase) -- so the CTAs arrive on
-// BAR_WAYS counters (cta % BAR_WAYS, 128 bytes apart) and lanes 0..BAR_WAYS-1 of warp 0 poll one each.  Measured and lost:
-// per-CTA flags polled by a warp (~5 us: 148 warps re-reading the lines the flags are stored to) and a two-level counter
-// tree (3.3 us: three dependent L2 round trips instead of two).
-// The counters only grow, across launches too: flags[cta] records how many barriers the CTA has passed so far (every CTA
-// passes the same number per launch), the targets continue from there and nothing is ever reset; compared through signed
-// differences.  `issue` runs on the last warp while warp 0 waits: the bulk copies of the next weight slices are issued here.
+// Grid barrier.  Every CTA adds one to ONE counter (release: the CTA's writes of the phase, ordered before it by the CTA
+// barrier, become visible with it) and polls it (acquire) until all G arrivals of this barrier are in.  Measured (per-CTA
+// %globaltimer stamps, tools/stack_check.py): the first CTA leaves 0.9-1.0 us after the last one arrived.  Measured and lost:
+//   * the arrivals spread over 8 counters polled by 8 lanes (relaxed loads + acquire fence): 1.2-2.6 us;
+//   * per-CTA flags polled by a warp: ~5 us (148 warps re-reading the lines the flags are being stored to);
+//   * a two-level counter tree (groups of 16, last arrival adds to a root): 3.3 us, three dependent L2 round trips;
+//   * issuing the next weight slices' bulk copies just before / inside the barrier: 2.1-2.6 us -- 148 SMs x 40-58 KB arrive as
+//     one burst through HBM -> L2 -> SM and the arrive / poll traffic queues behind it.  `issue` therefore runs AFTER the
+//     barrier (last warp): the burst then overlaps the L2 latency of the phase's activation loads and its shared-memory work.
+// The counter only grows, across launches too: flags[cta] records how many barriers the CTA has passed so far (every CTA
+// passes the same number per launch), the targets continue from there and nothing is ever reset; compared through a
+// signed difference.
 template <typename F>
 __device__ __forceinline__ void grid_barrier(unsigned int* flags, unsigned int target, int G, F&& issue, unsigned long long* arr = nullptr) {
     __syncthreads();
@@ -219,7 +227,54 @@ ST_NOINLINE void slice_gemm(const __half* act, int astr, int M, const __half* w,
     const uint32_t gstep = (uint32_t)(8 * wstr) * 2u;
     const int kend = (warp + 1) * kw;
     float d[MAXG][4] = {};
-    if (ng == 1 && kw % (16 * MAXG) == 0) {
+    if (M <= 8) {
+        // up to 8 token rows: the WEIGHT rows go on the MMA-M side (16 per tile) and the tokens on N = 8 -- half the HMMAs of
+        // the other orientation for the QKV / FFN1 slices (21 / 28 rows: 2 tiles instead of 3 / 4 groups); the legacy
+        // mma.sync pipe of sm_100 retires one m16n8k16 per ~40 clocks per SM sub-partition, and it is what bounds these loops
+        const int nt = (ng + 1) >> 1;
+        const uint32_t wp0 = smem_u32(w) + (uint32_t)(g * wstr + wk0 + c * 2) * 2u;       // weight row g (and g + 8) of a tile
+        const uint32_t wp1 = wp0 + gstep;
+        const uint32_t tp = smem_u32(act) + (uint32_t)(g * astr + c * 2) * 2u;            // token g
+        if (nt == 1 && kw % (16 * MAXG) == 0) {
+#pragma unroll 2
+            for (int kk = warp * kw; kk < kend; kk += 16 * MAXG) {
+                uint32_t a[MAXG][4], b[MAXG][2];
+#pragma unroll
+                for (int s = 0; s < MAXG; ++s) {
+                    const uint32_t k = (uint32_t)(kk + 16 * s) * 2u;
+                    a[s][0] = lds32s(wp0 + k);
+                    a[s][1] = lds32s(wp1 + k);
+                    a[s][2] = lds32s(wp0 + k + 16);
+                    a[s][3] = lds32s(wp1 + k + 16);
+                    b[s][0] = lo ? lds32s(tp + k) : 0u;
+                    b[s][1] = lo ? lds32s(tp + k + 16) : 0u;
+                }
+#pragma unroll
+                for (int s = 0; s < MAXG; ++s) mma16816(d[s], a[s], b[s]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) d[0][r] = (d[0][r] + d[1][r]) + (d[2][r] + d[3][r]);
+        } else {
+#pragma unroll 2
+            for (int kk = warp * kw; kk < kend; kk += 16) {
+                const uint32_t k = (uint32_t)kk * 2u;
+                uint32_t b[2];
+                b[0] = lo ? lds32s(tp + k) : 0u;
+                b[1] = lo ? lds32s(tp + k + 16) : 0u;
+#pragma unroll
+                for (int ti = 0; ti < MAXG / 2; ++ti)
+                    if (ti < nt) {
+                        uint32_t a[4];
+                        a[0] = lds32s(wp0 + ti * 2 * gstep + k);
+                        a[1] = lds32s(wp1 + ti * 2 * gstep + k);
+                        a[2] = lds32s(wp0 + ti * 2 * gstep + k + 16);
+                        a[3] = lds32s(wp1 + ti * 2 * gstep + k + 16);
+                        mma16816(d[ti], a, b);
+                    }
+            }
+        }
+        ng = nt;                                               // tiles stored below
+    } else if (ng == 1 && kw % (16 * MAXG) == 0) {
 #pragma unroll 2
         for (int kk = warp * kw; kk < kend; kk += 16 * MAXG) {
             uint32_t a[MAXG][4], b[MAXG][2];
@@ -267,9 +322,11 @@ ST_NOINLINE void slice_gemm(const __half* act, int astr, int M, const __half* w,
         }
 }
 // element (token m, weight row j of the slice): sum over the warps in warp order (deterministic)
-__device__ __forceinline__ float red_sum(const float* red, int m, int j) {
-    const int gi = j >> 3, n = j & 7;
-    const int idx = (gi * 32 + (m & 7) * 4 + (n >> 1)) * 4 + (n & 1) + 2 * (m >> 3);
+// (wm: slice_gemm put the weight rows on the MMA-M side -- tile = 16 weight rows x 8 tokens)
+__device__ __forceinline__ float red_sum(const float* red, int m, int j, bool wm) {
+    const int gi = wm ? j >> 4 : j >> 3, n = j & 7;
+    const int idx = wm ? (gi * 32 + n * 4 + (m >> 1)) * 4 + (m & 1) + 2 * ((j >> 3) & 1)
+                       : (gi * 32 + (m & 7) * 4 + (n >> 1)) * 4 + (n & 1) + 2 * (m >> 3);
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < ST_WARPS; ++w) s += red[w * MAXG * 128 + idx];
@@ -480,6 +537,7 @@ stream_stack_kernel(const __grid_constant__ StackArgs p, const __grid_constant__
     const int G = gridDim.x, cta = blockIdx.x;
     const int D = p.D, FF = p.FF, H = p.a.H, t = p.a.t, M = p.a.n * t;
     const int wsD = D + 8, wsF = FF + 8;                  // padded row strides (halves): rows shift by 4 banks
+    const bool wm = M <= 8;                               // orientation of the MMA tiles (slice_gemm)
     __half* S1 = reinterpret_cast<__half*>(smem + lay.s1);       // QKV slice, then this layer's FFN1 slice
     __half* S2 = reinterpret_cast<__half*>(smem + lay.s2);       // FFN2 slice
     __half* S3 = reinterpret_cast<__half*>(smem + lay.s3);       // out-proj slice
@@ -540,7 +598,7 @@ stream_stack_kernel(const __grid_constant__ StackArgs p, const __grid_constant__
         ST_STAMP(2);
         for (int e = tid; e < M * qn; e += ST_THREADS) {
             const int m = e / qn, j = e - m * qn, col = qr0 + j;
-            const float v = red_sum(RED, m, j) + (e == tid ? pb : __ldg(w.bqkv + col));
+            const float v = red_sum(RED, m, j, wm) + (e == tid ? pb : __ldg(w.bqkv + col));
             if (lay.dbg & 1) continue;
             if (col < D) p.q32[(long long)m * D + col] = v;                       // Q stays fp32
             else {
@@ -549,7 +607,11 @@ stream_stack_kernel(const __grid_constant__ StackArgs p, const __grid_constant__
             }
         }
         ST_STAMP(3);
-        grid_barrier(p.bar, base + ++epoch, G, [&] { if (lane == 0) load_rows(S1, w.w1, fr0, fn, D, &bars[0]); }, arr ? arr + 2 * G * 0 : nullptr);   // this layer's FFN1 slice
+        grid_barrier(p.bar, base + ++epoch, G, [&] {
+            if (lane != 0) return;
+            load_rows(S1, w.w1, fr0, fn, D, &bars[0]);                  // this layer's FFN1 and FFN2 slices: they land while most
+            if (l > 0) load_rows(S2, w.w2, or0, on, FF, &bars[1]);      // CTAs idle through the attention phase
+        }, arr ? arr + 2 * G * 0 : nullptr);
         if (p.trace && cta == 0 && tid == 0) p.trace[epoch] = gtime();
         // ---------------- attention units on the first n*H CTAs ----------------
         if (has_attn) {
@@ -580,7 +642,7 @@ stream_stack_kernel(const __grid_constant__ StackArgs p, const __grid_constant__
         for (int e = tid; e < M * on; e += ST_THREADS) {
             const int m = e / on, j = e - m * on, col = or0 + j;
             float* xp = p.x + (long long)m * D + col;
-            const float xv = e == tid ? (red_sum(RED, m, j) + pb) + px : (red_sum(RED, m, j) + __ldg(w.bo + col)) + __ldcg(xp);
+            const float xv = e == tid ? (red_sum(RED, m, j, wm) + pb) + px : (red_sum(RED, m, j, wm) + __ldg(w.bo + col)) + __ldcg(xp);
             if (!(lay.dbg & 1)) *xp = xv;
         }
         ST_STAMP(3);
@@ -602,7 +664,7 @@ stream_stack_kernel(const __grid_constant__ StackArgs p, const __grid_constant__
         ST_STAMP(2);
         for (int e = tid; e < M * fn; e += ST_THREADS) {
             const int m = e / fn, j = e - m * fn, col = fr0 + j;
-            const float v = fmaxf(red_sum(RED, m, j) + (e == tid ? pb : __ldg(w.b1 + col)), 0.f);
+            const float v = fmaxf(red_sum(RED, m, j, wm) + (e == tid ? pb : __ldg(w.b1 + col)), 0.f);
             if (p.sat && v > 65504.f) atomicAdd(p.sat, 1ULL);
             if (!(lay.dbg & 1)) p.ffh[(long long)m * FF + col] = from_f<__half>(v);
         }
@@ -632,14 +694,13 @@ stream_stack_kernel(const __grid_constant__ StackArgs p, const __grid_constant__
             for (int e = tid; e < M * on; e += ST_THREADS) {
                 const int m = e / on, j = e - m * on, col = or0 + j;
                 float* xp = p.x + (long long)m * D + col;
-                const float xv = e == tid ? (red_sum(RED, m, j) + pb) + px : (red_sum(RED, m, j) + __ldg(w.b2 + col)) + __ldcg(xp);
+                const float xv = e == tid ? (red_sum(RED, m, j, wm) + pb) + px : (red_sum(RED, m, j, wm) + __ldg(w.b2 + col)) + __ldcg(xp);
                 if (!(lay.dbg & 1)) *xp = xv;
             }
             ST_STAMP(3);
         }
         grid_barrier(p.bar, base + ++epoch, G, [&] {
             if (!more || lane != 0) return;
-            load_rows(S2, p.layers[l + 1].w2, or0, on, FF, &bars[1]);
             if (has_attn) attn_issue(p.a, ge, p.layers[l + 1], ah, aKs, aPs, aVs, &bars[3]);   // next layer's ring / rel-pos rows
         }, arr ? arr + 2 * G * 4 : nullptr);
         if (p.trace && cta == 0 && tid == 0) p.trace[epoch] = gtime();
