@@ -1086,9 +1086,25 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
     // fat, short-K GEMM with several waves of tiles: the persistent kernel (epilogue of tile i under the MMAs of tile i+1)
     if (g_persist && g_forced.swap < 0 && g_forced.bn <= 0 && g_forced.split <= 0 && M > 384 && K / BK <= 64 && N % 16 == 0 &&
         !ep.ln_gamma) {
-        const int bn = N % 256 == 0 || N > 1024 ? 256 : (N % 128 == 0 ? 128 : 256);
-        const int ta = (M + BM - 1) / BM, tb = (N + bn - 1) / bn;
-        if ((long long)ta * tb >= 2LL * g_sm_count) {
+        int bn = N % 256 == 0 || N > 1024 ? 256 : (N % 128 == 0 ? 128 : 256);
+        // Mid-size row counts (streaming steps of ~400-700 sessions, short offline batches; >= 12 row tiles): the persistent
+        // kernel also takes GEMMs of 0.8-2 waves, with 128-column tiles when 256-column ones would give < 1.6 waves (N = 1024
+        // at 1920 rows: 60 tiles for 148 SMs).  480-session step 4.27 -> 3.77 ms, 640 sessions 5.39 -> 5.23; at 10 row tiles
+        // (320 sessions) the tile-per-CTA plans of choose_plan stay 1.5 % ahead, hence the row-tile threshold.
+        static int min_w10 = -1, bn128_below_w10 = -1, ta_min = -1;
+        if (min_w10 < 0) {
+            const char* e1 = getenv("FO_PERSIST_WAVES_X10");
+            const char* e2 = getenv("FO_PERSIST_BN128_X10");
+            const char* e3 = getenv("FO_PERSIST_TA_MIN");
+            min_w10 = e1 ? atoi(e1) : 8;
+            bn128_below_w10 = e2 ? atoi(e2) : 16;
+            ta_min = e3 ? atoi(e3) : 12;
+        }
+        const int ta = (M + BM - 1) / BM;
+        const bool relaxed = ta >= ta_min;
+        if (relaxed && bn == 256 && N % 128 == 0 && (long long)ta * ((N + 255) / 256) * 10 < (long long)bn128_below_w10 * g_sm_count) bn = 128;
+        const int tb = (N + bn - 1) / bn;
+        if ((long long)ta * tb * 10 >= (long long)(relaxed ? min_w10 : 20) * g_sm_count) {
             TcPersistParams pp;
             memset(&pp, 0, sizeof(pp));
             pp.rows_a = M;

@@ -624,3 +624,39 @@ def test_multilayered_conv1d_feed_forward_offline(golden, dtype, tol):
             eng.encode_stream(ids, torch.zeros(1, cfg.chunk_feat_frames, cfg.feat_dim))
     finally:
         eng.close()
+
+
+def test_stream_480_sessions_mid_size_gemm_plans_vs_oracle():
+    """A 480-session step (1920 token rows, 15 row tiles: the mean active set of the ragged trace of config 3) takes the
+    persistent tcgen05 GEMM with 128-column tiles for QKV / out-proj / FFN2 and 256-column tiles for FFN1 (fo_gemm_tc.cu,
+    'mid-size row counts'); sampled sessions against per-session oracle runs on the same bf16-rounded weights."""
+    import torch
+    from freeze_omni_b200.config import load_path_config
+    from freeze_omni_b200.engine import Engine
+    from freeze_omni_b200.weights import make_adapter_state, make_encoder_state
+    from oracle import freeze_omni_oracle as O
+
+    cfg = load_path_config("shipped")
+    esd, asd = make_encoder_state(cfg, 0), make_adapter_state(cfg, 0)
+    keep = ("pos_bias", "conv.0.weight")
+    bf = lambda sd: {k: (v.bfloat16().float() if v.dim() >= 2 and not any(t in k for t in keep) else v) for k, v in sd.items()}  # noqa: E731
+    eng = Engine(cfg, esd, asd, dtype=torch.bfloat16, max_sessions=480)
+    try:
+        S, sampled = 480, (0, 217, 479)
+        ids = eng.alloc(S)
+        g = torch.Generator().manual_seed(77)
+        oracle = {s: O.StreamSession(cfg, bf(esd), bf(asd)) for s in sampled}
+        p0 = eng.get_option("tc_persist_launches")
+        we = wy = 0.0
+        for i in range(3):
+            pcm = (0.05 * torch.randn(S, cfg.samples_per_chunk, generator=g) * 32768).round().clamp(-32768, 32767).to(torch.int16)
+            enc, y = eng.stream_step(ids, pcm.cuda(), 1.0)
+            for s, o in oracle.items():
+                _, eo, yo = o.step_pcm(pcm[s].float(), 1.0)
+                we = max(we, float((enc[s].cpu() - eo[0]).abs().max()))
+                wy = max(wy, float((y[s].cpu() - yo[0]).abs().max()))
+        print("480 sessions x 3 chunks: max-abs vs oracle encoder %.4g adapter %.4g" % (we, wy))
+        assert eng.get_option("tc_persist_launches") - p0 >= 4 * 24, "the layer GEMMs of a 1920-row step must take the persistent kernel"
+        assert we < 2e-2 and wy < 2e-2
+    finally:
+        eng.close()
