@@ -1090,7 +1090,8 @@ int gemm_tc(const void* A, int act_fp16, const AGather& ga, const void* W, int M
         // Mid-size row counts (streaming steps of ~400-700 sessions, short offline batches; >= 12 row tiles): the persistent
         // kernel also takes GEMMs of 0.8-2 waves, with 128-column tiles when 256-column ones would give < 1.6 waves (N = 1024
         // at 1920 rows: 60 tiles for 148 SMs).  480-session step 4.27 -> 3.77 ms, 640 sessions 5.39 -> 5.23; at 10 row tiles
-        // (320 sessions) the tile-per-CTA plans of choose_plan stay 1.5 % ahead, hence the row-tile threshold.
+        // (320 sessions) the tile-per-CTA plans of choose_plan stay 1.5 % ahead, hence the row-tile threshold.  A cost model
+        // (rounds over the SMs x relative tile time) instead of the two thresholds measured within +-3 % at 384-960 sessions.
         static int min_w10 = -1, bn128_below_w10 = -1, ta_min = -1;
         if (min_w10 < 0) {
             const char* e1 = getenv("FO_PERSIST_WAVES_X10");

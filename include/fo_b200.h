@@ -220,8 +220,12 @@ int fo_stats(fo_ctx* ctx, fo_stats_t* out);
  *   "defer_reduce" 1: split-K GEMMs of the residual stream leave the reduction to the LayerNorm that follows
  *   "tc_persist" 1: persistent tile loop for fat short-K GEMMs (offline path)       "fuse_ln" 0: LayerNorm inside the residual GEMM's epilogue
  *   "session_groups" 1 (..4): layer kernels of session groups on parallel streams
+ *   "stack_rows" 8 (0..16): streaming steps of up to this many token rows (sessions x encoder frames per call) run all
+ *       transformer layers in ONE cooperative launch (csrc/fo_stack.cu; bf16 contexts, pre-norm linear-FFN layers) instead of
+ *       the per-kernel chain; the first such step builds the kernel's row-padded copy of the layer matrices (+ 2 x 12 D^2 bytes
+ *       per layer, 604 MB for the shipped model).  0 = always the chain.
  *   "profile_gemm" 0/1, "debug_skip" (timing attribution), "tc_swap"/"tc_bn"/"tc_split" (-1 = cost model): development
- * get-only: "tc_launches", "tc_persist_launches", "ring_cap", "max_t", "profile_gemm_us", "profile_gemm_count".
+ * get-only: "tc_launches", "tc_persist_launches", "stack_launches", "ring_cap", "max_t", "profile_gemm_us", "profile_gemm_count".
  * Development environment variables read once per process: FO_TC_OCC, FO_TC_KB, FO_TC_KBD, FO_TC_SMAX, FO_TC_CAP, FO_TC_SKINNY (tile
  * plan of the skinny GEMMs), FO_PDL_MIN, FO_PERSIST_DBG, FO_TC_TRACE. */
 int fo_set_option(fo_ctx* ctx, const char* name, int64_t value);
