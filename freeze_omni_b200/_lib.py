@@ -57,6 +57,7 @@ SYMBOLS = {
     "fo_stream_step": (C.c_int, [_P, _I32P, C.c_int, _P, C.c_int, C.c_float, _P, _P, _P]),
     "fo_debug_trace_read": (C.c_int, [_P, _P, C.c_int64, _I64P]),
     "fo_debug_plan": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fo_debug_stack_plan": (C.c_int, [C.c_int] * 9 + [C.POINTER(C.c_int)] * 5),
     "fo_stream_step_async": (C.c_int, [_P, _I32P, C.c_int, _P, C.c_int, C.c_float, _P, _P, _P, C.POINTER(C.c_int64)]),
     "fo_stream_wait": (C.c_int, [_P, C.c_int64]),
     "fo_stream_step_embeds": (C.c_int, [_P, _I32P, C.c_int, _P, C.c_int, C.c_float, _P, _P, C.c_int64, C.c_int64, _P]),

@@ -2167,6 +2167,13 @@ int fo_debug_trace_read(fo_ctx* c, uint64_t* out, int64_t cap_records, int64_t* 
     return 0;
 }
 
+int fo_debug_stack_plan(int d_model, int ffn_dim, int heads, int n_sessions, int frames, int window, int layers, int sms,
+                        int smem_max, int* smem_bytes, int* ffn2_chunk, int* rows_qkv, int* rows_ffn1, int* rows_out) {
+    FO_CHECK(smem_bytes && ffn2_chunk && rows_qkv && rows_ffn1 && rows_out, "fo_debug_stack_plan: null argument");
+    return stack_plan(d_model, ffn_dim, heads, n_sessions, frames, window, layers, sms, smem_max, smem_bytes, ffn2_chunk, rows_qkv,
+                      rows_ffn1, rows_out);
+}
+
 int fo_debug_plan(int64_t act_rows, int n_out, int K, int can_defer, int* swap, int* bn, int* split) {
     FO_CHECK(act_rows > 0 && n_out > 0 && K > 0 && K % 64 == 0 && swap && bn && split, "fo_debug_plan: bad argument");
     gemm_tc_plan(act_rows, n_out, K, can_defer, swap, bn, split);

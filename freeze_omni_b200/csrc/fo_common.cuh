@@ -419,6 +419,10 @@ struct StackArgs {
 constexpr int STACK_MAX_ROWS = 16;
 // 0 = launched; 1 = shape not supported (the caller runs the per-kernel chain); < 0 error
 int stream_stack(const StackArgs& a, cudaStream_t st);
+// host-only: does a step of n sessions x t frames qualify on a device of `sms` SMs with smem_max bytes of shared memory per CTA,
+// and with which plan (dynamic shared memory, K chunk of the FFN2 activations, weight rows per CTA and phase); 1 = no
+int stack_plan(int D, int FF, int H, int n, int t, int window, int L, int sms, int smem_max, int* smem_bytes, int* ffn2_chunk,
+               int* rows_qkv, int* rows_ffn1, int* rows_out);
 
 // ---- conversions -----------------------------------------------------------------------------------
 int f32_to_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);

@@ -743,6 +743,50 @@ stream_stack_kernel(const __grid_constant__ StackArgs p, const __grid_constant__
 
 }  // namespace
 
+// Shared-memory plan of the kernel for a step shape on a device of G SMs with smem_max bytes per CTA; false = the step does
+// not qualify (pure host logic: fo_debug_stack_plan exposes it to the CPU tests).
+static bool stack_layout(int D, int FF, int H, int n, int t, int window, int L, int G, int smem_max, StackLayout* lay, int* smem) {
+    const int M = n * t;
+    if (G < 1 || M < 1 || M > STACK_MAX_ROWS || t > 8 || H * DK != D || D % 128 || D > 1024 || FF % 128 || FF > 4096 ||
+        n * H > G || window + t > 128 || L < 1)
+        return false;
+    auto cdivi = [](int x, int y) { return (x + y - 1) / y; };
+    const int rowD = D * 2 + 16, rowF = FF * 2 + 16;
+    const int r1 = std::max(cdivi(3 * D, G), cdivi(FF, G)), r2 = cdivi(D, G);
+    if (r1 > 8 * MAXG || r2 > 8 * MAXG) return false;
+    int off = 0;
+    auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
+    lay->s1 = take(r1 * rowD);
+    lay->s2 = take(r2 * rowF);
+    lay->s3 = take(r2 * rowD);
+    lay->act_bytes = M * rowD;
+    // FFN2's activation rows (M x FF fp16) pass through the same buffer in K chunks (a multiple of 128 columns each)
+    int kc = FF;
+    while (kc > 128 && (M * (kc * 2 + 16) > std::max(lay->act_bytes, 33024) || FF % kc)) kc -= 128;
+    lay->kc = kc;
+    lay->dbg = 0;
+    lay->act_bytes = std::max(lay->act_bytes, M * (kc * 2 + 16));
+    lay->act = take(lay->act_bytes);
+    lay->red = take(ST_WARPS * MAXG * 128 * 4);
+    const int rows = window + t, vrows = (rows + 15) & ~15;
+    lay->attn = take((2 * rows + vrows) * DK * 2 + 2 * t * DK * 2 + t * vrows * 2 + t * std::max(vrows, DK) * 4);
+    *smem = off;
+    return off <= smem_max;
+}
+
+int stack_plan(int D, int FF, int H, int n, int t, int window, int L, int sms, int smem_max, int* smem_bytes, int* ffn2_chunk,
+               int* rows_qkv, int* rows_ffn1, int* rows_out) {
+    StackLayout lay;
+    int smem = 0;
+    if (!stack_layout(D, FF, H, n, t, window, L, sms, smem_max, &lay, &smem)) return 1;
+    *smem_bytes = smem;
+    *ffn2_chunk = lay.kc;
+    *rows_qkv = (3 * D + sms - 1) / sms;
+    *rows_ffn1 = (FF + sms - 1) / sms;
+    *rows_out = (D + sms - 1) / sms;
+    return 0;
+}
+
 int stream_stack(const StackArgs& a, cudaStream_t st) {
     static int sm_count = 0, smem_max = 0, coop = 0;
     if (!sm_count) {
@@ -752,35 +796,13 @@ int stream_stack(const StackArgs& a, cudaStream_t st) {
         FO_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         FO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     }
-    const int D = a.D, FF = a.FF, H = a.a.H, t = a.a.t, n = a.a.n, M = n * t, G = sm_count;
-    if (!coop || M < 1 || M > STACK_MAX_ROWS || t > 8 || H * DK != D || D % 128 || D > 1024 || FF % 128 || FF > 4096 ||
-        n * H > G || a.a.window + t > 128 || a.L < 1)
-        return 1;
-    auto cdivi = [](int x, int y) { return (x + y - 1) / y; };
-    const int rowD = D * 2 + 16, rowF = FF * 2 + 16;
-    const int r1 = std::max(cdivi(3 * D, G), cdivi(FF, G)), r2 = cdivi(D, G);
-    if (r1 > 8 * MAXG || r2 > 8 * MAXG) return 1;
+    const int G = sm_count;
     StackLayout lay;
-    int off = 0;
-    auto take = [&](int bytes) { const int o = off; off += (bytes + 127) & ~127; return o; };
-    lay.s1 = take(r1 * rowD);
-    lay.s2 = take(r2 * rowF);
-    lay.s3 = take(r2 * rowD);
-    lay.act_bytes = M * rowD;
-    // FFN2's activation rows (M x FF fp16) pass through the same buffer in K chunks (a multiple of 128 columns each)
-    int kc = FF;
-    while (kc > 128 && (M * (kc * 2 + 16) > std::max(lay.act_bytes, 33024) || FF % kc)) kc -= 128;
-    lay.kc = kc;
+    int smem = 0;
+    if (!coop || !stack_layout(a.D, a.FF, a.a.H, a.a.n, a.a.t, a.a.window, a.L, G, smem_max, &lay, &smem)) return 1;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("FO_STACK_DBG"); dbg = e ? atoi(e) : 0; }
     lay.dbg = dbg;
-    lay.act_bytes = std::max(lay.act_bytes, M * (kc * 2 + 16));
-    lay.act = take(lay.act_bytes);
-    lay.red = take(ST_WARPS * MAXG * 128 * 4);
-    const int rows = a.a.window + t, vrows = (rows + 15) & ~15;
-    lay.attn = take((2 * rows + vrows) * DK * 2 + 2 * t * DK * 2 + t * vrows * 2 + t * std::max(vrows, DK) * 4);
-    const int smem = off;
-    if (smem > smem_max) return 1;
     static int attr_smem = 0;
     if (smem > attr_smem) {
         FO_CUDA(cudaFuncSetAttribute(stream_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

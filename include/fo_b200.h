@@ -240,6 +240,12 @@ int fo_debug_trace_read(fo_ctx* ctx, uint64_t* out, int64_t cap_records, int64_t
 /* host-only: the tile plan of the tcgen05 GEMM for (activation rows, output columns, K) -- swap = weights on the UMMA-M side,
  * bn = UMMA N, split = K splits; can_defer = a consumer kernel finishes the split-K sum.  Needs no GPU (CPU tests of the plan). */
 int fo_debug_plan(int64_t act_rows, int n_out, int K, int can_defer, int* swap, int* bn, int* split);
+/* host-only: whether a streaming step of n_sessions x frames token rows takes the one-launch layer stack (csrc/fo_stack.cu,
+ * option "stack_rows") on a device of `sms` SMs with smem_max bytes of opt-in shared memory per CTA, and its plan: dynamic
+ * shared memory, K chunk of the FFN2 activations, weight rows per CTA of the QKV / FFN1 / out-proj (= FFN2) slices.
+ * Returns 0 and the plan, or 1 when the step does not qualify.  Needs no GPU (CPU tests). */
+int fo_debug_stack_plan(int d_model, int ffn_dim, int heads, int n_sessions, int frames, int window, int layers, int sms,
+                        int smem_max, int* smem_bytes, int* ffn2_chunk, int* rows_qkv, int* rows_ffn1, int* rows_out);
 /* one GEMM of the library, exposed for kernel-level parity tests and roofline measurement:
  * C[M,N] = A[M,K] * W[N,K]^T (+bias) in the context's dtype, fp32 in/out on device pointers. */
 int fo_debug_gemm(fo_ctx* ctx, const float* A, const float* W, const float* bias, float* C,
