@@ -678,7 +678,7 @@ def main():
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / K,
                         "how": "fo_stream_step_async + fo_stream_wait: pinned-host int16 PCM in, fp32 embeddings back to the host "
-                               "every step, copies on the library's copy stream overlapping the next step's kernels",
+                               "every step; uploads and read-backs on the library's own two copy streams, overlapping the neighbouring steps' kernels (this loop therefore hides the staging copies that the device-resident loop of `value` runs in-stream)",
                         "sync_each_step": {"value": e2e_sync, "ms_per_step": ms_e2e_sync / K,
                                            "how": "fo_stream_step with host buffers + stream synchronisation after every step"}},
                 "gpu_launches": int(launches),

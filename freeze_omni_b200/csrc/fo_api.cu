@@ -135,7 +135,9 @@ struct fo_ctx {
     int fuse_ln = 0;                          // LayerNorm inside the epilogue of the GEMM that completes the residual rows
                                               // (measured slower than the stand-alone kernel at 64-256 sessions: off)
     // fo_stream_step_async: host <-> device copies on an internal stream, staging buffers double-buffered by ticket parity
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;       // read-backs (device -> host) of the pipelined steps
+    cudaStream_t upload_stream = nullptr;     // their PCM uploads: a stream of their own, so that the upload of step i+1 does not queue
+                                              // behind the read-back of step i (which waits for step i's kernels)
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     long long async_ticket = 0;
     unsigned long long* trace_buf = nullptr;  // development (FO_TRACE_BUILD): CTA timeline records, 8 x u64 each
@@ -1332,6 +1334,7 @@ int fo_destroy(fo_ctx* c) {
     for (auto& kv : c->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->upload_stream) cudaStreamDestroy(c->upload_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
         if (c->ev_compute[i]) cudaEventDestroy(c->ev_compute[i]);
@@ -1878,6 +1881,7 @@ int fo_stream_step_async(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     cudaStream_t st = (cudaStream_t)stream;
     if (!c->copy_stream) {
         FO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        FO_CUDA(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             FO_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
             FO_CUDA(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
@@ -1894,11 +1898,11 @@ int fo_stream_step_async(fo_ctx* c, const int32_t* ids, int n, const void* pcm, 
     // inputs: copy stream, once the step that last read this PCM buffer (two tickets ago) is done
     void* stage;
     FO_TRY(ws_ensure(c, ws_pcm(buf), (size_t)n * c->chunk_samples * 4, &stage));
-    if (c->async_ticket >= 2) FO_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_compute[buf], 0));
+    if (c->async_ticket >= 2) FO_CUDA(cudaStreamWaitEvent(c->upload_stream, c->ev_compute[buf], 0));
     // a synchronous step still queued on `st` stages its PCM in WS_PCM as well and reads the shared intermediates
-    if (c->ev_sync) FO_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_sync, 0));
-    FO_CUDA(cudaMemcpyAsync(stage, pcm, (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4), cudaMemcpyDefault, c->copy_stream));
-    FO_CUDA(cudaEventRecord(c->ev_in[buf], c->copy_stream));
+    if (c->ev_sync) FO_CUDA(cudaStreamWaitEvent(c->upload_stream, c->ev_sync, 0));
+    FO_CUDA(cudaMemcpyAsync(stage, pcm, (size_t)n * c->chunk_samples * (pcm_dtype == FO_I16 ? 2 : 4), cudaMemcpyDefault, c->upload_stream));
+    FO_CUDA(cudaEventRecord(c->ev_in[buf], c->upload_stream));
     FO_CUDA(cudaStreamWaitEvent(st, c->ev_in[buf], 0));
     // outputs of two tickets ago must have left this buffer set before the step overwrites it
     if (c->async_ticket >= 2) FO_CUDA(cudaStreamWaitEvent(st, c->ev_out[buf], 0));

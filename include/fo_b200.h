@@ -164,7 +164,7 @@ int fo_stream_step(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int 
                    float* enc_out, float* adapter_out, void* stream);
 /* pipelined form for HOST buffers (a server loop that already holds the next chunk; the reference runs this loop one chunk
  * and one session at a time, bin/dialog_state_pred.py:793-814 -> models/audioLLM.py:380-387): returns once the step is enqueued.
- * The PCM upload and the read-back of enc_out / adapter_out run on an internal copy stream with double-buffered staging,
+ * The PCM upload and the read-back of enc_out / adapter_out run on two internal copy streams with double-buffered staging,
  * so the copies of step i overlap the kernels of step i+1; the outputs of a step are valid after fo_stream_wait(ticket).
  * At most two steps may be outstanding; the host buffers of a step must stay untouched until its wait returns. */
 int fo_stream_step_async(fo_ctx* ctx, const int32_t* ids, int n, const void* pcm, int pcm_dtype, float scale,
